@@ -1,0 +1,435 @@
+"""Generate tests/golden/*.npz by running the REFERENCE package itself.
+
+Runs only in the build container (needs /root/reference).  It copies the
+reference's python package to a scratch directory (nothing is copied into this
+repo), builds its cffi spline exactly as the reference does
+(`python rvspecfit/ffibuilder.py`), stubs the absent third-party imports
+(h5py, astropy, numdifftools, matplotlib), injects seeded synthetic template
+banks (rvspecfit_b200/synth.py) straight into the reference's caches
+(spec_inter.interp_cache, fitter_ccf.CCFCache -- SURVEY.md §8c) and records what
+the reference computes.  The resulting fixtures travel to the GPU box; the
+reference does not.
+
+    python tests/golden/make_golden.py            # all fixtures
+    python tests/golden/make_golden.py kat chisq  # a subset
+
+numdifftools is absent, so `process` fixtures are produced with
+ndf.Hessian replaced by oracle.central_hessian: param_err / param_covar /
+bad_hessian in those fixtures are NOT reference outputs ("parity unpinned").
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from rvspecfit_b200 import synth  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from helpers import PROBE_PARAMS  # noqa: E402
+
+REF_SRC = '/root/reference/py/rvspecfit'
+
+
+def load_reference():
+    work = os.environ.get('RVS_REF_WORK') or os.path.join(tempfile.gettempdir(), 'rvs_ref_work')
+    pkg = os.path.join(work, 'rvspecfit')
+    if not os.path.exists(os.path.join(pkg, '_version.py')):
+        if os.path.exists(work):
+            shutil.rmtree(work)
+        os.makedirs(work)
+        shutil.copytree(REF_SRC, pkg)
+        with open(os.path.join(pkg, '_version.py'), 'w') as fp:
+            fp.write("version = '0+golden'\n__version__ = version\n")
+        subprocess.check_call([sys.executable, 'rvspecfit/ffibuilder.py'], cwd=work,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for m in ['h5py', 'astropy', 'astropy.io', 'astropy.io.fits', 'numdifftools',
+              'matplotlib', 'matplotlib.pyplot']:
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.path.insert(0, work)
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import oracle
+    ndf = sys.modules['numdifftools']
+
+    class MinStepGenerator:
+        def __init__(self, base_step=None):
+            self.base_step = base_step
+
+    class Hessian:
+        def __init__(self, f, step=None):
+            self.f, self.step = f, step
+
+        def __call__(self, x):
+            steps = self.step.base_step if self.step is not None else \
+                [oracle.HESS_STEP[k] for k in synth.PARNAMES]
+            return oracle.central_hessian(self.f, x, steps)
+    ndf.MinStepGenerator, ndf.Hessian = MinStepGenerator, Hessian
+    import rvspecfit  # noqa: F401
+    from rvspecfit import (spec_fit, spec_inter, vel_fit, fitter_ccf, make_ccf,
+                           read_grid, utils, spliner, make_nd)
+    return types.SimpleNamespace(spec_fit=spec_fit, spec_inter=spec_inter,
+                                 vel_fit=vel_fit, fitter_ccf=fitter_ccf,
+                                 make_ccf=make_ccf, read_grid=read_grid, utils=utils,
+                                 spliner=spliner, make_nd=make_nd, oracle=oracle)
+
+
+def inject_grid(R, setup, name=None):
+    name = name or setup['name']
+    si = R.spec_inter
+    si.interp_cache.template_lib = 'synthetic/'
+    it = si.SpecInterpolator(
+        name, si.GridInterp(setup['uvecs'], setup['idgrid'], setup['vec'],
+                            setup['dats'], exp=True),
+        si.GridOutsideCheck(setup['uvecs'], setup['vec'], setup['idgrid']),
+        setup['lam'], R.read_grid.LogParamMapper([0]), setup['parnames'],
+        log_step=True)
+    si.interp_cache.interps[name] = it
+    return it
+
+
+def inject_tri(R, setup, name):
+    """Delaunay product assembled with the reference's own make_nd logic
+    (make_nd.py:101-140) from in-memory arrays."""
+    import scipy.spatial
+    si = R.spec_inter
+    vec = setup['vec'].astype(float)
+    state = np.random.get_state()
+    np.random.seed(1)
+    vec = vec + np.random.uniform(-1e-6, 1e-6, size=vec.shape)
+    np.random.set_state(state)
+    edge = R.make_nd.getedgevertices(vec)
+    near = scipy.spatial.cKDTree(vec.T).query(edge.T)[1]
+    nspec = setup['dats'].shape[0]
+    vec = np.hstack((vec, edge))
+    specs = np.append(setup['dats'], np.array([setup['dats'][_] for _ in near]), axis=0)
+    flags = np.concatenate((np.zeros(nspec), np.ones(edge.shape[1])))
+    specs = specs.astype(np.float64)
+    flags = flags.astype(np.float64)[:, None]
+    tri = scipy.spatial.Delaunay(vec.astype(np.float64).T)
+    si.interp_cache.template_lib = 'synthetic/'
+    it = si.SpecInterpolator(name, si.TriInterp(tri, specs, exp=True),
+                             si.TriInterp(tri, flags, exp=False), setup['lam'],
+                             R.read_grid.LogParamMapper([0]), setup['parnames'],
+                             log_step=True)
+    si.interp_cache.interps[name] = it
+    return it
+
+
+CONFIG = dict(min_vel=-1000, max_vel=1000, vel_step0=5, max_vsini=500, min_vsini=0.1,
+              min_vel_step=0.2, second_minimizer=True, template_lib='synthetic/')
+
+
+def frozen_config(R, **kw):
+    c = dict(CONFIG)
+    c.update(kw)
+    return R.utils.freezeDict(c)
+
+
+def checksum(a):
+    return float(np.asarray(a, dtype=np.float64).sum())
+
+
+# ------------------------------------------------------------------ fixtures
+def gold_kat(R):
+    """Known-answer vectors of the native spline (tests/test_spline.py shapes),
+    the vsini kernel / convolution and the continuum-marginalised chi-square."""
+    rs = np.random.RandomState(11)
+    out = {}
+    for tag, x in (('lin', np.linspace(1000, 2000, 1000)),
+                   ('log', 10**np.linspace(3, 4, 1000))):
+        y = np.sin(x / 10) + rs.normal(size=len(x))
+        ex = np.sort(rs.uniform(x[0], min(x[-1], 2000) - 1e-3, size=2000))
+        s = R.spliner.Spline(x, y, log_step=(tag == 'log'))
+        out.update({f'spl_{tag}_x': x, f'spl_{tag}_y': y, f'spl_{tag}_ex': ex,
+                    f'spl_{tag}_A': s.A, f'spl_{tag}_B': s.B, f'spl_{tag}_C': s.C,
+                    f'spl_{tag}_D': s.D, f'spl_{tag}_val': s(ex)})
+    Rs = np.array([1e-3, 0.05, 0.4, 0.999, 1.0, 1.7, 3.2, 12.5, 40.01])
+    out['vsini_R'] = Rs
+    for i, r in enumerate(Rs):
+        out[f'vsini_k{i}'] = R.spec_fit.compute_vsini_kernel(r)
+    lam = synth.template_wavelengths(4550, 5450, 1.0)
+    templ = 1 - 0.5 * np.exp(-0.5 * ((lam - 5000.3) / 1.5)**2) + 0.01 * rs.normal(size=len(lam))
+    vs = np.array([0., 1e-7, 3., 30., 150., 499.])
+    out['conv_lam'], out['conv_templ'], out['conv_vsini'] = lam, templ, vs
+    for i, v in enumerate(vs):
+        out[f'conv_out{i}'] = R.spec_fit.convolve_vsini(lam, templ, v)
+    # chi-square kernel: cholesky route, svd route with coefficients
+    npix = 700
+    lam_o = np.linspace(4600, 5400, npix)
+    t = 1 - 0.4 * np.exp(-0.5 * ((lam_o - 5003) / 2.)**2)
+    es = 0.02 * (1 + 0.5 * rs.uniform(size=npix))
+    sp = t * (1 + 0.2 * (lam_o - 5000) / 400) * 3.3 + es * rs.normal(size=npix)
+    out.update(c0_lam=lam_o, c0_templ=t, c0_spec=sp, c0_espec=es)
+    for npoly, rbf in ((5, True), (10, True), (15, True), (10, False), (2, True)):
+        P = R.spec_fit.get_poly_basis(lam_o, npoly, rbf=rbf)
+        tag = f'{npoly}_{int(rbf)}'
+        out[f'c0_basis_{tag}'] = P
+        out[f'c0_chol_{tag}'] = R.spec_fit.get_chisq0(sp, t, P, espec=es)
+        c, co = R.spec_fit.get_chisq0(sp, t, P, get_coeffs=True, espec=es)
+        out[f'c0_svd_{tag}'] = c
+        out[f'c0_coeffs_{tag}'] = co
+    np.savez_compressed(os.path.join(HERE, 'kat.npz'), **out)
+
+
+
+
+def gold_interp(R):
+    """Template evaluation: polylinear (with and without holes) and Delaunay."""
+    out = {}
+    full = synth.make_setup('test', 'tiny', seed=3)
+    holed = synth.make_setup('test', 'tiny', seed=3, holes=3)
+    out['params'] = np.array(PROBE_PARAMS)
+    for tag, st in (('grid', full), ('holes', holed)):
+        it = inject_grid(R, st, name='g_' + tag)
+        out[f'{tag}_dats_sum'] = checksum(st['dats'])
+        out[f'{tag}_spec'] = np.array([it.eval(p) for p in PROBE_PARAMS])
+        out[f'{tag}_outside'] = np.array([float(it.outsideFlag(p)) for p in PROBE_PARAMS])
+    it = inject_tri(R, full, 'g_tri')
+    sp, of = [], []
+    for p in PROBE_PARAMS:
+        s = it.eval(p)
+        sp.append(np.full(len(full['lam']), np.nan) if np.ndim(s) == 0 else s)
+        of.append(float(it.outsideFlag(p)))
+    out['tri_spec'], out['tri_outside'] = np.array(sp), np.array(of)
+    np.savez_compressed(os.path.join(HERE, 'interp.npz'), **out)
+
+
+def make_objects(arms, layout, n, seed0, sn_range=(20, 200), vel_sig=150., bad_frac=0.01,
+                 lam_override=None):
+    """n synthetic multi-arm objects; returns list of dict(params, vel, arms=[(name,lam,spec,espec,bad)])."""
+    pars = synth.random_params(layout, n, seed0)
+    rs = np.random.RandomState(seed0 + 1)
+    objs = []
+    for i in range(n):
+        vel = rs.normal(0, vel_sig)
+        sn = np.exp(rs.uniform(*np.log(sn_range)))
+        data = []
+        for a, st in enumerate(arms):
+            lam = None if lam_override is None else lam_override[a]
+            lam, spec, espec, bad = synth.fake_spectrum(st, pars[i], vel, sn,
+                                                        seed0 + 100 * i + a, lam=lam,
+                                                        bad_frac=bad_frac)
+            data.append((st['name'], lam, spec, espec, bad))
+        objs.append(dict(params=pars[i], vel=vel, sn=sn, arms=data))
+    return objs
+
+
+def specdata_of(R, obj):
+    return [R.spec_fit.SpecData(nm, lam, sp, es, badmask=bad)
+            for nm, lam, sp, es, bad in obj['arms']]
+
+
+def pack_objects(objs, out, prefix):
+    out[prefix + 'n'] = len(objs)
+    out[prefix + 'params'] = np.array([o['params'] for o in objs])
+    out[prefix + 'vel'] = np.array([o['vel'] for o in objs])
+    for i, o in enumerate(objs):
+        out[f'{prefix}{i}_names'] = np.array([a[0] for a in o['arms']])
+        for a, (nm, lam, sp, es, bad) in enumerate(o['arms']):
+            out[f'{prefix}{i}_{a}_lam'] = lam
+            out[f'{prefix}{i}_{a}_spec'] = sp
+            out[f'{prefix}{i}_{a}_espec'] = es
+            out[f'{prefix}{i}_{a}_bad'] = bad
+
+
+def gold_chisq(R):
+    """get_chisq / find_best on a single-arm test-shape object (polylinear and
+    Delaunay) and on a DESI-shaped 3-arm object."""
+    out = {}
+    cfg = frozen_config(R)
+    st = synth.make_setup('test', 'tiny', seed=3)
+    inject_grid(R, st, 'test')
+    tri = dict(st)
+    tri['name'] = 'test_tri'
+    inject_tri(R, st, 'test_tri')
+    objs = make_objects([st], 'tiny', 2, 500, bad_frac=0.02)
+    pack_objects(objs, out, 'one_')
+    out['one_dats_sum'] = checksum(st['dats'])
+    rs = np.random.RandomState(5)
+    # evaluation points: (vel, teff, logg, feh, alpha, vsini or -1 for None)
+    ev = []
+    for k in range(14):
+        p = synth.random_params('tiny', 1, 900 + k)[0]
+        ev.append([rs.uniform(-600, 600), *p, [-1, 0., 5., 40., 180.][k % 5]])
+    ev.append([100., 9500., 2.0, -1.0, 0.2, 10.])     # off grid -> penalty
+    ev.append([-50., 5000., 2.0, -2.6, 0.2, -1])      # off grid
+    ev = np.array(ev)
+    out['one_eval'] = ev
+    for npoly, rbf in ((15, True), (5, True), (8, False)):
+        opts = {'npoly': npoly, 'rbf_continuum': rbf}
+        for name in ('test', 'test_tri'):
+            res = np.zeros((len(objs), len(ev)))
+            for i, o in enumerate(objs):
+                sd = specdata_of(R, o)
+                if name != 'test':
+                    sd = [R.spec_fit.SpecData(name, s.lam, s.spec, s.espec, badmask=s.badmask)
+                          for s in sd]
+                for j, e in enumerate(ev):
+                    rot = None if e[5] < 0 else (e[5],)
+                    res[i, j] = R.spec_fit.get_chisq(sd, e[0], tuple(e[1:5]), rot,
+                                                     options=opts, config=cfg)
+            out[f'one_chisq_{name}_{npoly}_{int(rbf)}'] = res
+    # full_output at one point
+    sd = specdata_of(R, objs[0])
+    fo = R.spec_fit.get_chisq(sd, ev[2, 0], tuple(ev[2, 1:5]), (ev[2, 5],),
+                              options={'npoly': 15}, config=cfg, full_output=True)
+    out['one_full_chisq'] = fo['chisq']
+    out['one_full_chisq_array'] = np.array(fo['chisq_array'])
+    out['one_full_npix'] = np.array(fo['npix_array'])
+    out['one_full_model'] = fo['models'][0]
+    out['one_full_raw'] = fo['raw_models'][0]
+    out['one_cont'] = R.spec_fit.get_chisq_continuum(sd, options={'npoly': 15})['chisq_array']
+    # RV scan
+    vg = np.arange(-1000, 1000, 5.)
+    plist = [tuple(objs[0]['params']), (5000., 2.0, -1.0, 0.2), (7000., 4.0, -0.5, 0.)]
+    for tag, rot in (('norot', None), ('rot', (25.,))):
+        chi = np.zeros((len(vg), len(plist)))
+        cache = R.spec_fit.LRUDict(100)
+        for j, p in enumerate(plist):
+            for i, v in enumerate(vg):
+                chi[i, j] = R.spec_fit.get_chisq(sd, v, p, rot, options={'npoly': 15},
+                                                 config=cfg, cache=cache)
+        fb = R.spec_fit.find_best(sd, vg, plist, rot_params=rot, options={'npoly': 15},
+                                  config=cfg)
+        out[f'scan_{tag}_chisq'] = chi
+        for k in ('best_chi', 'best_vel', 'vel_err', 'kurtosis', 'skewness', 'probs'):
+            out[f'scan_{tag}_{k}'] = fb[k]
+        out[f'scan_{tag}_best_param'] = np.array(fb['best_param'])
+    out['scan_vel_grid'] = vg
+    out['scan_params'] = np.array(plist)
+
+    # DESI-shaped three-arm object, tiny node layout, npoly 10, +-1500 km/s
+    arms = [synth.make_setup(a, 'tiny', seed=21 + k)
+            for k, a in enumerate(('desi_b', 'desi_r', 'desi_z'))]
+    for a in arms:
+        inject_grid(R, a)
+    cfg3 = frozen_config(R, min_vel=-1500, max_vel=1500)
+    o3 = make_objects(arms, 'tiny', 1, 700, bad_frac=0.01)
+    pack_objects(o3, out, 'desi_')
+    out['desi_dats_sum'] = np.array([checksum(a['dats']) for a in arms])
+    sd3 = specdata_of(R, o3[0])
+    ev3 = ev[:8].copy()
+    ev3[:, 0] *= 2
+    out['desi_eval'] = ev3
+    out['desi_chisq'] = np.array([
+        R.spec_fit.get_chisq(sd3, e[0], tuple(e[1:5]), None if e[5] < 0 else (e[5],),
+                             options={'npoly': 10}, config=cfg3) for e in ev3])
+    vg3 = np.arange(-1500, 1500, 5.)
+    p3 = tuple(o3[0]['params'])
+    cache = R.spec_fit.LRUDict(100)
+    out['desi_scan_chisq'] = np.array([
+        R.spec_fit.get_chisq(sd3, v, p3, (12.,), options={'npoly': 10}, config=cfg3,
+                             cache=cache) for v in vg3])
+    fb = R.spec_fit.find_best(sd3, vg3, [p3], rot_params=(12.,), options={'npoly': 10},
+                              config=cfg3)
+    for k in ('best_chi', 'best_vel', 'vel_err', 'kurtosis', 'skewness'):
+        out[f'desi_scan_{k}'] = fb[k]
+    np.savez_compressed(os.path.join(HERE, 'chisq.npz'), **out)
+
+
+def gold_process(R):
+    """vel_fit.process / firstguess on BASELINE config-1-shaped input (7^4
+    regular grid, 800 px, npoly 15, vsini free) and on a DESI-shaped object."""
+    out = {}
+    cfg = frozen_config(R)
+    st = synth.make_setup('test', 'test', seed=3)
+    inject_grid(R, st, 'test')
+    out['test_dats_sum'] = checksum(st['dats'])
+    objs = make_objects([st], 'test', 3, 4000, sn_range=(60, 150), vel_sig=100.,
+                        bad_frac=0.0)
+    pack_objects(objs, out, 'c1_')
+    start = {'logg': 2, 'teff': 5000, 'feh': -0.2, 'alpha': 0.2, 'vsini': 0.1}
+    keys = ('vel', 'vel_err', 'vel_skewness', 'vel_kurtosis', 'vsini', 'chisq', 'logl')
+    for i, o in enumerate(objs):
+        sd = specdata_of(R, o)
+        for tag, c in (('bfgs', cfg), ('nm', frozen_config(R, second_minimizer=False))):
+            res = R.vel_fit.process(sd, dict(start), fixParam=[], config=c,
+                                    options={'npoly': 15})
+            for k in keys:
+                out[f'c1_{i}_{tag}_{k}'] = res[k]
+            out[f'c1_{i}_{tag}_param'] = np.array([res['param'][k] for k in synth.PARNAMES])
+            out[f'c1_{i}_{tag}_param_err'] = np.array([res['param_err'][k]
+                                                       for k in synth.PARNAMES])
+            out[f'c1_{i}_{tag}_chisq_array'] = np.array(res['chisq_array'])
+            out[f'c1_{i}_{tag}_yfit'] = res['yfit'][0]
+            out[f'c1_{i}_{tag}_success'] = res['minimize_success']
+        if i == 0:
+            res = R.vel_fit.process(sd, dict(start), fixParam=['vsini', 'alpha'],
+                                    config=cfg, options={'npoly': 15},
+                                    priors={'teff': (5200., 300.)})
+            out['c1_0_fix_vel'] = res['vel']
+            out['c1_0_fix_param'] = np.array([res['param'][k] for k in synth.PARNAMES])
+            out['c1_0_fix_chisq'] = res['chisq']
+    fg = R.vel_fit.firstguess(specdata_of(R, objs[0]), config=cfg, options={'npoly': 15},
+                              paramsgrid={'logg': [1, 3, 4.5], 'teff': [4000, 6000, 9000],
+                                          'feh': [-1.5, -0.5], 'alpha': [0.2]},
+                              vsinigrid=(None, 50))
+    out['c1_fg'] = np.array([fg[k] for k in synth.PARNAMES] + [fg.get('vsini', -1)])
+    np.savez_compressed(os.path.join(HERE, 'process.npz'), **out)
+
+
+def gold_ccf(R):
+    """fitter_ccf.fit on a Gaia-RVS-shaped window and on two arms, with the
+    bank built by the reference's own make_ccf.preprocess_model_list."""
+    out = {}
+    for tag, shapes, every, npts in (('rvs', ('gaiarvs',), 9, 2048),
+                                     ('two', ('desi_b', 'desi_r'), 12, 4096)):
+        arms = [synth.make_setup(s, 'tiny', seed=31 + k) for k, s in enumerate(shapes)]
+        cfg = frozen_config(R, max_vel=600 if tag == 'rvs' else 1000, vel_step0=2.5)
+        CC = R.fitter_ccf.CCFCache
+        vsinis = [0., 30., 300.] if tag == 'rvs' else [0., 100.]
+        for a in arms:
+            sh = synth.SHAPES[a['shape']]
+            conf = R.make_ccf.get_ccf_config(logl0=np.log(sh['t_lo']),
+                                             logl1=np.log(sh['t_hi']), npoints=npts)
+            inds = np.arange(0, a['dats'].shape[0], every)
+            specs = np.exp(a['dats'][inds].astype(np.float64))
+            vec = a['vec'].T[inds].copy()
+            vec[:, 0] = 10**vec[:, 0]
+            models, params, vs = R.make_ccf.preprocess_model_list(a['lam'], specs, vec,
+                                                                  conf, vsinis=vsinis)
+            nm = a['name']
+            CC.ccfs[nm] = np.fft.rfft(models, axis=1)
+            CC.ccf2s[nm] = np.fft.rfft(models**2, axis=1)
+            CC.ccf_models[nm] = models
+            CC.ccf_info[nm] = dict(params=params, ccfconf=conf, vsinis=vs,
+                                   parnames=a['parnames'])
+            out[f'{tag}_{nm}_models'] = models.astype(np.float64)
+            out[f'{tag}_{nm}_params'] = params
+            out[f'{tag}_{nm}_vsinis'] = np.array(vs)
+            out[f'{tag}_{nm}_conf'] = np.array([conf['logl0'], conf['logl1'],
+                                                conf['npoints'], conf['splinestep']])
+        objs = make_objects(arms, 'tiny', 2, 8100, sn_range=(30, 80), vel_sig=120.)
+        pack_objects(objs, out, tag + '_')
+        for i, o in enumerate(objs):
+            sd = specdata_of(R, o)
+            for a, s in enumerate(sd):
+                ps, pi = R.make_ccf.preprocess_data(s.lam, s.spec, s.espec,
+                                                    badmask=s.badmask,
+                                                    ccfconf=CC.ccf_info[s.name]['ccfconf'])
+                out[f'{tag}_{i}_{a}_proc_spec'] = ps
+                out[f'{tag}_{i}_{a}_proc_ivar'] = pi
+            res = R.fitter_ccf.fit(sd, cfg)
+            out[f'{tag}_{i}_best_vel'] = res['best_vel']
+            out[f'{tag}_{i}_best_vsini'] = res['best_vsini']
+            out[f'{tag}_{i}_best_ccf'] = res['best_ccf']
+            out[f'{tag}_{i}_best_par'] = np.array([res['best_par'][k] for k in synth.PARNAMES])
+            out[f'{tag}_{i}_vel_grid'] = res['vel_grid']
+    np.savez_compressed(os.path.join(HERE, 'ccf.npz'), **out)
+
+
+ALL = dict(kat=gold_kat, interp=gold_interp, chisq=gold_chisq, process=gold_process,
+           ccf=gold_ccf)
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or list(ALL)
+    R = load_reference()
+    for w in which:
+        print('generating', w, flush=True)
+        ALL[w](R)
+    print('done')
