@@ -1,0 +1,178 @@
+/*
+ * rvs_b200.h -- C ABI of librvs_b200.so, the sm_100a implementation of the
+ * rvspecfit per-spectrum likelihood hot path.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Pointers named d_* are DEVICE pointers,
+ *     h_* are HOST pointers.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = default stream).  Every call is stream-ordered and re-entrant;
+ *     the library keeps no global state besides cached cuFFT plans.
+ *   - Return value: 0 on success, a negative RVS_E_* code on a call-level
+ *     error (rvs_last_error() gives the text).  Per-item conditions are
+ *     reported through int32 status arrays (RVS_ST_* bits), never by aborting:
+ *     the Python mirror turns them into the exceptions the reference raises.
+ *   - All arithmetic is fp64; the template grid is stored fp32 (or fp64) as
+ *     the reference stores it (make_interpol.py:363-364) and promoted on use.
+ *
+ * Reference interfaces replaced (paths under /root/reference/py/rvspecfit/):
+ *   rvs_spline_construct / rvs_spline_eval  <- cffi `_spliner.construct`,
+ *       `_spliner.evaler` (ffibuilder.py:10-17, src/spliner.c:7-108)
+ *   rvs_template_build   <- GridInterp.__call__ / TriInterp.__call__ weighted
+ *       sum + exp (spec_inter.py:134-194, 35-59), convolve_vsini +
+ *       compute_vsini_kernel (spec_fit.py:565-682), Spline.__init__
+ *       (spliner.py:10-32)
+ *   rvs_obs_prepare, rvs_basis_build <- SpecData.__init__ products and
+ *       get_poly_basis (spec_fit.py:103-108, 148-176)
+ *   rvs_chisq_scan, rvs_chisq_fused <- evalRV + get_chisq0 per arm inside
+ *       get_chisq / find_best (spec_fit.py:707-727, 205-249, 879-975, 1062-1071)
+ *   rvs_scan_stats       <- find_best tail (spec_fit.py:1072-1092)
+ *   rvs_ccf_*            <- fitter_ccf.fit hot loop (fitter_ccf.py:126-232)
+ */
+#ifndef RVS_B200_H
+#define RVS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVS_E_ARG -1      /* bad argument (size, null pointer, unsupported npoly) */
+#define RVS_E_CUDA -2     /* CUDA runtime / cuFFT error */
+#define RVS_E_NODEVICE -3 /* no CUDA device */
+#define RVS_E_LIMIT -4    /* problem exceeds a compiled-in limit */
+
+/* per-item status bits */
+#define RVS_ST_OK 0
+#define RVS_ST_TEMPLATE_BAD 1 /* template not finite or |value| > 1e100 */
+#define RVS_ST_NOT_PD 2       /* continuum normal matrix not positive definite /
+                                 result not finite: caller takes the SVD route */
+#define RVS_ST_RANGE 4        /* evaluation wavelength outside the template */
+#define RVS_ST_TAPS 8         /* vsini kernel longer than RVS_MAX_TAPS (truncated) */
+
+#define RVS_MAX_NPOLY 16
+#define RVS_MAX_TAPS 2048
+
+const char *rvs_last_error(void);
+int rvs_version(void);
+/* number of CUDA kernels this library has launched in this process (for
+ * bench.py's gpu_launches) */
+int64_t rvs_launch_count(void);
+
+/* ---- native spline: drop-in for the reference's cffi module ------------- */
+/* Host-buffer entry points with the reference's exact signatures and status
+ * codes (0 / -1 evaluation point outside knots / -2 knots not uniform).  They
+ * run on the GPU (copy in, kernel, copy out). */
+void rvs_spline_construct(double *h_xs, double *h_ys, int N, double *h_A, double *h_B,
+                          double *h_C, double *h_D, double *h_h);
+int rvs_spline_eval(double *h_evalx, int nevalx, int N, double *h_xs, double *h_hs,
+                    double *h_As, double *h_Bs, double *h_Cs, double *h_Ds, int log_step,
+                    double *h_ret);
+
+/* ---- descriptors (plain C structs of pointers and sizes) ----------------- */
+/* Knot grid of one spectral setup (template wavelength grid) and its Thomas
+ * tables.  Filled on the host by rvs_knot_tables / rvs_knot_info; the d_*
+ * members are device copies of the host arrays those functions produce. */
+typedef struct {
+  const double *d_lam_t; /* [npix_t] knots */
+  const double *d_h;     /* [npix_t-1] x[i+1]-x[i] */
+  const double *d_hinv;  /* [npix_t-1] 1/h */
+  const double *d_cp;    /* [npix_t-2] modified super-diagonal (spliner.c:33-37) */
+  const double *d_winv;  /* [npix_t-2] reciprocal pivots */
+  int32_t npix_t;
+  int32_t log_step;      /* 1: knots uniform in ln(x); 0: uniform in x */
+  double x0, xlast;      /* first / last knot */
+  double q0, qstep_inv;  /* ln(x0) (or x0) and 1/step of the uniform coordinate */
+  double lnstep;         /* ln(x[1]/x[0]) (vsini kernel scale) */
+} rvs_knots;
+
+/* Ragged batch of observed spectra of one setup and their derived products
+ * (rvs_obs_prepare, rvs_basis_build).  Object i owns pixels
+ * [off[i], off[i+1]) of every pool; its continuum basis row r is
+ * d_P[r*pstride + boff[i] + p]. */
+typedef struct {
+  const double *d_lam, *d_loglam, *d_dn, *d_einv; /* pixel pools */
+  const double *d_sumlog2;                        /* [B] 2*sum ln sigma */
+  const int64_t *d_off;                           /* [B+1] */
+  const double *d_P;
+  int64_t pstride;
+  const int64_t *d_boff; /* [B] */
+  int32_t npoly;
+  int32_t nobj;
+} rvs_obs;
+
+/* ---- template evaluation ------------------------------------------------- */
+/* Host helpers (plain C, no device work).  rvs_knot_tables: h, hinv (n-1
+ * each), cp, winv (n-2 each).  rvs_knot_info fills the scalar members of
+ * rvs_knots from the host knot array and returns 0, or -2 if the knots are
+ * not uniform to 1e-10 (the reference evaler's validation, spliner.c:84-96). */
+void rvs_knot_tables(const double *h_x, int n, double *h_h, double *h_hinv, double *h_cp,
+                     double *h_winv);
+int rvs_knot_info(const double *h_x, int n, int log_step, rvs_knots *out);
+
+/* For each item k < K:
+ *   s[p]  = sum_j w[k,j] * grid[ids[k,j], p]       (fp64 accumulate)
+ *   y     = log_spec ? exp(s) : s
+ *   y     = vsini[k] > 0 ? rotational broadening of y : y
+ *   z     = second derivatives of the natural cubic spline through (lam_t, y)
+ * Output d_yz[(k*yz_stride + p)*2 + {0,1}] = y[p], z[p].
+ * d_grid: fp32 (grid_f64=0) or fp64 rows of length npix_t, row stride `ld`
+ * elements (ld % 4 == 0, base 16-byte aligned).  d_ids int32 [K,nvert];
+ * d_w fp64 [K,nvert].  d_vsini may be NULL.  d_status int32[K] receives
+ * RVS_ST_TEMPLATE_BAD / RVS_ST_TAPS. */
+int rvs_template_build(const void *d_grid, int grid_f64, int64_t ld, const rvs_knots *knots,
+                       const int32_t *d_ids, const double *d_w, int nvert,
+                       const double *d_vsini, int log_spec, int K, double *d_yz,
+                       int64_t yz_stride, int32_t *d_status, void *stream);
+
+/* ---- observed-spectrum products ------------------------------------------ */
+/* Produces loglam = ln(lam), dn = spec/sigma, einv = 1/sigma with
+ * sigma = sqrt(espec^2 + sys^2) (sys may be 0), and
+ * sumlog2[i] = 2*sum ln sigma  (the 2*log(espec).sum() term). */
+int rvs_obs_prepare(const double *d_lam, const double *d_spec, const double *d_espec,
+                    const int64_t *d_off, int B, double espec_sys, double *d_loglam,
+                    double *d_dn, double *d_einv, double *d_sumlog2, void *stream);
+
+/* Continuum basis of G wavelength grids: grid g owns pixels
+ * [goff[g], goff[g+1]) of d_lam (ntot = goff[G] pixels in all) and writes rows
+ * r<npoly to d_P[r*pstride + p].  rbf=1: {1,t,t^2} + Gaussian RBFs; rbf=0:
+ * Chebyshev (spec_fit.py:148-176). */
+int rvs_basis_build(const double *d_lam, const int64_t *d_goff, int G, int64_t ntot, int npoly,
+                    int rbf, int64_t pstride, double *d_P, void *stream);
+
+/* ---- chi-square ----------------------------------------------------------- */
+/* For item k < K and trial j < nv:  resample template row tix[k] of d_yz at
+ * velocity vels[k*nv+j] onto object oix[k]'s wavelengths, solve the continuum
+ * normal equations and return
+ *   chisq[k*nv+j] = 2 sum ln L_ii + sumlog2 + |D - a^T G|^2
+ * and status[k*nv+j] (RVS_ST_NOT_PD, RVS_ST_RANGE).
+ * Optional outputs (may be NULL; nv must be 1): d_coeffs [K,npoly]; d_raw,
+ * d_model: resampled template and continuum-multiplied model written at
+ * d_moff[k] + p. */
+int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
+                   const rvs_knots *knots, const rvs_obs *obs, const int32_t *d_oix,
+                   const double *d_vels, int nv, int K, double *d_chisq, int32_t *d_status,
+                   double *d_coeffs, double *d_raw, double *d_model, const int64_t *d_moff,
+                   void *stream);
+
+/* Fused optimiser-phase evaluation: template build (as rvs_template_build) and
+ * chi-square at ONE velocity per item without the HBM round trip of the
+ * spline.  Item k uses object oix[k]; outputs as rvs_chisq_scan with nv=1,
+ * status additionally carries the template bits. */
+int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld, const rvs_knots *knots,
+                    const int32_t *d_ids, const double *d_w, int nvert, const double *d_vsini,
+                    int log_spec, const rvs_obs *obs, const int32_t *d_oix,
+                    const double *d_vels, int K, double *d_chisq, int32_t *d_status,
+                    void *stream);
+
+/* RV-grid statistics of find_best for S scans: scan s has nv velocities
+ * vels[s*nv..] and chi-squares chisq[(s*npar+q)*nv + j] for npar templates.
+ * out[s*8..] = best_chi, best_vel, vel_err, skewness, kurtosis, i_vel, i_par, 0;
+ * probs (may be NULL) [S,nv]. */
+int rvs_scan_stats(const double *d_vels, const double *d_chisq, int S, int npar, int nv,
+                   int quadratic, double *d_out, double *d_probs, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

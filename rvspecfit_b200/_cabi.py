@@ -1,0 +1,102 @@
+"""ctypes binding of librvs_b200.so (include/rvs_b200.h).
+
+The product has no CPU path: if the shared library is missing, or no CUDA
+device is present when a compute entry point is called, this module raises.
+PyTorch is used only to own device memory and streams; every compute call goes
+through the C ABI with raw device pointers.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'librvs_b200.so')
+
+c_dp = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_dbl = ctypes.c_double
+
+ST_OK, ST_TEMPLATE_BAD, ST_NOT_PD, ST_RANGE, ST_TAPS = 0, 1, 2, 4, 8
+MAX_NPOLY = 16
+
+
+class Knots(ctypes.Structure):
+    """struct rvs_knots"""
+    _fields_ = [('d_lam_t', c_dp), ('d_h', c_dp), ('d_hinv', c_dp), ('d_cp', c_dp),
+                ('d_winv', c_dp), ('npix_t', ctypes.c_int32), ('log_step', ctypes.c_int32),
+                ('x0', c_dbl), ('xlast', c_dbl), ('q0', c_dbl), ('qstep_inv', c_dbl),
+                ('lnstep', c_dbl)]
+
+
+class Obs(ctypes.Structure):
+    """struct rvs_obs"""
+    _fields_ = [('d_lam', c_dp), ('d_loglam', c_dp), ('d_dn', c_dp), ('d_einv', c_dp),
+                ('d_sumlog2', c_dp), ('d_off', c_dp), ('d_P', c_dp), ('pstride', c_i64),
+                ('d_boff', c_dp), ('npoly', ctypes.c_int32), ('nobj', ctypes.c_int32)]
+
+
+class CcfArm(ctypes.Structure):
+    """struct rvs_ccf_arm"""
+    _fields_ = [('d_fft', c_dp), ('d_fft2', c_dp), ('npoints', ctypes.c_int32),
+                ('ntempl', ctypes.c_int32), ('continuum', ctypes.c_int32),
+                ('nsub', ctypes.c_int32), ('d_subind', c_dp), ('d_subvel', c_dp)]
+
+
+# name -> (restype, argtypes); every symbol include/rvs_b200.h declares
+SIGNATURES = {
+    'rvs_last_error': (ctypes.c_char_p, []),
+    'rvs_version': (c_int, []),
+    'rvs_launch_count': (c_i64, []),
+    'rvs_spline_construct': (None, [c_dp, c_dp, c_int, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    'rvs_spline_eval': (c_int, [c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_int,
+                                c_dp]),
+    'rvs_knot_tables': (None, [c_dp, c_int, c_dp, c_dp, c_dp, c_dp]),
+    'rvs_knot_info': (c_int, [c_dp, c_int, c_int, ctypes.POINTER(Knots)]),
+    'rvs_template_build': (c_int, [c_dp, c_int, c_i64, ctypes.POINTER(Knots), c_dp, c_dp, c_int,
+                                   c_dp, c_int, c_int, c_dp, c_i64, c_dp, c_dp]),
+    'rvs_obs_prepare': (c_int, [c_dp, c_dp, c_dp, c_dp, c_int, c_dbl, c_dp, c_dp, c_dp, c_dp,
+                                c_dp]),
+    'rvs_basis_build': (c_int, [c_dp, c_dp, c_int, c_i64, c_int, c_int, c_i64, c_dp, c_dp]),
+    'rvs_chisq_scan': (c_int, [c_dp, c_i64, c_dp, ctypes.POINTER(Knots), ctypes.POINTER(Obs),
+                               c_dp, c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                               c_dp]),
+    'rvs_chisq_fused': (c_int, [c_dp, c_int, c_i64, ctypes.POINTER(Knots), c_dp, c_dp, c_int,
+                                c_dp, c_int, ctypes.POINTER(Obs), c_dp, c_dp, c_int, c_dp, c_dp,
+                                c_dp]),
+    'rvs_scan_stats': (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} not found: build it with `python __graft_entry__.py build` '
+                '(make -C rvspecfit_b200/csrc).  There is no CPU fallback.')
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)      # AttributeError if the symbol is missing
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+class RvsError(RuntimeError):
+    pass
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().rvs_last_error().decode()
+        raise RvsError(f'{what} failed with code {rc}: {msg}')
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('rvspecfit_b200 needs a CUDA device (sm_100a); there is no CPU path')
+    return torch

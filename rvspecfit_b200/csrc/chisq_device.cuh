@@ -1,0 +1,183 @@
+// Device functions of the chi-square evaluation shared by chisq.cu and fused.cu:
+// spline evaluation from (y,z) pairs, Gram accumulators, warp reductions and
+// the small Cholesky solve.  See chisq.cu for the reference lines they follow.
+#pragma once
+#include <math.h>
+
+#include "common.cuh"
+
+namespace rvs {
+
+// ------------------------------------------------------------------ chi-square
+struct ScanArgs {
+  const double2 *yz;
+  int64_t yz_stride;
+  const int32_t *tix;
+  const double *lam_t, *h, *hinv;
+  int npix_t, log_step;
+  double x0, xlast, q0, qstep_inv;  // knot-grid origin (ln or linear) and 1/step
+  const double *lam, *loglam, *dn, *einv, *sumlog2;
+  const int64_t *off;
+  const int32_t *oix;
+  const double *P;
+  int64_t pstride;
+  const int64_t *boff;
+  const double *vels;
+  int nv, K;
+  double *chisq;
+  int32_t *status;
+  double *coeffs, *raw, *model;
+  const int64_t *moff;
+};
+
+constexpr int SCAN_WARPS = 8;
+
+// spline value at rest wavelength x (spliner.c:97-106) from (y,z) pairs
+__device__ __forceinline__ double spline_eval(const ScanArgs &a, const double2 *yz, double x,
+                                              double q) {
+  int pos = (int)((q - a.q0) * a.qstep_inv);
+  pos = max(0, min(pos, a.npix_t - 2));
+  const double2 c0 = __ldg(yz + pos), c1 = __ldg(yz + pos + 1);
+  const double xl = __ldg(a.lam_t + pos), xr = __ldg(a.lam_t + pos + 1);
+  const double hh = __ldg(a.h + pos), hi = __ldg(a.hinv + pos);
+  const double t1 = hi * (1. / 6), t2 = hh * (1. / 6);
+  const double A = c1.y * t1, B = c0.y * t1;
+  const double C = c1.x * hi - c1.y * t2, D = c0.x * hi - c0.y * t2;
+  const double dl = x - xl, dr = xr - x;
+  return A * dl * dl * dl + B * dr * dr * dr + C * dl + D * dr;
+}
+
+// Reduce N per-lane values over the 32 lanes of a warp with N/2+N/4+... shuffles
+// instead of 5N.  After run(), slot r < ceil(N/32) of lane L holds the warp total
+// of original entry index(r, L) (or index < 0: padding).  Fixed summation tree,
+// hence deterministic.
+template <int N, int O>
+struct WarpScatterReduce {
+  static constexpr int H = (N + 1) / 2;
+  __device__ __forceinline__ static void run(double *v, int lane) {
+    const bool up = (lane & O) != 0;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      const double a = v[i];
+      const double b = (i + H < N) ? v[i + H] : 0.0;
+      const double send = up ? a : b;
+      const double keep = up ? b : a;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+    }
+    if constexpr (O > 1) WarpScatterReduce<H, O / 2>::run(v, lane);
+  }
+  __device__ __forceinline__ static int index(int r, int lane) {
+    int sub;
+    if constexpr (O > 1) sub = WarpScatterReduce<H, O / 2>::index(r, lane);
+    else sub = (r < H) ? r : -1;
+    if (sub < 0) return -1;
+    const int idx = sub + ((lane & O) ? H : 0);
+    return idx < N ? idx : -1;
+  }
+};
+
+template <int N>
+__device__ __forceinline__ void warp_reduce_store(double (&v)[N], double *dst, int lane) {
+  WarpScatterReduce<N, 16>::run(v, lane);
+#pragma unroll
+  for (int r = 0; r < (N + 31) / 32; r++) {
+    const int idx = WarpScatterReduce<N, 16>::index(r, lane);
+    if (idx >= 0) dst[idx] = v[r];
+  }
+}
+
+// Lower-triangle accumulators of rows [R0,R1) of M = G G^T (+ v = G d)
+template <int NP, int R0, int R1>
+struct GramAcc {
+  static constexpr int NM = (R1 * (R1 + 1) - R0 * (R0 + 1)) / 2;
+  double m[NM > 0 ? NM : 1];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < NM; i++) m[i] = 0;
+  }
+  __device__ __forceinline__ void add(const double (&g)[NP]) {
+    int c = 0;
+#pragma unroll
+    for (int i = R0; i < R1; i++) {
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        m[c] = fma(g[i], g[j], m[c]);
+        c++;
+      }
+    }
+  }
+  // transposed butterfly reduction over the warp; the lane that ends up owning
+  // entry c stores it to the packed lower triangle (rows R0.. are contiguous)
+  __device__ __forceinline__ void reduce_store(double *Ms, int lane) {
+    WarpScatterReduce<NM, 16>::run(m, lane);
+#pragma unroll
+    for (int r = 0; r < (NM + 31) / 32; r++) {
+      const int idx = WarpScatterReduce<NM, 16>::index(r, lane);
+      if (idx >= 0) Ms[R0 * (R0 + 1) / 2 + idx] = m[r];
+    }
+  }
+};
+
+template <int NP>
+__device__ __forceinline__ void load_basis(const double *P, int64_t pstride, int64_t col,
+                                           double tn, double (&g)[NP]) {
+#pragma unroll
+  for (int i = 0; i < NP; i++) g[i] = __ldg(P + i * pstride + col) * tn;
+}
+
+// Warp-cooperative Cholesky solve on a packed lower triangle in shared memory.
+// On return a[] holds the coefficients; returns 2*sum ln L_ii, or NaN if M is
+// not positive definite.
+template <int NP>
+__device__ __forceinline__ double chol_solve(double *Ms, double *a, int lane) {
+  double ldet = 0;
+  bool ok = true;
+  for (int j = 0; j < NP; j++) {
+    // diagonal
+    double s = Ms[j * (j + 1) / 2 + j];
+    for (int k = 0; k < j; k++) {
+      const double l = Ms[j * (j + 1) / 2 + k];
+      s -= l * l;
+    }
+    if (!(s > 0) || isinf(s)) ok = false;
+    const double ljj = sqrt(s);
+    ldet += 2.0 * log(ljj);
+    __syncwarp();
+    const int i = j + 1 + lane;
+    if (i < NP) {
+      double t = Ms[i * (i + 1) / 2 + j];
+      for (int k = 0; k < j; k++) t -= Ms[i * (i + 1) / 2 + k] * Ms[j * (j + 1) / 2 + k];
+      Ms[i * (i + 1) / 2 + j] = t / ljj;
+    }
+    if (lane == 0) Ms[j * (j + 1) / 2 + j] = ljj;
+    __syncwarp();
+  }
+  // L y = v ; L^T a = y   (every lane redundantly, operands broadcast from smem)
+  double y[NP];
+#pragma unroll
+  for (int i = 0; i < NP; i++) {
+    double t = a[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) t -= Ms[i * (i + 1) / 2 + k] * y[k];
+    y[i] = t / Ms[i * (i + 1) / 2 + i];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = NP - 1; i >= 0; i--) {
+    double t = y[i];
+#pragma unroll
+    for (int k = i + 1; k < NP; k++) t -= Ms[k * (k + 1) / 2 + i] * y[k];
+    y[i] = t / Ms[i * (i + 1) / 2 + i];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NP; i++) a[i] = y[i];
+  }
+  __syncwarp();
+  return ok ? ldet : nan("");
+}
+
+
+int fill_scan_args(ScanArgs &a, const rvs_knots *kn, const rvs_obs *obs);
+
+}  // namespace rvs

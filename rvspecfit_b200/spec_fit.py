@@ -1,0 +1,482 @@
+"""Likelihood of a spectrum given a template, on the GPU.
+
+Mirror of the reference's spec_fit.py (paths under
+/root/reference/py/rvspecfit/): `SpecData`, `get_chisq`, `find_best`,
+`get_chisq_continuum` keep their signatures, return values and error
+behaviour; `LikelihoodEngine` is the batched sibling they are built on.
+
+All arithmetic of the path -- template interpolation, vsini broadening, spline
+construction, Doppler resampling, continuum normal equations, chi-square, RV
+scan statistics -- runs in librvs_b200.so.  The host resolves grid vertices
+(spec_inter.TemplateBank.locate), adds the additive penalty terms
+(spec_fit.py:863,888-896) and raises the reference's exceptions.
+"""
+import ctypes
+import random
+
+import numpy as np
+import scipy.linalg
+
+from . import _cabi, _dev, spec_inter
+
+SPEED_OF_LIGHT = 299792.458  # km/s, spec_fit.py:23
+
+
+class SpecData:
+    """A single spectroscopic dataset (reference spec_fit.py:70-145)."""
+
+    def __init__(self, name, lam, spec, espec, badmask=None, resolution=None,
+                 dtype=np.float64):
+        if resolution is not None:
+            raise NotImplementedError('resolution matrices are not on the GPU path yet '
+                                      '(SURVEY.md section 8 row f4)')
+        self.name = name
+        self.lam = np.ascontiguousarray(lam, dtype=dtype)
+        self.spec = np.ascontiguousarray(spec, dtype=dtype)
+        self.espec = np.ascontiguousarray(espec, dtype=dtype)
+        self.resolution = None
+        self.spec_error_ratio = np.ascontiguousarray(spec / espec, dtype=dtype)
+        if badmask is None:
+            badmask = np.zeros(len(self.spec), dtype=bool)
+        self.badmask = np.asarray(badmask, dtype=bool)
+        for a in (self.lam, self.spec, self.espec, self.badmask):
+            a.setflags(write=False)
+        self.objid = random.getrandbits(128)
+
+    def __hash__(self):
+        return self.objid
+
+
+class SpectrumBatch:
+    """Ragged batch of spectra of ONE setup in device memory, with the derived
+    per-pixel products and the continuum basis (spec_fit.py:103-108,148-176)."""
+
+    def __init__(self, specdatas):
+        self.n = len(specdatas)
+        self.npix = np.array([len(s.lam) for s in specdatas], dtype=np.int64)
+        self.off = np.concatenate([[0], np.cumsum(self.npix)]).astype(np.int64)
+        self.lam0 = np.array([s.lam[0] for s in specdatas])
+        self.lam1 = np.array([s.lam[-1] for s in specdatas])
+        self.h_lam = np.concatenate([s.lam for s in specdatas])
+        self.h_spec = np.concatenate([s.spec for s in specdatas])
+        self.h_espec = np.concatenate([s.espec for s in specdatas])
+        self.h_bad = np.concatenate([s.badmask for s in specdatas])
+        self.d_lam = _dev.upload(self.h_lam, np.float64)
+        self.d_spec = _dev.upload(self.h_spec, np.float64)
+        self.d_espec = _dev.upload(self.h_espec, np.float64)
+        self.d_off = _dev.upload(self.off, np.int64)
+        # wavelength grids shared between objects share one basis
+        seen, gid, first = {}, np.zeros(self.n, dtype=np.int64), []
+        for i, s in enumerate(specdatas):
+            key = (len(s.lam), s.lam[:4].tobytes(), s.lam[-4:].tobytes(),
+                   float(s.lam.sum()))
+            if key not in seen:
+                seen[key] = len(first)
+                first.append(i)
+            gid[i] = seen[key]
+        self.grid_of = gid
+        self.grid_first = np.array(first, dtype=np.int64)
+        self._prod, self._basis = {}, {}
+
+    def products(self, sys_err=0.0):
+        key = float(sys_err)
+        if key not in self._prod:
+            ntot = int(self.off[-1])
+            loglam, dn, einv = [_dev.empty((ntot,), np.float64) for _ in range(3)]
+            sumlog2 = _dev.empty((self.n,), np.float64)
+            rc = _cabi.lib().rvs_obs_prepare(
+                _dev.ptr(self.d_lam), _dev.ptr(self.d_spec), _dev.ptr(self.d_espec),
+                _dev.ptr(self.d_off), self.n, key, _dev.ptr(loglam), _dev.ptr(dn),
+                _dev.ptr(einv), _dev.ptr(sumlog2), _dev.stream())
+            _cabi.check(rc, 'rvs_obs_prepare')
+            self._prod[key] = (loglam, dn, einv, sumlog2)
+        return self._prod[key]
+
+    def basis(self, npoly, rbf):
+        key = (int(npoly), bool(rbf))
+        if key not in self._basis:
+            gl = [self.h_lam[self.off[i]:self.off[i + 1]] for i in self.grid_first]
+            goff = np.concatenate([[0], np.cumsum([len(_) for _ in gl])]).astype(np.int64)
+            ntot = int(goff[-1])
+            d_gl = _dev.upload(np.concatenate(gl), np.float64)
+            d_goff = _dev.upload(goff, np.int64)
+            P = _dev.empty((npoly, ntot), np.float64)
+            rc = _cabi.lib().rvs_basis_build(_dev.ptr(d_gl), _dev.ptr(d_goff), len(gl), ntot,
+                                             int(npoly), int(bool(rbf)), ntot, _dev.ptr(P),
+                                             _dev.stream())
+            _cabi.check(rc, 'rvs_basis_build')
+            boff = _dev.upload(goff[:-1][self.grid_of], np.int64)
+            self._basis[key] = (P, ntot, boff)
+        return self._basis[key]
+
+    def obs(self, npoly, rbf, sys_err=0.0):
+        """struct rvs_obs (plus the tensors that must stay alive)."""
+        loglam, dn, einv, sumlog2 = self.products(sys_err)
+        P, pstride, boff = self.basis(npoly, rbf)
+        o = _cabi.Obs()
+        o.d_lam, o.d_loglam, o.d_dn, o.d_einv = (self.d_lam.data_ptr(), loglam.data_ptr(),
+                                                 dn.data_ptr(), einv.data_ptr())
+        o.d_sumlog2, o.d_off, o.d_P = sumlog2.data_ptr(), self.d_off.data_ptr(), P.data_ptr()
+        o.pstride, o.d_boff, o.npoly, o.nobj = pstride, boff.data_ptr(), int(npoly), self.n
+        return o
+
+
+def _overlap_ok(t0, t1, s0, s1, vmin, vmax):
+    """spec_fit.py:786-794, vectorised; True where the template covers the data."""
+    ok = np.ones(np.broadcast(s0, vmin).shape, dtype=bool)
+    for v in (vmin, vmax):
+        corr = np.sqrt((1 + v / SPEED_OF_LIGHT) / (1 - v / SPEED_OF_LIGHT))
+        ok &= ~((t0 * corr > s0) | (t1 * corr < s1))
+    return ok
+
+
+class LikelihoodEngine:
+    """Batched -2 log L over many objects.
+
+    objects: list of objects, each a list of SpecData (one per arm; arms may
+    differ between objects).  Every evaluation call takes `obj` (K,) indices
+    into that list, so that one object can be evaluated at many trial points in
+    one launch.
+    """
+
+    def __init__(self, objects, config, options=None, fused=True):
+        options = options or {}
+        self.config = config
+        self.npoly = options.get('npoly') or 5
+        self.rbf = options.get('rbf_continuum', True)
+        self.fused = fused
+        if self.npoly > _cabi.MAX_NPOLY:
+            raise ValueError(f'npoly={self.npoly} > {_cabi.MAX_NPOLY} is not supported')
+        self.objects = [[o] if isinstance(o, SpecData) else list(o) for o in objects]
+        self.nobj = len(self.objects)
+        self.setups = []
+        for o in self.objects:
+            for sd in o:
+                if sd.name not in self.setups:
+                    self.setups.append(sd.name)
+        self.badchi = np.array([10 * sum(len(sd.lam) for sd in o) for o in self.objects],
+                               dtype=np.float64)
+        self.arms = {}
+        for name in self.setups:
+            members, index = [], np.full(self.nobj, -1, dtype=np.int64)
+            for i, o in enumerate(self.objects):
+                for sd in o:
+                    if sd.name == name:
+                        index[i] = len(members)
+                        members.append(sd)
+            bank = spec_inter.getInterpolator(name, config).bank
+            self.arms[name] = dict(batch=SpectrumBatch(members), index=index, bank=bank)
+        self.parnames = self.arms[self.setups[0]]['bank'].parnames
+        self.n_eval = 0
+
+    # ------------------------------------------------------------------ core
+    def _arm_eval(self, arm, sel, obj, vels, params, vsini, sys_err, want_model):
+        """chi-square of one arm for the items `sel` (indices into the call's
+        item list).  vels (K, nv).  Returns chisq (k, nv), status (k, nv),
+        outside (k,), tstatus (k,), extras."""
+        bank, batch = arm['bank'], arm['batch']
+        L = _cabi.lib()
+        k = len(sel)
+        nv = vels.shape[1]
+        ids, w, outside = bank.locate(params[sel])
+        oix = arm['index'][obj[sel]].astype(np.int32)
+        obs = batch.obs(self.npoly, self.rbf, sys_err)
+        d_oix = _dev.upload(oix, np.int32)
+        d_vels = _dev.upload(vels[sel], np.float64)
+        d_chi = _dev.empty((k, nv), np.float64)
+        d_st = _dev.empty((k, nv), np.int32)
+        vs = None if vsini is None else np.ascontiguousarray(vsini[sel], dtype=np.float64)
+        extras = None
+        if self.fused and nv == 1 and not want_model:
+            d_ids = _dev.upload(ids, np.int32)
+            d_w = _dev.upload(w, np.float64)
+            d_vs = None if vs is None else _dev.upload(vs, np.float64)
+            rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
+                                   ctypes.byref(bank.knots), _dev.ptr(d_ids), _dev.ptr(d_w),
+                                   bank.nvert, _dev.ptr(d_vs), int(bank.log_spec),
+                                   ctypes.byref(obs), _dev.ptr(d_oix), _dev.ptr(d_vels), k,
+                                   _dev.ptr(d_chi), _dev.ptr(d_st), _dev.stream())
+            _cabi.check(rc, 'rvs_chisq_fused')
+            st = _dev.download(d_st)
+            tstatus = st[:, 0] & (_cabi.ST_TEMPLATE_BAD | _cabi.ST_TAPS)
+        else:
+            yz, d_tst = bank.build(ids, w, vs)
+            d_tix = _dev.upload(np.arange(k), np.int32)
+            d_co = d_raw = d_mod = d_moff = None
+            if want_model:
+                npx = batch.npix[oix]
+                moff = np.concatenate([[0], np.cumsum(npx)]).astype(np.int64)
+                d_moff = _dev.upload(moff[:-1], np.int64)
+                d_co = _dev.empty((k, self.npoly), np.float64)
+                d_raw = _dev.empty((int(moff[-1]),), np.float64)
+                d_mod = _dev.empty((int(moff[-1]),), np.float64)
+            rc = L.rvs_chisq_scan(_dev.ptr(yz), bank.npix_t, _dev.ptr(d_tix),
+                                  ctypes.byref(bank.knots), ctypes.byref(obs), _dev.ptr(d_oix),
+                                  _dev.ptr(d_vels), nv, k, _dev.ptr(d_chi), _dev.ptr(d_st),
+                                  _dev.ptr(d_co), _dev.ptr(d_raw), _dev.ptr(d_mod),
+                                  _dev.ptr(d_moff), _dev.stream())
+            _cabi.check(rc, 'rvs_chisq_scan')
+            st = _dev.download(d_st)
+            tstatus = _dev.download(d_tst)
+            if want_model:
+                extras = dict(coeffs=_dev.download(d_co), raw=_dev.download(d_raw),
+                              model=_dev.download(d_mod), moff=moff, oix=oix)
+        return _dev.download(d_chi), st, outside, tstatus, extras
+
+    def evaluate(self, obj, vels, params, vsini=None, outside_penalty=True,
+                 espec_systematic=None, want_model=False, raise_errors=False):
+        """-2 log L for K items.  obj (K,), vels (K,) or (K, nv), params (K, ndim),
+        vsini (K,) or None.  Returns chisq with the shape of vels (plus an info
+        dict when want_model).  Semantics of reference get_chisq
+        (spec_fit.py:860-989) per item."""
+        obj = np.asarray(obj, dtype=np.int64)
+        params = np.array(params, dtype=np.float64, ndmin=2)
+        vels = np.asarray(vels, dtype=np.float64)
+        flat = vels.ndim == 1
+        v2 = vels[:, None] if flat else vels
+        K, nv = v2.shape
+        self.n_eval += K * nv
+        total = np.zeros((K, nv))
+        info = dict(arms={}) if want_model else None
+        min_vel, max_vel = self.config['min_vel'], self.config['max_vel']
+        for name in self.setups:
+            arm = self.arms[name]
+            sel = np.nonzero(arm['index'][obj] >= 0)[0]
+            if len(sel) == 0:
+                continue
+            if isinstance(espec_systematic, dict):
+                sys_err = float(espec_systematic[name])
+            else:
+                sys_err = float(espec_systematic or 0.0)
+            chi, st, outside, tstatus, extras = self._arm_eval(
+                arm, sel, obj, v2, params, vsini, sys_err, want_model)
+            bad = self.badchi[obj[sel]]
+            # template unusable: outside not finite, or off-grid and not finite/huge
+            tbad = ~np.isfinite(outside) | ((outside > 0) & ((tstatus & 1) != 0))
+            pen = np.where(tbad, 1000 * bad, (outside * bad) if outside_penalty else 0.0)
+            pen = np.where(np.isfinite(pen), pen, 1000 * bad)
+            batch = arm['batch']
+            oix = arm['index'][obj[sel]]
+            vlo = np.minimum(min_vel, v2[sel].min(axis=1))
+            vhi = np.maximum(max_vel, v2[sel].max(axis=1))
+            cover = _overlap_ok(arm['bank'].lam[0], arm['bank'].lam[-1], batch.lam0[oix],
+                                batch.lam1[oix], vlo, vhi) | tbad
+            if raise_errors and not cover.all():
+                i = int(np.nonzero(~cover)[0][0])
+                raise RuntimeError(
+                    f"The template library ({arm['bank'].lam[0]},{arm['bank'].lam[-1]})  "
+                    f"doesn't cover this wavelength range ({batch.lam0[oix[i]]},"
+                    f"{batch.lam1[oix[i]]}) with velocities {vlo[i]} {vhi[i]}")
+            notfin = ~np.isfinite(chi) & ~tbad[:, None]
+            if notfin.any():
+                chi = self._svd_rescue(arm, sel, obj, v2, params, vsini, sys_err, chi, notfin)
+                notfin = ~np.isfinite(chi) & ~tbad[:, None]
+                # spec_fit.py:963-974: tolerated only off-grid with a finite template
+                skip = notfin & (outside > 0)[:, None]
+                if raise_errors and (notfin & ~skip).any():
+                    raise RuntimeError('The log(likelihood) value is not finite'
+                                       f'when processing spectral configuration {name}')
+                chi = np.where(skip, 0.0, chi)
+            chi = np.where(tbad[:, None], 0.0, chi)
+            chi = np.where(cover[:, None], chi, np.nan)
+            total[sel] += pen[:, None] + chi
+            if want_model:
+                info['arms'][name] = dict(sel=sel, extras=extras, tbad=tbad, outside=outside)
+        out = total[:, 0] if flat else total
+        return (out, info) if want_model else out
+
+    def _svd_rescue(self, arm, sel, obj, v2, params, vsini, sys_err, chi, notfin):
+        """SVD route of the reference (spec_fit.py:255-303, 337-354) for the rare
+        items whose normal matrix was not positive definite on the device.  The
+        resampled template comes from the GPU; only the npoly x npoly
+        factorisation is redone on the host."""
+        chi = chi.copy()
+        batch = arm['batch']
+        for r, c in zip(*np.nonzero(notfin)):
+            one = np.array([sel[r]])
+            _, _, _, _, ex = self._arm_eval(arm, one, obj, v2[:, c:c + 1], params, vsini,
+                                            sys_err, True)
+            o = int(ex['oix'][0])
+            sl = slice(batch.off[o], batch.off[o + 1])
+            es = batch.h_espec[sl]
+            if sys_err:
+                es = np.sqrt(sys_err**2 + es**2)
+            polys = get_poly_basis(batch.h_lam[sl], self.npoly, self.rbf)
+            chi[r, c] = _chisq0_svd(batch.h_spec[sl], ex['raw'], polys, es)[0]
+        return chi
+
+
+def get_poly_basis(lam, npoly, rbf=True):
+    """Host copy of the continuum basis (spec_fit.py:148-176); used only by the
+    SVD rescue and by callers that want the basis itself."""
+    t = (lam - lam[0]) / (lam[-1] - lam[0]) * 2 - 1
+    P = np.zeros((npoly, len(lam)))
+    if not rbf:
+        for i in range(npoly):
+            c = np.zeros(npoly)
+            c[i] = 1
+            P[i] = np.polynomial.Chebyshev(c)(t)
+        return P
+    for i in range(min(3, npoly)):
+        P[i] = t**i
+    nr = npoly - 3
+    if nr > 0:
+        cen = np.linspace(-1, 1, nr, True)
+        P[3:] = np.exp(-0.5 * (t[None, :] - cen[:, None])**2 / (1. / nr)**2)
+    return P
+
+
+def _chisq0_svd(spec, templ, polys, espec):
+    """spec_fit.py:255-303."""
+    D = spec / espec
+    G = (templ / espec)[None, :] * polys
+    v = G @ D[:, None]
+    u, s, vt = scipy.linalg.svd(G @ G.T, check_finite=False)
+    a = vt.T @ ((1. / s)[:, None] * u.T) @ v
+    chisq = np.sum(np.log(s)) + 2 * np.log(espec).sum() + np.linalg.norm(D - a.T @ G)**2
+    return chisq, a.flatten()
+
+
+# ------------------------------------------------------ reference-shaped API
+_engine_cache = {}
+
+
+def _engine_for(specdata, config, options):
+    cfgkey = tuple(sorted((k, str(v)) for k, v in config.items()))
+    key = (tuple(sd.objid for sd in specdata), cfgkey, (options or {}).get('npoly') or 5,
+           (options or {}).get('rbf_continuum', True))
+    if key not in _engine_cache:
+        if len(_engine_cache) > 16:
+            _engine_cache.pop(next(iter(_engine_cache)))
+        _engine_cache[key] = LikelihoodEngine([list(specdata)], config, options)
+    return _engine_cache[key]
+
+
+def param_dict_to_tuple(paramDict, setup, config):
+    """spec_fit.py:730-736."""
+    it = spec_inter.getInterpolator(setup, config)
+    return tuple(paramDict[_] for _ in it.parnames)
+
+
+def get_chisq(specdata, vel, atm_params, rot_params=None, resol_params=None, options=None,
+              config=None, cache=None, full_output=False, fast_interp=False,
+              espec_systematic=None, outside_penalty=True):
+    """-2 log L of the dataset at a velocity, atmospheric and rotation
+    parameters: reference spec_fit.py:797-989, same arguments and returns.
+    `cache` is accepted and ignored (the spline never leaves the device)."""
+    if resol_params is not None:
+        raise NotImplementedError('resol_params: SURVEY.md section 8 row f4')
+    if fast_interp:
+        raise NotImplementedError('fast_interp is not on the GPU path')
+    if isinstance(specdata, SpecData):
+        specdata = [specdata]
+    eng = _engine_for(specdata, config, options or {})
+    vs = None if rot_params is None else np.array([rot_params[0]], dtype=np.float64)
+    par = np.array([tuple(atm_params)], dtype=np.float64)
+    if not full_output:
+        return float(eng.evaluate([0], np.array([float(vel)]), par, vs,
+                                  outside_penalty=outside_penalty,
+                                  espec_systematic=espec_systematic, raise_errors=True)[0])
+    chi, info = eng.evaluate([0], np.array([float(vel)]), par, vs,
+                             outside_penalty=outside_penalty,
+                             espec_systematic=espec_systematic, want_model=True,
+                             raise_errors=True)
+    ret = dict(chisq=float(chi[0]), logl=-0.5 * float(chi[0]), chisq_array=[],
+               red_chisq_array=[], npix_array=[], models=[], raw_models=[])
+    for sd in specdata:
+        a = info['arms'][sd.name]
+        if a['tbad'][0]:
+            ret['chisq_array'].append(np.nan)
+            ret['red_chisq_array'].append(np.nan)
+            ret['models'].append(np.zeros(len(sd.lam)) + np.nan)
+            continue
+        ex = a['extras']
+        model, raw = ex['model'][:len(sd.lam)], ex['raw'][:len(sd.lam)]
+        dev = (model - sd.spec) / sd.espec
+        good = ~sd.badmask
+        c = float(np.sum(dev[good]**2))
+        ret['models'].append(model)
+        ret['raw_models'].append(raw)
+        ret['chisq_array'].append(c)
+        ret['npix_array'].append(int(good.sum()))
+        ret['red_chisq_array'].append(c / good.sum())
+    return ret
+
+
+def get_chisq_continuum(specdata, options=None):
+    """Continuum-only fit (spec_fit.py:739-783): the chi-square kernel with a
+    unit template."""
+    options = options or {}
+    npoly = options.get('npoly') or 5
+    rbf = options.get('rbf_continuum', True)
+    if isinstance(specdata, SpecData):
+        specdata = [specdata]
+    L = _cabi.lib()
+    ca, ra = np.zeros(len(specdata)), np.zeros(len(specdata))
+    for i, sd in enumerate(specdata):
+        batch = SpectrumBatch([sd])
+        obs = batch.obs(npoly, rbf)
+        # unit template on a 4-knot linear grid covering the data: y=1, z=0
+        x = np.linspace(sd.lam[0] * 0.5, sd.lam[-1] * 2, 4)
+        h, hinv, cp, winv = np.zeros(3), np.zeros(3), np.zeros(2), np.zeros(2)
+        L.rvs_knot_tables(_dev.hptr(x), 4, _dev.hptr(h), _dev.hptr(hinv), _dev.hptr(cp),
+                          _dev.hptr(winv))
+        kn = _cabi.Knots()
+        L.rvs_knot_info(_dev.hptr(x), 4, 0, ctypes.byref(kn))
+        tabs = [_dev.upload(_, np.float64) for _ in (x, h, hinv, cp, winv)]
+        kn.d_lam_t, kn.d_h, kn.d_hinv, kn.d_cp, kn.d_winv = [t.data_ptr() for t in tabs]
+        yz = _dev.upload(np.tile([1.0, 0.0], (1, 4, 1)), np.float64)
+        d_z32 = _dev.zeros((1,), np.int32)
+        d_vel = _dev.zeros((1, 1), np.float64)
+        d_chi, d_st = _dev.empty((1, 1), np.float64), _dev.empty((1, 1), np.int32)
+        d_co = _dev.empty((1, npoly), np.float64)
+        d_raw, d_mod = _dev.empty((len(sd.lam),), np.float64), _dev.empty((len(sd.lam),), np.float64)
+        d_moff = _dev.zeros((1,), np.int64)
+        rc = L.rvs_chisq_scan(_dev.ptr(yz), 4, _dev.ptr(d_z32), ctypes.byref(kn),
+                              ctypes.byref(obs), _dev.ptr(d_z32), _dev.ptr(d_vel), 1, 1,
+                              _dev.ptr(d_chi), _dev.ptr(d_st), _dev.ptr(d_co), _dev.ptr(d_raw),
+                              _dev.ptr(d_mod), _dev.ptr(d_moff), _dev.stream())
+        _cabi.check(rc, 'rvs_chisq_scan')
+        dev = (_dev.download(d_mod) - sd.spec) / sd.espec
+        good = ~sd.badmask
+        ca[i] = np.sum(dev[good]**2)
+        ra[i] = ca[i] / good.sum()
+    return dict(chisq_array=ca, redchisq_array=ra)
+
+
+def scan_stats(vel_grid, chisq, quadratic=True):
+    """find_best tail (spec_fit.py:1072-1092) on the device.  vel_grid (S, nv),
+    chisq (S, npar, nv).  Returns (out (S, 8), probs (S, nv))."""
+    vel_grid = np.asarray(vel_grid, dtype=np.float64)
+    S, npar, nv = chisq.shape
+    d_v, d_c = _dev.upload(vel_grid, np.float64), _dev.upload(chisq, np.float64)
+    d_out, d_pr = _dev.empty((S, 8), np.float64), _dev.empty((S, nv), np.float64)
+    rc = _cabi.lib().rvs_scan_stats(_dev.ptr(d_v), _dev.ptr(d_c), S, npar, nv, int(quadratic),
+                                    _dev.ptr(d_out), _dev.ptr(d_pr), _dev.stream())
+    _cabi.check(rc, 'rvs_scan_stats')
+    return _dev.download(d_out), _dev.download(d_pr)
+
+
+def find_best(specdata, vel_grid, params_list, rot_params=None, resol_params=None,
+              options=None, config=None, quadratic=True):
+    """Best template and velocity on a grid: reference spec_fit.py:1018-1092,
+    same arguments and returned keys."""
+    if resol_params is not None:
+        raise NotImplementedError('resol_params: SURVEY.md section 8 row f4')
+    if isinstance(specdata, SpecData):
+        specdata = [specdata]
+    eng = _engine_for(specdata, config, options or {})
+    vel_grid = np.asarray(vel_grid, dtype=np.float64)
+    npar, nv = len(params_list), len(vel_grid)
+    par = np.array([tuple(p) for p in params_list], dtype=np.float64)
+    vs = None if rot_params is None else np.full(npar, rot_params[0], dtype=np.float64)
+    chisq = eng.evaluate(np.zeros(npar, dtype=np.int64), np.tile(vel_grid, (npar, 1)), par, vs,
+                         raise_errors=True)                      # (npar, nv)
+    out, probs = scan_stats(vel_grid[None, :], chisq[None, :, :], quadratic)
+    o = out[0]
+    i1, i2 = int(o[5]), int(o[6])
+    if quadratic and 0 < i1 < nv - 1:
+        assert vel_grid[i1 - 1] < o[1] < vel_grid[i1 + 1]      # spec_fit.py:1014
+    return dict(best_chi=float(o[0]), best_vel=float(o[1]), vel_err=float(o[2]),
+                best_param=params_list[i2], kurtosis=float(o[4]), skewness=float(o[3]),
+                probs=probs[0])

@@ -1,0 +1,280 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the
+fixtures the reference itself produced (tests/golden).  Needs a B200.
+
+Tolerances: BASELINE.json asks chi-square within 1e-6 relative, RV within
+0.01 km/s, parameters within 1 % of sigma.  The kernels are fp64 end to end
+and are held to 1e-9 relative on chi-square here (summation order and the
+fp64 library functions differ from numpy's, nothing else)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import PROBE_PARAMS, config, relerr, setup, unpack_objects
+from rvspecfit_b200 import _cabi, _dev, spec_fit, spec_inter, vel_fit
+
+pytestmark = pytest.mark.gpu
+CHI_RTOL = 1e-9
+
+
+def _register(st, kind='regulargrid', name=None):
+    bank = spec_inter.bank_from_setup(st, kind=kind, name=name)
+    spec_inter.register_bank(bank, template_lib='synthetic/')
+    return bank
+
+
+def _sd(obj, rename=None, cls=spec_fit.SpecData):
+    return [cls(rename or nm, lam, sp, es, bad) for nm, lam, sp, es, bad in obj['arms']]
+
+
+def test_spline_cabi_dropin(golden):
+    """rvs_spline_construct / rvs_spline_eval against the reference's own
+    outputs (tests/test_spline.py shapes)."""
+    g = golden('kat')
+    L = _cabi.lib()
+    vp = _dev.hptr
+    for tag in ('lin', 'log'):
+        x, y, ex = [np.ascontiguousarray(g[f'spl_{tag}_{k}']) for k in ('x', 'y', 'ex')]
+        n = len(x)
+        A, B, C, D, h = [np.zeros(n - 1) for _ in range(5)]
+        L.rvs_spline_construct(vp(x), vp(y), n, vp(A), vp(B), vp(C), vp(D), vp(h))
+        for k, arr in zip('ABCD', (A, B, C, D)):
+            assert np.allclose(arr, g[f'spl_{tag}_{k}'], rtol=1e-11, atol=1e-14), k
+        out = np.zeros(len(ex))
+        st = L.rvs_spline_eval(vp(ex), len(ex), n, vp(x), vp(h), vp(A), vp(B), vp(C), vp(D),
+                               int(tag == 'log'), vp(out))
+        assert st == 0
+        assert np.allclose(out, g[f'spl_{tag}_val'], rtol=1e-11, atol=1e-12)
+        bad = np.ascontiguousarray([x[0] - 1, x[5]])
+        assert L.rvs_spline_eval(vp(bad), 2, n, vp(x), vp(h), vp(A), vp(B), vp(C), vp(D),
+                                 int(tag == 'log'), vp(out)) == -1
+        xb = x.copy()
+        xb[1] += 0.3 * (x[1] - x[0])
+        assert L.rvs_spline_eval(vp(ex), len(ex), n, vp(xb), vp(h), vp(A), vp(B), vp(C), vp(D),
+                                 int(tag == 'log'), vp(out)) == -2
+
+
+def test_template_interpolation(golden):
+    g = golden('interp')
+    pp = np.array(PROBE_PARAMS)
+    for tag, holes in (('grid', 0), ('holes', 3)):
+        st = setup('test', 'tiny', 3, holes=holes, name='p_' + tag)
+        bank = _register(st)
+        spec, outside = bank.template(pp)
+        assert np.allclose(spec, g[f'{tag}_spec'], rtol=1e-13)
+        assert np.allclose(outside, g[f'{tag}_outside'], rtol=1e-13)
+        it = spec_inter.getInterpolator('p_' + tag, config())
+        assert np.allclose(it.eval(dict(zip(st['parnames'], pp[1]))), g[f'{tag}_spec'][1],
+                           rtol=1e-13)
+    st = setup('test', 'tiny', 3, name='p_tri')
+    bank = _register(st, kind='triangulation')
+    spec, outside = bank.template(pp)
+    want_o = g['tri_outside']
+    assert np.array_equal(np.isnan(outside), np.isnan(want_o))
+    ok = ~np.isnan(want_o)
+    assert np.allclose(outside[ok], want_o[ok], rtol=1e-9, atol=1e-12)
+    assert np.allclose(spec[ok], g['tri_spec'][ok], rtol=1e-12)
+
+
+def test_vsini_broadening_and_spline_vs_oracle(golden):
+    """Broadened templates and their spline second derivatives against the
+    oracle (scipy convolution + serial Thomas solve), incl. sub-pixel and very
+    wide kernels."""
+    g = golden('kat')
+    lam, templ = g['conv_lam'], g['conv_templ']
+    # a one-node bank whose single row is log(templ): interpolation = identity
+    dats = np.tile(np.log(templ), (2, 1))
+    bank = spec_inter.TemplateBank('conv', lam, dats, ('a',), kind='regulargrid',
+                                   uvecs=[np.array([0., 1.])], idgrid=np.array([0, 1]),
+                                   vecs=np.array([[0., 1.]]), log_ids=())
+    for i, v in enumerate(g['conv_vsini']):
+        ids = np.zeros((1, 2), dtype=np.int32)
+        w = np.array([[1., 0.]])
+        yz, st = bank.build(ids, w, np.array([v]))
+        yz = _dev.download(yz)[0]
+        assert np.allclose(yz[:, 0], g[f'conv_out{i}'], rtol=1e-12, atol=1e-14), v
+        s = oracle.Spline(lam, np.ascontiguousarray(yz[:, 0]))
+        z = np.concatenate([[0.], s.A * 6 * s.h])
+        assert np.allclose(yz[:, 1], z, rtol=1e-9, atol=1e-12 * np.abs(z).max())
+
+
+def test_basis_and_products():
+    rs = np.random.RandomState(3)
+    lam1 = np.linspace(4000, 5000, 777)
+    lam2 = np.exp(np.linspace(np.log(6000), np.log(9000), 1234))
+    sds = [spec_fit.SpecData('x', l, 1 + rs.uniform(size=len(l)), 0.1 + rs.uniform(size=len(l)))
+           for l in (lam1, lam2, lam1)]
+    b = spec_fit.SpectrumBatch(sds)
+    assert list(b.grid_of) == [0, 1, 0]
+    for npoly, rbf in ((1, True), (3, True), (10, True), (16, True), (7, False)):
+        P, ntot, boff = b.basis(npoly, rbf)
+        P = _dev.download(P)
+        assert ntot == 777 + 1234
+        assert np.allclose(P[:, :777], oracle.continuum_basis(lam1, npoly, rbf), rtol=1e-13,
+                           atol=1e-15)
+        assert np.allclose(P[:, 777:], oracle.continuum_basis(lam2, npoly, rbf), rtol=1e-12,
+                           atol=1e-14)
+    loglam, dn, einv, sumlog2 = [_dev.download(_) for _ in b.products(0.05)]
+    es = np.sqrt(0.05**2 + b.h_espec**2)
+    assert np.allclose(dn, b.h_spec / es, rtol=1e-15)
+    assert np.allclose(loglam, np.log(b.h_lam), rtol=1e-15)
+    assert np.allclose(sumlog2[1], 2 * np.log(es[777:777 + 1234]).sum(), rtol=1e-13)
+
+
+@pytest.mark.parametrize('fused', [True, False])
+def test_get_chisq_matches_reference(golden, fused):
+    g = golden('chisq')
+    st = setup('test', 'tiny', 3, name='test')
+    _register(st)
+    _register(setup('test', 'tiny', 3), kind='triangulation', name='test_tri')
+    objs = unpack_objects(g, 'one_')
+    ev = g['one_eval']
+    cfg = config()
+    for npoly, rbf in ((15, True), (5, True), (8, False)):
+        opts = {'npoly': npoly, 'rbf_continuum': rbf}
+        for name in ('test', 'test_tri'):
+            want = g[f'one_chisq_{name}_{npoly}_{int(rbf)}']
+            eng = spec_fit.LikelihoodEngine([_sd(o, name) for o in objs], cfg, opts,
+                                            fused=fused)
+            K = len(ev)
+            for i in range(len(objs)):
+                got = eng.evaluate(np.full(K, i), ev[:, 0], ev[:, 1:5],
+                                   np.where(ev[:, 5] < 0, 0.0, ev[:, 5]))
+                assert relerr(got, want[i]) < CHI_RTOL, (name, npoly, rbf, i)
+    # the reference-shaped single call
+    sd = _sd(objs[0])
+    e = ev[3]
+    c = spec_fit.get_chisq(sd, e[0], tuple(e[1:5]), (e[5],), options={'npoly': 15}, config=cfg)
+    assert abs(c - g['one_chisq_test_15_1'][0, 3]) < CHI_RTOL * abs(c)
+    c = spec_fit.get_chisq(sd, ev[0, 0], tuple(ev[0, 1:5]), None, options={'npoly': 15},
+                           config=cfg)
+    assert abs(c - g['one_chisq_test_15_1'][0, 0]) < CHI_RTOL * abs(c)
+
+
+def test_full_output_and_continuum(golden):
+    g = golden('chisq')
+    _register(setup('test', 'tiny', 3, name='test'))
+    objs = unpack_objects(g, 'one_')
+    sd = _sd(objs[0])
+    ev = g['one_eval']
+    fo = spec_fit.get_chisq(sd, ev[2, 0], tuple(ev[2, 1:5]), (ev[2, 5],),
+                            options={'npoly': 15}, config=config(), full_output=True)
+    assert abs(fo['chisq'] - g['one_full_chisq']) < 1e-8 * abs(fo['chisq'])
+    assert np.allclose(fo['chisq_array'], g['one_full_chisq_array'], rtol=1e-7)
+    assert np.array_equal(fo['npix_array'], g['one_full_npix'])
+    assert np.allclose(fo['raw_models'][0], g['one_full_raw'], rtol=1e-12)
+    assert np.allclose(fo['models'][0], g['one_full_model'], rtol=1e-6)
+    cc = spec_fit.get_chisq_continuum(sd, options={'npoly': 15})['chisq_array']
+    assert np.allclose(cc, g['one_cont'], rtol=1e-7)
+
+
+def test_find_best_matches_reference(golden):
+    g = golden('chisq')
+    _register(setup('test', 'tiny', 3, name='test'))
+    sd = _sd(unpack_objects(g, 'one_')[0])
+    vg, plist = g['scan_vel_grid'], [tuple(_) for _ in g['scan_params']]
+    cfg = config()
+    eng = spec_fit.LikelihoodEngine([sd], cfg, {'npoly': 15})
+    for tag, rot in (('norot', None), ('rot', (25.,))):
+        vs = None if rot is None else np.full(len(plist), rot[0])
+        chi = eng.evaluate(np.zeros(len(plist), dtype=int), np.tile(vg, (len(plist), 1)),
+                           np.array(plist), vs)
+        assert relerr(chi.T, g[f'scan_{tag}_chisq']) < CHI_RTOL
+        fb = spec_fit.find_best(sd, vg, plist, rot_params=rot, options={'npoly': 15}, config=cfg)
+        for k in ('best_chi', 'best_vel', 'vel_err', 'kurtosis', 'skewness'):
+            assert np.isclose(fb[k], g[f'scan_{tag}_{k}'], rtol=1e-7, atol=1e-9), k
+        assert abs(fb['best_vel'] - g[f'scan_{tag}_best_vel']) < 1e-6   # << 0.01 km/s
+        assert np.allclose(fb['probs'], g[f'scan_{tag}_probs'], rtol=1e-6, atol=1e-12)
+        assert np.allclose(fb['best_param'], g[f'scan_{tag}_best_param'])
+
+
+def test_desi_three_arm_matches_reference(golden):
+    g = golden('chisq')
+    for k, a in enumerate(('desi_b', 'desi_r', 'desi_z')):
+        _register(setup(a, 'tiny', 21 + k))
+    o = unpack_objects(g, 'desi_')[0]
+    sd = _sd(o)
+    cfg = config(min_vel=-1500, max_vel=1500)
+    ev = g['desi_eval']
+    for fused in (True, False):
+        eng = spec_fit.LikelihoodEngine([sd], cfg, {'npoly': 10}, fused=fused)
+        got = eng.evaluate(np.zeros(len(ev), dtype=int), ev[:, 0], ev[:, 1:5],
+                           np.where(ev[:, 5] < 0, 0.0, ev[:, 5]))
+        assert relerr(got, g['desi_chisq']) < CHI_RTOL
+    vg = np.arange(-1500, 1500, 5.)
+    chi = eng.evaluate([0], vg[None, :], np.array([o['params']]), np.array([12.]))
+    assert relerr(chi[0], g['desi_scan_chisq']) < CHI_RTOL
+    fb = spec_fit.find_best(sd, vg, [tuple(o['params'])], rot_params=(12.,),
+                            options={'npoly': 10}, config=cfg)
+    for k in ('best_chi', 'best_vel', 'vel_err', 'kurtosis', 'skewness'):
+        assert np.isclose(fb[k], g[f'desi_scan_{k}'], rtol=1e-7, atol=1e-9), k
+
+
+def test_scan_stats_edge_cases():
+    rs = np.random.RandomState(0)
+    for nv, npar in ((7, 1), (600, 3), (33, 5)):
+        v = np.sort(rs.uniform(-500, 500, nv))
+        chi = rs.uniform(50, 60, size=(npar, nv))
+        for where in ('mid', 'first', 'last'):
+            c = chi.copy()
+            j = {'mid': nv // 2, 'first': 0, 'last': nv - 1}[where]
+            c[npar - 1, j] = 10. - (where == 'mid') * 0
+            if where == 'mid':
+                c[npar - 1, j - 1], c[npar - 1, j + 1] = 11., 12.
+            out, pr = spec_fit.scan_stats(v[None], c[None])
+            want = oracle.scan_statistics(v, c.T.copy())
+            assert np.isclose(out[0, 0], want['best_chi'])
+            assert np.isclose(out[0, 1], want['best_vel'], rtol=1e-10)
+            assert np.isclose(out[0, 2], want['vel_err'], rtol=1e-10)
+            assert np.isclose(out[0, 3], want['skewness'], rtol=1e-9, atol=1e-12)
+            assert np.isclose(out[0, 4], want['kurtosis'], rtol=1e-9)
+            assert int(out[0, 6]) == want['ibest']
+            assert np.allclose(pr[0], want['probs'], rtol=1e-10)
+
+
+def test_error_behaviour():
+    st = setup('test', 'tiny', 3, name='test')
+    _register(st)
+    lam = np.linspace(4400, 5400, 500)      # bluer than the template coverage
+    sd = [spec_fit.SpecData('test', lam, np.ones(500), np.full(500, 0.1))]
+    with pytest.raises(RuntimeError):
+        spec_fit.get_chisq(sd, 0., (5000., 2., -1., 0.2), None, options={'npoly': 5},
+                           config=config())
+    with pytest.raises(ValueError):
+        spec_inter.getInterpolator('test', config()).eval({'teff': 5000.})
+
+
+def test_process_matches_reference(golden):
+    """BASELINE config 1 shape: vel_fit.process through the GPU likelihood vs the
+    reference's own result.  RV within 0.01 km/s, parameters within 1 % of the
+    reference's sigma (BASELINE.json)."""
+    g = golden('process')
+    _register(setup('test', 'test', 3, name='test'))
+    objs = unpack_objects(g, 'c1_')
+    start = {'logg': 2, 'teff': 5000, 'feh': -0.2, 'alpha': 0.2, 'vsini': 0.1}
+    for i in (0, 1):
+        sd = _sd(objs[i])
+        for tag, cfg in (('nm', config(second_minimizer=False)), ('bfgs', config())):
+            if i == 1 and tag == 'nm':
+                continue
+            res = vel_fit.process(sd, dict(start), fixParam=[], config=cfg,
+                                  options={'npoly': 15})
+            perr = g[f'c1_{i}_{tag}_param_err']
+            par = np.array([res['param'][k] for k in ('teff', 'logg', 'feh', 'alpha')])
+            assert abs(res['vel'] - g[f'c1_{i}_{tag}_vel']) < 0.01, (i, tag)
+            assert np.all(np.abs(par - g[f'c1_{i}_{tag}_param']) < 0.01 * perr), (i, tag)
+            assert abs(res['chisq'] - g[f'c1_{i}_{tag}_chisq']) < 1e-6 * abs(res['chisq'])
+            assert np.isclose(res['vel_err'], g[f'c1_{i}_{tag}_vel_err'], rtol=1e-3)
+            assert np.allclose(res['yfit'][0], g[f'c1_{i}_{tag}_yfit'], rtol=1e-5)
+    res = vel_fit.process(_sd(objs[0]), dict(start), fixParam=['vsini', 'alpha'],
+                          config=config(), options={'npoly': 15},
+                          priors={'teff': (5200., 300.)})
+    assert abs(res['vel'] - g['c1_0_fix_vel']) < 0.01
+    assert abs(res['chisq'] - g['c1_0_fix_chisq']) < 1e-6 * abs(res['chisq'])
+    fg = vel_fit.firstguess(_sd(objs[0]), config=config(), options={'npoly': 15},
+                            paramsgrid={'logg': [1, 3, 4.5], 'teff': [4000, 6000, 9000],
+                                        'feh': [-1.5, -0.5], 'alpha': [0.2]},
+                            vsinigrid=(None, 50))
+    got = np.array([fg[k] for k in ('teff', 'logg', 'feh', 'alpha')] + [fg.get('vsini', -1)])
+    assert np.allclose(got, g['c1_fg'])
