@@ -1,0 +1,392 @@
+"""Throughput of the per-spectrum likelihood hot path on B200 (and, with
+--impl reference, of its CPU restatement on the host cores).
+
+    python bench.py --gpus N --steps K --warmup W [--workload desi|sdss|test]
+
+One "step" = one pass of the hot path over one batch of synthetic spectra:
+per spectrum an RV-grid chi-square scan (arange(min_vel, max_vel, 5) trials of
+one template, + find_best statistics) followed by the optimiser-phase
+evaluations (each a NEW template: interpolate, broaden, spline, resample,
+continuum solve, chi-square).  See DESIGN.md "Measurement" for what the step
+contains in this round.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from rvspecfit_b200 import synth  # noqa: E402
+
+WORKLOADS = {
+    # three DESI arms, 40x11x13x5 polylinear grid
+    'desi': dict(arms=('desi_b', 'desi_r', 'desi_z'), layout='desi', npoly=10,
+                 min_vel=-1500, max_vel=1500),
+    # config 2: SDSS/BOSS single arm, 24x9x9x4 grid
+    'sdss': dict(arms=('sdss',), layout='sdss', npoly=10, min_vel=-1500, max_vel=1500),
+    # config 1 shape (correctness-sized; fits L2, not a roofline workload)
+    'test': dict(arms=('test',), layout='test', npoly=15, min_vel=-1000, max_vel=1000),
+}
+# evaluations of one reference vel_fit.process call on a DESI-shaped object
+# (SURVEY.md section 6/8d probe): 2866 get_chisq, 1293 of them with a new template
+EVALS_PER_FIT = 1293
+
+
+def make_config(w):
+    return dict(min_vel=w['min_vel'], max_vel=w['max_vel'], vel_step0=5, max_vsini=500,
+                min_vsini=0.1, min_vel_step=0.2, second_minimizer=True,
+                template_lib='synthetic/')
+
+
+def grid_cache_path(wname, arm):
+    d = '/dev/shm' if os.path.isdir('/dev/shm') else '/tmp'
+    return os.path.join(d, f'rvs_bench_grid_{wname}_{arm}.npy')
+
+
+def make_inputs(wname, nspec, seed, mmap_grids=False):
+    """Synthetic banks + spectra (host numpy).  Objects are lists of
+    (name, lam, spec, espec, badmask).  With mmap_grids the template rows are
+    read from the files the parent process wrote (shared page cache, like the
+    reference's mmap of interpdat_<setup>.npy, spec_inter.py:353-355)."""
+    w = WORKLOADS[wname]
+    setups = []
+    for k, a in enumerate(w['arms']):
+        dats = np.load(grid_cache_path(wname, a), mmap_mode='r') if mmap_grids else None
+        setups.append(synth.make_setup(a, w['layout'], seed=21 + k, dats=dats))
+    pars = synth.random_params(w['layout'], nspec, seed)
+    rs = np.random.RandomState(seed + 1)
+    vel = rs.normal(0, 150., nspec)
+    sn = np.exp(rs.uniform(np.log(5), np.log(100), nspec))
+    arms = [synth.fast_spectra(st, pars, vel, sn, seed + 10 + k) for k, st in enumerate(setups)]
+    objects = [[(st['name'], a[0], a[1][i], a[2][i], a[3][i]) for st, a in zip(setups, arms)]
+               for i in range(nspec)]
+    return setups, objects, pars, vel
+
+
+def trial_points(pars, vel, layout, nevals, seed):
+    """Optimiser-like trial points around the truth: (nevals, B, 4) params,
+    (nevals, B) velocities and vsini."""
+    rs = np.random.RandomState(seed)
+    B = len(vel)
+    g = synth.GRIDS[layout]
+    lo = np.array([g[k][0] for k in synth.PARNAMES])
+    hi = np.array([g[k][-1] for k in synth.PARNAMES])
+    scale = np.array([150., 0.25, 0.2, 0.1])
+    p = pars[None] + scale * rs.normal(size=(nevals, B, 4))
+    eps = 1e-3 * (hi - lo)
+    p = np.clip(p, lo + eps, hi - eps)
+    v = vel[None] + 3.0 * rs.normal(size=(nevals, B))
+    vs = np.abs(10 + 8 * rs.normal(size=(nevals, B)))
+    return p, v, vs
+
+
+def algorithmic_bytes(setups, objects, nvert=16):
+    """nv * sum_arms Npix_t * sizeof(grid) + sum_arms Npix_obs*16 + 8."""
+    npt = sum(len(s['lam']) for s in setups)
+    npo = sum(len(a[1]) for a in objects[0])
+    return nvert * npt * 4 + npo * 16 + 8, npt, npo
+
+
+# ------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for t, line in self.rows:
+            if not (t0 <= t <= t1 + 0.3):
+                continue
+            f = [x.strip() for x in line.split(',')]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, val in zip(names, f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from rvspecfit_b200 import _cabi, spec_fit, spec_inter, batch_fit
+    w = WORKLOADS[args.workload]
+    cfg = make_config(w)
+    B = args.batch
+    # weak scaling: every rank owns its own B spectra; the template grid is
+    # replicated in each GPU's HBM; no data-path collective
+    setups, objects, pars, vel = make_inputs(args.workload, B, 1000 + 7919 * rank)
+    for st in setups:
+        spec_inter.register_bank(spec_inter.bank_from_setup(st), template_lib='synthetic/')
+    opts = {'npoly': w['npoly']}
+    beval, npt, npo = algorithmic_bytes(setups, objects)
+    tp, tv, tvs = trial_points(pars, vel, w['layout'], args.evals, 5 + rank)
+    vgrid = np.arange(cfg['min_vel'], cfg['max_vel'], cfg['vel_step0'])
+    start = np.tile(np.array([[5500., 3.0, -1.0, 0.2]]), (B, 1))
+
+    def to_specdata():
+        return [[spec_fit.SpecData(*a) for a in o] for o in objects]
+
+    timer = batch_fit.KernelTimer()
+
+    def hot_path(eng):
+        """The step body on a ready engine; returns a small result array."""
+        res = batch_fit.scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=timer)
+        return res
+
+    def step_resident(eng):
+        return hot_path(eng)
+
+    def step_e2e():
+        eng = spec_fit.LikelihoodEngine(to_specdata(), cfg, opts)   # H2D of the spectra
+        return hot_path(eng)                                         # D2H of the results
+
+    eng = spec_fit.LikelihoodEngine(to_specdata(), cfg, opts)
+    L = _cabi.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, nsteps, nwarm, sample_clocks=False):
+        for _ in range(nwarm):
+            fn()
+        timer.reset()
+        barrier()
+        l0 = L.rvs_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk = ClockSampler(local) if sample_clocks else None
+        t0 = time.time()
+        e0.record()
+        for _ in range(nsteps):
+            out = fn()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        clocks = clk.stop(t0, t1) if clk else None
+        if world > 1:
+            t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, L.rvs_launch_count() - l0, clocks, out, timer.summary()
+
+    ms, launches, clocks, out, ksum = timed(lambda: step_resident(eng), args.steps, args.warmup,
+                                            sample_clocks=True)
+    ms_e2e, _, _, _, _ = timed(step_e2e, max(1, min(args.steps, 2)), 1)
+    n_e2e = max(1, min(args.steps, 2))
+    h2d = sum(3 * 8 * len(a[1]) + len(a[1]) for o in objects for a in o)
+    d2h = int(np.asarray(out).nbytes)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else \
+        'fallback 6650 GB/s (B200_PROFILING.md)'
+    roof = None
+    if ksum.get('fused_ms_per_launch'):
+        ach = beval * ksum['fused_items_per_launch'] / (ksum['fused_ms_per_launch'] * 1e-3) / 1e9
+        roof = dict(bound='hbm', kernel='chisq_fused_kernel', achieved=ach, peak=hbm_peak,
+                    unit='GB/s', frac=ach / hbm_peak, traffic=None, peak_source=peak_src,
+                    algorithmic_bytes_per_eval=beval,
+                    evals_per_launch=ksum['fused_items_per_launch'],
+                    ms_per_launch=ksum['fused_ms_per_launch'])
+    nspec_total = B * world
+    per_step = ms / args.steps
+    line = {
+        'metric': 'spectra/sec (RV-grid chi2 scan + fit evaluations)',
+        'value': nspec_total / (per_step * 1e-3), 'unit': 'spectra/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': f'{args.workload}: arms {list(w["arms"])}, {npo} obs px, '
+                               f'{npt} template px, grid {w["layout"]} '
+                               f'({setups[0]["dats"].shape[0]} nodes, fp32), npoly {w["npoly"]}',
+                   'spectra_per_gpu_per_step': B, 'rv_trials': len(vgrid),
+                   'fit_evals_per_spectrum': args.evals,
+                   'step': 'per spectrum: 1 RV-grid scan + fit_evals_per_spectrum '
+                           'template-changing chi2 evaluations (count of one reference '
+                           'process() call, SURVEY.md 8d)',
+                   'l2': 'template grid (>=0.7 GB per arm) is larger than L2; rows gathered '
+                         'at random per evaluation',
+                   'parallelism': f'spectra sharded over {world} GPU(s), grid replicated'},
+        'chisq_evals_per_s': nspec_total * (args.evals + len(vgrid)) / (per_step * 1e-3),
+        'e2e': {'value': nspec_total / (ms_e2e / n_e2e * 1e-3), 'unit': 'spectra/s',
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof,
+        'kernels': ksum,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line['cpu_baseline'] = cpu_baseline(args, bounded=True)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ CPU arm
+def _cpu_worker(job):
+    """One object through the oracle: the same step body as the GPU arm."""
+    wname, seed, idx, nevals, nscan = job
+    os.environ['OMP_NUM_THREADS'] = '1'
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import oracle
+    w = WORKLOADS[wname]
+    cfg = make_config(w)
+    key = (wname, seed)
+    if _cpu_worker.cache.get('key') != key:
+        setups, objects, pars, vel = make_inputs(wname, _cpu_worker.nspec, seed, mmap_grids=True)
+        for st in setups:
+            oracle.register_setup(st)
+        _cpu_worker.cache = dict(key=key, objects=objects, pars=pars, vel=vel)
+    c = _cpu_worker.cache
+    sd = [oracle.SpecData(*a) for a in c['objects'][idx]]
+    opts = {'npoly': w['npoly']}
+    tp, tv, tvs = trial_points(c['pars'], c['vel'], w['layout'], nevals, 5)
+    vgrid = np.arange(cfg['min_vel'], cfg['max_vel'], cfg['vel_step0'])[:nscan]
+    t0 = time.time()
+    fb = oracle.find_best(sd, vgrid, [(5500., 3.0, -1.0, 0.2)], rot=None, options=opts,
+                          config=cfg)
+    acc = fb['best_chi']
+    for e in range(nevals):
+        acc += oracle.get_chisq(sd, tv[e, idx], tuple(tp[e, idx]), (tvs[e, idx],),
+                                options=opts, config=cfg)
+    return time.time() - t0, acc
+
+
+_cpu_worker.cache = {}
+_cpu_worker.nspec = 0
+
+
+def _cpu_init(nspec):
+    _cpu_worker.nspec = nspec
+
+
+def cpu_baseline(args, bounded=True):
+    """The oracle port on all host cores, one object per task in a spawn pool
+    (the reference's own pattern, desi_fit.py:1475-1479), on a bounded sample
+    of the same workload: `cores` objects, a fraction of the evaluations, scaled
+    linearly to the full per-spectrum count."""
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    w = WORKLOADS[args.workload]
+    vg = np.arange(w['min_vel'], w['max_vel'], 5)
+    frac = args.cpu_fraction
+    nevals = max(1, int(args.evals * frac))
+    nscan = max(3, int(len(vg) * frac))
+    nobj = 2 * cores
+    for k, a in enumerate(w['arms']):       # template rows shared through the page cache
+        path = grid_cache_path(args.workload, a)
+        if not os.path.exists(path):
+            st = synth.make_setup(a, w['layout'], seed=21 + k)
+            np.save(path + '.tmp.npy', st['dats'])
+            os.replace(path + '.tmp.npy', path)
+    jobs = [(args.workload, 1000, i, nevals, nscan) for i in range(nobj)]
+    t0 = time.time()
+    with cf.ProcessPoolExecutor(cores, mp_context=mp.get_context('spawn'),
+                                initializer=_cpu_init, initargs=(nobj,)) as ex:
+        list(ex.map(_cpu_worker, [(j[0], j[1], j[2], 1, 3) for j in jobs[:cores]]))  # warm-up: per-worker banks
+        t1 = time.time()
+        res = list(ex.map(_cpu_worker, jobs))
+        t2 = time.time()
+    wall = t2 - t1
+    scale = (args.evals + len(vg)) / (nevals + nscan)
+    return dict(value=nobj / (wall * scale), unit='spectra/s', cores=cores, kind='port',
+                sample=f'{nobj} spectra x ({nscan} RV trials + {nevals} evaluations) on {cores} '
+                       f'processes, scaled x{scale:.1f} to the full per-spectrum count; '
+                       f'setup {t1 - t0:.1f}s excluded', wall_s=wall,
+                per_object_s=float(np.mean([r[0] for r in res])) * scale)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    vals = []
+    for _ in range(args.warmup + args.steps):
+        vals.append(cpu_baseline(args))
+    cb = vals[-1]
+    v = float(np.mean([x['value'] for x in vals[args.warmup:]])) if args.steps else cb['value']
+    cb['value'] = v
+    setups = [a for a in w['arms']]
+    line = {'impl': 'reference', 'metric': 'spectra/sec (RV-grid chi2 scan + fit evaluations)',
+            'value': v, 'unit': 'spectra/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', 1)),
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cb['wall_s'] * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': f'{args.workload}: arms {setups}',
+                       'fit_evals_per_spectrum': args.evals},
+            'cpu_baseline': cb,
+            'e2e': {'value': v, 'unit': 'spectra/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='desi', choices=list(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=1024, help='spectra per GPU per step')
+    ap.add_argument('--evals', type=int, default=EVALS_PER_FIT)
+    ap.add_argument('--cpu-fraction', type=float, default=0.25,
+                    help='fraction of the per-spectrum evaluations the CPU sample runs')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -118,7 +118,9 @@ int rvs_knot_info(const double *h_x, int n, int log_step, rvs_knots *out);
  * Output d_yz[(k*yz_stride + p)*2 + {0,1}] = y[p], z[p].
  * d_grid: fp32 (grid_f64=0) or fp64 rows of length npix_t, row stride `ld`
  * elements (ld % 4 == 0, base 16-byte aligned).  d_ids int32 [K,nvert];
- * d_w fp64 [K,nvert].  d_vsini may be NULL.  d_status int32[K] receives
+ * d_w fp64 [K,nvert].  An item with ids[k,1] < 0 is a single-row item: row
+ * ids[k,0] alone, exp rounded to the row's precision (the reference's off-grid
+ * nearest-node value, spec_inter.py:160-167).  d_vsini may be NULL.  d_status int32[K] receives
  * RVS_ST_TEMPLATE_BAD / RVS_ST_TAPS. */
 int rvs_template_build(const void *d_grid, int grid_f64, int64_t ld, const rvs_knots *knots,
                        const int32_t *d_ids, const double *d_w, int nvert,

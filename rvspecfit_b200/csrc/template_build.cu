@@ -28,8 +28,9 @@ __global__ void __launch_bounds__(TB_THREADS) template_build_kernel(TemplateArgs
   }
   if (threadIdx.x == 0) { s_bad = 0; s_taps = 0; }
   __syncthreads();
+  const bool f32row = single_row_item(a, s_ids, s_w);
   int bad = 0;
-  gather_rows<GT, NV>(a, s_ids, s_w, ya, bad);
+  gather_rows<GT, NV>(a, s_ids, s_w, ya, bad, f32row);
   if (bad) s_bad = 1;
   __syncthreads();
   double *py, *pz;

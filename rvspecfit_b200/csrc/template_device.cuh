@@ -98,9 +98,29 @@ struct TemplateArgs {
   int npad;  // smem row length
 };
 
+// An item whose second vertex id is negative is a single-row item: the
+// reference returns exp(dats[nearest]) for off-grid points (spec_inter.py:
+// 160,167), and numpy evaluates that exp in the row's own precision (float32
+// for the stored grids).  Such items are evaluated the same way: fp64 exp of
+// the fp32 value, rounded to fp32.  Returns true for them and rewrites the
+// vertex list to {row, w=1; row, w=0 ...} (block-uniform, syncs).
+__device__ __forceinline__ bool single_row_item(const TemplateArgs &a, int32_t *s_ids,
+                                                double *s_w) {
+  const bool single = a.nvert > 1 && s_ids[1] < 0;
+  __syncthreads();
+  if (single && threadIdx.x >= 1 && threadIdx.x < a.nvert) {
+    s_ids[threadIdx.x] = s_ids[0];
+    s_w[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  return single;
+}
+
 template <typename GT, int NV>
 __device__ __forceinline__ void gather_rows(const TemplateArgs &a, const int32_t *s_ids,
-                                            const double *s_w, double *ya, int &bad) {
+                                            const double *s_w, double *ya, int &bad,
+                                            bool f32row) {
+  const bool round32 = f32row && sizeof(GT) == 4 && a.log_spec;
   constexpr int VEC = RowLoader<GT>::VEC;
   const int nvec = a.npix_t / VEC;
   const GT *base = static_cast<const GT *>(a.grid);
@@ -126,7 +146,8 @@ __device__ __forceinline__ void gather_rows(const TemplateArgs &a, const int32_t
     }
 #pragma unroll
     for (int e = 0; e < VEC; e++) {
-      const double y = a.log_spec ? exp(acc[e]) : acc[e];
+      double y = a.log_spec ? exp(acc[e]) : acc[e];
+      if (round32) y = (double)(float)y;
       if (!(fabs(y) <= 1e100)) bad = 1;  // also catches NaN
       ya[q * VEC + e] = y;
     }
@@ -135,7 +156,8 @@ __device__ __forceinline__ void gather_rows(const TemplateArgs &a, const int32_t
     double acc = 0;
     for (int j = 0; j < nv; j++)
       acc = fma(s_w[j], (double)base[(int64_t)s_ids[j] * a.ld + p], acc);
-    const double y = a.log_spec ? exp(acc) : acc;
+    double y = a.log_spec ? exp(acc) : acc;
+    if (round32) y = (double)(float)y;
     if (!(fabs(y) <= 1e100)) bad = 1;
     ya[p] = y;
   }

@@ -168,6 +168,7 @@ class LikelihoodEngine:
             self.arms[name] = dict(batch=SpectrumBatch(members), index=index, bank=bank)
         self.parnames = self.arms[self.setups[0]]['bank'].parnames
         self.n_eval = 0
+        self.timer = None
 
     # ------------------------------------------------------------------ core
     def _arm_eval(self, arm, sel, obj, vels, params, vsini, sys_err, want_model):
@@ -191,16 +192,22 @@ class LikelihoodEngine:
             d_ids = _dev.upload(ids, np.int32)
             d_w = _dev.upload(w, np.float64)
             d_vs = None if vs is None else _dev.upload(vs, np.float64)
+            t0 = self.timer.start() if self.timer else None
             rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
                                    ctypes.byref(bank.knots), _dev.ptr(d_ids), _dev.ptr(d_w),
                                    bank.nvert, _dev.ptr(d_vs), int(bank.log_spec),
                                    ctypes.byref(obs), _dev.ptr(d_oix), _dev.ptr(d_vels), k,
                                    _dev.ptr(d_chi), _dev.ptr(d_st), _dev.stream())
             _cabi.check(rc, 'rvs_chisq_fused')
+            if t0 is not None:
+                self.timer.stop('fused', t0, k)
             st = _dev.download(d_st)
             tstatus = st[:, 0] & (_cabi.ST_TEMPLATE_BAD | _cabi.ST_TAPS)
         else:
+            t0 = self.timer.start() if self.timer else None
             yz, d_tst = bank.build(ids, w, vs)
+            if t0 is not None:
+                self.timer.stop('build', t0, k)
             d_tix = _dev.upload(np.arange(k), np.int32)
             d_co = d_raw = d_mod = d_moff = None
             if want_model:
@@ -210,12 +217,15 @@ class LikelihoodEngine:
                 d_co = _dev.empty((k, self.npoly), np.float64)
                 d_raw = _dev.empty((int(moff[-1]),), np.float64)
                 d_mod = _dev.empty((int(moff[-1]),), np.float64)
+            t0 = self.timer.start() if self.timer else None
             rc = L.rvs_chisq_scan(_dev.ptr(yz), bank.npix_t, _dev.ptr(d_tix),
                                   ctypes.byref(bank.knots), ctypes.byref(obs), _dev.ptr(d_oix),
                                   _dev.ptr(d_vels), nv, k, _dev.ptr(d_chi), _dev.ptr(d_st),
                                   _dev.ptr(d_co), _dev.ptr(d_raw), _dev.ptr(d_mod),
                                   _dev.ptr(d_moff), _dev.stream())
             _cabi.check(rc, 'rvs_chisq_scan')
+            if t0 is not None:
+                self.timer.stop('scan', t0, k * nv)
             st = _dev.download(d_st)
             tstatus = _dev.download(d_tst)
             if want_model:

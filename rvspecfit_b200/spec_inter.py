@@ -128,9 +128,11 @@ class TemplateBank:
             if len(bad):
                 fin = np.isfinite(q[bad]).all(axis=1)
                 w[bad, 0] = 1
+                if self.nvert > 1:
+                    ids[bad, 1] = -1     # single-row item (see rvs_b200.h)
                 if fin.any():
                     dist, near = self.tree.query(q[bad[fin]] / self.ptp[None, :])
-                    ids[bad[fin]] = near[:, None]
+                    ids[bad[fin], 0] = near
                     outside[bad[fin]] = dist
                 # non-finite mapped parameters (teff <= 0): first node
                 # (spec_inter.py:156-159); no finite off-grid measure exists

@@ -157,10 +157,12 @@ def regular_index(vec_mapped):
     return uvecs, idgrid
 
 
-def make_setup(shape, layout, seed=1, holes=0):
+def make_setup(shape, layout, seed=1, holes=0, dats=None):
     """Build one spectral setup: dict(lam, dats float32 (Nnode,Npix), vec
     (mapped, log10 teff), uvecs, idgrid, parnames, log_step, lib, basis).
-    `holes` removes that many interior nodes (idgrid == -1 there)."""
+    `holes` removes that many interior nodes (idgrid == -1 there).  `dats` may
+    supply the (memory-mapped) rows made by an earlier call with the same
+    arguments."""
     sh = SHAPES[shape]
     lam = template_wavelengths(sh['t_lo'], sh['t_hi'], sh['t_step'])
     lib = SynthLibrary(sh['t_lo'], sh['t_hi'], seed=seed)
@@ -172,7 +174,8 @@ def make_setup(shape, layout, seed=1, holes=0):
         keep[rs.choice(vec.shape[1], holes, replace=False)] = False
         vecfull = vec
         vec = vec[:, keep]
-    dats = lib.logflux(basis, *vec).astype(np.float32)
+    if dats is None:
+        dats = lib.logflux(basis, *vec).astype(np.float32)
     vmap = vec.copy()
     vmap[0] = np.log10(vmap[0])
     if holes:
@@ -236,3 +239,31 @@ def random_params(layout, n, seed, margin=0.05):
         d = (hi - lo) * margin
         out[:, j] = rs.uniform(lo + d, hi - d, n)
     return out
+
+
+def fast_spectra(setup, params, vel, sn, seed, cont_amp=0.3, bad_frac=0.01):
+    """Many observed spectra of one setup at once (bench / batch tests): the
+    library's group basis is interpolated from the template grid to the
+    Doppler-shifted wavelengths instead of being re-evaluated line by line.
+    params (B,4), vel (B,), sn (B,).  Returns lam (npix,), spec, espec (B,npix),
+    badmask (B,npix)."""
+    rs = np.random.RandomState(seed)
+    lam = SHAPES[setup['shape']]['obs']()
+    B = len(vel)
+    if 'basis' not in setup:
+        setup['basis'] = setup['lib'].line_basis(setup['lam'], setup['resol'])
+    coef = setup['lib'].coeffs(*np.asarray(params).T)          # (B, R)
+    x = (lam - lam[0]) / (lam[-1] - lam[0]) * 2 - 1
+    spec = np.empty((B, len(lam)))
+    for i in range(B):
+        lr = lam * doppler_factor(vel[i])
+        lf = np.zeros(len(lam))
+        for r in range(coef.shape[1]):
+            lf -= coef[i, r] * np.interp(lr, setup['lam'], setup['basis'][r])
+        cont = 1 + cont_amp * np.polynomial.chebyshev.chebval(x, rs.uniform(-1, 1, 4) / 2.)
+        spec[i] = np.exp(lf) * np.maximum(cont, 0.2) * 10**rs.uniform(-1, 2)
+    espec = np.abs(spec) / np.asarray(sn)[:, None] + 1e-6 * np.abs(spec).mean(axis=1)[:, None]
+    spec = spec + espec * rs.normal(size=spec.shape)
+    bad = rs.uniform(size=spec.shape) < bad_frac
+    espec = np.where(bad, espec * 1000, espec)
+    return lam, spec, espec, bad

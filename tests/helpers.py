@@ -56,3 +56,18 @@ def setup(shape, layout, seed, holes=0, name=None):
 def relerr(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def close(a, b, rtol, atol=0.0, what=''):
+    """allclose that reports the worst deviation in units of the tolerance."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert np.array_equal(nan_a, nan_b), f'{what}: NaN pattern differs'
+    err = np.abs(a - b)[~nan_a]
+    tol = (atol + rtol * np.abs(b))[~nan_a]
+    if err.size == 0:
+        return True
+    worst = np.max(err / np.maximum(tol, 1e-300))
+    assert worst <= 1, f'{what}: worst deviation {worst:.3g} x tolerance (rtol={rtol}, atol={atol})'
+    return True

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import PROBE_PARAMS, config, relerr, setup, unpack_objects
+from helpers import PROBE_PARAMS, close, config, relerr, setup, unpack_objects
 from rvspecfit_b200 import _cabi, _dev, spec_fit, spec_inter, vel_fit
 
 pytestmark = pytest.mark.gpu
@@ -40,12 +40,12 @@ def test_spline_cabi_dropin(golden):
         A, B, C, D, h = [np.zeros(n - 1) for _ in range(5)]
         L.rvs_spline_construct(vp(x), vp(y), n, vp(A), vp(B), vp(C), vp(D), vp(h))
         for k, arr in zip('ABCD', (A, B, C, D)):
-            assert np.allclose(arr, g[f'spl_{tag}_{k}'], rtol=1e-11, atol=1e-14), k
+            close(arr, g[f'spl_{tag}_{k}'], rtol=1e-11, atol=1e-14), k
         out = np.zeros(len(ex))
         st = L.rvs_spline_eval(vp(ex), len(ex), n, vp(x), vp(h), vp(A), vp(B), vp(C), vp(D),
                                int(tag == 'log'), vp(out))
         assert st == 0
-        assert np.allclose(out, g[f'spl_{tag}_val'], rtol=1e-11, atol=1e-12)
+        close(out, g[f'spl_{tag}_val'], rtol=1e-11, atol=1e-12)
         bad = np.ascontiguousarray([x[0] - 1, x[5]])
         assert L.rvs_spline_eval(vp(bad), 2, n, vp(x), vp(h), vp(A), vp(B), vp(C), vp(D),
                                  int(tag == 'log'), vp(out)) == -1
@@ -62,10 +62,15 @@ def test_template_interpolation(golden):
         st = setup('test', 'tiny', 3, holes=holes, name='p_' + tag)
         bank = _register(st)
         spec, outside = bank.template(pp)
-        assert np.allclose(spec, g[f'{tag}_spec'], rtol=1e-13)
-        assert np.allclose(outside, g[f'{tag}_outside'], rtol=1e-13)
+        on = g[f'{tag}_outside'] == 0
+        close(spec[on], g[f'{tag}_spec'][on], rtol=1e-13)
+        # off-grid: the reference returns exp() of the float32 row evaluated in
+        # float32 (numpy), reproduced as fp64 exp rounded to fp32: <= 1 fp32 ulp
+        close(spec[~on], g[f"{tag}_spec"][~on], rtol=4e-7)
+        assert (spec[~on] == g[f"{tag}_spec"][~on]).mean() > 0.5
+        close(outside, g[f'{tag}_outside'], rtol=1e-13)
         it = spec_inter.getInterpolator('p_' + tag, config())
-        assert np.allclose(it.eval(dict(zip(st['parnames'], pp[1]))), g[f'{tag}_spec'][1],
+        close(it.eval(dict(zip(st['parnames'], pp[1]))), g[f'{tag}_spec'][1],
                            rtol=1e-13)
     st = setup('test', 'tiny', 3, name='p_tri')
     bank = _register(st, kind='triangulation')
@@ -73,8 +78,8 @@ def test_template_interpolation(golden):
     want_o = g['tri_outside']
     assert np.array_equal(np.isnan(outside), np.isnan(want_o))
     ok = ~np.isnan(want_o)
-    assert np.allclose(outside[ok], want_o[ok], rtol=1e-9, atol=1e-12)
-    assert np.allclose(spec[ok], g['tri_spec'][ok], rtol=1e-12)
+    close(outside[ok], want_o[ok], rtol=1e-9, atol=1e-12)
+    close(spec[ok], g['tri_spec'][ok], rtol=1e-12)
 
 
 def test_vsini_broadening_and_spline_vs_oracle(golden):
@@ -93,10 +98,10 @@ def test_vsini_broadening_and_spline_vs_oracle(golden):
         w = np.array([[1., 0.]])
         yz, st = bank.build(ids, w, np.array([v]))
         yz = _dev.download(yz)[0]
-        assert np.allclose(yz[:, 0], g[f'conv_out{i}'], rtol=1e-12, atol=1e-14), v
+        close(yz[:, 0], g[f'conv_out{i}'], rtol=1e-12, atol=1e-14), v
         s = oracle.Spline(lam, np.ascontiguousarray(yz[:, 0]))
         z = np.concatenate([[0.], s.A * 6 * s.h])
-        assert np.allclose(yz[:, 1], z, rtol=1e-9, atol=1e-12 * np.abs(z).max())
+        close(yz[:, 1], z, rtol=1e-9, atol=1e-12 * np.abs(z).max())
 
 
 def test_basis_and_products():
@@ -111,15 +116,15 @@ def test_basis_and_products():
         P, ntot, boff = b.basis(npoly, rbf)
         P = _dev.download(P)
         assert ntot == 777 + 1234
-        assert np.allclose(P[:, :777], oracle.continuum_basis(lam1, npoly, rbf), rtol=1e-13,
+        close(P[:, :777], oracle.continuum_basis(lam1, npoly, rbf), rtol=1e-13,
                            atol=1e-15)
-        assert np.allclose(P[:, 777:], oracle.continuum_basis(lam2, npoly, rbf), rtol=1e-12,
+        close(P[:, 777:], oracle.continuum_basis(lam2, npoly, rbf), rtol=1e-12,
                            atol=1e-14)
     loglam, dn, einv, sumlog2 = [_dev.download(_) for _ in b.products(0.05)]
     es = np.sqrt(0.05**2 + b.h_espec**2)
-    assert np.allclose(dn, b.h_spec / es, rtol=1e-15)
-    assert np.allclose(loglam, np.log(b.h_lam), rtol=1e-15)
-    assert np.allclose(sumlog2[1], 2 * np.log(es[777:777 + 1234]).sum(), rtol=1e-13)
+    close(dn, b.h_spec / es, rtol=1e-15)
+    close(loglam, np.log(b.h_lam), rtol=1e-15)
+    close(sumlog2[1], 2 * np.log(es[777:777 + 1234]).sum(), rtol=1e-13)
 
 
 @pytest.mark.parametrize('fused', [True, False])
@@ -141,7 +146,10 @@ def test_get_chisq_matches_reference(golden, fused):
             for i in range(len(objs)):
                 got = eng.evaluate(np.full(K, i), ev[:, 0], ev[:, 1:5],
                                    np.where(ev[:, 5] < 0, 0.0, ev[:, 5]))
-                assert relerr(got, want[i]) < CHI_RTOL, (name, npoly, rbf, i)
+                on = np.arange(K) < K - 2 if name == 'test' else np.ones(K, dtype=bool)
+                assert relerr(got[on], want[i][on]) < CHI_RTOL, (name, npoly, rbf, i)
+                # the two off-grid points carry the reference's float32 exp
+                assert relerr(got, want[i]) < 1e-6, (name, npoly, rbf, i)
     # the reference-shaped single call
     sd = _sd(objs[0])
     e = ev[3]
@@ -161,12 +169,12 @@ def test_full_output_and_continuum(golden):
     fo = spec_fit.get_chisq(sd, ev[2, 0], tuple(ev[2, 1:5]), (ev[2, 5],),
                             options={'npoly': 15}, config=config(), full_output=True)
     assert abs(fo['chisq'] - g['one_full_chisq']) < 1e-8 * abs(fo['chisq'])
-    assert np.allclose(fo['chisq_array'], g['one_full_chisq_array'], rtol=1e-7)
+    close(fo['chisq_array'], g['one_full_chisq_array'], rtol=1e-7)
     assert np.array_equal(fo['npix_array'], g['one_full_npix'])
-    assert np.allclose(fo['raw_models'][0], g['one_full_raw'], rtol=1e-12)
-    assert np.allclose(fo['models'][0], g['one_full_model'], rtol=1e-6)
+    close(fo['raw_models'][0], g['one_full_raw'], rtol=1e-12)
+    close(fo['models'][0], g['one_full_model'], rtol=1e-6)
     cc = spec_fit.get_chisq_continuum(sd, options={'npoly': 15})['chisq_array']
-    assert np.allclose(cc, g['one_cont'], rtol=1e-7)
+    close(cc, g['one_cont'], rtol=1e-7)
 
 
 def test_find_best_matches_reference(golden):
@@ -185,8 +193,8 @@ def test_find_best_matches_reference(golden):
         for k in ('best_chi', 'best_vel', 'vel_err', 'kurtosis', 'skewness'):
             assert np.isclose(fb[k], g[f'scan_{tag}_{k}'], rtol=1e-7, atol=1e-9), k
         assert abs(fb['best_vel'] - g[f'scan_{tag}_best_vel']) < 1e-6   # << 0.01 km/s
-        assert np.allclose(fb['probs'], g[f'scan_{tag}_probs'], rtol=1e-6, atol=1e-12)
-        assert np.allclose(fb['best_param'], g[f'scan_{tag}_best_param'])
+        close(fb['probs'], g[f'scan_{tag}_probs'], rtol=1e-6, atol=1e-12)
+        close(fb['best_param'], g[f'scan_{tag}_best_param'], rtol=1e-12)
 
 
 def test_desi_three_arm_matches_reference(golden):
@@ -230,7 +238,7 @@ def test_scan_stats_edge_cases():
             assert np.isclose(out[0, 3], want['skewness'], rtol=1e-9, atol=1e-12)
             assert np.isclose(out[0, 4], want['kurtosis'], rtol=1e-9)
             assert int(out[0, 6]) == want['ibest']
-            assert np.allclose(pr[0], want['probs'], rtol=1e-10)
+            close(pr[0], want['probs'], rtol=1e-10)
 
 
 def test_error_behaviour():
@@ -266,7 +274,7 @@ def test_process_matches_reference(golden):
             assert np.all(np.abs(par - g[f'c1_{i}_{tag}_param']) < 0.01 * perr), (i, tag)
             assert abs(res['chisq'] - g[f'c1_{i}_{tag}_chisq']) < 1e-6 * abs(res['chisq'])
             assert np.isclose(res['vel_err'], g[f'c1_{i}_{tag}_vel_err'], rtol=1e-3)
-            assert np.allclose(res['yfit'][0], g[f'c1_{i}_{tag}_yfit'], rtol=1e-5)
+            close(res['yfit'][0], g[f'c1_{i}_{tag}_yfit'], rtol=1e-5)
     res = vel_fit.process(_sd(objs[0]), dict(start), fixParam=['vsini', 'alpha'],
                           config=config(), options={'npoly': 15},
                           priors={'teff': (5200., 300.)})
@@ -277,4 +285,4 @@ def test_process_matches_reference(golden):
                                         'feh': [-1.5, -0.5], 'alpha': [0.2]},
                             vsinigrid=(None, 50))
     got = np.array([fg[k] for k in ('teff', 'logg', 'feh', 'alpha')] + [fg.get('vsini', -1)])
-    assert np.allclose(got, g['c1_fg'])
+    close(got, g['c1_fg'], rtol=1e-12)
