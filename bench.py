@@ -229,13 +229,18 @@ def run_gpu(args):
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else \
         'fallback 6650 GB/s (B200_PROFILING.md)'
     roof = None
-    if ksum.get('fused_ms_per_launch'):
-        ach = beval * ksum['fused_items_per_launch'] / (ksum['fused_ms_per_launch'] * 1e-3) / 1e9
-        roof = dict(bound='hbm', kernel='chisq_fused_kernel', achieved=ach, peak=hbm_peak,
-                    unit='GB/s', frac=ach / hbm_peak, traffic=None, peak_source=peak_src,
-                    algorithmic_bytes_per_eval=beval,
-                    evals_per_launch=ksum['fused_items_per_launch'],
-                    ms_per_launch=ksum['fused_ms_per_launch'])
+    if ksum.get('fused_ms_total'):
+        # one evaluation of one spectrum = one item in each arm's launch; the
+        # algorithmic bytes are SURVEY.md 8d's per-evaluation figure
+        narm = len(setups)
+        evals = ksum['fused_items_per_launch'] * ksum['fused_launches'] / narm
+        ach = beval * evals / (ksum['fused_ms_total'] * 1e-3) / 1e9
+        roof = dict(bound='hbm', kernel='slice_kernel + gram_kernel (rvs_chisq_fused)',
+                    achieved=ach, peak=hbm_peak, unit='GB/s', frac=ach / hbm_peak, traffic=None,
+                    peak_source=peak_src, algorithmic_bytes_per_eval=beval,
+                    evals_timed=evals, ms_total=ksum['fused_ms_total'],
+                    ms_per_launch=ksum['fused_ms_per_launch'],
+                    items_per_launch=ksum['fused_items_per_launch'])
     nspec_total = B * world
     per_step = ms / args.steps
     line = {

@@ -48,7 +48,9 @@ extern "C" {
 #define RVS_ST_NOT_PD 2       /* continuum normal matrix not positive definite /
                                  result not finite: caller takes the SVD route */
 #define RVS_ST_RANGE 4        /* evaluation wavelength outside the template */
-#define RVS_ST_TAPS 8         /* vsini kernel longer than RVS_MAX_TAPS (truncated) */
+#define RVS_ST_TAPS 8         /* vsini kernel longer than the tap capacity (truncated) */
+#define RVS_ST_LIMIT 16       /* item does not fit the fused path's shared-memory window:
+                                 re-evaluate it with rvs_template_build + rvs_chisq_scan */
 
 #define RVS_MAX_NPOLY 16
 #define RVS_MAX_TAPS 2048
@@ -159,13 +161,21 @@ int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
 
 /* Fused optimiser-phase evaluation: template build (as rvs_template_build) and
  * chi-square at ONE velocity per item without the HBM round trip of the
- * spline.  Item k uses object oix[k]; outputs as rvs_chisq_scan with nv=1,
- * status additionally carries the template bits. */
+ * spline.  Item k uses object oix[k].  Only the part of the template that the
+ * object covers at that velocity is gathered.  vsini_max: upper bound of
+ * d_vsini (sizes the tap buffer; 0 if d_vsini is NULL).  d_tn: workspace
+ * [K, tn_stride] doubles, tn_stride >= the longest object.  Outputs
+ * chisq[K], status[K] (template bits | RVS_ST_NOT_PD | RVS_ST_RANGE |
+ * RVS_ST_LIMIT).  rvs_fused_slices: how many CTAs share one item. */
+int rvs_fused_slices(int npix_t);
+/* debugging aid: when set (device buffer of >= 16 + 2*window doubles), slice 0 of
+ * item 0 of every rvs_chisq_fused call dumps its window there; NULL disables */
+void rvs_set_debug_buffer(double *d_buf);
 int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld, const rvs_knots *knots,
                     const int32_t *d_ids, const double *d_w, int nvert, const double *d_vsini,
-                    int log_spec, const rvs_obs *obs, const int32_t *d_oix,
-                    const double *d_vels, int K, double *d_chisq, int32_t *d_status,
-                    void *stream);
+                    double vsini_max, int log_spec, const rvs_obs *obs, const int32_t *d_oix,
+                    const double *d_vels, int K, double *d_tn, int64_t tn_stride,
+                    double *d_chisq, int32_t *d_status, void *stream);
 
 /* RV-grid statistics of find_best for S scans: scan s has nv velocities
  * vels[s*nv..] and chi-squares chisq[(s*npar+q)*nv + j] for npar templates.

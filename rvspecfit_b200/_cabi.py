@@ -16,7 +16,7 @@ c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
 c_dbl = ctypes.c_double
 
-ST_OK, ST_TEMPLATE_BAD, ST_NOT_PD, ST_RANGE, ST_TAPS = 0, 1, 2, 4, 8
+ST_OK, ST_TEMPLATE_BAD, ST_NOT_PD, ST_RANGE, ST_TAPS, ST_LIMIT = 0, 1, 2, 4, 8, 16
 MAX_NPOLY = 16
 
 
@@ -60,9 +60,11 @@ SIGNATURES = {
     'rvs_chisq_scan': (c_int, [c_dp, c_i64, c_dp, ctypes.POINTER(Knots), ctypes.POINTER(Obs),
                                c_dp, c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                c_dp]),
+    'rvs_fused_slices': (c_int, [c_int]),
+    'rvs_set_debug_buffer': (None, [c_dp]),
     'rvs_chisq_fused': (c_int, [c_dp, c_int, c_i64, ctypes.POINTER(Knots), c_dp, c_dp, c_int,
-                                c_dp, c_int, ctypes.POINTER(Obs), c_dp, c_dp, c_int, c_dp, c_dp,
-                                c_dp]),
+                                c_dp, c_dbl, c_int, ctypes.POINTER(Obs), c_dp, c_dp, c_int,
+                                c_dp, c_i64, c_dp, c_dp, c_dp]),
     'rvs_scan_stats': (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
 }
 

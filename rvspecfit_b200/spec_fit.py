@@ -170,6 +170,11 @@ class LikelihoodEngine:
         self.n_eval = 0
         self.timer = None
 
+    def _workspace(self, n):
+        if getattr(self, '_ws', None) is None or self._ws.numel() < n:
+            self._ws = _dev.empty((int(n * 1.25) + 1024,), np.float64)
+        return self._ws
+
     # ------------------------------------------------------------------ core
     def _arm_eval(self, arm, sel, obj, vels, params, vsini, sys_err, want_model):
         """chi-square of one arm for the items `sel` (indices into the call's
@@ -192,17 +197,32 @@ class LikelihoodEngine:
             d_ids = _dev.upload(ids, np.int32)
             d_w = _dev.upload(w, np.float64)
             d_vs = None if vs is None else _dev.upload(vs, np.float64)
+            vmax = 0.0 if vs is None else float(np.max(vs, initial=0.0))
+            stride = int(batch.npix.max())
+            d_tn = self._workspace(k * stride)
             t0 = self.timer.start() if self.timer else None
             rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
                                    ctypes.byref(bank.knots), _dev.ptr(d_ids), _dev.ptr(d_w),
-                                   bank.nvert, _dev.ptr(d_vs), int(bank.log_spec),
+                                   bank.nvert, _dev.ptr(d_vs), vmax, int(bank.log_spec),
                                    ctypes.byref(obs), _dev.ptr(d_oix), _dev.ptr(d_vels), k,
-                                   _dev.ptr(d_chi), _dev.ptr(d_st), _dev.stream())
+                                   _dev.ptr(d_tn), stride, _dev.ptr(d_chi), _dev.ptr(d_st),
+                                   _dev.stream())
             _cabi.check(rc, 'rvs_chisq_fused')
             if t0 is not None:
                 self.timer.stop('fused', t0, k)
+            chi = _dev.download(d_chi)
             st = _dev.download(d_st)
+            redo = np.nonzero(st[:, 0] & _cabi.ST_LIMIT)[0]
+            if len(redo):      # window did not fit the fused path: general path
+                self.fused = False
+                try:
+                    c2, s2, _, t2, _ = self._arm_eval(arm, sel[redo], obj, vels, params, vsini,
+                                                      sys_err, False)
+                finally:
+                    self.fused = True
+                chi[redo], st[redo] = c2, s2 | t2[:, None]
             tstatus = st[:, 0] & (_cabi.ST_TEMPLATE_BAD | _cabi.ST_TAPS)
+            return chi, st, outside, tstatus, None
         else:
             t0 = self.timer.start() if self.timer else None
             yz, d_tst = bank.build(ids, w, vs)
