@@ -53,7 +53,8 @@ extern "C" {
                                  re-evaluate it with rvs_template_build + rvs_chisq_scan */
 
 #define RVS_MAX_NPOLY 16
-#define RVS_MAX_TAPS 2048
+#define RVS_MAX_TAPS 2048      /* one-sided vsini taps, rvs_template_build */
+#define RVS_MAX_FUSED_TAPS 128 /* one-sided vsini taps, rvs_chisq_fused */
 
 const char *rvs_last_error(void);
 int rvs_version(void);
@@ -86,21 +87,28 @@ typedef struct {
   double x0, xlast;      /* first / last knot */
   double q0, qstep_inv;  /* ln(x0) (or x0) and 1/step of the uniform coordinate */
   double lnstep;         /* ln(x[1]/x[0]) (vsini kernel scale) */
+  double ratio;          /* h[k+1]/h[k] of the ideal grid: (x[n-1]/x[0])^(1/(n-1)), or 1 */
+  double ratio_dev;      /* max_k |h[k+1] / (ratio h[k]) - 1| of the actual knots */
 } rvs_knots;
 
 /* Ragged batch of observed spectra of one setup and their derived products
- * (rvs_obs_prepare, rvs_basis_build).  Object i owns pixels
- * [off[i], off[i+1]) of every pool; its continuum basis row r is
- * d_P[r*pstride + boff[i] + p]. */
+ * (rvs_obs_prepare, rvs_basis_build).  Object i owns pixels [off[i], off[i+1])
+ * of the OBJECT pools (dn, einv).  Its wavelength grid -- shared with every
+ * other object observed on the same pixels, as all DESI spectra of an arm are --
+ * starts at goff[i] in the GRID pools (lam, loglam, P).  The continuum basis is
+ * pixel-major: value r of grid pixel p is d_P[(goff[i] + p) * npp + r], npp =
+ * npoly rounded up to even (16-byte rows). */
 typedef struct {
-  const double *d_lam, *d_loglam, *d_dn, *d_einv; /* pixel pools */
-  const double *d_sumlog2;                        /* [B] 2*sum ln sigma */
-  const int64_t *d_off;                           /* [B+1] */
-  const double *d_P;
-  int64_t pstride;
-  const int64_t *d_boff; /* [B] */
+  const double *d_lam, *d_loglam; /* grid pools */
+  const double *d_P;              /* grid pool, [ntot_grid][npp] */
+  const int64_t *d_goff;          /* [B] */
+  const double *d_dn, *d_einv;    /* object pools */
+  const double *d_sumlog2;        /* [B] 2*sum ln sigma */
+  const int64_t *d_off;           /* [B+1] */
   int32_t npoly;
+  int32_t npp;
   int32_t nobj;
+  int32_t reserved;
 } rvs_obs;
 
 /* ---- template evaluation ------------------------------------------------- */
@@ -130,19 +138,19 @@ int rvs_template_build(const void *d_grid, int grid_f64, int64_t ld, const rvs_k
                        int64_t yz_stride, int32_t *d_status, void *stream);
 
 /* ---- observed-spectrum products ------------------------------------------ */
-/* Produces loglam = ln(lam), dn = spec/sigma, einv = 1/sigma with
- * sigma = sqrt(espec^2 + sys^2) (sys may be 0), and
- * sumlog2[i] = 2*sum ln sigma  (the 2*log(espec).sum() term). */
-int rvs_obs_prepare(const double *d_lam, const double *d_spec, const double *d_espec,
-                    const int64_t *d_off, int B, double espec_sys, double *d_loglam,
-                    double *d_dn, double *d_einv, double *d_sumlog2, void *stream);
+/* Object pools: dn = spec/sigma, einv = 1/sigma with sigma = sqrt(espec^2 +
+ * sys^2) (sys may be 0), and sumlog2[i] = 2*sum ln sigma (the
+ * 2*log(espec).sum() term of spec_fit.py:247). */
+int rvs_obs_prepare(const double *d_spec, const double *d_espec, const int64_t *d_off, int B,
+                    double espec_sys, double *d_dn, double *d_einv, double *d_sumlog2,
+                    void *stream);
 
-/* Continuum basis of G wavelength grids: grid g owns pixels
- * [goff[g], goff[g+1]) of d_lam (ntot = goff[G] pixels in all) and writes rows
- * r<npoly to d_P[r*pstride + p].  rbf=1: {1,t,t^2} + Gaussian RBFs; rbf=0:
- * Chebyshev (spec_fit.py:148-176). */
-int rvs_basis_build(const double *d_lam, const int64_t *d_goff, int G, int64_t ntot, int npoly,
-                    int rbf, int64_t pstride, double *d_P, void *stream);
+/* Grid pools of G wavelength grids: grid g owns pixels [gstart[g], gstart[g+1])
+ * of d_lam (ntot = gstart[G] pixels in all).  Writes loglam = ln(lam) and the
+ * continuum basis rows d_P[p*npp + r], r < npoly (zero for npoly <= r < npp).
+ * rbf=1: {1,t,t^2} + Gaussian RBFs; rbf=0: Chebyshev (spec_fit.py:148-176). */
+int rvs_basis_build(const double *d_lam, const int64_t *d_gstart, int G, int64_t ntot, int npoly,
+                    int rbf, int npp, double *d_loglam, double *d_P, void *stream);
 
 /* ---- chi-square ----------------------------------------------------------- */
 /* For item k < K and trial j < nv:  resample template row tix[k] of d_yz at
@@ -164,17 +172,19 @@ int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
  * spline.  Item k uses object oix[k].  Only the part of the template that the
  * object covers at that velocity is gathered.  vsini_max: upper bound of
  * d_vsini (sizes the tap buffer; 0 if d_vsini is NULL).  d_tn: workspace
- * [K, tn_stride] doubles, tn_stride >= the longest object.  Outputs
- * chisq[K], status[K] (template bits | RVS_ST_NOT_PD | RVS_ST_RANGE |
- * RVS_ST_LIMIT).  rvs_fused_slices: how many CTAs share one item. */
-int rvs_fused_slices(int npix_t);
-/* debugging aid: when set (device buffer of >= 16 + 2*window doubles), slice 0 of
- * item 0 of every rvs_chisq_fused call dumps its window there; NULL disables */
-void rvs_set_debug_buffer(double *d_buf);
+ * [K, tn_stride] doubles, tn_stride >= the longest object.  d_work: workspace
+ * of rvs_fused_workspace(K, tapcap) doubles, tapcap = ceil(vsini_max /
+ * (c lnstep) + 1) + 1 (may be NULL when d_vsini is NULL).  Outputs chisq[K],
+ * status[K] (template bits | RVS_ST_NOT_PD | RVS_ST_RANGE | RVS_ST_LIMIT).
+ * Needs knots->ratio_dev < 1e-8 (exactly uniform or log-uniform knots) and
+ * tapcap <= RVS_MAX_FUSED_TAPS, else RVS_E_LIMIT: use the general path.
+ * rvs_fused_chunks: how many warps share one item. */
+int rvs_fused_chunks(int npix_t, int tapcap);
+int64_t rvs_fused_workspace(int K, int tapcap);
 int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld, const rvs_knots *knots,
                     const int32_t *d_ids, const double *d_w, int nvert, const double *d_vsini,
                     double vsini_max, int log_spec, const rvs_obs *obs, const int32_t *d_oix,
-                    const double *d_vels, int K, double *d_tn, int64_t tn_stride,
+                    const double *d_vels, int K, double *d_tn, int64_t tn_stride, double *d_work,
                     double *d_chisq, int32_t *d_status, void *stream);
 
 /* RV-grid statistics of find_best for S scans: scan s has nv velocities

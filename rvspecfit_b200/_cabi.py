@@ -18,6 +18,7 @@ c_dbl = ctypes.c_double
 
 ST_OK, ST_TEMPLATE_BAD, ST_NOT_PD, ST_RANGE, ST_TAPS, ST_LIMIT = 0, 1, 2, 4, 8, 16
 MAX_NPOLY = 16
+MAX_FUSED_TAPS = 128
 
 
 class Knots(ctypes.Structure):
@@ -25,14 +26,15 @@ class Knots(ctypes.Structure):
     _fields_ = [('d_lam_t', c_dp), ('d_h', c_dp), ('d_hinv', c_dp), ('d_cp', c_dp),
                 ('d_winv', c_dp), ('npix_t', ctypes.c_int32), ('log_step', ctypes.c_int32),
                 ('x0', c_dbl), ('xlast', c_dbl), ('q0', c_dbl), ('qstep_inv', c_dbl),
-                ('lnstep', c_dbl)]
+                ('lnstep', c_dbl), ('ratio', c_dbl), ('ratio_dev', c_dbl)]
 
 
 class Obs(ctypes.Structure):
     """struct rvs_obs"""
-    _fields_ = [('d_lam', c_dp), ('d_loglam', c_dp), ('d_dn', c_dp), ('d_einv', c_dp),
-                ('d_sumlog2', c_dp), ('d_off', c_dp), ('d_P', c_dp), ('pstride', c_i64),
-                ('d_boff', c_dp), ('npoly', ctypes.c_int32), ('nobj', ctypes.c_int32)]
+    _fields_ = [('d_lam', c_dp), ('d_loglam', c_dp), ('d_P', c_dp), ('d_goff', c_dp),
+                ('d_dn', c_dp), ('d_einv', c_dp), ('d_sumlog2', c_dp), ('d_off', c_dp),
+                ('npoly', ctypes.c_int32), ('npp', ctypes.c_int32), ('nobj', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)]
 
 
 class CcfArm(ctypes.Structure):
@@ -54,17 +56,17 @@ SIGNATURES = {
     'rvs_knot_info': (c_int, [c_dp, c_int, c_int, ctypes.POINTER(Knots)]),
     'rvs_template_build': (c_int, [c_dp, c_int, c_i64, ctypes.POINTER(Knots), c_dp, c_dp, c_int,
                                    c_dp, c_int, c_int, c_dp, c_i64, c_dp, c_dp]),
-    'rvs_obs_prepare': (c_int, [c_dp, c_dp, c_dp, c_dp, c_int, c_dbl, c_dp, c_dp, c_dp, c_dp,
+    'rvs_obs_prepare': (c_int, [c_dp, c_dp, c_dp, c_int, c_dbl, c_dp, c_dp, c_dp, c_dp]),
+    'rvs_basis_build': (c_int, [c_dp, c_dp, c_int, c_i64, c_int, c_int, c_int, c_dp, c_dp,
                                 c_dp]),
-    'rvs_basis_build': (c_int, [c_dp, c_dp, c_int, c_i64, c_int, c_int, c_i64, c_dp, c_dp]),
     'rvs_chisq_scan': (c_int, [c_dp, c_i64, c_dp, ctypes.POINTER(Knots), ctypes.POINTER(Obs),
                                c_dp, c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                c_dp]),
-    'rvs_fused_slices': (c_int, [c_int]),
-    'rvs_set_debug_buffer': (None, [c_dp]),
+    'rvs_fused_chunks': (c_int, [c_int, c_int]),
+    'rvs_fused_workspace': (c_i64, [c_int, c_int]),
     'rvs_chisq_fused': (c_int, [c_dp, c_int, c_i64, ctypes.POINTER(Knots), c_dp, c_dp, c_int,
                                 c_dp, c_dbl, c_int, ctypes.POINTER(Obs), c_dp, c_dp, c_int,
-                                c_dp, c_i64, c_dp, c_dp, c_dp]),
+                                c_dp, c_i64, c_dp, c_dp, c_dp, c_dp]),
     'rvs_scan_stats': (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
 }
 

@@ -12,16 +12,14 @@
 namespace rvs {
 
 // ------------------------------------------------------------- obs products
-__global__ void obs_prepare_kernel(const double *lam, const double *spec, const double *espec,
-                                   const int64_t *off, double sys, double *loglam, double *dn,
-                                   double *einv, double *sumlog2) {
+__global__ void obs_prepare_kernel(const double *spec, const double *espec, const int64_t *off,
+                                   double sys, double *dn, double *einv, double *sumlog2) {
   const int i = blockIdx.x;
   const int64_t p0 = off[i], p1 = off[i + 1];
   double s = 0;
   for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
     double e = espec[p];
     if (sys != 0) e = sqrt(sys * sys + e * e);
-    loglam[p] = log(lam[p]);
     dn[p] = spec[p] / e;
     einv[p] = 1.0 / e;
     s += log(e);
@@ -38,7 +36,7 @@ __global__ void obs_prepare_kernel(const double *lam, const double *spec, const 
 }
 
 __global__ void basis_kernel(const double *lam, const int64_t *goff, int G, int64_t ntot,
-                             int npoly, int rbf, int64_t pstride, double *P) {
+                             int npoly, int rbf, int npp, double *loglam, double *P) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ntot) return;
   int lo = 0, hi = G;  // grid g with goff[g] <= p < goff[g+1]
@@ -49,10 +47,13 @@ __global__ void basis_kernel(const double *lam, const int64_t *goff, int G, int6
   const int64_t p0 = goff[lo], p1 = goff[lo + 1];
   const double l0 = lam[p0], l1 = lam[p1 - 1];
   const double t = (lam[p] - l0) / (l1 - l0) * 2 - 1;
+  loglam[p] = log(lam[p]);
+  double *row = P + p * npp;
+  for (int r = npoly; r < npp; r++) row[r] = 0;
   if (rbf) {
     double pw = 1;
     for (int r = 0; r < min(3, npoly); r++) {
-      P[r * pstride + p] = pw;
+      row[r] = pw;
       pw *= t;
     }
     const int nr = npoly - 3;
@@ -63,13 +64,13 @@ __global__ void basis_kernel(const double *lam, const int64_t *goff, int G, int6
         // numpy.linspace(-1, 1, nr): start + r*step, last point forced to stop
         const double c = (nr > 1 && r == nr - 1) ? 1.0 : -1.0 + r * step;
         const double dlt = t - c;
-        P[(3 + r) * pstride + p] = exp(-0.5 * (dlt * dlt) / (sig * sig));
+        row[3 + r] = exp(-0.5 * (dlt * dlt) / (sig * sig));
       }
     }
   } else {
     double tm = 1, tc = t;
     for (int r = 0; r < npoly; r++) {
-      P[r * pstride + p] = (r == 0) ? 1.0 : tc;
+      row[r] = (r == 0) ? 1.0 : tc;
       if (r >= 1) {
         const double tn = 2 * t * tc - tm;
         tm = tc;
@@ -90,9 +91,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) chisq_scan_kernel(ScanArgs a)
   const int obj = a.oix[k];
   const int64_t p0 = a.off[obj];
   const int npix = (int)(a.off[obj + 1] - p0);
-  const int64_t b0 = a.boff[obj];
+  const int64_t b0 = a.goff[obj];
   const double2 *yz = a.yz + (int64_t)a.tix[k] * a.yz_stride;
-  const double *lam = a.lam + p0, *ql = (a.log_step ? a.loglam : a.lam) + p0;
+  const double *lam = a.lam + b0, *ql = (a.log_step ? a.loglam : a.lam) + b0;
+  const double *Pb = a.P + b0 * a.npp;
   const double *dn = a.dn + p0, *einv = a.einv + p0;
 
   for (int j = blockIdx.y * SCAN_WARPS + wid; j < a.nv; j += gridDim.y * SCAN_WARPS) {
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) chisq_scan_kernel(ScanArgs a)
         const double q = a.log_step ? ql[p] + qf : x;
         const double tn = spline_eval(a, yz, x, q) * einv[p];
         double g[NP];
-        load_basis<NP>(a.P, a.pstride, b0 + p, tn, g);
+        load_basis<NP>(Pb + (int64_t)p * a.npp, tn, g);
         const double d = dn[p];
 #pragma unroll
         for (int i = 0; i < NP; i++) v[i] = fma(g[i], d, v[i]);
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) chisq_scan_kernel(ScanArgs a)
         const double q = a.log_step ? ql[p] + qf : x;
         const double tn = spline_eval(a, yz, x, q) * einv[p];
         double g[NP];
-        load_basis<NP>(a.P, a.pstride, b0 + p, tn, g);
+        load_basis<NP>(Pb + (int64_t)p * a.npp, tn, g);
         acc.add(g);
       }
       acc.reduce_store(sM[wid], lane);
@@ -152,18 +154,19 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) chisq_scan_kernel(ScanArgs a)
       const double q = a.log_step ? ql[p] + qf : x;
       const double tv = spline_eval(a, yz, x, q);
       const double tn = tv * einv[p];
+      double g[NP];
+      load_basis<NP>(Pb + (int64_t)p * a.npp, tn, g);
       double mval = 0;
 #pragma unroll
-      for (int i = 0; i < NP; i++)
-        mval = fma(co[i], __ldg(a.P + i * a.pstride + b0 + p) * tn, mval);
+      for (int i = 0; i < NP; i++) mval = fma(co[i], g[i], mval);
       const double r = dn[p] - mval;
       rss = fma(r, r, rss);
       if (want_model) {
         a.raw[a.moff[k] + p] = tv;
+        load_basis<NP>(Pb + (int64_t)p * a.npp, tv, g);
         double cont = 0;
 #pragma unroll
-        for (int i = 0; i < NP; i++)
-          cont = fma(co[i], __ldg(a.P + i * a.pstride + b0 + p) * tv, cont);
+        for (int i = 0; i < NP; i++) cont = fma(co[i], g[i], cont);
         a.model[a.moff[k] + p] = cont;
       }
     }
@@ -286,30 +289,32 @@ __global__ void scan_stats_kernel(const double *vels, const double *chisq, int n
 
 }  // namespace rvs
 
-extern "C" int rvs_obs_prepare(const double *d_lam, const double *d_spec, const double *d_espec,
-                               const int64_t *d_off, int B, double espec_sys, double *d_loglam,
-                               double *d_dn, double *d_einv, double *d_sumlog2, void *stream) {
+extern "C" int rvs_obs_prepare(const double *d_spec, const double *d_espec, const int64_t *d_off,
+                               int B, double espec_sys, double *d_dn, double *d_einv,
+                               double *d_sumlog2, void *stream) {
   using namespace rvs;
   if (B == 0) return 0;
-  RVS_REQUIRE(d_lam && d_spec && d_espec && d_off && d_loglam && d_dn && d_einv && d_sumlog2,
-              RVS_E_ARG, "rvs_obs_prepare: null pointer");
-  obs_prepare_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(d_lam, d_spec, d_espec, d_off,
-                                                          espec_sys, d_loglam, d_dn, d_einv,
-                                                          d_sumlog2);
+  RVS_REQUIRE(d_spec && d_espec && d_off && d_dn && d_einv && d_sumlog2, RVS_E_ARG,
+              "rvs_obs_prepare: null pointer");
+  obs_prepare_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(d_spec, d_espec, d_off, espec_sys,
+                                                          d_dn, d_einv, d_sumlog2);
   RVS_LAUNCH_OK();
   return 0;
 }
 
-extern "C" int rvs_basis_build(const double *d_lam, const int64_t *d_goff, int G, int64_t ntot,
-                               int npoly, int rbf, int64_t pstride, double *d_P, void *stream) {
+extern "C" int rvs_basis_build(const double *d_lam, const int64_t *d_gstart, int G, int64_t ntot,
+                               int npoly, int rbf, int npp, double *d_loglam, double *d_P,
+                               void *stream) {
   using namespace rvs;
   if (G == 0 || ntot == 0) return 0;
-  RVS_REQUIRE(d_lam && d_goff && d_P, RVS_E_ARG, "rvs_basis_build: null pointer");
+  RVS_REQUIRE(d_lam && d_gstart && d_P && d_loglam, RVS_E_ARG, "rvs_basis_build: null pointer");
   RVS_REQUIRE(npoly >= 1 && npoly <= RVS_MAX_NPOLY, RVS_E_ARG,
               "rvs_basis_build: npoly=%d outside 1..%d", npoly, RVS_MAX_NPOLY);
+  RVS_REQUIRE(npp >= npoly && npp % 2 == 0 && ((uintptr_t)d_P & 15) == 0, RVS_E_ARG,
+              "rvs_basis_build: npp=%d must be even and >= npoly, d_P 16-byte aligned", npp);
   const int bx = (int)((ntot + 255) / 256);
-  basis_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(d_lam, d_goff, G, ntot, npoly, rbf,
-                                                     pstride, d_P);
+  basis_kernel<<<bx, 256, 0, (cudaStream_t)stream>>>(d_lam, d_gstart, G, ntot, npoly, rbf, npp,
+                                                     d_loglam, d_P);
   RVS_LAUNCH_OK();
   return 0;
 }
@@ -318,7 +323,7 @@ namespace rvs {
 int fill_scan_args(ScanArgs &a, const rvs_knots *kn, const rvs_obs *obs) {
   RVS_REQUIRE(kn && obs && kn->d_lam_t && kn->d_h && kn->d_hinv && obs->d_lam &&
                   obs->d_loglam && obs->d_dn && obs->d_einv && obs->d_sumlog2 && obs->d_off &&
-                  obs->d_P && obs->d_boff,
+                  obs->d_P && obs->d_goff,
               RVS_E_ARG, "chisq: null pointer in descriptor");
   RVS_REQUIRE(obs->npoly >= 1 && obs->npoly <= RVS_MAX_NPOLY, RVS_E_ARG,
               "chisq: npoly=%d outside 1..%d", obs->npoly, RVS_MAX_NPOLY);
@@ -326,8 +331,10 @@ int fill_scan_args(ScanArgs &a, const rvs_knots *kn, const rvs_obs *obs) {
   a.log_step = kn->log_step; a.x0 = kn->x0; a.xlast = kn->xlast; a.q0 = kn->q0;
   a.qstep_inv = kn->qstep_inv;
   a.lam = obs->d_lam; a.loglam = obs->d_loglam; a.dn = obs->d_dn; a.einv = obs->d_einv;
-  a.sumlog2 = obs->d_sumlog2; a.off = obs->d_off; a.P = obs->d_P; a.pstride = obs->pstride;
-  a.boff = obs->d_boff;
+  a.sumlog2 = obs->d_sumlog2; a.off = obs->d_off; a.goff = obs->d_goff; a.P = obs->d_P;
+  a.npp = obs->npp;
+  RVS_REQUIRE(obs->npp >= obs->npoly && obs->npp % 2 == 0 && ((uintptr_t)obs->d_P & 15) == 0,
+              RVS_E_ARG, "chisq: basis rows must be npp = even >= npoly doubles, 16-byte aligned");
   return 0;
 }
 }  // namespace rvs

@@ -16,12 +16,11 @@ struct ScanArgs {
   const double *lam_t, *h, *hinv;
   int npix_t, log_step;
   double x0, xlast, q0, qstep_inv;  // knot-grid origin (ln or linear) and 1/step
-  const double *lam, *loglam, *dn, *einv, *sumlog2;
-  const int64_t *off;
+  const double *lam, *loglam, *dn, *einv, *sumlog2;  // lam, loglam, P: grid pools
+  const int64_t *off, *goff;
   const int32_t *oix;
-  const double *P;
-  int64_t pstride;
-  const int64_t *boff;
+  const double *P;  // pixel-major [pixel][npp]
+  int npp;
   const double *vels;
   int nv, K;
   double *chisq;
@@ -118,57 +117,70 @@ struct GramAcc {
   }
 };
 
+// g[i] = P_i(pixel) * tn from the pixel-major basis (rows of npp doubles, npp even,
+// 16-byte aligned)
 template <int NP>
-__device__ __forceinline__ void load_basis(const double *P, int64_t pstride, int64_t col,
-                                           double tn, double (&g)[NP]) {
+__device__ __forceinline__ void load_basis(const double *Prow, double tn, double (&g)[NP]) {
+  const double2 *P2 = reinterpret_cast<const double2 *>(Prow);
 #pragma unroll
-  for (int i = 0; i < NP; i++) g[i] = __ldg(P + i * pstride + col) * tn;
+  for (int i = 0; i < NP / 2; i++) {
+    const double2 v = __ldg(P2 + i);
+    g[2 * i] = v.x * tn;
+    g[2 * i + 1] = v.y * tn;
+  }
+  if (NP & 1) g[NP - 1] = __ldg(Prow + NP - 1) * tn;
 }
 
-// Warp-cooperative Cholesky solve on a packed lower triangle in shared memory.
-// On return a[] holds the coefficients; returns 2*sum ln L_ii, or NaN if M is
-// not positive definite.
+// Warp-cooperative Cholesky solve of M a = v.  Ms: packed lower triangle of M in
+// shared memory (overwritten with L), a: v in, coefficients out.  Lane i owns
+// row i in registers; the right-looking update exchanges column entries by
+// shuffle, the forward substitution rides along, and the logarithms of the
+// pivots are taken once, in parallel, at the end (2 sum ln L_ii = sum ln s_j).
+// Returns that sum, or NaN if M is not positive definite.  All 32 lanes must call.
 template <int NP>
 __device__ __forceinline__ double chol_solve(double *Ms, double *a, int lane) {
-  double ldet = 0;
+  static_assert(NP <= 32, "one lane per row");
+  double row[NP];
+#pragma unroll
+  for (int l = 0; l < NP; l++) row[l] = (lane < NP && l <= lane) ? Ms[lane * (lane + 1) / 2 + l] : 0.0;
+  double rhs = lane < NP ? a[lane] : 0.0;
+  double spiv = 1.0, myinv = 0.0;
   bool ok = true;
+#pragma unroll
   for (int j = 0; j < NP; j++) {
-    // diagonal
-    double s = Ms[j * (j + 1) / 2 + j];
-    for (int k = 0; k < j; k++) {
-      const double l = Ms[j * (j + 1) / 2 + k];
-      s -= l * l;
-    }
+    const double s = __shfl_sync(0xffffffffu, row[j], j);
     if (!(s > 0) || isinf(s)) ok = false;
-    const double ljj = sqrt(s);
-    ldet += 2.0 * log(ljj);
-    __syncwarp();
-    const int i = j + 1 + lane;
-    if (i < NP) {
-      double t = Ms[i * (i + 1) / 2 + j];
-      for (int k = 0; k < j; k++) t -= Ms[i * (i + 1) / 2 + k] * Ms[j * (j + 1) / 2 + k];
-      Ms[i * (i + 1) / 2 + j] = t / ljj;
+    const double inv = rsqrt(s);
+    const double lij = row[j] * inv;  // L_ij for lanes i >= j (L_jj = s / sqrt(s))
+    row[j] = lij;
+    const double yj = __shfl_sync(0xffffffffu, rhs, j) * inv;
+    if (lane > j) rhs = fma(-lij, yj, rhs);
+    if (lane == j) { rhs = yj; spiv = s; myinv = inv; }
+#pragma unroll
+    for (int l = j + 1; l < NP; l++) {
+      const double llj = __shfl_sync(0xffffffffu, lij, l);
+      if (lane >= l) row[l] = fma(-lij, llj, row[l]);
     }
-    if (lane == 0) Ms[j * (j + 1) / 2 + j] = ljj;
-    __syncwarp();
   }
-  // L y = v ; L^T a = y   (every lane redundantly, operands broadcast from smem)
-  double y[NP];
+  const double ldet = warp_sum(lane < NP ? log(spiv) : 0.0);
+  // back substitution L^T a = y: every lane redundantly, operands broadcast from smem
+  if (lane < NP) {
 #pragma unroll
-  for (int i = 0; i < NP; i++) {
-    double t = a[i];
-#pragma unroll
-    for (int k = 0; k < i; k++) t -= Ms[i * (i + 1) / 2 + k] * y[k];
-    y[i] = t / Ms[i * (i + 1) / 2 + i];
+    for (int l = 0; l < NP; l++)
+      if (l < lane) Ms[lane * (lane + 1) / 2 + l] = row[l];
+    Ms[lane * (lane + 1) / 2 + lane] = myinv;  // reciprocal diagonal
+    a[lane] = rhs;                             // y
   }
   __syncwarp();
+  double y[NP];
 #pragma unroll
   for (int i = NP - 1; i >= 0; i--) {
-    double t = y[i];
+    double t = a[i];
 #pragma unroll
-    for (int k = i + 1; k < NP; k++) t -= Ms[k * (k + 1) / 2 + i] * y[k];
-    y[i] = t / Ms[i * (i + 1) / 2 + i];
+    for (int k = i + 1; k < NP; k++) t = fma(-Ms[k * (k + 1) / 2 + i], y[k], t);
+    y[i] = t * Ms[i * (i + 1) / 2 + i];
   }
+  __syncwarp();
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < NP; i++) a[i] = y[i];

@@ -1,0 +1,420 @@
+// Fused optimiser-phase evaluation, stage A ("chunk kernel"): one WARP per
+// (item, chunk).  A chunk is a contiguous range of at most `C` template knots
+// and the observed pixels that fall on them at the item's velocity.  The warp
+//   1. gathers its window of the 2^d (or d+1) grid rows with streaming 16-byte
+//      loads, accumulates the corner-weighted sum in fp64 and exponentiates,
+//   2. applies the rotational-broadening taps (prepared by taps_kernel),
+//   3. solves the natural cubic spline on the window,
+//   4. resamples onto its pixels and writes T/sigma.
+// Warps never synchronise with each other (only __syncwarp / shuffles), so the
+// 20-odd resident warps of an SM sit in different phases and the memory phase
+// of one overlaps the fp64 phases of the others.  Stage B (gram_kernel.cuh)
+// does the continuum solve.
+//
+// Spline solve.  The template knots are uniform in x or in ln x (validated by
+// rvs_knot_info, as the reference's evaler requires, spliner.c:84-96), so
+// h[k+1] = r h[k] with one ratio r.  In the scaled unknown s_k = z_k h_k^2 / 6
+// the reference's tridiagonal system (spliner.c:21-41)
+//     h_k z_k + 2 (h_k + h_{k+1}) z_{k+1} + h_{k+1} z_{k+2} = 6 (b_{k+1} - b_k)
+// becomes the constant-coefficient system
+//     s_k + c1 s_{k+1} + c2 s_{k+2} = dy_{k+1} / r - dy_k,
+//     c1 = 2 (1 + r) / r^2,  c2 = 1 / r^3,
+// whose Thomas pivots converge to a constant within ~15 rows of knot 0
+// (table wtab[] holds the exact ones there).  No per-knot tables are read.  The
+// window carries SPL_HALO extra rows on each side: the influence of the
+// artificial window ends decays as 0.268^k, below fp64 rounding after 32 rows
+// (exact natural boundary where the window touches an end of the template).
+// Evaluation in [x_i, x_{i+1}):  u = (x - x_i)/h_i, v = (x_{i+1} - x)/h_i,
+//     T = v y_i + u y_{i+1} + s_i (v^3 - v) + (s_{i+1}/r^2) (u^3 - u),
+// algebraically the reference's A dl^3 + B dr^3 + C dl + D dr (spliner.c:97-106).
+#pragma once
+#include "chisq_device.cuh"
+#include "template_device.cuh"
+
+namespace rvs {
+
+constexpr int CK_WARPS = 4;
+constexpr int CK_THREADS = CK_WARPS * 32;
+constexpr int CK_NT = 32;  // rows next to knot 0 with tabulated pivots
+constexpr int CK_MINB = 6;  // resident CTAs per SM the register budget allows
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+constexpr unsigned FULL = 0xffffffffu;
+
+struct ChunkArgs {
+  // template side
+  const void *grid;
+  int64_t ld;
+  int npix_t;
+  const int32_t *ids;
+  const double *w;
+  int nvert;
+  const double *taps;   // [K, tapstride] normalised one-sided weights (taps_kernel) or NULL
+  const int32_t *kmax;  // [K] number of one-sided taps (0: no broadening)
+  int tapstride;
+  const double *lam_t, *hinv;
+  int log_spec, log_step;
+  double x0, xlast, q0, qstep_inv;
+  double rinv, r2inv, c2, winv_inf;
+  double wtab[CK_NT];
+  // observed side
+  const double *lam, *loglam;  // grid pools (see rvs_obs)
+  const double *einv;          // object pool
+  const int64_t *off, *goff;
+  const int32_t *oix;
+  const double *vels;
+  // outputs
+  double *tn;
+  int64_t tn_stride;
+  int32_t *status;
+  int wcap;  // doubles per smem buffer per warp
+  int nch;   // chunks per item (upper bound; surplus chunks exit)
+  int C;     // knots per chunk (upper bound)
+  int K;
+};
+
+// one-sided, normalised rotation taps of every item (spec_fit.py:565-625)
+struct TapsArgs {
+  const double *vsini;
+  double lnstep;
+  int tapcap, tapstride, K;
+  double *taps;
+  int32_t *kmax;
+  int32_t *status;
+};
+
+__global__ void __launch_bounds__(128) taps_kernel(TapsArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= a.K) return;
+  const double vs = a.vsini[k];
+  int kmax = 0;
+  if (vs > 0) {
+    const double R = (vs / RVS_C_KMS) / a.lnstep;
+    if (R >= 1e-9) {
+      kmax = (int)ceil(R + 1);
+      if (kmax > a.tapcap) {
+        kmax = a.tapcap;
+        if (lane == 0) atomicOr(a.status + k, RVS_ST_TAPS);
+      }
+      double *t = a.taps + (int64_t)k * a.tapstride;
+      double part = 0;
+      for (int j = lane; j <= kmax; j += 32) {
+        const double wv = rot_weight(j, R);
+        t[j] = wv;
+        part += (j == 0) ? wv : 2 * wv;
+      }
+      const double tot = warp_sum(part);
+      __syncwarp();
+      for (int j = lane; j <= kmax; j += 32) t[j] = t[j] / tot;
+    }
+  }
+  if (lane == 0) a.kmax[k] = kmax;
+}
+
+// Scans over the warp of affine maps x -> A + B x.
+// up:   maps composed in lane order (lane l acts after lanes < l); returns the
+//       value entering this lane when `xin` enters lane 0.
+// down: maps composed in reverse lane order (lane l acts after lanes > l); returns
+//       the value entering this lane when `xin` enters lane 31.
+__device__ __forceinline__ double warp_affine_up(double A, double B, double xin, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double Ap = __shfl_up_sync(FULL, A, o);
+    const double Bp = __shfl_up_sync(FULL, B, o);
+    if (lane >= o) {
+      A = fma(B, Ap, A);
+      B = B * Bp;
+    }
+  }
+  const double Ai = __shfl_up_sync(FULL, A, 1);
+  const double Bi = __shfl_up_sync(FULL, B, 1);
+  return lane == 0 ? xin : fma(Bi, xin, Ai);
+}
+__device__ __forceinline__ double warp_affine_down(double A, double B, double xin, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double Ap = __shfl_down_sync(FULL, A, o);
+    const double Bp = __shfl_down_sync(FULL, B, o);
+    if (lane + o < 32) {
+      A = fma(B, Ap, A);
+      B = B * Bp;
+    }
+  }
+  const double Ai = __shfl_down_sync(FULL, A, 1);
+  const double Bi = __shfl_down_sync(FULL, B, 1);
+  return lane == 31 ? xin : fma(Bi, xin, Ai);
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+template <typename GT, int NV>
+__global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int64_t s_off[CK_WARPS][32];  // element offset of each grid row
+  __shared__ double s_w[CK_WARPS][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t wg = (int64_t)blockIdx.x * CK_WARPS + wid;
+  const int k = (int)(wg / a.nch), s = (int)(wg - (int64_t)k * a.nch);
+  if (k >= a.K) return;
+  double *B0 = sm + (size_t)wid * 2 * a.wcap, *B1 = B0 + a.wcap;
+  const int n = a.npix_t;
+  const int obj = a.oix[k];
+  const int64_t p0 = a.off[obj];
+  const int npix = (int)(a.off[obj + 1] - p0);
+  const int64_t gp0 = a.goff[obj];
+  const double *lam = a.lam + gp0, *ql = (a.log_step ? a.loglam : a.lam) + gp0;
+  const double beta = a.vels[k] / RVS_C_KMS;
+  const double f = sqrt((1 - beta) / (1 + beta));
+  const double qf = a.log_step ? log(f) : 0.0;
+  // knot interval of the rest-frame coordinate q (ln x or x)
+  auto pos_q = [&](double q) -> int {
+    const int pos = (int)((q - a.q0) * a.qstep_inv);
+    return max(0, min(pos, n - 2));
+  };
+  auto pos_of = [&](int p) -> int { return pos_q(a.log_step ? ql[p] + qf : lam[p] * f); };
+  const double lam_first = lam[0], lam_last = lam[npix - 1];
+  const double ql_first = a.log_step ? ql[0] : lam_first, ql_last = a.log_step ? ql[npix - 1] : lam_last;
+  const int posmin = pos_q(a.log_step ? ql_first + qf : lam_first * f);
+  const int posmax = pos_q(a.log_step ? ql_last + qf : lam_last * f);
+  const int nk = posmax + 1 - posmin;
+  const int S = min(a.nch, (nk + a.C - 1) / a.C);  // chunks this item really has
+  if (s == 0 && lane == 0) {
+    // the reference checks the first and last evaluation points (spliner.c:78-83)
+    const double xa = lam_first * f, xb = lam_last * f;
+    int st = 0;
+    if (xa < a.x0 || xb < a.x0 || xa >= a.xlast || xb >= a.xlast) st |= RVS_ST_RANGE;
+    if ((int64_t)a.nch * a.C < nk) st |= RVS_ST_LIMIT;
+    if (st) atomicOr(a.status + k, st);
+  }
+  if (s >= S) return;
+  const int c0 = posmin + (int)((int64_t)nk * s / S), c1 = posmin + (int)((int64_t)nk * (s + 1) / S);
+  if (c1 <= c0) return;
+  const int kmax = a.kmax ? a.kmax[k] : 0;
+  // knot windows (global indices, inclusive): Y on [ya0, ya1], raw y on [ya0-kmax, ya1+kmax]
+  // which may stick out of the template: those knots are the zero padding of the
+  // reference's 'same' convolution (spec_fit.py:677-680)
+  const int ya0 = max(0, c0 - SPL_HALO - 1), ya1 = min(n - 1, c1 + SPL_HALO + 2);
+  const int w0 = (ya0 - kmax) & ~3;  // first knot of the window (multiple of 4, may be < 0)
+  const int W0 = ((ya1 + kmax + 1 - w0) + 3) & ~3;
+  if (W0 + 2 > a.wcap) {  // does not fit: the caller re-evaluates this item on the general path
+    if (lane == 0) atomicOr(a.status + k, RVS_ST_LIMIT);
+    return;
+  }
+  if (lane < a.nvert) {
+    s_off[wid][lane] = (int64_t)a.ids[(int64_t)k * a.nvert + lane] * a.ld;
+    s_w[wid][lane] = a.w[(int64_t)k * a.nvert + lane];
+  }
+  __syncwarp();
+  // single-row item (off-grid nearest node): exp rounded to the row's precision
+  const bool f32row = a.nvert > 1 && s_off[wid][1] < 0;
+  __syncwarp();
+  if (f32row && lane >= 1 && lane < a.nvert) { s_off[wid][lane] = s_off[wid][0]; s_w[wid][lane] = 0; }
+  __syncwarp();
+  // ---- pixel range [plo, phi) of the chunk: first pixel whose knot interval is
+  // >= c.  pos is non-decreasing in p.  A linear guess in lambda and in ln lambda,
+  // checked on 16 pixels each, settles uniform and log-uniform pixel grids in
+  // one round of loads; anything else takes the 32-way search.
+  auto first_px_with_pos_ge = [&](int c) -> int {
+    const double xt = __ldg(a.lam_t + c) / f;  // observed wavelength that lands on knot c
+    const double gl = (xt - lam_first) / (lam_last - lam_first);
+    const double gq = a.log_step ? (log(xt) - ql_first) / (ql_last - ql_first) : gl;
+    const int guess = (int)((lane < 16 ? gl : gq) * (npix - 1));
+    const int pt = guess - 7 + (lane & 15);  // candidates guess-7 .. guess+8
+    const bool inside = pt >= 0 && pt < npix;
+    const bool less = pt < 0 || (inside && pos_of(pt) < c);
+    const unsigned mless = __ballot_sync(FULL, less);
+    // `less` is a prefix of each half-window (virtual pixels < 0 count as less,
+    // >= npix as not less): a half settles the answer when the transition is inside
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int cnt = __popc((mless >> (16 * h)) & 0xffffu);
+      const int g0 = __shfl_sync(FULL, guess, 16 * h);
+      if (cnt > 0 && cnt < 16) return min(npix, max(0, g0 - 7 + cnt));
+      if (cnt == 0 && g0 - 7 <= 0) return 0;
+      if (cnt == 16 && g0 + 8 >= npix - 1) return npix;
+    }
+    int lo = 0, hi = npix;  // pos_of(p) < c for p < lo ; pos_of(p) >= c for p >= hi
+    while (hi > lo) {
+      const int span = hi - lo;
+      const int pp = lo + (int)(((int64_t)span * lane) >> 5);
+      const unsigned ml = __ballot_sync(FULL, pos_of(pp) < c);
+      const int nf = __popc(ml);
+      if (nf == 0) { hi = lo; break; }
+      const int lo2 = lo + (int)(((int64_t)span * (nf - 1)) >> 5) + 1;
+      const int hi2 = nf == 32 ? hi : lo + (int)(((int64_t)span * nf) >> 5);
+      lo = lo2;
+      hi = hi2;
+    }
+    return lo;
+  };
+  const int plo = (s == 0) ? 0 : first_px_with_pos_ge(c0);
+  const int phi = (s == S - 1) ? npix : first_px_with_pos_ge(c1);
+  // bring what the resampling will read into L1 while the gather is in flight
+  {
+    const double *einv = a.einv + p0;
+    for (int p = plo + lane * 16; p < phi; p += 32 * 16) {
+      prefetch_l1(lam + p);
+      prefetch_l1(einv + p);
+      if (a.log_step) prefetch_l1(ql + p);
+    }
+    for (int c = c0 + lane * 16; c <= c1 + 1 && c < n; c += 32 * 16) {
+      prefetch_l1(a.lam_t + c);
+      if (c < n - 1) prefetch_l1(a.hinv + c);
+    }
+  }
+  int flag = 0;
+  // ---- gather + exp over the window: B0[i] = y at knot w0 + i (0 outside the template)
+  {
+    constexpr int VEC = RowLoader<GT>::VEC;
+    const bool round32 = f32row && sizeof(GT) == 4 && a.log_spec;
+    const GT *base = static_cast<const GT *>(a.grid);
+    const int nv = NV > 0 ? NV : a.nvert;
+    for (int i0 = lane * VEC; i0 < W0; i0 += 32 * VEC) {
+      const int g = w0 + i0;  // multiple of VEC
+      double acc[4] = {0, 0, 0, 0};
+      if (g >= 0 && g < a.ld) {
+        const GT *col = base + g;
+        if (NV > 0) {
+          constexpr int HALF = NV > 8 ? (NV + 1) / 2 : (NV > 0 ? NV : 1);
+          {
+            double r[HALF][4];
+#pragma unroll
+            for (int j = 0; j < HALF; j++) RowLoader<GT>::load(col + s_off[wid][j], 0, r[j]);
+#pragma unroll
+            for (int j = 0; j < HALF; j++) {
+              const double wj = s_w[wid][j];
+#pragma unroll
+              for (int e = 0; e < VEC; e++) acc[e] = fma(wj, r[j][e], acc[e]);
+            }
+          }
+          if (HALF < NV) {
+            double r[NV - HALF > 0 ? NV - HALF : 1][4];
+#pragma unroll
+            for (int j = HALF; j < NV; j++) RowLoader<GT>::load(col + s_off[wid][j], 0, r[j - HALF]);
+#pragma unroll
+            for (int j = HALF; j < NV; j++) {
+              const double wj = s_w[wid][j];
+#pragma unroll
+              for (int e = 0; e < VEC; e++) acc[e] = fma(wj, r[j - HALF][e], acc[e]);
+            }
+          }
+        } else {
+          for (int j = 0; j < nv; j++) {
+            double r[4];
+            RowLoader<GT>::load(col + s_off[wid][j], 0, r);
+            const double wj = s_w[wid][j];
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc[e] = fma(wj, r[e], acc[e]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+          double y = a.log_spec ? exp(acc[e]) : acc[e];
+          if (round32) y = (double)(float)y;
+          if (g + e >= n) y = 0;  // row padding, never a knot
+          else if (!(fabs(y) <= 1e100)) flag |= RVS_ST_TEMPLATE_BAD;
+          acc[e] = y;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; e += 2)
+        *reinterpret_cast<double2 *>(B0 + i0 + e) = make_double2(acc[e], acc[e + 1]);
+    }
+  }
+  __syncwarp();
+  // ---- rotational broadening onto [ya0, ya1]
+  double *Y, *Dz;  // Y[j] = y at knot ya0 + j ; Dz: spline scratch with one guard slot each side
+  if (kmax > 0) {
+    const double *taps = a.taps + (int64_t)k * a.tapstride;
+    const double t0 = __ldg(taps);
+    const double *src = B0 + (ya0 - w0);
+    const int WY = ya1 - ya0 + 1;
+    for (int j = lane; j < WY; j += 32) {
+      double sum = t0 * src[j];
+      for (int t = 1; t <= kmax; t++) sum = fma(__ldg(taps + t), src[j - t] + src[j + t], sum);
+      B1[j] = sum;
+    }
+    __syncwarp();
+    Y = B1;
+    Dz = B0 + 1;
+  } else {
+    Y = B0 + (ya0 - w0);
+    Dz = B1 + 1;
+  }
+  // ---- spline rows kr0 <= kk < kr1 (row kk couples knots kk, kk+1, kk+2; unknown
+  // s_{kk+1}).  Dz[r] holds the right-hand side, then d, then s at knot kr0 + r + 1.
+  // Guards Dz[-1] (knot kr0) and Dz[nrow] (knot kr1 + 1) are the natural boundary
+  // values 0 whenever the window reaches an end of the template.
+  const int m = n - 2;
+  const int kr0 = ya0, kr1 = min(m, ya1 - 1);
+  const int nrow = kr1 - kr0;
+  int ch = (nrow + 31) >> 5;
+  ch |= 1;  // odd stride between lanes: no shared-memory bank conflicts
+  const int r0 = min(nrow, lane * ch), r1 = min(nrow, r0 + ch);
+  if (lane == 0) { Dz[-1] = 0; Dz[nrow] = 0; }
+  auto solve = [&](auto near_start) {
+    // pivot reciprocal of row kk: tabulated next to knot 0, constant elsewhere
+    auto winv = [&](int kk) -> double {
+      if (decltype(near_start)::value) return kk < CK_NT ? a.wtab[kk] : a.winv_inf;
+      return a.winv_inf;
+    };
+    // forward: d_k = (rho_k - d_{k-1}) / omega_k  ==  a_k + b_k d_{k-1}
+    double A = 0, Bc = 1;
+    if (r0 < r1) {
+      double y1 = Y[r0 + 1];
+      double dy0 = y1 - Y[r0];
+      for (int r = r0; r < r1; r++) {
+        const double y2 = Y[r + 2];
+        const double dy1 = y2 - y1;
+        const double wi = winv(kr0 + r);
+        const double ak = fma(dy1, a.rinv, -dy0) * wi;
+        Dz[r] = ak;
+        A = fma(-wi, A, ak);
+        Bc = -wi * Bc;
+        y1 = y2;
+        dy0 = dy1;
+      }
+    }
+    double d = warp_affine_up(A, Bc, 0.0, lane);  // d_{kr0-1} := 0 (exact at kr0 == 0)
+    // forward apply, and composition of the backward maps of the same rows:
+    // s_{k+1} = d_k - gamma_k s_{k+2}, gamma_k = c2 / omega_k; the lane's map takes
+    // the s entering above its rows to the s leaving below them
+    A = 0;
+    Bc = 1;
+    for (int r = r0; r < r1; r++) {
+      const double wi = winv(kr0 + r);
+      d = fma(-wi, d, Dz[r]);
+      Dz[r] = d;
+      A = fma(Bc, d, A);
+      Bc = Bc * (-a.c2 * wi);
+    }
+    double zz = warp_affine_down(A, Bc, 0.0, lane);  // s_{kr1+1} := 0 (exact at kr1 == m)
+    for (int r = r1 - 1; r >= r0; r--) {
+      const double ck = -a.c2 * winv(kr0 + r);
+      zz = fma(ck, zz, Dz[r]);
+      Dz[r] = zz;  // = s at knot kr0 + r + 1
+    }
+  };
+  if (kr0 < CK_NT) solve(TrueTag{}); else solve(FalseTag{});
+  __syncwarp();
+  // ---- resample onto the chunk's pixels
+  const double *einv = a.einv + p0;
+  double *tn = a.tn + (int64_t)k * a.tn_stride;
+  for (int p = plo + lane; p < phi; p += 32) {
+    const double lp = lam[p];
+    const double x = lp * f;
+    const int pos = pos_q(a.log_step ? ql[p] + qf : x);
+    const int j = pos - ya0;
+    const double y0v = Y[j], y1v = Y[j + 1];
+    const double s0 = Dz[pos - 1 - kr0], s1 = Dz[pos - kr0] * a.r2inv;
+    const double u = (x - __ldg(a.lam_t + pos)) * __ldg(a.hinv + pos), v = 1.0 - u;
+    const double t = fma(u, fma(s1, fma(u, u, -1.0), y1v), v * fma(s0, fma(v, v, -1.0), y0v));
+    tn[p] = t * einv[p];
+  }
+  if (flag) atomicOr(a.status + k, flag);  // per lane: rare
+}
+
+}  // namespace rvs

@@ -93,6 +93,14 @@ extern "C" int rvs_knot_info(const double *x, int n, int log_step, rvs_knots *ou
     out->q0 = x[0];
     out->qstep_inv = 1.0 / s1;
   }
+  // constant ratio of consecutive knot spacings (rvs_chisq_fused's spline solve)
+  out->ratio = log_step ? exp(log(x[n - 1] / x[0]) / (n - 1)) : 1.0;
+  double dev = 0;
+  for (int k = 0; k + 2 < n; k++) {
+    const double h0 = x[k + 1] - x[k], h1 = x[k + 2] - x[k + 1];
+    dev = fmax(dev, fabs(h1 / (out->ratio * h0) - 1));
+  }
+  out->ratio_dev = dev;
   return 0;
 }
 

@@ -61,11 +61,11 @@ class SpectrumBatch:
         self.h_spec = np.concatenate([s.spec for s in specdatas])
         self.h_espec = np.concatenate([s.espec for s in specdatas])
         self.h_bad = np.concatenate([s.badmask for s in specdatas])
-        self.d_lam = _dev.upload(self.h_lam, np.float64)
         self.d_spec = _dev.upload(self.h_spec, np.float64)
         self.d_espec = _dev.upload(self.h_espec, np.float64)
         self.d_off = _dev.upload(self.off, np.int64)
-        # wavelength grids shared between objects share one basis
+        # objects observed on the same pixels share one wavelength grid: one copy
+        # of lam / ln(lam) / continuum basis in the grid pools (rvs_obs)
         seen, gid, first = {}, np.zeros(self.n, dtype=np.int64), []
         for i, s in enumerate(specdatas):
             key = (len(s.lam), s.lam[:4].tobytes(), s.lam[-4:].tobytes(),
@@ -76,48 +76,51 @@ class SpectrumBatch:
             gid[i] = seen[key]
         self.grid_of = gid
         self.grid_first = np.array(first, dtype=np.int64)
+        gl = [self.h_lam[self.off[i]:self.off[i + 1]] for i in self.grid_first]
+        self.gstart = np.concatenate([[0], np.cumsum([len(_) for _ in gl])]).astype(np.int64)
+        self.d_glam = _dev.upload(np.concatenate(gl), np.float64)
+        self.d_gstart = _dev.upload(self.gstart, np.int64)
+        self.d_goff = _dev.upload(self.gstart[:-1][gid], np.int64)
         self._prod, self._basis = {}, {}
 
     def products(self, sys_err=0.0):
         key = float(sys_err)
         if key not in self._prod:
             ntot = int(self.off[-1])
-            loglam, dn, einv = [_dev.empty((ntot,), np.float64) for _ in range(3)]
+            dn, einv = [_dev.empty((ntot,), np.float64) for _ in range(2)]
             sumlog2 = _dev.empty((self.n,), np.float64)
             rc = _cabi.lib().rvs_obs_prepare(
-                _dev.ptr(self.d_lam), _dev.ptr(self.d_spec), _dev.ptr(self.d_espec),
-                _dev.ptr(self.d_off), self.n, key, _dev.ptr(loglam), _dev.ptr(dn),
-                _dev.ptr(einv), _dev.ptr(sumlog2), _dev.stream())
+                _dev.ptr(self.d_spec), _dev.ptr(self.d_espec), _dev.ptr(self.d_off), self.n, key,
+                _dev.ptr(dn), _dev.ptr(einv), _dev.ptr(sumlog2), _dev.stream())
             _cabi.check(rc, 'rvs_obs_prepare')
-            self._prod[key] = (loglam, dn, einv, sumlog2)
+            self._prod[key] = (dn, einv, sumlog2)
         return self._prod[key]
 
     def basis(self, npoly, rbf):
+        """(loglam, P) of the grid pools; P is pixel-major [pixel][npp]."""
         key = (int(npoly), bool(rbf))
         if key not in self._basis:
-            gl = [self.h_lam[self.off[i]:self.off[i + 1]] for i in self.grid_first]
-            goff = np.concatenate([[0], np.cumsum([len(_) for _ in gl])]).astype(np.int64)
-            ntot = int(goff[-1])
-            d_gl = _dev.upload(np.concatenate(gl), np.float64)
-            d_goff = _dev.upload(goff, np.int64)
-            P = _dev.empty((npoly, ntot), np.float64)
-            rc = _cabi.lib().rvs_basis_build(_dev.ptr(d_gl), _dev.ptr(d_goff), len(gl), ntot,
-                                             int(npoly), int(bool(rbf)), ntot, _dev.ptr(P),
+            ntot = int(self.gstart[-1])
+            npp = (npoly + 1) // 2 * 2
+            P = _dev.empty((ntot, npp), np.float64)
+            loglam = _dev.empty((ntot,), np.float64)
+            rc = _cabi.lib().rvs_basis_build(_dev.ptr(self.d_glam), _dev.ptr(self.d_gstart),
+                                             len(self.grid_first), ntot, int(npoly),
+                                             int(bool(rbf)), npp, _dev.ptr(loglam), _dev.ptr(P),
                                              _dev.stream())
             _cabi.check(rc, 'rvs_basis_build')
-            boff = _dev.upload(goff[:-1][self.grid_of], np.int64)
-            self._basis[key] = (P, ntot, boff)
+            self._basis[key] = (loglam, P, npp)
         return self._basis[key]
 
     def obs(self, npoly, rbf, sys_err=0.0):
-        """struct rvs_obs (plus the tensors that must stay alive)."""
-        loglam, dn, einv, sumlog2 = self.products(sys_err)
-        P, pstride, boff = self.basis(npoly, rbf)
+        """struct rvs_obs (the tensors it points to stay alive in the caches)."""
+        dn, einv, sumlog2 = self.products(sys_err)
+        loglam, P, npp = self.basis(npoly, rbf)
         o = _cabi.Obs()
-        o.d_lam, o.d_loglam, o.d_dn, o.d_einv = (self.d_lam.data_ptr(), loglam.data_ptr(),
-                                                 dn.data_ptr(), einv.data_ptr())
-        o.d_sumlog2, o.d_off, o.d_P = sumlog2.data_ptr(), self.d_off.data_ptr(), P.data_ptr()
-        o.pstride, o.d_boff, o.npoly, o.nobj = pstride, boff.data_ptr(), int(npoly), self.n
+        o.d_lam, o.d_loglam, o.d_P = self.d_glam.data_ptr(), loglam.data_ptr(), P.data_ptr()
+        o.d_goff, o.d_dn, o.d_einv = self.d_goff.data_ptr(), dn.data_ptr(), einv.data_ptr()
+        o.d_sumlog2, o.d_off = sumlog2.data_ptr(), self.d_off.data_ptr()
+        o.npoly, o.npp, o.nobj = int(npoly), npp, self.n
         return o
 
 
@@ -170,6 +173,15 @@ class LikelihoodEngine:
         self.n_eval = 0
         self.timer = None
 
+    @staticmethod
+    def _fusable(bank, vs):
+        """The fused kernel needs exactly (log-)uniform knots and a rotation
+        kernel of at most MAX_FUSED_TAPS one-sided taps (rvs_b200.h)."""
+        if not bank.knots.ratio_dev < 1e-8:
+            return False
+        vmax = 0.0 if vs is None else float(np.max(vs, initial=0.0))
+        return bank.tapcap(vmax) <= _cabi.MAX_FUSED_TAPS
+
     def _workspace(self, n):
         if getattr(self, '_ws', None) is None or self._ws.numel() < n:
             self._ws = _dev.empty((int(n * 1.25) + 1024,), np.float64)
@@ -193,20 +205,26 @@ class LikelihoodEngine:
         d_st = _dev.empty((k, nv), np.int32)
         vs = None if vsini is None else np.ascontiguousarray(vsini[sel], dtype=np.float64)
         extras = None
-        if self.fused and nv == 1 and not want_model:
+        if self.fused and nv == 1 and not want_model and self._fusable(bank, vs):
             d_ids = _dev.upload(ids, np.int32)
             d_w = _dev.upload(w, np.float64)
             d_vs = None if vs is None else _dev.upload(vs, np.float64)
             vmax = 0.0 if vs is None else float(np.max(vs, initial=0.0))
             stride = int(batch.npix.max())
             d_tn = self._workspace(k * stride)
+            d_work = None
+            if vs is not None and vmax > 0:
+                nwork = L.rvs_fused_workspace(k, bank.tapcap(vmax))
+                if getattr(self, '_work', None) is None or self._work.numel() < nwork:
+                    self._work = _dev.empty((int(nwork * 1.25) + 64,), np.float64)
+                d_work = self._work
             t0 = self.timer.start() if self.timer else None
             rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
                                    ctypes.byref(bank.knots), _dev.ptr(d_ids), _dev.ptr(d_w),
                                    bank.nvert, _dev.ptr(d_vs), vmax, int(bank.log_spec),
                                    ctypes.byref(obs), _dev.ptr(d_oix), _dev.ptr(d_vels), k,
-                                   _dev.ptr(d_tn), stride, _dev.ptr(d_chi), _dev.ptr(d_st),
-                                   _dev.stream())
+                                   _dev.ptr(d_tn), stride, _dev.ptr(d_work), _dev.ptr(d_chi),
+                                   _dev.ptr(d_st), _dev.stream())
             _cabi.check(rc, 'rvs_chisq_fused')
             if t0 is not None:
                 self.timer.stop('fused', t0, k)

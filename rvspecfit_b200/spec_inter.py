@@ -92,6 +92,13 @@ class TemplateBank:
         else:
             raise RuntimeError('Unrecognized interpolation type ' + str(kind))
 
+    def tapcap(self, vsini_max):
+        """One-sided length of the rotation kernel at vsini_max (+1), as
+        rvs_chisq_fused sizes it (spec_fit.py:666-667,590)."""
+        if not vsini_max > 0:
+            return 0
+        return int(np.ceil(vsini_max / 299792.458 / self.knots.lnstep + 1)) + 1
+
     # ---------------------------------------------------------- host: vertices
     def locate(self, params):
         """(ids int32 (K,nvert), w float64 (K,nvert), outside float64 (K,)).

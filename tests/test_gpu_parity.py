@@ -113,17 +113,19 @@ def test_basis_and_products():
     b = spec_fit.SpectrumBatch(sds)
     assert list(b.grid_of) == [0, 1, 0]
     for npoly, rbf in ((1, True), (3, True), (10, True), (16, True), (7, False)):
-        P, ntot, boff = b.basis(npoly, rbf)
+        loglam, P, npp = b.basis(npoly, rbf)
         P = _dev.download(P)
-        assert ntot == 777 + 1234
-        close(P[:, :777], oracle.continuum_basis(lam1, npoly, rbf), rtol=1e-13,
-                           atol=1e-15)
-        close(P[:, 777:], oracle.continuum_basis(lam2, npoly, rbf), rtol=1e-12,
-                           atol=1e-14)
-    loglam, dn, einv, sumlog2 = [_dev.download(_) for _ in b.products(0.05)]
+        assert P.shape == (777 + 1234, npp) and npp % 2 == 0 and npp >= npoly
+        close(P[:777, :npoly].T, oracle.continuum_basis(lam1, npoly, rbf), rtol=1e-13,
+              atol=1e-15)
+        close(P[777:, :npoly].T, oracle.continuum_basis(lam2, npoly, rbf), rtol=1e-12,
+              atol=1e-14)
+        assert (P[:, npoly:] == 0).all()
+        close(_dev.download(loglam), np.log(np.concatenate([lam1, lam2])), rtol=1e-15)
+    dn, einv, sumlog2 = [_dev.download(_) for _ in b.products(0.05)]
     es = np.sqrt(0.05**2 + b.h_espec**2)
     close(dn, b.h_spec / es, rtol=1e-15)
-    close(loglam, np.log(b.h_lam), rtol=1e-15)
+    close(einv, 1 / es, rtol=1e-15)
     close(sumlog2[1], 2 * np.log(es[777:777 + 1234]).sum(), rtol=1e-13)
 
 
