@@ -194,6 +194,44 @@ int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld, const rvs_knot
 int rvs_scan_stats(const double *d_vels, const double *d_chisq, int S, int npar, int nv,
                    int quadratic, double *d_out, double *d_probs, void *stream);
 
+/* ---- cross-correlation first guess (fitter_ccf.py:126-232) ---------------- */
+/* One arm's CCF template bank and the lag -> velocity-grid table.  d_fft,
+ * d_fft2: rfft of the preprocessed models and of their squares, complex128
+ * interleaved [ntempl][npoints/2+1] (CCFCache.ccfs / ccf2s, fitter_ccf.py:51-56).
+ * Velocity-grid point j is interpolated linearly between the CCF pixels lo[j]
+ * and hi[j] (indices into the length-npoints inverse transform, i.e. the
+ * reference's subind[idx-1], subind[idx], fitter_ccf.py:132-150,205):
+ *   value = (y_hi - y_lo) / dx[j] * dxn[j] + y_lo,
+ * dx = vels[hi]-vels[lo], dxn = vel_grid[j]-vels[lo] (scipy interp1d).
+ * continuum=1: chi2 = -2 ccf0 + ccf1; 0: -ccf0^2/ccf1 (fitter_ccf.py:198-201). */
+typedef struct {
+  const double *d_fft, *d_fft2;
+  const int32_t *d_lo, *d_hi; /* [nvel] */
+  const double *d_dxn, *d_dx; /* [nvel] */
+  int32_t npoints, ntempl, continuum, nvel;
+} rvs_ccf_arm;
+
+/* Bytes of workspace that let rvs_ccf_accumulate process nb objects per pass. */
+int64_t rvs_ccf_workspace(const rvs_ccf_arm *arm, int nb);
+
+/* Adds one arm's contribution for B objects.  d_pspec, d_pivar: [B][npoints]
+ * preprocessed spectrum and inverse variance (make_ccf.preprocess_data).
+ * Object b accumulates into row d_row[b] (NULL: b) of d_chisq
+ * [nrow][ntempl][nvel] and d_sse[nrow] (+= sum pspec^2 pivar); the caller
+ * zeroes both before the first arm.  d_work: 256-byte aligned workspace of
+ * work_bytes (>= rvs_ccf_workspace(arm, 1)); objects are processed in as
+ * large passes as it allows. */
+int rvs_ccf_accumulate(const rvs_ccf_arm *arm, const double *d_pspec, const double *d_pivar,
+                       int B, const int32_t *d_row, double *d_chisq, double *d_sse, void *d_work,
+                       int64_t work_bytes, void *stream);
+
+/* Per row: all_chisqs = chisq + sse; best template = argmin_t min_v, best pixel,
+ * parabola vertex if it opens upwards (fitter_ccf.py:206-222).
+ * out[row*8..] = best_id, best_pix, best_vel, best value, finite flag, 0,0,0;
+ * d_best_ccf (may be NULL) [nrow][nvel] = all_chisqs[best_id]. */
+int rvs_ccf_best(const double *d_chisq, const double *d_sse, const double *d_velgrid, int nrow,
+                 int ntempl, int nvel, double *d_out, double *d_best_ccf, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,9 +39,10 @@ class Obs(ctypes.Structure):
 
 class CcfArm(ctypes.Structure):
     """struct rvs_ccf_arm"""
-    _fields_ = [('d_fft', c_dp), ('d_fft2', c_dp), ('npoints', ctypes.c_int32),
+    _fields_ = [('d_fft', c_dp), ('d_fft2', c_dp), ('d_lo', c_dp), ('d_hi', c_dp),
+                ('d_dxn', c_dp), ('d_dx', c_dp), ('npoints', ctypes.c_int32),
                 ('ntempl', ctypes.c_int32), ('continuum', ctypes.c_int32),
-                ('nsub', ctypes.c_int32), ('d_subind', c_dp), ('d_subvel', c_dp)]
+                ('nvel', ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/rvs_b200.h declares
@@ -68,6 +69,10 @@ SIGNATURES = {
                                 c_dp, c_dbl, c_int, ctypes.POINTER(Obs), c_dp, c_dp, c_int,
                                 c_dp, c_i64, c_dp, c_dp, c_dp, c_dp]),
     'rvs_scan_stats': (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
+    'rvs_ccf_workspace': (c_i64, [ctypes.POINTER(CcfArm), c_int]),
+    'rvs_ccf_accumulate': (c_int, [ctypes.POINTER(CcfArm), c_dp, c_dp, c_int, c_dp, c_dp, c_dp,
+                                   c_dp, c_i64, c_dp]),
+    'rvs_ccf_best': (c_int, [c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
 }
 
 _lib = None

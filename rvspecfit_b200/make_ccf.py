@@ -1,0 +1,131 @@
+"""Host-side preparation around the CCF kernel.
+
+Mirror of the parts of the reference's make_ccf.py (paths under
+/root/reference/py/rvspecfit/) that `fitter_ccf.fit` calls before its hot loop:
+`get_ccf_config` (make_ccf.py:67-102), `get_continuum` (:105-164),
+`preprocess_model` (:167-212), `preprocess_data` (:330-414).  These steps are
+SURVEY.md section 8 row f3 ("next"): they stay on the host (numpy / scipy, as in
+the reference) and feed the device path in fitter_ccf.py with the
+continuum-normalised spectrum and inverse variance on the CCF pixel grid.
+"""
+import logging
+
+import numpy as np
+import scipy.interpolate
+import scipy.optimize
+import scipy.signal
+import scipy.stats
+
+C_CCF = 3e5      # km/s; the CCF code's rounded speed of light (fitter_ccf.py:132)
+
+
+def get_ccf_config(logl0=None, logl1=None, npoints=None, splinestep=1000, maxcontpts=20):
+    """CCF configuration dictionary (make_ccf.py:67-102)."""
+    conf = dict(logl0=logl0, logl1=logl1, npoints=npoints, continuum=splinestep is not None,
+                maxcontpts=maxcontpts)
+    if splinestep is not None:
+        widest = C_CCF * (np.exp((logl1 - logl0) / maxcontpts) - 1)
+        conf['splinestep'] = max(splinestep, widest)
+    return conf
+
+
+def _continuum_model(p, nodes, lam):
+    log_cont = scipy.interpolate.UnivariateSpline(nodes, p, s=0, k=2)(lam)
+    return np.exp(np.clip(log_cont, -100, 100))
+
+
+def get_continuum(lam0, spec0, espec0, ccfconf=None):
+    """Quadratic-spline continuum in log flux with a soft-L1 loss
+    (make_ccf.py:105-164)."""
+    lo = lam0.min()
+    dlog = np.log(1 + ccfconf['splinestep'] / C_CCF)
+    nnodes = int(np.ceil(np.log(lam0.max() / lo) / dlog))
+    k = np.arange(nnodes + 1)
+    nodes = lo * np.exp(k[:-1] * dlog)
+    edges = lo * np.exp((k - 0.5) * dlog)
+    med = np.median(spec0)
+    if med <= 0:
+        med = abs(med) or 1
+        logging.warning('The spectrum has a median that is non-positive...')
+    binned = scipy.stats.binned_statistic(lam0, spec0, 'median', bins=edges).statistic
+    start = np.log(np.maximum(binned, 1e-3 * med))
+    start[~np.isfinite(start)] = np.log(med)
+    sol = scipy.optimize.least_squares(
+        lambda p: (_continuum_model(p, nodes, lam0) - spec0) / espec0, start, loss='soft_l1')
+    return _continuum_model(sol['x'], nodes, lam0)
+
+
+def interp_masker(lam, spec, badmask):
+    """Bridge masked pixels linearly, extend the edges flat (make_ccf.py:287-327)."""
+    out = np.array(spec, dtype=np.float64)
+    good = np.flatnonzero(~badmask)
+    bad = np.flatnonzero(badmask)
+    if good.size == 0:
+        logging.warning('All the pixels are masked for the ccf determination')
+        out[~np.isfinite(out)] = 1
+        return out
+    nxt = np.searchsorted(good, bad)
+    at_left, at_right = nxt == 0, nxt == good.size
+    inner = ~(at_left | at_right)
+    ia, ib = good[nxt[inner] - 1], good[nxt[inner]]
+    la, lb, l0 = lam[ia], lam[ib], lam[bad[inner]]
+    out[bad[at_left]] = spec[good[0]]
+    out[bad[at_right]] = spec[good[-1]]
+    out[bad[inner]] = (-(la - l0) * spec[ib] + (lb - l0) * spec[ia]) / (lb - la)
+    return out
+
+
+def preprocess_data(lam, spec0, espec, ccfconf=None, badmask=None, maxerr=10):
+    """Continuum-normalise a spectrum and put it (and its inverse variance) on
+    the CCF's log-wavelength pixels (make_ccf.py:330-414).  Returns
+    (proc_spec, proc_ivar), each of length npoints."""
+    grid_lam = np.exp(np.linspace(ccfconf['logl0'], ccfconf['logl1'], ccfconf['npoints']))
+    err = np.array(espec, dtype=np.float64)
+    flux = np.array(spec0, dtype=np.float64)
+    bad = np.zeros(len(err), dtype=bool) if badmask is None else np.asarray(badmask, dtype=bool)
+    smooth = scipy.signal.medfilt(flux, 11)
+    typical_err = np.nanmedian(err)
+    if ccfconf['continuum']:
+        bad = bad | (err > maxerr * typical_err) | (smooth <= 0)
+    err[bad] = 1e9 * typical_err
+    flux = interp_masker(lam, flux, bad)
+    cont = get_continuum(lam, flux, err, ccfconf=ccfconf) if ccfconf['continuum'] else 1
+    ivar = 1. / err**2
+    ivar[bad] = 0
+    med = np.median(flux)
+    cont = np.maximum(1e-2 * med, cont) if med > 0 else np.maximum(cont, 1)
+    norm = spec0 / cont
+    ivar = cont**2 * ivar
+    norm[bad] = 0
+    # linear interpolation onto the CCF pixels; the variance follows the weights
+    left = np.searchsorted(lam, grid_lam) - 1
+    inside = (left >= 0) & (left <= len(lam) - 2)
+    li = left[inside]
+    ri = li + 1
+    wr = (grid_lam[inside] - lam[li]) / (lam[ri] - lam[li])
+    wl = 1 - wr
+    out_spec, out_ivar = np.zeros(len(grid_lam)), np.zeros(len(grid_lam))
+    out_spec[inside] = wl * norm[li] + wr * norm[ri]
+    il, ir = ivar[li], ivar[ri]
+    out_ivar[inside] = il * ir / (wl**2 * ir + wr**2 * il + ((il * ir) == 0).astype(int))
+    return out_spec, out_ivar
+
+
+def preprocess_model(logl, lammodel, model0, vsini=None, ccfconf=None, broaden=None):
+    """Template on the CCF pixels, continuum-normalised (make_ccf.py:167-212).
+    `broaden(lam, spec, vsini)` applies the rotation kernel (bank preparation is
+    an offline step; pass spec_inter's device routine or a host one)."""
+    m = model0
+    if vsini:
+        if broaden is None:
+            raise ValueError('preprocess_model: vsini given without a broadening routine')
+        m = broaden(lammodel, model0, vsini)
+    cont = 1
+    if ccfconf['continuum']:
+        cont = get_continuum(lammodel, m, np.maximum(m * 1e-5, 1e-2 * np.median(m)),
+                             ccfconf=ccfconf)
+        cont = np.maximum(cont, 1e-2 * np.median(cont))
+    ll = np.log(lammodel)
+    if not (ll[0] <= logl[0] <= ll[-1]) or not (ll[0] <= logl[-1] <= ll[-1]):
+        logging.warning('The required wavelength range is bigger than the template wavelengths')
+    return scipy.interpolate.interp1d(ll, m / cont, bounds_error=False, fill_value=1)(logl)

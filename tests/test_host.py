@@ -1,0 +1,89 @@
+"""Host-side logic of the product that needs no GPU: CCF preprocessing against
+the reference's own outputs, the HDF5 dictionary decoder, optimiser helpers."""
+import types
+
+import numpy as np
+
+from helpers import close, unpack_objects
+from rvspecfit_b200 import bank_io, make_ccf, vel_fit
+
+
+def test_preprocess_data_matches_reference(golden):
+    """make_ccf.preprocess_data (host, row f3) vs the reference's proc_spec /
+    proc_ivar stored in tests/golden/ccf.npz."""
+    g = golden('ccf')
+    for tag, shapes in (('rvs', ('gaiarvs',)), ('two', ('desi_b', 'desi_r'))):
+        for i, o in enumerate(unpack_objects(g, tag + '_')):
+            for a, (nm, lam, sp, es, bad) in enumerate(o['arms']):
+                c = g[f'{tag}_{nm}_conf']
+                conf = make_ccf.get_ccf_config(c[0], c[1], int(c[2]))
+                assert np.isclose(conf['splinestep'], c[3])
+                ps, pi = make_ccf.preprocess_data(lam, sp, es, ccfconf=conf, badmask=bad)
+                close(ps, g[f'{tag}_{i}_{a}_proc_spec'], rtol=1e-7, atol=1e-9, what='proc_spec')
+                close(pi, g[f'{tag}_{i}_{a}_proc_ivar'], rtol=1e-6, atol=1e-12 * pi.max(),
+                      what='proc_ivar')
+
+
+def test_interp_masker_edges():
+    lam = np.arange(10.)
+    spec = np.arange(10.) * 2
+    bad = np.zeros(10, dtype=bool)
+    bad[[0, 1, 4, 5, 9]] = True
+    out = make_ccf.interp_masker(lam, spec, bad)
+    assert np.array_equal(out, [4, 4, 4, 6, 8, 10, 12, 14, 16, 16])
+    allbad = make_ccf.interp_masker(lam, np.full(10, np.nan), np.ones(10, dtype=bool))
+    assert np.array_equal(allbad, np.ones(10))
+
+
+class _FakeItem:
+    def __init__(self, val, kind):
+        self.val, self.attrs = val, {'type': kind}
+        self.dtype = np.asarray(val).dtype if not isinstance(val, bytes) else np.dtype('S')
+
+    def __getitem__(self, key):
+        return self.val if key == () else np.asarray(self.val)[key]
+
+
+class _FakeGroup(dict):
+    def __init__(self, d, kind=None):
+        super().__init__(d)
+        self.attrs = {} if kind is None else {'type': kind}
+
+
+def test_h5_dictionary_decoder():
+    """The typed-attribute scheme of the reference serializer
+    (serializer.py:112-157), decoded without h5py through stand-in objects."""
+    fake = types.SimpleNamespace(Group=_FakeGroup, Dataset=_FakeItem)
+    root = _FakeGroup({
+        'lam': _FakeItem(np.arange(4.), 'ndarray'),
+        'parnames': _FakeItem(np.array(['teff', 'logg'], dtype=object), 'list'),
+        'log_step': _FakeItem(np.bool_(True), 'scalar'),
+        'revision': _FakeItem(b'v1', 'str'),
+        'nothing': _FakeItem(0, 'None'),
+        'uvecs': _FakeGroup({'__item_0': _FakeItem(np.array([1., 2.]), 'ndarray'),
+                             '__item_1': _FakeItem(np.array([3., 4., 5.]), 'ndarray')},
+                            'flattened_list'),
+        'mapper_args': _FakeGroup({'__item_0': _FakeItem(np.array([0]), 'list')},
+                                  'flattened_tuple'),
+    })
+    d = bank_io._decode(root, fake)
+    assert d['parnames'] == ['teff', 'logg'] and d['revision'] == 'v1' and d['nothing'] is None
+    assert isinstance(d['uvecs'], list) and len(d['uvecs'][1]) == 3
+    assert isinstance(d['mapper_args'], tuple) and list(d['mapper_args'][0]) == [0]
+
+
+def test_simplex_and_hessian_helpers():
+    """Deterministic pieces of vel_fit that the batched driver shares with the
+    single-object path."""
+    vm = vel_fit.VSiniMapper(500)
+    cur, simp = vel_fit._get_simplex_start(12., fixParam=[], specParamNames=('teff', 'logg'),
+                                           paramDict0={'teff': 5000, 'logg': 2, 'vsini': 3},
+                                           vsiniMapper=vm, fitVsini=True)
+    assert simp.shape == (5, 4) and np.array_equal(simp[0], cur)
+    R = np.random.RandomState(43434)
+    assert np.allclose(simp[1:], cur + np.array([5, 3, 300, 0.5]) * R.normal(size=(4, 4)))
+    H = vel_fit.central_hessian(lambda x: 0.5 * (3 * x[0]**2 + x[0] * x[1] + 2 * x[1]**2),
+                                [0.3, -0.2], [1e-2, 1e-2])
+    assert np.allclose(H, [[3, 0.5], [0.5, 2]], atol=1e-8)
+    err, cov, bad = vel_fit._uncertainties_from_hessian(np.array([[4., 0.], [0., -1.]]))
+    assert bad and err[0] == 0.5
