@@ -17,6 +17,8 @@
  * Reference interfaces replaced (paths under /root/reference/py/rvspecfit/):
  *   rvs_spline_construct / rvs_spline_eval  <- cffi `_spliner.construct`,
  *       `_spliner.evaler` (ffibuilder.py:10-17, src/spliner.c:7-108)
+ *   rvs_locate_grid      <- GridInterp.__call__ vertex and weight location
+ *       (spec_inter.py:153-194)
  *   rvs_template_build   <- GridInterp.__call__ / TriInterp.__call__ weighted
  *       sum + exp (spec_inter.py:134-194, 35-59), convolve_vsini +
  *       compute_vsini_kernel (spec_fit.py:565-682), Spline.__init__
@@ -111,7 +113,30 @@ typedef struct {
   int32_t reserved;
 } rvs_obs;
 
+/* Regular template grid in mapped parameter space (spec_inter.py:97-132):
+ * unique node coordinates of every dimension, concatenated (dimension i starts
+ * at uoff[i] and has len[i] entries), and the C-order table of node ids
+ * (-1 = no template at that grid point). */
+#define RVS_MAX_GRID_DIM 5
+typedef struct {
+  const double *d_uvec;
+  const int32_t *d_idgrid;
+  int32_t ndim;
+  int32_t len[RVS_MAX_GRID_DIM];
+  int32_t uoff[RVS_MAX_GRID_DIM];
+  int32_t reserved;
+} rvs_gridmap;
+
 /* ---- template evaluation ------------------------------------------------- */
+/* Polylinear vertex location (GridInterp.__call__, spec_inter.py:153-194) for
+ * K mapped parameter vectors, coordinate i of item k at d_q[i*q_stride + k].
+ * Writes the 2^ndim corner ids and weights (the d_ids / d_w of
+ * rvs_template_build and rvs_chisq_fused) and d_flag[k] = 1 for the points the
+ * host must resolve (off-grid, missing corner, non-finite): those get the
+ * placeholder "row 0 alone". */
+int rvs_locate_grid(const rvs_gridmap *gm, const double *d_q, int64_t q_stride, int K,
+                    int32_t *d_ids, double *d_w, int32_t *d_flag, void *stream);
+
 /* Host helpers (plain C, no device work).  rvs_knot_tables: h, hinv (n-1
  * each), cp, winv (n-2 each).  rvs_knot_info fills the scalar members of
  * rvs_knots from the host knot array and returns 0, or -2 if the knots are
@@ -169,7 +194,8 @@ int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
 
 /* Fused optimiser-phase evaluation: template build (as rvs_template_build) and
  * chi-square at ONE velocity per item without the HBM round trip of the
- * spline.  Item k uses object oix[k].  Only the part of the template that the
+ * spline.  Item k uses object oix[k] (oix[k] < 0: the object
+ * has no spectrum in this setup; chisq[k] = 0, status[k] = 0).  Only the part of the template that the
  * object covers at that velocity is gathered.  vsini_max: upper bound of
  * d_vsini (sizes the tap buffer; 0 if d_vsini is NULL).  d_tn: workspace
  * [K, tn_stride] doubles, tn_stride >= the longest object.  d_work: workspace

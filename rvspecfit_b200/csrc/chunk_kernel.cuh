@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a)
   double *B0 = sm + (size_t)wid * 2 * a.wcap, *B1 = B0 + a.wcap;
   const int n = a.npix_t;
   const int obj = a.oix[k];
+  if (obj < 0) return;  // the object has no spectrum in this setup
   const int64_t p0 = a.off[obj];
   const int npix = (int)(a.off[obj + 1] - p0);
   const int64_t gp0 = a.goff[obj];

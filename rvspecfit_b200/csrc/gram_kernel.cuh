@@ -111,6 +111,10 @@ __global__ void __launch_bounds__(GR_THREADS) gram_kernel(GramArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int k = blockIdx.x;
   const int obj = a.oix[k];
+  if (obj < 0) {  // the object has no spectrum in this setup (uniform over the CTA)
+    if (tid == 0) a.chisq[k] = 0;
+    return;
+  }
   const int64_t p0 = a.off[obj];
   const int npix = (int)(a.off[obj + 1] - p0);
   const double *Pb = a.P + a.goff[obj] * a.npp;

@@ -172,6 +172,23 @@ class LikelihoodEngine:
         self.parnames = self.arms[self.setups[0]]['bank'].parnames
         self.n_eval = 0
         self.timer = None
+        # fast path (see _evaluate_fast): per-arm object index on the host, and
+        # whether the template covers each object over [min_vel, max_vel]
+        # (spec_fit.py:786-794 evaluated once instead of per call)
+        self._oix = np.stack([self.arms[n]['index'] for n in self.setups]).astype(np.int32)
+        cov = np.ones((len(self.setups), self.nobj), dtype=bool)
+        for a, n in enumerate(self.setups):
+            arm = self.arms[n]
+            has = arm['index'] >= 0
+            ix = arm['index'][has]
+            cov[a, has] = _overlap_ok(arm['bank'].lam[0], arm['bank'].lam[-1],
+                                      arm['batch'].lam0[ix], arm['batch'].lam1[ix],
+                                      config['min_vel'], config['max_vel'])
+        self._cover0 = cov.all(axis=0)
+        self._fast_banks = all(
+            self.arms[n]['bank'].kind == 'regulargrid' and self.arms[n]['bank'].gridmap is not None
+            and self.arms[n]['bank'].knots.ratio_dev < 1e-8 for n in self.setups)
+        self._buf = {}
 
     @staticmethod
     def _fusable(bank, vs):
@@ -271,6 +288,76 @@ class LikelihoodEngine:
                               model=_dev.download(d_mod), moff=moff, oix=oix)
         return _dev.download(d_chi), st, outside, tstatus, extras
 
+    def _scratch(self, name, shape, dtype):
+        """Device buffer reused between calls (grown by 25 % when too small)."""
+        n = int(np.prod(shape))
+        t = self._buf.get(name)
+        if t is None or t.numel() < n:
+            t = _dev.empty((int(n * 1.25) + 64,), dtype)
+            self._buf[name] = t
+        return t[:n].view(*shape)
+
+    def _evaluate_fast(self, obj, vels, params, vsini, sys_errs):
+        """Optimiser-phase evaluation of K items at one velocity each with no
+        host work per item: one upload of (vel, vsini, mapped parameters), then
+        per arm vertex location, rotation taps, the fused template/resampling
+        kernel and the continuum solve, all stream-ordered; one download of the
+        per-arm chi-squares and flags.  Items that need anything else (off-grid
+        or missing-corner points, template not finite, normal matrix not PD,
+        velocity outside [min_vel, max_vel], template not covering the data)
+        come back flagged and are re-evaluated by the general path.
+        Returns (total (K,), redo (K,) bool)."""
+        L = _cabi.lib()
+        K = len(obj)
+        narm = len(self.setups)
+        bank0 = self.arms[self.setups[0]]['bank']
+        nd = bank0.ndim
+        host_in = np.empty((2 + nd, K))
+        host_in[0] = vels
+        host_in[1] = 0.0 if vsini is None else vsini
+        host_in[2:] = spec_inter.map_params(params, bank0.log_ids).T
+        d_in = _dev.upload(host_in, np.float64)
+        d_oix = _dev.upload(self._oix[:, obj], np.int32)
+        vmax = 0.0 if vsini is None else float(np.max(vsini, initial=0.0))
+        d_chi = self._scratch('chi', (narm, K), np.float64)
+        d_flags = self._scratch('flags', (2, narm, K), np.int32)
+        nvert = bank0.nvert
+        d_ids = self._scratch('ids', (K, nvert), np.int32)
+        d_w = self._scratch('w', (K, nvert), np.float64)
+        stream = _dev.stream()
+        for a, name in enumerate(self.setups):
+            arm = self.arms[name]
+            bank, batch = arm['bank'], arm['batch']
+            obs = batch.obs(self.npoly, self.rbf, sys_errs[a])
+            q = d_in[2:]
+            if bank.log_ids != bank0.log_ids:
+                q = _dev.upload(spec_inter.map_params(params, bank.log_ids).T, np.float64)
+            rc = L.rvs_locate_grid(ctypes.byref(bank.gridmap), _dev.ptr(q), K, K, _dev.ptr(d_ids),
+                                   _dev.ptr(d_w), _dev.ptr(d_flags[1, a]), stream)
+            _cabi.check(rc, 'rvs_locate_grid')
+            stride = int(batch.npix.max())
+            d_tn = self._scratch('tn', (K * stride,), np.float64)
+            d_work = None
+            if vmax > 0:
+                d_work = self._scratch('work', (L.rvs_fused_workspace(K, bank.tapcap(vmax)),),
+                                       np.float64)
+            t0 = self.timer.start() if self.timer else None
+            rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
+                                   ctypes.byref(bank.knots), _dev.ptr(d_ids), _dev.ptr(d_w),
+                                   bank.nvert, _dev.ptr(d_in[1]) if vmax > 0 else None, vmax,
+                                   int(bank.log_spec), ctypes.byref(obs), _dev.ptr(d_oix[a]),
+                                   _dev.ptr(d_in[0]), K, _dev.ptr(d_tn), stride, _dev.ptr(d_work),
+                                   _dev.ptr(d_chi[a]), _dev.ptr(d_flags[0, a]), stream)
+            _cabi.check(rc, 'rvs_chisq_fused')
+            if t0 is not None:
+                self.timer.stop('fused', t0, K)
+        chi = _dev.download(d_chi)
+        flags = _dev.download(d_flags)
+        redo = (flags != 0).any(axis=(0, 1)) | ~np.isfinite(chi).all(axis=0)
+        redo |= ~self._cover0[obj] | (vels < self.config['min_vel']) | \
+            (vels > self.config['max_vel'])
+        return np.add.reduce(chi, axis=0), redo
+
     def evaluate(self, obj, vels, params, vsini=None, outside_penalty=True,
                  espec_systematic=None, want_model=False, raise_errors=False):
         """-2 log L for K items.  obj (K,), vels (K,) or (K, nv), params (K, ndim),
@@ -280,6 +367,33 @@ class LikelihoodEngine:
         obj = np.asarray(obj, dtype=np.int64)
         params = np.array(params, dtype=np.float64, ndmin=2)
         vels = np.asarray(vels, dtype=np.float64)
+        flat = vels.ndim == 1
+        if (flat and self.fused and self._fast_banks and not want_model and len(obj) > 0
+                and (vsini is None or
+                     all(self.arms[n]['bank'].tapcap(float(np.max(vsini, initial=0.0)))
+                         <= _cabi.MAX_FUSED_TAPS for n in self.setups))):
+            if isinstance(espec_systematic, dict):
+                sys_errs = [float(espec_systematic[n]) for n in self.setups]
+            else:
+                sys_errs = [float(espec_systematic or 0.0)] * len(self.setups)
+            vs = None if vsini is None else np.asarray(vsini, dtype=np.float64)
+            self.n_eval += len(obj)
+            total, redo = self._evaluate_fast(obj, vels, params, vs, sys_errs)
+            if redo.any():
+                r = np.nonzero(redo)[0]
+                self.n_eval -= len(r)
+                total[r] = self._evaluate_general(
+                    obj[r], vels[r], params[r], None if vs is None else vs[r], outside_penalty,
+                    espec_systematic, False, raise_errors)
+            return total
+        return self._evaluate_general(obj, vels, params, vsini, outside_penalty,
+                                      espec_systematic, want_model, raise_errors)
+
+    def _evaluate_general(self, obj, vels, params, vsini, outside_penalty, espec_systematic,
+                          want_model, raise_errors):
+        """The general path: host vertex location (any interpolator kind, off-grid
+        nearest node), any number of velocities per item, model output, SVD
+        rescue, the reference's exceptions."""
         flat = vels.ndim == 1
         v2 = vels[:, None] if flat else vels
         K, nv = v2.shape

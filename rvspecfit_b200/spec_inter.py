@@ -84,6 +84,17 @@ class TemplateBank:
             vecs = np.asarray(vecs, dtype=np.float64)
             self.ptp = np.ptp(vecs, axis=1)
             self.tree = scipy.spatial.cKDTree(vecs.T / self.ptp[None, :])
+            self.gridmap = None
+            if self.ndim <= 5:      # device-side vertex location (rvs_locate_grid)
+                uoff = np.concatenate([[0], np.cumsum(self.lens)])
+                self._gm = (_dev.upload(np.concatenate(self.uvecs), np.float64),
+                            _dev.upload(self.idgrid.reshape(-1), np.int32))
+                gm = _cabi.GridMap()
+                gm.d_uvec, gm.d_idgrid = self._gm[0].data_ptr(), self._gm[1].data_ptr()
+                gm.ndim = self.ndim
+                for i in range(self.ndim):
+                    gm.len[i], gm.uoff[i] = int(self.lens[i]), int(uoff[i])
+                self.gridmap = gm
         elif kind == 'triangulation':
             self.triang = triang
             self.ndim = triang.ndim

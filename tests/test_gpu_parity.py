@@ -221,6 +221,63 @@ def test_desi_three_arm_matches_reference(golden):
         assert np.isclose(fb[k], g[f'desi_scan_{k}'], rtol=1e-7, atol=1e-9), k
 
 
+def test_ragged_arms_in_one_launch(golden):
+    """Objects that lack some arms evaluated in the same launches as complete
+    ones (absent arm = skipped item), against the oracle per object."""
+    g = golden('chisq')
+    for k, a in enumerate(('desi_b', 'desi_r', 'desi_z')):
+        st = setup(a, 'tiny', 21 + k)
+        _register(st)
+        oracle.register_setup(st)
+    o = unpack_objects(g, 'desi_')[0]
+    sd, osd = _sd(o), _sd(o, cls=oracle.SpecData)
+    cfg = config(min_vel=-1500, max_vel=1500)
+    ev = g['desi_eval'][:6]
+    subsets = [slice(0, 3), slice(0, 2), slice(2, 3), slice(1, 2)]
+    eng = spec_fit.LikelihoodEngine([sd[s] for s in subsets], cfg, {'npoly': 10})
+    K = len(ev)
+    obj = np.tile(np.arange(len(subsets)), K)
+    rep = np.repeat(np.arange(K), len(subsets))
+    vs = np.where(ev[:, 5] < 0, 0.0, ev[:, 5])
+    got = eng.evaluate(obj, ev[rep, 0], ev[rep, 1:5], vs[rep])
+    for j, (i, e) in enumerate(zip(obj, rep)):
+        want = oracle.get_chisq(osd[subsets[i]], ev[e, 0], tuple(ev[e, 1:5]), (vs[e],),
+                                options={'npoly': 10}, config=cfg)
+        assert abs(got[j] - want) < CHI_RTOL * abs(want), (i, e)
+
+
+def test_locate_grid_bit_identical():
+    """rvs_locate_grid reproduces the host vertex ids and weights bit for bit and
+    flags exactly the points the host resolves through the KD-tree."""
+    st = setup('test', 'tiny', 3, holes=3, name='test_holes')
+    bank = _register(st)
+    rs = np.random.RandomState(5)
+    lo = np.array([st['uvecs'][i][0] for i in range(4)])
+    hi = np.array([st['uvecs'][i][-1] for i in range(4)])
+    q = lo + (hi - lo) * rs.uniform(-0.05, 1.05, size=(4000, 4))
+    q[:50] = np.array([st['uvecs'][i][rs.randint(0, len(st['uvecs'][i]), 50)] for i in range(4)]).T
+    q[50, 0] = np.nan
+    q[51, 1] = np.inf
+    params = q.copy()
+    params[:, 0] = 10**q[:, 0]
+    qm = spec_inter.map_params(params, bank.log_ids)
+    ids, w, outside = bank.locate(params)
+    K = len(q)
+    d_q = _dev.upload(qm.T, np.float64)
+    d_ids, d_w = _dev.empty((K, 16), np.int32), _dev.empty((K, 16), np.float64)
+    d_flag = _dev.empty((K,), np.int32)
+    rc = _cabi.lib().rvs_locate_grid(ctypes.byref(bank.gridmap), _dev.ptr(d_q), K, K,
+                                     _dev.ptr(d_ids), _dev.ptr(d_w), _dev.ptr(d_flag),
+                                     _dev.stream())
+    assert rc == 0
+    flag = _dev.download(d_flag).astype(bool)
+    host_flag = (outside != 0) | (ids[:, 1] < 0)
+    assert np.array_equal(flag, host_flag)
+    assert 100 < flag.sum() < K - 100
+    assert np.array_equal(_dev.download(d_ids)[~flag], ids[~flag])
+    assert np.array_equal(_dev.download(d_w)[~flag], w[~flag])
+
+
 def test_scan_stats_edge_cases():
     rs = np.random.RandomState(0)
     for nv, npar in ((7, 1), (600, 3), (33, 5)):
