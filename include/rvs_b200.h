@@ -110,7 +110,8 @@ typedef struct {
   int32_t npoly;
   int32_t npp;
   int32_t nobj;
-  int32_t reserved;
+  int32_t shared_grid; /* 1: every object has the same pixels (one entry in the grid pools):
+                          enables the batched GEMM form of the continuum solve */
 } rvs_obs;
 
 /* Regular template grid in mapped parameter space (spec_inter.py:97-132):
@@ -200,7 +201,7 @@ int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
  * d_vsini (sizes the tap buffer; 0 if d_vsini is NULL).  d_tn: workspace
  * [K, tn_stride] doubles, tn_stride >= the longest object.  d_work: workspace
  * of rvs_fused_workspace(K, tapcap) doubles, tapcap = ceil(vsini_max /
- * (c lnstep) + 1) + 1 (may be NULL when d_vsini is NULL).  Outputs chisq[K],
+ * (c lnstep) + 1) + 1 (0 when d_vsini is NULL or vsini_max <= 0).  Outputs chisq[K],
  * status[K] (template bits | RVS_ST_NOT_PD | RVS_ST_RANGE | RVS_ST_LIMIT).
  * Needs knots->ratio_dev < 1e-8 (exactly uniform or log-uniform knots) and
  * tapcap <= RVS_MAX_FUSED_TAPS, else RVS_E_LIMIT: use the general path.

@@ -320,6 +320,11 @@ extern "C" int rvs_basis_build(const double *d_lam, const int64_t *d_gstart, int
 }
 
 namespace rvs {
+int launch_scan_mma_group0(const ScanArgs &, int, cudaStream_t);
+int launch_scan_mma_group1(const ScanArgs &, int, cudaStream_t);
+int launch_scan_mma_group2(const ScanArgs &, int, cudaStream_t);
+int launch_scan_mma_group3(const ScanArgs &, int, cudaStream_t);
+
 int fill_scan_args(ScanArgs &a, const rvs_knots *kn, const rvs_obs *obs) {
   RVS_REQUIRE(kn && obs && kn->d_lam_t && kn->d_h && kn->d_hinv && obs->d_lam &&
                   obs->d_loglam && obs->d_dn && obs->d_einv && obs->d_sumlog2 && obs->d_off &&
@@ -358,6 +363,14 @@ extern "C" int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32
   a.oix = d_oix; a.vels = d_vels; a.nv = nv; a.K = K; a.chisq = d_chisq; a.status = d_status;
   a.coeffs = d_coeffs; a.raw = d_raw; a.model = d_model; a.moff = d_moff;
   cudaStream_t st = (cudaStream_t)stream;
+  if (nv >= 4 && !d_coeffs && !d_raw && !d_model) {
+    // several trials per template: the trials are the columns of an FP64 GEMM (scan_mma.cuh)
+    const int np = obs->npoly;
+    if (np <= 7) return launch_scan_mma_group0(a, np, st);
+    if (np <= 10) return launch_scan_mma_group1(a, np, st);
+    if (np <= 13) return launch_scan_mma_group2(a, np, st);
+    return launch_scan_mma_group3(a, np, st);
+  }
   switch (obs->npoly) {
 #define RVS_CASE(N) case N: return launch_scan<N>(a, st);
     RVS_CASE(1) RVS_CASE(2) RVS_CASE(3) RVS_CASE(4) RVS_CASE(5) RVS_CASE(6) RVS_CASE(7)

@@ -5,12 +5,17 @@
 // L2-resident between the two stages).
 #include "chunk_kernel.cuh"
 #include "gram_kernel.cuh"
+#include "gram_mma.cuh"
 
 namespace rvs {
 int launch_gram_group0(const GramArgs &, int, int, cudaStream_t);
 int launch_gram_group1(const GramArgs &, int, int, cudaStream_t);
 int launch_gram_group2(const GramArgs &, int, int, cudaStream_t);
 int launch_gram_group3(const GramArgs &, int, int, cudaStream_t);
+int launch_gram_mma_group0(const GramMmaArgs &, int, cudaStream_t);
+int launch_gram_mma_group1(const GramMmaArgs &, int, cudaStream_t);
+int launch_gram_mma_group2(const GramMmaArgs &, int, cudaStream_t);
+int launch_gram_mma_group3(const GramMmaArgs &, int, cudaStream_t);
 
 template <typename GT, int NV>
 static int launch_chunk_one(const ChunkArgs &a, size_t smem, cudaStream_t st) {
@@ -36,8 +41,8 @@ extern "C" int rvs_fused_chunks(int npix_t, int tapcap) {
 }
 
 extern "C" int64_t rvs_fused_workspace(int K, int tapcap) {
-  // doubles: taps [K, tapcap+1] followed by kmax (int32) [K]
-  return (int64_t)K * (tapcap + 1) + (K + 1) / 2;
+  // doubles: taps [K, tapcap+1], kmax (int32) [K], scratch of the Gram GEMM pair
+  return (int64_t)K * (tapcap + 1) + (K + 1) / 2 + rvs::GramScratch(K).total();
 }
 
 extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
@@ -68,7 +73,7 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
   RVS_REQUIRE(tapcap <= RVS_MAX_FUSED_TAPS, RVS_E_LIMIT,
               "rvs_chisq_fused: vsini_max=%g needs %d taps (fused limit %d); use "
               "rvs_template_build + rvs_chisq_scan", vsini_max, tapcap, RVS_MAX_FUSED_TAPS);
-  RVS_REQUIRE(tapcap == 0 || d_work, RVS_E_ARG, "rvs_chisq_fused: d_work is NULL");
+  RVS_REQUIRE(d_work, RVS_E_ARG, "rvs_chisq_fused: d_work is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   RVS_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * K, st));
   ChunkArgs a;
@@ -113,11 +118,28 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
   else if (nvert == 5) rc = launch_chunk_one<float, 5>(a, smem, st);
   else rc = launch_chunk_one<float, 0>(a, smem, st);
   if (rc) return rc;
+  const int np = obs->npoly;
+  if (obs->shared_grid) {  // one wavelength grid for all objects: Gram stage as an FP64 GEMM
+    GramMmaArgs m;
+    m.tn = d_tn; m.tn_stride = tn_stride; m.dn = obs->d_dn; m.sumlog2 = obs->d_sumlog2;
+    m.off = obs->d_off; m.goff = obs->d_goff; m.oix = d_oix; m.P = obs->d_P; m.npp = obs->npp;
+    m.K = K; m.KS = 1; m.chisq = d_chisq; m.status = d_status;
+    const GramScratch gs(K);
+    double *w = d_work + (int64_t)K * (tapcap + 1) + (K + 1) / 2;
+    m.part = w; w += gs.part();
+    m.coef = w; w += gs.coef();
+    m.logdet = w; w += gs.logdet();
+    m.rpart = w; w += gs.rpart();
+    m.ticket = reinterpret_cast<unsigned *>(w);
+    if (np <= 7) return launch_gram_mma_group0(m, np, st);
+    if (np <= 10) return launch_gram_mma_group1(m, np, st);
+    if (np <= 13) return launch_gram_mma_group2(m, np, st);
+    return launch_gram_mma_group3(m, np, st);
+  }
   GramArgs g;
   g.tn = d_tn; g.tn_stride = tn_stride; g.dn = obs->d_dn; g.sumlog2 = obs->d_sumlog2;
   g.off = obs->d_off; g.goff = obs->d_goff; g.oix = d_oix; g.P = obs->d_P; g.npp = obs->npp;
   g.chisq = d_chisq; g.status = d_status;
-  const int np = obs->npoly;
   if (np <= 7) return launch_gram_group0(g, np, K, st);
   if (np <= 10) return launch_gram_group1(g, np, K, st);
   if (np <= 13) return launch_gram_group2(g, np, K, st);

@@ -1,6 +1,10 @@
 // One quarter of the npoly instantiations of the stage-B (Gram) kernel; compiled
 // four times with -DRVS_NP_GROUP=0..3 so that the translation units build in parallel.
+#include <algorithm>
+
 #include "gram_kernel.cuh"
+#include "gram_mma.cuh"
+#include "scan_mma.cuh"
 
 #ifndef RVS_NP_GROUP
 #error "compile with -DRVS_NP_GROUP=0..3"
@@ -19,6 +23,73 @@ static int launch_gram_np(const GramArgs &a, int K, cudaStream_t st) {
   gram_kernel<NP><<<K, GR_THREADS, smem, st>>>(a);
   RVS_LAUNCH_OK();
   return 0;
+}
+
+template <int NP>
+static int launch_gram_mma_np(GramMmaArgs a, cudaStream_t st) {
+  constexpr int NT = NP <= 10 ? 2 : 1;
+  constexpr int NI = 8 * NT;
+  RVS_REQUIRE(a.npp == ((NP + 1) & ~1), RVS_E_ARG, "gram: basis rows of %d doubles, expected %d",
+              a.npp, (NP + 1) & ~1);
+  const int groups = (a.K + NI - 1) / NI;
+  a.KS = std::min(GM_MAX_KS, std::max(1, (512 + groups - 1) / groups));
+  RVS_CUDA_OK(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned) * groups, st));
+  dim3 grid(groups, a.KS);
+  gram_mma_kernel<NP, NT><<<grid, GM_THREADS, 0, st>>>(a);
+  RVS_LAUNCH_OK();
+  gram_solve_kernel<NP, NT><<<(a.K + GM_WARPS - 1) / GM_WARPS, GM_THREADS, 0, st>>>(a);
+  RVS_LAUNCH_OK();
+  resid_mma_kernel<NP, NT><<<grid, GM_THREADS, 0, st>>>(a);
+  RVS_LAUNCH_OK();
+  return 0;
+}
+
+template <int NP>
+static int launch_scan_mma_np(const ScanArgs &a, cudaStream_t st) {
+  constexpr int NT = NP <= 10 ? 2 : 1;
+  constexpr int NI = 8 * NT;
+  RVS_REQUIRE(a.npp == ((NP + 1) & ~1), RVS_E_ARG, "scan: basis rows of %d doubles, expected %d",
+              a.npp, (NP + 1) & ~1);
+  const int by = (a.nv + NI - 1) / NI;
+  RVS_REQUIRE(by <= 65535, RVS_E_LIMIT, "scan: %d velocity trials per item", a.nv);
+  dim3 grid(a.K, by);
+  chisq_scan_mma_kernel<NP, NT><<<grid, GM_THREADS, 0, st>>>(a);
+  RVS_LAUNCH_OK();
+  return 0;
+}
+
+int RVS_CAT(launch_scan_mma_group, RVS_NP_GROUP)(const ScanArgs &a, int npoly, cudaStream_t st) {
+  switch (npoly) {
+#define RVS_CASE(N) case N: return launch_scan_mma_np<N>(a, st);
+#if RVS_NP_GROUP == 0
+    RVS_CASE(1) RVS_CASE(2) RVS_CASE(3) RVS_CASE(4) RVS_CASE(5) RVS_CASE(6) RVS_CASE(7)
+#elif RVS_NP_GROUP == 1
+    RVS_CASE(8) RVS_CASE(9) RVS_CASE(10)
+#elif RVS_NP_GROUP == 2
+    RVS_CASE(11) RVS_CASE(12) RVS_CASE(13)
+#else
+    RVS_CASE(14) RVS_CASE(15) RVS_CASE(16)
+#endif
+#undef RVS_CASE
+  }
+  return RVS_E_ARG;
+}
+
+int RVS_CAT(launch_gram_mma_group, RVS_NP_GROUP)(const GramMmaArgs &a, int npoly, cudaStream_t st) {
+  switch (npoly) {
+#define RVS_CASE(N) case N: return launch_gram_mma_np<N>(a, st);
+#if RVS_NP_GROUP == 0
+    RVS_CASE(1) RVS_CASE(2) RVS_CASE(3) RVS_CASE(4) RVS_CASE(5) RVS_CASE(6) RVS_CASE(7)
+#elif RVS_NP_GROUP == 1
+    RVS_CASE(8) RVS_CASE(9) RVS_CASE(10)
+#elif RVS_NP_GROUP == 2
+    RVS_CASE(11) RVS_CASE(12) RVS_CASE(13)
+#else
+    RVS_CASE(14) RVS_CASE(15) RVS_CASE(16)
+#endif
+#undef RVS_CASE
+  }
+  return RVS_E_ARG;
 }
 
 int RVS_CAT(launch_gram_group, RVS_NP_GROUP)(const GramArgs &a, int npoly, int K, cudaStream_t st) {

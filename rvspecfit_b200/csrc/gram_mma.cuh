@@ -1,0 +1,370 @@
+// Fused optimiser-phase evaluation, stage B for batches whose objects share one
+// wavelength grid (all spectra of a DESI arm do): the continuum normal
+// equations of 8*NT items at a time as an FP64 tensor-core GEMM
+//     [M | v](out, item) = sum_px A(out, px) B(px, item),
+//     A = P_i P_j (packed lower triangle, rows 0..NTRI-1)  with  B = (T/sigma)^2,
+//     A = P_i     (rows of the second tile set)            with  B = (T/sigma)(D/sigma),
+// (spec_fit.py:230-241: Minv = sum P_i P_j T^2/sigma^2, v = sum P_i T S/sigma^2)
+// issued as mma.sync m8n8k4 f64 (DMMA).  The basis products are formed on the
+// fly from the pixel-major basis (L1-resident), every thread computing exactly
+// the A elements of its own fragments; the shared basis is read once per 8*NT
+// items instead of once per item, which is what bounded the per-item kernel
+// (gram_kernel.cuh) at L2 bandwidth.
+//
+// Work decomposition: grid = (item groups, KS pixel splits), 4 warps per CTA,
+// each warp a contiguous run of pixels.  Partial sums go to global memory;
+// gram_solve_kernel (one warp per item) adds them IN FIXED ORDER and runs the
+// Cholesky solve.  resid_mma_kernel evaluates |D - a^T G|^2 the same way:
+// cont(px, item) = sum_i P_i(px) a_i(item) by DMMA, then
+// r = D/sigma - T/sigma * cont (the reference's second pass, spec_fit.py:242-249);
+// the last CTA of a group to finish (atomic ticket) adds the partial norms in
+// fixed order, so results do not depend on scheduling.
+#pragma once
+#include "chisq_device.cuh"
+
+namespace rvs {
+
+constexpr int GM_WARPS = 4;
+constexpr int GM_THREADS = GM_WARPS * 32;
+constexpr int GM_MAX_KS = 16;
+
+struct GramMmaArgs {
+  const double *tn;
+  int64_t tn_stride;
+  const double *dn, *sumlog2;
+  const int64_t *off, *goff;
+  const int32_t *oix;
+  const double *P;  // pixel-major [pixel][npp]
+  int npp;
+  int K;
+  int KS;            // pixel splits (CTAs per group)
+  double *part;      // [groups][KS][ROWS][8*NT] partial sums
+  double *coef;      // [groups*8*NT][NP]
+  double *logdet;    // [groups*8*NT]
+  double *rpart;     // [groups][KS][8*NT] partial residual norms
+  unsigned *ticket;  // [groups] zeroed before the launch (resid_mma_kernel)
+  double *chisq;
+  int32_t *status;
+};
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+template <int NP>
+struct GramTiles {
+  static constexpr int NTRI = NP * (NP + 1) / 2;
+  static constexpr int MT_M = (NTRI + 7) / 8;  // tiles of basis products
+  static constexpr int MT_V = (NP + 7) / 8;    // tiles of the basis itself
+  static constexpr int MT = MT_M + MT_V;
+  static constexpr int ROWS = MT * 8;
+};
+
+// Sum of the warps' accumulator fragments, added in warp order 0,1,2,3 (hence
+// deterministic), left in s[row][col] for the whole CTA.  All threads call.
+template <int MT, int NT>
+__device__ __forceinline__ void warp_ordered_sum(const double (&acc)[MT][NT][2],
+                                                 double (*s)[8 * NT + 1], int wid, int r, int c) {
+  for (int w = 0; w < GM_WARPS; w++) {
+    if (wid == w) {
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+          double *d = &s[mt * 8 + r][nt * 8 + 2 * c];
+          if (w == 0) { d[0] = acc[mt][nt][0]; d[1] = acc[mt][nt][1]; }
+          else { d[0] += acc[mt][nt][0]; d[1] += acc[mt][nt][1]; }
+        }
+    }
+    __syncthreads();
+  }
+}
+
+// rows of the packed lower triangle this thread supplies to its A fragments:
+// entry o = 8 mt + r  ->  (i, j), i >= j (clamped to a valid entry past the end;
+// the caller zeroes those)
+template <int NP>
+__device__ __forceinline__ void tri_rows(int r, int (&ia)[GramTiles<NP>::MT_M],
+                                         int (&ja)[GramTiles<NP>::MT_M]) {
+  int i = 0;  // row of entry o: o and i only grow from one tile to the next
+#pragma unroll
+  for (int mt = 0; mt < GramTiles<NP>::MT_M; mt++) {
+    const int o = min(mt * 8 + r, GramTiles<NP>::NTRI - 1);
+    while ((i + 1) * (i + 2) / 2 <= o) i++;
+    ia[mt] = i;
+    ja[mt] = o - i * (i + 1) / 2;
+  }
+}
+
+// reference item of a group (first present one) defines the shared grid
+struct GroupGeom {
+  int npix;
+  int64_t goff;
+};
+
+template <int NT>
+__device__ __forceinline__ GroupGeom group_geom(const GramMmaArgs &a, int g) {
+  GroupGeom gg{0, 0};
+  for (int e = 0; e < 8 * NT; e++) {
+    const int k = g * 8 * NT + e;
+    if (k >= a.K) break;
+    const int obj = a.oix[k];
+    if (obj >= 0) {
+      gg.npix = (int)(a.off[obj + 1] - a.off[obj]);
+      gg.goff = a.goff[obj];
+      break;
+    }
+  }
+  return gg;
+}
+
+template <int NP, int NT>
+__global__ void __launch_bounds__(GM_THREADS) gram_mma_kernel(GramMmaArgs a) {
+  using TL = GramTiles<NP>;
+  constexpr int NI = 8 * NT;
+  __shared__ double s_red[TL::ROWS][NI + 1];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = blockIdx.x, ks = blockIdx.y;
+  const int r = lane >> 2, c = lane & 3;
+  const GroupGeom gg = group_geom<NT>(a, g);
+  const int npix = gg.npix;
+  const double *Pb = a.P + gg.goff * a.npp;
+  // this thread's B columns: item r of every n-tile
+  const double *tnp[NT], *dnp[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) {
+    const int k = g * NI + nt * 8 + r;
+    const int obj = k < a.K ? a.oix[k] : -1;
+    tnp[nt] = obj >= 0 ? a.tn + (int64_t)k * a.tn_stride : nullptr;
+    dnp[nt] = obj >= 0 ? a.dn + a.off[obj] : nullptr;
+  }
+  // this thread's A rows: packed-triangle entry o = 8 mt + r  ->  (i, j), i >= j
+  int ia[TL::MT_M], ja[TL::MT_M];
+  tri_rows<NP>(r, ia, ja);
+  double acc[TL::MT][NT][2];
+#pragma unroll
+  for (int mt = 0; mt < TL::MT; mt++)
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0;
+  // pixel run of this warp: segment (ks, wid) of 4*KS, lengths a multiple of 4
+  const int nseg = GM_WARPS * a.KS;
+  const int seglen = ((npix + nseg - 1) / nseg + 3) & ~3;
+  const int pbeg = (ks * GM_WARPS + wid) * seglen;
+  const int pend = min(npix, pbeg + seglen);
+  // B operands one k-step ahead (they come from L2: written by stage A)
+  double tq[NT], dq[NT];
+  auto load_b = [&](int p4) {
+    const int p = p4 + c;
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      tq[nt] = 0;
+      dq[nt] = 0;
+      if (p < pend && tnp[nt]) { tq[nt] = __ldcg(tnp[nt] + p); dq[nt] = __ldg(dnp[nt] + p); }
+    }
+  };
+  load_b(pbeg);
+  for (int p4 = pbeg; p4 < pend; p4 += 4) {
+    const int p = p4 + c;
+    const bool in = p < pend;
+    const double *Prow = Pb + (int64_t)(in ? p : 0) * a.npp;
+    double pa[TL::MT_M], pb[TL::MT_M], pv[TL::MT_V];
+#pragma unroll
+    for (int mt = 0; mt < TL::MT_M; mt++) {
+      pa[mt] = __ldg(Prow + ia[mt]);
+      pb[mt] = __ldg(Prow + ja[mt]);
+    }
+#pragma unroll
+    for (int mv = 0; mv < TL::MT_V; mv++) pv[mv] = __ldg(Prow + min(mv * 8 + r, NP - 1));
+    double bsq[NT], btd[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      bsq[nt] = tq[nt] * tq[nt];
+      btd[nt] = tq[nt] * dq[nt];
+    }
+    load_b(p4 + 4);
+#pragma unroll
+    for (int mt = 0; mt < TL::MT_M; mt++) {
+      const double av = (in && mt * 8 + r < TL::NTRI) ? pa[mt] * pb[mt] : 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], av, bsq[nt]);
+    }
+#pragma unroll
+    for (int mv = 0; mv < TL::MT_V; mv++) {
+      const double av = (in && mv * 8 + r < NP) ? pv[mv] : 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++)
+        dmma884(acc[TL::MT_M + mv][nt][0], acc[TL::MT_M + mv][nt][1], av, btd[nt]);
+    }
+  }
+  // ---- cross-warp sum in fixed (warp) order, partial of this CTA to global
+  warp_ordered_sum<TL::MT, NT>(acc, s_red, wid, r, c);
+  double *part = a.part + ((int64_t)g * a.KS + ks) * (TL::ROWS * NI);
+  for (int e = tid; e < TL::ROWS * NI; e += GM_THREADS) {
+    const int row = e / NI, col = e - row * NI;
+    part[e] = s_red[row][col];
+  }
+}
+
+// One warp per item: total of the pixel-split partials in fixed order, Cholesky
+// solve (spec_fit.py:236-241), coefficients and log-determinant to global.
+template <int NP, int NT>
+__global__ void __launch_bounds__(GM_THREADS) gram_solve_kernel(GramMmaArgs a) {
+  using TL = GramTiles<NP>;
+  constexpr int NI = 8 * NT;
+  __shared__ double sM[GM_WARPS][TL::NTRI];
+  __shared__ double sV[GM_WARPS][NP];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int k = blockIdx.x * GM_WARPS + wid;
+  if (k >= a.K) return;
+  const int obj = a.oix[k];
+  if (obj < 0) return;
+  const int g = k / NI, e = k - g * NI;
+  const GroupGeom gg = group_geom<NT>(a, g);
+  const bool same = (int)(a.off[obj + 1] - a.off[obj]) == gg.npix && a.goff[obj] == gg.goff;
+  const double *gp = a.part + (int64_t)g * a.KS * (TL::ROWS * NI);
+  for (int o = lane; o < TL::NTRI + NP; o += 32) {
+    const int row = o < TL::NTRI ? o : TL::MT_M * 8 + (o - TL::NTRI);
+    double v[GM_MAX_KS];
+#pragma unroll
+    for (int s = 0; s < GM_MAX_KS; s++)
+      v[s] = s < a.KS ? __ldcg(gp + (int64_t)s * (TL::ROWS * NI) + row * NI + e) : 0.0;
+    double t = 0;
+#pragma unroll
+    for (int s = 0; s < GM_MAX_KS; s++) t += v[s];
+    if (o < TL::NTRI) sM[wid][o] = t; else sV[wid][o - TL::NTRI] = t;
+  }
+  __syncwarp();
+  const double ld = chol_solve<NP>(sM[wid], sV[wid], lane);
+  if (lane < NP) a.coef[(int64_t)k * NP + lane] = sV[wid][lane];
+  if (lane == 0) {
+    a.logdet[k] = ld;
+    if (!same) atomicOr(a.status + k, RVS_ST_LIMIT);  // not on the group's grid: general path
+  }
+}
+
+template <int NP, int NT>
+__global__ void __launch_bounds__(GM_THREADS) resid_mma_kernel(GramMmaArgs a) {
+  constexpr int NI = 8 * NT;
+  constexpr int KST = (NP + 3) / 4;  // k-steps over the basis index
+  __shared__ double s_red[GM_WARPS][NI];
+  __shared__ unsigned s_last;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = blockIdx.x, ks = blockIdx.y;
+  const int r = lane >> 2, c = lane & 3;
+  const GroupGeom gg = group_geom<NT>(a, g);
+  const int npix = gg.npix;
+  const double *Pb = a.P + gg.goff * a.npp;
+  // B fragments: coefficient i = 4 s + c of item r (+ 8 nt)
+  double bco[KST][NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) {
+    const int k = g * NI + nt * 8 + r;
+    const bool have = k < a.K && a.oix[k] >= 0;
+#pragma unroll
+    for (int s = 0; s < KST; s++) {
+      const int i = 4 * s + c;
+      bco[s][nt] = (have && i < NP) ? __ldcg(a.coef + (int64_t)k * NP + i) : 0.0;
+    }
+  }
+  // C fragment columns: items 2c, 2c+1 of every n-tile
+  const double *tnp[NT][2], *dnp[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int k = g * NI + nt * 8 + 2 * c + e;
+      const int obj = k < a.K ? a.oix[k] : -1;
+      tnp[nt][e] = obj >= 0 ? a.tn + (int64_t)k * a.tn_stride : nullptr;
+      dnp[nt][e] = obj >= 0 ? a.dn + a.off[obj] : nullptr;
+    }
+  double rss[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) rss[nt][0] = rss[nt][1] = 0;
+  const int nseg = GM_WARPS * a.KS;
+  const int seglen = ((npix + nseg - 1) / nseg + 7) & ~7;
+  const int pbeg = (ks * GM_WARPS + wid) * seglen;
+  const int pend = min(npix, pbeg + seglen);
+  for (int p8 = pbeg; p8 < pend; p8 += 8) {
+    const int p = p8 + r;
+    const bool in = p < pend;
+    const double *Prow = Pb + (int64_t)(in ? p : 0) * a.npp;
+    double cont[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) cont[nt][0] = cont[nt][1] = 0;
+#pragma unroll
+    for (int s = 0; s < KST; s++) {
+      const int i = 4 * s + c;
+      const double av = (in && i < NP) ? __ldg(Prow + i) : 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) dmma884(cont[nt][0], cont[nt][1], av, bco[s][nt]);
+    }
+    if (in) {
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+          if (tnp[nt][e]) {
+            const double res = fma(-tnp[nt][e][p], cont[nt][e], __ldg(dnp[nt][e] + p));
+            rss[nt][e] = fma(res, res, rss[nt][e]);
+          }
+    }
+  }
+  // sum over the 8 pixel rows of the fragment (lanes with equal c), then warps
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      double v = rss[nt][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (r == 0) s_red[wid][nt * 8 + 2 * c + e] = v;
+    }
+  __syncthreads();
+  double *rp = a.rpart + ((int64_t)g * a.KS + ks) * NI;
+  if (tid < NI) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < GM_WARPS; w++) t += s_red[w][tid];
+    rp[tid] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(a.ticket + g, 1u) == (unsigned)(a.KS - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < NI) {
+    const int k = g * NI + tid;
+    if (k < a.K) {
+      const int obj = a.oix[k];
+      if (obj < 0) {
+        a.chisq[k] = 0;
+      } else {
+        double t = 0;
+        for (int s = 0; s < a.KS; s++) t += __ldcg(a.rpart + ((int64_t)g * a.KS + s) * NI + tid);
+        const double chi = a.logdet[k] + a.sumlog2[obj] + t;
+        a.chisq[k] = chi;
+        if (!isfinite(chi)) atomicOr(a.status + k, RVS_ST_NOT_PD);
+      }
+    }
+  }
+}
+
+// Scratch of the pair of kernels for K items (any npoly, any NT), carved out of
+// the caller's workspace.  Sizes are per 8 items, with K rounded up to 16 (a
+// group of NT = 2 holds 16): KS <= 16 partials of at most 152 rows (npoly 16).
+struct GramScratch {
+  int64_t g8;  // 8-item units
+  __host__ __device__ explicit GramScratch(int64_t K) : g8(2 * ((K + 15) / 16)) {}
+  __host__ __device__ int64_t part() const { return g8 * GM_MAX_KS * 152 * 8; }
+  __host__ __device__ int64_t coef() const { return g8 * 8 * RVS_MAX_NPOLY; }
+  __host__ __device__ int64_t logdet() const { return g8 * 8; }
+  __host__ __device__ int64_t rpart() const { return g8 * GM_MAX_KS * 8; }
+  __host__ __device__ int64_t ticket() const { return g8 + 8; }  // 2 x uint32 per unit
+  __host__ __device__ int64_t total() const { return part() + coef() + logdet() + rpart() + ticket(); }
+};
+
+}  // namespace rvs

@@ -121,6 +121,7 @@ class SpectrumBatch:
         o.d_goff, o.d_dn, o.d_einv = self.d_goff.data_ptr(), dn.data_ptr(), einv.data_ptr()
         o.d_sumlog2, o.d_off = sumlog2.data_ptr(), self.d_off.data_ptr()
         o.npoly, o.npp, o.nobj = int(npoly), npp, self.n
+        o.shared_grid = int(len(self.grid_first) == 1)
         return o
 
 
@@ -229,12 +230,10 @@ class LikelihoodEngine:
             vmax = 0.0 if vs is None else float(np.max(vs, initial=0.0))
             stride = int(batch.npix.max())
             d_tn = self._workspace(k * stride)
-            d_work = None
-            if vs is not None and vmax > 0:
-                nwork = L.rvs_fused_workspace(k, bank.tapcap(vmax))
-                if getattr(self, '_work', None) is None or self._work.numel() < nwork:
-                    self._work = _dev.empty((int(nwork * 1.25) + 64,), np.float64)
-                d_work = self._work
+            nwork = L.rvs_fused_workspace(k, bank.tapcap(vmax))
+            if getattr(self, '_work', None) is None or self._work.numel() < nwork:
+                self._work = _dev.empty((int(nwork * 1.25) + 64,), np.float64)
+            d_work = self._work
             t0 = self.timer.start() if self.timer else None
             rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
                                    ctypes.byref(bank.knots), _dev.ptr(d_ids), _dev.ptr(d_w),
@@ -337,10 +336,8 @@ class LikelihoodEngine:
             _cabi.check(rc, 'rvs_locate_grid')
             stride = int(batch.npix.max())
             d_tn = self._scratch('tn', (K * stride,), np.float64)
-            d_work = None
-            if vmax > 0:
-                d_work = self._scratch('work', (L.rvs_fused_workspace(K, bank.tapcap(vmax)),),
-                                       np.float64)
+            d_work = self._scratch('work', (L.rvs_fused_workspace(K, bank.tapcap(vmax)),),
+                                   np.float64)
             t0 = self.timer.start() if self.timer else None
             rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
                                    ctypes.byref(bank.knots), _dev.ptr(d_ids), _dev.ptr(d_w),

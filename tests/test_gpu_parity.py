@@ -246,6 +246,43 @@ def test_ragged_arms_in_one_launch(golden):
         assert abs(got[j] - want) < CHI_RTOL * abs(want), (i, e)
 
 
+def test_mixed_wavelength_grids_take_per_item_solve(golden):
+    """Objects on different pixel grids in one engine: the continuum solve runs
+    per item (gram_kernel) instead of as the shared-basis GEMM (gram_mma_kernel);
+    both against the oracle, plus many trial points of ONE object (a group of
+    the GEMM path made of a single object) and a batch that is not a multiple of
+    the group size."""
+    g = golden('chisq')
+    st = setup('desi_b', 'tiny', 21)
+    _register(st)
+    oracle.register_setup(st)
+    o = unpack_objects(g, 'desi_')[0]
+    nm, lam, sp, es, bad = o['arms'][0]
+    cuts = [slice(0, None), slice(100, 2500), slice(7, 1900)]
+    sds = [[spec_fit.SpecData(nm, lam[c], sp[c], es[c], bad[c])] for c in cuts]
+    osds = [[oracle.SpecData(nm, lam[c], sp[c], es[c], bad[c])] for c in cuts]
+    cfg = config(min_vel=-1500, max_vel=1500)
+    ev = g['desi_eval'][:7]
+    vs = np.where(ev[:, 5] < 0, 0.0, ev[:, 5])
+    K = len(ev)
+    for npoly in (10, 13):
+        opts = {'npoly': npoly}
+        mixed = spec_fit.LikelihoodEngine(sds, cfg, opts)
+        assert mixed.arms[nm]['batch'].obs(npoly, True).shared_grid == 0
+        single = spec_fit.LikelihoodEngine(sds[1:2], cfg, opts)
+        assert single.arms[nm]['batch'].obs(npoly, True).shared_grid == 1
+        obj = np.repeat(np.arange(3), K)
+        rep = np.tile(np.arange(K), 3)
+        got = mixed.evaluate(obj, ev[rep, 0], ev[rep, 1:5], vs[rep])
+        got1 = single.evaluate(np.zeros(K, dtype=int), ev[:, 0], ev[:, 1:5], vs)
+        for j, (i, e) in enumerate(zip(obj, rep)):
+            want = oracle.get_chisq(osds[i], ev[e, 0], tuple(ev[e, 1:5]), (vs[e],), options=opts,
+                                    config=cfg)
+            assert abs(got[j] - want) < CHI_RTOL * abs(want), (npoly, i, e)
+            if i == 1:
+                assert abs(got1[e] - want) < CHI_RTOL * abs(want), (npoly, e)
+
+
 def test_locate_grid_bit_identical():
     """rvs_locate_grid reproduces the host vertex ids and weights bit for bit and
     flags exactly the points the host resolves through the KD-tree."""
