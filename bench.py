@@ -172,7 +172,8 @@ def run_gpu(args):
 
     def hot_path(eng):
         """The step body on a ready engine; returns a small result array."""
-        res = batch_fit.scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=timer)
+        res = batch_fit.scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=timer,
+                                           groups=args.groups)
         return res
 
     def step_resident(eng):
@@ -235,7 +236,7 @@ def run_gpu(args):
         narm = len(setups)
         evals = ksum['fused_items_per_launch'] * ksum['fused_launches'] / narm
         ach = beval * evals / (ksum['fused_ms_total'] * 1e-3) / 1e9
-        roof = dict(bound='hbm', kernel='slice_kernel + gram_kernel (rvs_chisq_fused)',
+        roof = dict(bound='hbm', kernel='rvs_chisq_fused: taps + chunk_kernel + gram_mma/solve/resid kernels',
                     achieved=ach, peak=hbm_peak, unit='GB/s', frac=ach / hbm_peak, traffic=None,
                     peak_source=peak_src, algorithmic_bytes_per_eval=beval,
                     evals_timed=evals, ms_total=ksum['fused_ms_total'],
@@ -253,7 +254,7 @@ def run_gpu(args):
                                f'{npt} template px, grid {w["layout"]} '
                                f'({setups[0]["dats"].shape[0]} nodes, fp32), npoly {w["npoly"]}',
                    'spectra_per_gpu_per_step': B, 'rv_trials': len(vgrid),
-                   'fit_evals_per_spectrum': args.evals,
+                   'fit_evals_per_spectrum': args.evals, 'lockstep_groups': args.groups,
                    'step': 'per spectrum: 1 RV-grid scan + fit_evals_per_spectrum '
                            'template-changing chi2 evaluations (count of one reference '
                            'process() call, SURVEY.md 8d)',
@@ -386,6 +387,8 @@ def main():
     ap.add_argument('--cpu-fraction', type=float, default=0.25,
                     help='fraction of the per-spectrum evaluations the CPU sample runs')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--groups', type=int, default=2,
+                    help='independent object groups stepped in ping-pong (host/GPU overlap)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -200,14 +200,14 @@ int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
  * object covers at that velocity is gathered.  vsini_max: upper bound of
  * d_vsini (sizes the tap buffer; 0 if d_vsini is NULL).  d_tn: workspace
  * [K, tn_stride] doubles, tn_stride >= the longest object.  d_work: workspace
- * of rvs_fused_workspace(K, tapcap) doubles, tapcap = ceil(vsini_max /
+ * (16-byte aligned) of rvs_fused_workspace(K, tapcap, knots->npix_t) doubles, tapcap = ceil(vsini_max /
  * (c lnstep) + 1) + 1 (0 when d_vsini is NULL or vsini_max <= 0).  Outputs chisq[K],
  * status[K] (template bits | RVS_ST_NOT_PD | RVS_ST_RANGE | RVS_ST_LIMIT).
  * Needs knots->ratio_dev < 1e-8 (exactly uniform or log-uniform knots) and
  * tapcap <= RVS_MAX_FUSED_TAPS, else RVS_E_LIMIT: use the general path.
  * rvs_fused_chunks: how many warps share one item. */
 int rvs_fused_chunks(int npix_t, int tapcap);
-int64_t rvs_fused_workspace(int K, int tapcap);
+int64_t rvs_fused_workspace(int K, int tapcap, int npix_t);
 int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld, const rvs_knots *knots,
                     const int32_t *d_ids, const double *d_w, int nvert, const double *d_vsini,
                     double vsini_max, int log_spec, const rvs_obs *obs, const int32_t *d_oix,

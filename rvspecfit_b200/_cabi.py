@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'librvs_b200.so')
+# RVS_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get('RVS_B200_LIB') or os.path.join(_HERE, 'librvs_b200.so')
 
 c_dp = ctypes.c_void_p
 c_i64 = ctypes.c_int64
@@ -73,7 +74,7 @@ SIGNATURES = {
                                c_dp, c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                c_dp]),
     'rvs_fused_chunks': (c_int, [c_int, c_int]),
-    'rvs_fused_workspace': (c_i64, [c_int, c_int]),
+    'rvs_fused_workspace': (c_i64, [c_int, c_int, c_int]),
     'rvs_chisq_fused': (c_int, [c_dp, c_int, c_i64, ctypes.POINTER(Knots), c_dp, c_dp, c_int,
                                 c_dp, c_dbl, c_int, ctypes.POINTER(Obs), c_dp, c_dp, c_int,
                                 c_dp, c_i64, c_dp, c_dp, c_dp, c_dp]),

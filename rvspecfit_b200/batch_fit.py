@@ -42,20 +42,30 @@ class KernelTimer:
         return out
 
 
-def scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=None):
+def scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=None, groups=2):
     """One pass of the hot path over the engine's objects: an RV-grid scan at
     the start parameters with find_best statistics, then len(tp) rounds of
-    optimiser-phase evaluations, each at new template parameters.  Returns
-    (B, 6): best_chi, best_vel, vel_err, skewness, kurtosis of the scan and the
-    smallest chi-square met in the evaluation rounds."""
+    optimiser-phase evaluations, each at new template parameters.  The objects
+    are stepped as `groups` independent groups in ping-pong (LikelihoodEngine.
+    submit / result): while the host digests the results of one group and
+    prepares its next trial points, the GPU works on the other.  Returns (B, 6):
+    best_chi, best_vel, vel_err, skewness, kurtosis of the scan and the smallest
+    chi-square met in the evaluation rounds."""
     B = eng.nobj
     obj = np.arange(B)
     eng.timer = timer
     chi = eng.evaluate(obj, np.tile(vgrid, (B, 1)), start, None)
     st, _ = spec_fit.scan_stats(np.tile(vgrid, (B, 1)), chi[:, None, :])
     best = np.full(B, np.inf)
+    parts = [p for p in np.array_split(obj, max(1, min(groups, B))) if len(p)]
+    pending = []
     for e in range(len(tp)):
-        c = eng.evaluate(obj, tv[e], tp[e], tvs[e])
-        best = np.minimum(best, c)
+        for p in parts:
+            if len(pending) >= len(parts):
+                q, h = pending.pop(0)
+                best[q] = np.minimum(best[q], h.result())
+            pending.append((p, eng.submit(p, tv[e][p], tp[e][p], tvs[e][p])))
+    for q, h in pending:
+        best[q] = np.minimum(best[q], h.result())
     eng.timer = None
     return np.concatenate([st[:, :5], best[:, None]], axis=1)

@@ -36,9 +36,18 @@ namespace rvs {
 constexpr int CK_WARPS = 4;
 constexpr int CK_THREADS = CK_WARPS * 32;
 constexpr int CK_NT = 32;  // rows next to knot 0 with tabulated pivots
-constexpr int CK_MINB = 6;  // resident CTAs per SM the register budget allows
+#ifndef RVS_CK_RING
+#define RVS_CK_RING 8
+#endif
+constexpr int CK_RING = RVS_CK_RING;  // slots (of 512 B) of the gather prefetch ring
+#ifndef RVS_CK_MINB
+#define RVS_CK_MINB 6
+#endif
+constexpr int CK_MINB = RVS_CK_MINB;  // resident CTAs per SM the register budget allows
 struct TrueTag { static constexpr bool value = true; };
 struct FalseTag { static constexpr bool value = false; };
+template <int N>
+struct IntTag { static constexpr int value = N; };
 constexpr unsigned FULL = 0xffffffffu;
 
 struct ChunkArgs {
@@ -49,9 +58,12 @@ struct ChunkArgs {
   const int32_t *ids;
   const double *w;
   int nvert;
-  const double *taps;   // [K, tapstride] normalised one-sided weights (taps_kernel) or NULL
-  const int32_t *kmax;  // [K] number of one-sided taps (0: no broadening)
+  const double *taps;   // [K, tapstride] normalised one-sided weights (prep_kernel) or NULL
   int tapstride;
+  // per-item records written by prep_kernel
+  const double *rec;      // [K][2]  Doppler factor f, ln f (0 on linear knot grids)
+  const int32_t *irec;    // [K][4]  posmin, nk, S (chunks the item really has), kmax
+  const int32_t *pbound;  // [K][nch+1] first pixel of every chunk, pbound[S] = npix
   const double *lam_t, *hinv;
   int log_spec, log_step;
   double x0, xlast, q0, qstep_inv;
@@ -73,29 +85,51 @@ struct ChunkArgs {
   int K;
 };
 
-// one-sided, normalised rotation taps of every item (spec_fit.py:565-625)
-struct TapsArgs {
-  const double *vsini;
+// Per-item preparation, one warp per item: Doppler factor, the knot range the
+// object covers at that velocity and its split into chunks, the first pixel of
+// every chunk, range / capacity status, and the one-sided normalised rotation
+// taps (spec_fit.py:565-625).  Everything a chunk warp would otherwise recompute
+// 32-fold per chunk.
+struct PrepArgs {
+  const double *vsini;  // may be NULL
   double lnstep;
   int tapcap, tapstride, K;
   double *taps;
-  int32_t *kmax;
+  // geometry
+  const double *lam_t;
+  int npix_t, log_step;
+  double x0, xlast, q0, qstep_inv, qstep;
+  const double *lam, *loglam;
+  const int64_t *off, *goff;
+  const int32_t *oix;
+  const double *vels;
+  int nch, C;
+  double *rec;
+  int32_t *irec, *pbound;
   int32_t *status;
 };
 
-__global__ void __launch_bounds__(128) taps_kernel(TapsArgs a) {
+__global__ void __launch_bounds__(128) prep_kernel(PrepArgs a) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= a.K) return;
-  const double vs = a.vsini[k];
-  int kmax = 0;
+  int32_t *irec = a.irec + (int64_t)k * 4;
+  const int obj = a.oix[k];
+  if (obj < 0) {  // no spectrum in this setup: no chunks
+    if (lane < 4) irec[lane] = 0;
+    if (lane == 0) a.status[k] = 0;
+    return;
+  }
+  // ---- rotation taps
+  int kmax = 0, st0 = 0;
+  const double vs = a.vsini ? a.vsini[k] : 0.0;
   if (vs > 0) {
     const double R = (vs / RVS_C_KMS) / a.lnstep;
     if (R >= 1e-9) {
       kmax = (int)ceil(R + 1);
       if (kmax > a.tapcap) {
         kmax = a.tapcap;
-        if (lane == 0) atomicOr(a.status + k, RVS_ST_TAPS);
+        st0 |= RVS_ST_TAPS;
       }
       double *t = a.taps + (int64_t)k * a.tapstride;
       double part = 0;
@@ -109,7 +143,74 @@ __global__ void __launch_bounds__(128) taps_kernel(TapsArgs a) {
       for (int j = lane; j <= kmax; j += 32) t[j] = t[j] / tot;
     }
   }
-  if (lane == 0) a.kmax[k] = kmax;
+  // ---- geometry
+  const int n = a.npix_t;
+  const int64_t p0 = a.off[obj];
+  const int npix = (int)(a.off[obj + 1] - p0);
+  const int64_t gp0 = a.goff[obj];
+  const double *lam = a.lam + gp0, *ql = (a.log_step ? a.loglam : a.lam) + gp0;
+  const double beta = a.vels[k] / RVS_C_KMS;
+  const double f = sqrt((1 - beta) / (1 + beta));
+  const double qf = a.log_step ? log(f) : 0.0;
+  // knot interval of the rest-frame coordinate q (ln x or x)
+  auto pos_q = [&](double q) -> int {
+    const int pos = (int)((q - a.q0) * a.qstep_inv);
+    return max(0, min(pos, n - 2));
+  };
+  auto pos_of = [&](int p) -> int { return pos_q(a.log_step ? ql[p] + qf : lam[p] * f); };
+  const double lam_first = lam[0], lam_last = lam[npix - 1];
+  const double ql_first = a.log_step ? ql[0] : lam_first, ql_last = a.log_step ? ql[npix - 1] : lam_last;
+  const int posmin = pos_q(a.log_step ? ql_first + qf : lam_first * f);
+  const int posmax = pos_q(a.log_step ? ql_last + qf : lam_last * f);
+  const int nk = posmax + 1 - posmin;
+  const int S = min(a.nch, (nk + a.C - 1) / a.C);  // chunks this item really has
+  if (lane == 0) {
+    // the reference checks the first and last evaluation points (spliner.c:78-83)
+    const double xa = lam_first * f, xb = lam_last * f;
+    int st = st0;
+    if (xa < a.x0 || xb < a.x0 || xa >= a.xlast || xb >= a.xlast) st |= RVS_ST_RANGE;
+    if ((int64_t)a.nch * a.C < nk) st |= RVS_ST_LIMIT;
+    a.status[k] = st;  // first kernel of the sequence: initialises the status word
+    a.rec[2 * (int64_t)k] = f;
+    a.rec[2 * (int64_t)k + 1] = qf;
+    irec[0] = posmin; irec[1] = nk; irec[2] = S; irec[3] = kmax;
+  }
+  // ---- first pixel of every chunk: the first pixel whose knot interval is >= c
+  // (pos is non-decreasing in p).  One lane per chunk boundary: a linear guess in
+  // ln lambda (exact to a pixel on uniform and log-uniform pixel grids), then a
+  // galloping bracket and a bisection, so any monotone pixel grid is handled.
+  auto first_px_with_pos_ge = [&](int c) -> int {
+    double gq;
+    if (a.log_step) gq = (a.q0 + c * a.qstep - qf - ql_first) / (ql_last - ql_first);
+    else gq = (__ldg(a.lam_t + c) / f - lam_first) / (lam_last - lam_first);
+    int g = (int)(gq * (npix - 1));
+    g = max(0, min(g, npix - 1));
+    int lo, hi;  // pos_of(lo) < c (or lo == -1), pos_of(hi) >= c (or hi == npix)
+    if (pos_of(g) >= c) {
+      hi = g;
+      int step = 1;
+      while (hi - step >= 0 && pos_of(hi - step) >= c) { hi -= step; step *= 2; }
+      lo = max(-1, hi - step);
+    } else {
+      lo = g;
+      int step = 1;
+      while (lo + step < npix && pos_of(lo + step) < c) { lo += step; step *= 2; }
+      hi = min(npix, lo + step);
+    }
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (pos_of(mid) >= c) hi = mid; else lo = mid;
+    }
+    return hi;
+  };
+  int32_t *pb = a.pbound + (int64_t)k * (a.nch + 1);
+  for (int s = lane; s <= S; s += 32) {
+    int v;
+    if (s == 0) v = 0;
+    else if (s == S) v = npix;
+    else v = first_px_with_pos_ge(posmin + (int)((int64_t)nk * s / S));
+    pb[s] = v;
+  }
 }
 
 // Scans over the warp of affine maps x -> A + B x.
@@ -161,39 +262,22 @@ __global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a)
   if (k >= a.K) return;
   double *B0 = sm + (size_t)wid * 2 * a.wcap, *B1 = B0 + a.wcap;
   const int n = a.npix_t;
+  const int4 ir = __ldg(reinterpret_cast<const int4 *>(a.irec) + k);  // posmin, nk, S, kmax
+  const int posmin = ir.x, nk = ir.y, S = ir.z;
+  if (s >= S) return;
+  const int c0 = posmin + (int)((int64_t)nk * s / S), c1 = posmin + (int)((int64_t)nk * (s + 1) / S);
+  if (c1 <= c0) return;
+  const int kmax = ir.w;
   const int obj = a.oix[k];
-  if (obj < 0) return;  // the object has no spectrum in this setup
   const int64_t p0 = a.off[obj];
-  const int npix = (int)(a.off[obj + 1] - p0);
   const int64_t gp0 = a.goff[obj];
   const double *lam = a.lam + gp0, *ql = (a.log_step ? a.loglam : a.lam) + gp0;
-  const double beta = a.vels[k] / RVS_C_KMS;
-  const double f = sqrt((1 - beta) / (1 + beta));
-  const double qf = a.log_step ? log(f) : 0.0;
-  // knot interval of the rest-frame coordinate q (ln x or x)
+  const double2 fq = __ldg(reinterpret_cast<const double2 *>(a.rec) + k);
+  const double f = fq.x, qf = fq.y;
   auto pos_q = [&](double q) -> int {
     const int pos = (int)((q - a.q0) * a.qstep_inv);
     return max(0, min(pos, n - 2));
   };
-  auto pos_of = [&](int p) -> int { return pos_q(a.log_step ? ql[p] + qf : lam[p] * f); };
-  const double lam_first = lam[0], lam_last = lam[npix - 1];
-  const double ql_first = a.log_step ? ql[0] : lam_first, ql_last = a.log_step ? ql[npix - 1] : lam_last;
-  const int posmin = pos_q(a.log_step ? ql_first + qf : lam_first * f);
-  const int posmax = pos_q(a.log_step ? ql_last + qf : lam_last * f);
-  const int nk = posmax + 1 - posmin;
-  const int S = min(a.nch, (nk + a.C - 1) / a.C);  // chunks this item really has
-  if (s == 0 && lane == 0) {
-    // the reference checks the first and last evaluation points (spliner.c:78-83)
-    const double xa = lam_first * f, xb = lam_last * f;
-    int st = 0;
-    if (xa < a.x0 || xb < a.x0 || xa >= a.xlast || xb >= a.xlast) st |= RVS_ST_RANGE;
-    if ((int64_t)a.nch * a.C < nk) st |= RVS_ST_LIMIT;
-    if (st) atomicOr(a.status + k, st);
-  }
-  if (s >= S) return;
-  const int c0 = posmin + (int)((int64_t)nk * s / S), c1 = posmin + (int)((int64_t)nk * (s + 1) / S);
-  if (c1 <= c0) return;
-  const int kmax = a.kmax ? a.kmax[k] : 0;
   // knot windows (global indices, inclusive): Y on [ya0, ya1], raw y on [ya0-kmax, ya1+kmax]
   // which may stick out of the template: those knots are the zero padding of the
   // reference's 'same' convolution (spec_fit.py:677-680)
@@ -214,45 +298,9 @@ __global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a)
   __syncwarp();
   if (f32row && lane >= 1 && lane < a.nvert) { s_off[wid][lane] = s_off[wid][0]; s_w[wid][lane] = 0; }
   __syncwarp();
-  // ---- pixel range [plo, phi) of the chunk: first pixel whose knot interval is
-  // >= c.  pos is non-decreasing in p.  A linear guess in lambda and in ln lambda,
-  // checked on 16 pixels each, settles uniform and log-uniform pixel grids in
-  // one round of loads; anything else takes the 32-way search.
-  auto first_px_with_pos_ge = [&](int c) -> int {
-    const double xt = __ldg(a.lam_t + c) / f;  // observed wavelength that lands on knot c
-    const double gl = (xt - lam_first) / (lam_last - lam_first);
-    const double gq = a.log_step ? (log(xt) - ql_first) / (ql_last - ql_first) : gl;
-    const int guess = (int)((lane < 16 ? gl : gq) * (npix - 1));
-    const int pt = guess - 7 + (lane & 15);  // candidates guess-7 .. guess+8
-    const bool inside = pt >= 0 && pt < npix;
-    const bool less = pt < 0 || (inside && pos_of(pt) < c);
-    const unsigned mless = __ballot_sync(FULL, less);
-    // `less` is a prefix of each half-window (virtual pixels < 0 count as less,
-    // >= npix as not less): a half settles the answer when the transition is inside
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int cnt = __popc((mless >> (16 * h)) & 0xffffu);
-      const int g0 = __shfl_sync(FULL, guess, 16 * h);
-      if (cnt > 0 && cnt < 16) return min(npix, max(0, g0 - 7 + cnt));
-      if (cnt == 0 && g0 - 7 <= 0) return 0;
-      if (cnt == 16 && g0 + 8 >= npix - 1) return npix;
-    }
-    int lo = 0, hi = npix;  // pos_of(p) < c for p < lo ; pos_of(p) >= c for p >= hi
-    while (hi > lo) {
-      const int span = hi - lo;
-      const int pp = lo + (int)(((int64_t)span * lane) >> 5);
-      const unsigned ml = __ballot_sync(FULL, pos_of(pp) < c);
-      const int nf = __popc(ml);
-      if (nf == 0) { hi = lo; break; }
-      const int lo2 = lo + (int)(((int64_t)span * (nf - 1)) >> 5) + 1;
-      const int hi2 = nf == 32 ? hi : lo + (int)(((int64_t)span * nf) >> 5);
-      lo = lo2;
-      hi = hi2;
-    }
-    return lo;
-  };
-  const int plo = (s == 0) ? 0 : first_px_with_pos_ge(c0);
-  const int phi = (s == S - 1) ? npix : first_px_with_pos_ge(c1);
+  // ---- pixel range [plo, phi) of the chunk (prep_kernel)
+  const int plo = __ldg(a.pbound + (int64_t)k * (a.nch + 1) + s);
+  const int phi = __ldg(a.pbound + (int64_t)k * (a.nch + 1) + s + 1);
   // bring what the resampling will read into L1 while the gather is in flight
   {
     const double *einv = a.einv + p0;
@@ -268,49 +316,36 @@ __global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a)
   }
   int flag = 0;
   // ---- gather + exp over the window: B0[i] = y at knot w0 + i (0 outside the template)
+  // The rows stream through a register-free prefetch ring: every lane keeps
+  // CK_RING 16-byte cp.async copies (L2 -> shared, bypassing L1 and the register
+  // file) in flight, one per (column block, row) in consumption order, into its own
+  // 16 bytes of each ring slot -- a lane only ever reads what it copied itself,
+  // so no barrier is involved -- and issues the next copy as soon as it has
+  // accumulated a slot.  Loads therefore stay in flight during the widening, the
+  // FMAs and the exp, and cost no registers.  The ring lives in B1, which the
+  // later stages only use after the gather.
   {
     constexpr int VEC = RowLoader<GT>::VEC;
+    using Raw = typename RowLoader<GT>::Raw;
     const bool round32 = f32row && sizeof(GT) == 4 && a.log_spec;
     const GT *base = static_cast<const GT *>(a.grid);
     const int nv = NV > 0 ? NV : a.nvert;
-    for (int i0 = lane * VEC; i0 < W0; i0 += 32 * VEC) {
-      const int g = w0 + i0;  // multiple of VEC
-      double acc[4] = {0, 0, 0, 0};
-      if (g >= 0 && g < a.ld) {
-        const GT *col = base + g;
-        if (NV > 0) {
-          constexpr int HALF = NV > 8 ? (NV + 1) / 2 : (NV > 0 ? NV : 1);
-          {
-            double r[HALF][4];
-#pragma unroll
-            for (int j = 0; j < HALF; j++) RowLoader<GT>::load(col + s_off[wid][j], 0, r[j]);
-#pragma unroll
-            for (int j = 0; j < HALF; j++) {
-              const double wj = s_w[wid][j];
-#pragma unroll
-              for (int e = 0; e < VEC; e++) acc[e] = fma(wj, r[j][e], acc[e]);
-            }
-          }
-          if (HALF < NV) {
-            double r[NV - HALF > 0 ? NV - HALF : 1][4];
-#pragma unroll
-            for (int j = HALF; j < NV; j++) RowLoader<GT>::load(col + s_off[wid][j], 0, r[j - HALF]);
-#pragma unroll
-            for (int j = HALF; j < NV; j++) {
-              const double wj = s_w[wid][j];
-#pragma unroll
-              for (int e = 0; e < VEC; e++) acc[e] = fma(wj, r[j - HALF][e], acc[e]);
-            }
-          }
-        } else {
-          for (int j = 0; j < nv; j++) {
-            double r[4];
-            RowLoader<GT>::load(col + s_off[wid][j], 0, r);
-            const double wj = s_w[wid][j];
-#pragma unroll
-            for (int e = 0; e < VEC; e++) acc[e] = fma(wj, r[e], acc[e]);
-          }
-        }
+    char *ring = reinterpret_cast<char *>(B1) + lane * 16;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    auto in_grid = [&](int i0) -> bool {
+      const int g = w0 + i0;
+      return i0 < W0 && g >= 0 && g < a.ld;
+    };
+    // CK_RING divides the row count (or equals it), so with the rows unrolled every
+    // slot index is a compile-time constant and there is no ring bookkeeping
+    constexpr int RG = NV > 0 ? (NV % CK_RING == 0 ? CK_RING : NV) : CK_RING;
+    static_assert(RG <= CK_RING, "row count must fit the ring or be a multiple of it");
+    auto copy16 = [&](int slot_i, const GT *src) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_s + slot_i * 512), "l"(src) : "memory");
+    };
+    auto commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+    auto finish = [&](double (&acc)[4], int g, bool have, int i0) {
+      if (have) {
 #pragma unroll
         for (int e = 0; e < VEC; e++) {
           double y = a.log_spec ? exp(acc[e]) : acc[e];
@@ -323,7 +358,77 @@ __global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a)
 #pragma unroll
       for (int e = 0; e < VEC; e += 2)
         *reinterpret_cast<double2 *>(B0 + i0 + e) = make_double2(acc[e], acc[e + 1]);
+    };
+    if (NV > 0) {
+      // prologue: rows 0 .. RG-2 of the lane's first column block
+      {
+        const bool have0 = in_grid(lane * VEC);
+        const GT *col = base + (w0 + lane * VEC);
+#pragma unroll
+        for (int u = 0; u < RG - 1; u++) {
+          if (have0) copy16(u, col + s_off[wid][u]);
+          commit();
+        }
+      }
+      for (int i0 = lane * VEC; i0 < W0; i0 += 32 * VEC) {
+        const int g = w0 + i0;  // multiple of VEC
+        double acc[4] = {0, 0, 0, 0};
+        const bool have = in_grid(i0), have_next = in_grid(i0 + 32 * VEC);
+        const GT *col = base + g, *col_next = col + 32 * VEC;
+#pragma unroll
+        for (int row = 0; row < NV; row++) {
+          // copy number (row + RG - 1) of the stream goes into the slot freed last
+          {
+            const int ahead = row + RG - 1;
+            if (ahead < NV) { if (have) copy16(ahead % RG, col + s_off[wid][ahead]); }
+            else if (have_next) copy16(ahead % RG, col_next + s_off[wid][ahead - NV]);
+            commit();
+          }
+          asm volatile("cp.async.wait_group %0;" ::"n"(RG - 1) : "memory");
+          if (have) {
+            const Raw v = *reinterpret_cast<const Raw *>(ring + (row % RG) * 512);
+            double r[4];
+            RowLoader<GT>::widen(v, r);
+            const double wj = s_w[wid][row];
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc[e] = fma(wj, r[e], acc[e]);
+          }
+        }
+        finish(acc, g, have, i0);
+      }
+    } else {
+      // generic row count: running ring counters
+      int is_i0 = lane * VEC, is_row = 0, is_slot = 0;
+      auto issue = [&]() {
+        if (in_grid(is_i0)) copy16(is_slot, base + (w0 + is_i0) + s_off[wid][is_row]);
+        commit();
+        if (++is_row == nv) { is_row = 0; is_i0 += 32 * VEC; }
+        if (++is_slot == CK_RING) is_slot = 0;
+      };
+#pragma unroll
+      for (int u = 0; u < CK_RING - 1; u++) issue();
+      int slot = 0;
+      for (int i0 = lane * VEC; i0 < W0; i0 += 32 * VEC) {
+        const int g = w0 + i0;
+        double acc[4] = {0, 0, 0, 0};
+        const bool have = in_grid(i0);
+        for (int row = 0; row < nv; row++) {
+          issue();
+          asm volatile("cp.async.wait_group %0;" ::"n"(CK_RING - 1) : "memory");
+          if (have) {
+            const Raw v = *reinterpret_cast<const Raw *>(ring + slot * 512);
+            double r[4];
+            RowLoader<GT>::widen(v, r);
+            const double wj = s_w[wid][row];
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc[e] = fma(wj, r[e], acc[e]);
+          }
+          if (++slot == CK_RING) slot = 0;
+        }
+        finish(acc, g, have, i0);
+      }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncwarp();
   // ---- rotational broadening onto [ya0, ya1]
@@ -333,10 +438,33 @@ __global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a)
     const double t0 = __ldg(taps);
     const double *src = B0 + (ya0 - w0);
     const int WY = ya1 - ya0 + 1;
-    for (int j = lane; j < WY; j += 32) {
-      double sum = t0 * src[j];
-      for (int t = 1; t <= kmax; t++) sum = fma(__ldg(taps + t), src[j - t] + src[j + t], sum);
-      B1[j] = sum;
+    // short kernels (the usual case: kmax = ceil(R + 1) is 2..4 for vsini up to
+    // ~100 km/s on a DESI-like grid) keep their taps in registers
+    auto conv_small = [&](auto kt) {
+      constexpr int KT = decltype(kt)::value;
+      double tp[KT];
+#pragma unroll
+      for (int t = 0; t < KT; t++) tp[t] = __ldg(taps + 1 + t);
+      for (int j = lane; j < WY; j += 32) {
+        double sum = t0 * src[j];
+#pragma unroll
+        for (int t = 1; t <= KT; t++) sum = fma(tp[t - 1], src[j - t] + src[j + t], sum);
+        B1[j] = sum;
+      }
+    };
+    switch (kmax) {
+      case 1: conv_small(IntTag<1>{}); break;
+      case 2: conv_small(IntTag<2>{}); break;
+      case 3: conv_small(IntTag<3>{}); break;
+      case 4: conv_small(IntTag<4>{}); break;
+      case 5: conv_small(IntTag<5>{}); break;
+      case 6: conv_small(IntTag<6>{}); break;
+      default:
+        for (int j = lane; j < WY; j += 32) {
+          double sum = t0 * src[j];
+          for (int t = 1; t <= kmax; t++) sum = fma(__ldg(taps + t), src[j - t] + src[j + t], sum);
+          B1[j] = sum;
+        }
     }
     __syncwarp();
     Y = B1;
@@ -401,19 +529,30 @@ __global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a)
   };
   if (kr0 < CK_NT) solve(TrueTag{}); else solve(FalseTag{});
   __syncwarp();
-  // ---- resample onto the chunk's pixels
+  // ---- resample onto the chunk's pixels, two pixels per lane and step with all
+  // loads of a step issued before any is used
   const double *einv = a.einv + p0;
   double *tn = a.tn + (int64_t)k * a.tn_stride;
-  for (int p = plo + lane; p < phi; p += 32) {
-    const double lp = lam[p];
-    const double x = lp * f;
-    const int pos = pos_q(a.log_step ? ql[p] + qf : x);
+  auto value_at = [&](double x, int pos, double xl, double hi) -> double {
     const int j = pos - ya0;
     const double y0v = Y[j], y1v = Y[j + 1];
     const double s0 = Dz[pos - 1 - kr0], s1 = Dz[pos - kr0] * a.r2inv;
-    const double u = (x - __ldg(a.lam_t + pos)) * __ldg(a.hinv + pos), v = 1.0 - u;
-    const double t = fma(u, fma(s1, fma(u, u, -1.0), y1v), v * fma(s0, fma(v, v, -1.0), y0v));
-    tn[p] = t * einv[p];
+    const double u = (x - xl) * hi, v = 1.0 - u;
+    return fma(u, fma(s1, fma(u, u, -1.0), y1v), v * fma(s0, fma(v, v, -1.0), y0v));
+  };
+  for (int pa = plo + lane; pa < phi; pa += 64) {
+    const int pb = pa + 32;
+    const bool two = pb < phi;
+    const int pbs = two ? pb : pa;
+    const double la = lam[pa], lb = lam[pbs];
+    const double qa = a.log_step ? ql[pa] : 0.0, qb = a.log_step ? ql[pbs] : 0.0;
+    const double ea = einv[pa], eb = einv[pbs];
+    const double xa = la * f, xb = lb * f;
+    const int posa = pos_q(a.log_step ? qa + qf : xa), posb = pos_q(a.log_step ? qb + qf : xb);
+    const double xla = __ldg(a.lam_t + posa), xlb = __ldg(a.lam_t + posb);
+    const double hia = __ldg(a.hinv + posa), hib = __ldg(a.hinv + posb);
+    tn[pa] = value_at(xa, posa, xla, hia) * ea;
+    if (two) tn[pb] = value_at(xb, posb, xlb, hib) * eb;
   }
   if (flag) atomicOr(a.status + k, flag);  // per lane: rare
 }

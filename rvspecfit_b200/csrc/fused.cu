@@ -3,6 +3,8 @@
 // stage B (gram_kernel.cuh: continuum solve -> chi-square).  The spline never
 // goes to HBM; the only intermediate is T/sigma (8 bytes per observed pixel,
 // L2-resident between the two stages).
+#include <algorithm>
+
 #include "chunk_kernel.cuh"
 #include "gram_kernel.cuh"
 #include "gram_mma.cuh"
@@ -40,9 +42,26 @@ extern "C" int rvs_fused_chunks(int npix_t, int tapcap) {
   return (npix_t + C - 1) / C;
 }
 
-extern "C" int64_t rvs_fused_workspace(int K, int tapcap) {
-  // doubles: taps [K, tapcap+1], kmax (int32) [K], scratch of the Gram GEMM pair
-  return (int64_t)K * (tapcap + 1) + (K + 1) / 2 + rvs::GramScratch(K).total();
+namespace rvs {
+// Layout of d_work (doubles): taps [K][tapcap+1] | rec [K][2] | irec (int32) [K][4] |
+// pbound (int32) [K][nch+1] | scratch of the Gram GEMM kernels.  Every section
+// starts 16-byte aligned.
+struct FusedWork {
+  int64_t taps, rec, irec, pbound, gram, total;
+  FusedWork(int64_t K, int tapcap, int nch) {
+    auto even = [](int64_t v) { return (v + 1) & ~int64_t(1); };
+    taps = 0;
+    rec = taps + even(K * (tapcap + 1));
+    irec = rec + 2 * K;
+    pbound = irec + 2 * K;
+    gram = pbound + even((K * (nch + 1) + 1) / 2);
+    total = gram + GramScratch(K).total();
+  }
+};
+}  // namespace rvs
+
+extern "C" int64_t rvs_fused_workspace(int K, int tapcap, int npix_t) {
+  return rvs::FusedWork(K, tapcap, rvs_fused_chunks(npix_t, tapcap)).total;
 }
 
 extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
@@ -75,18 +94,29 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
               "rvs_template_build + rvs_chisq_scan", vsini_max, tapcap, RVS_MAX_FUSED_TAPS);
   RVS_REQUIRE(d_work, RVS_E_ARG, "rvs_chisq_fused: d_work is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  RVS_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * K, st));
+  RVS_REQUIRE(((uintptr_t)d_work & 15) == 0, RVS_E_ARG, "rvs_chisq_fused: d_work alignment");
   ChunkArgs a;
-  a.taps = nullptr; a.kmax = nullptr; a.tapstride = tapcap + 1;
-  if (tapcap > 0) {
-    TapsArgs t;
-    t.vsini = d_vsini; t.lnstep = knots->lnstep; t.tapcap = tapcap; t.tapstride = tapcap + 1;
-    t.K = K; t.taps = d_work;
-    t.kmax = reinterpret_cast<int32_t *>(d_work + (int64_t)K * (tapcap + 1));
-    t.status = d_status;
-    taps_kernel<<<(K + 3) / 4, 128, 0, st>>>(t);
+  a.C = chunk_knots(tapcap);
+  a.nch = (n + a.C - 1) / a.C;
+  const FusedWork fw(K, tapcap, a.nch);
+  a.tapstride = tapcap + 1;
+  a.taps = d_work + fw.taps;
+  a.rec = d_work + fw.rec;
+  a.irec = reinterpret_cast<int32_t *>(d_work + fw.irec);
+  a.pbound = reinterpret_cast<int32_t *>(d_work + fw.pbound);
+  {
+    PrepArgs t;
+    t.vsini = tapcap > 0 ? d_vsini : nullptr; t.lnstep = knots->lnstep; t.tapcap = tapcap;
+    t.tapstride = tapcap + 1; t.K = K; t.taps = d_work + fw.taps;
+    t.lam_t = knots->d_lam_t; t.npix_t = n; t.log_step = knots->log_step; t.x0 = knots->x0;
+    t.xlast = knots->xlast; t.q0 = knots->q0; t.qstep_inv = knots->qstep_inv;
+    t.qstep = 1.0 / knots->qstep_inv;
+    t.lam = obs->d_lam; t.loglam = obs->d_loglam; t.off = obs->d_off; t.goff = obs->d_goff;
+    t.oix = d_oix; t.vels = d_vels; t.nch = a.nch; t.C = a.C;
+    t.rec = d_work + fw.rec; t.irec = reinterpret_cast<int32_t *>(d_work + fw.irec);
+    t.pbound = reinterpret_cast<int32_t *>(d_work + fw.pbound); t.status = d_status;
+    prep_kernel<<<(K + 3) / 4, 128, 0, st>>>(t);
     RVS_LAUNCH_OK();
-    a.taps = t.taps; a.kmax = t.kmax;
   }
   a.grid = d_grid; a.ld = ld; a.npix_t = n; a.ids = d_ids; a.w = d_w; a.nvert = nvert;
   a.lam_t = knots->d_lam_t; a.hinv = knots->d_hinv; a.log_spec = log_spec;
@@ -108,9 +138,8 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
   a.goff = obs->d_goff;
   a.oix = d_oix; a.vels = d_vels; a.tn = d_tn; a.tn_stride = tn_stride; a.status = d_status;
   a.K = K;
-  a.C = chunk_knots(tapcap);
-  a.nch = (n + a.C - 1) / a.C;
   a.wcap = (a.C + 2 * (SPL_HALO + 3 + tapcap) + 12 + 3) & ~3;
+  a.wcap = std::max(a.wcap, CK_RING * 512 / 8);  // the gather's prefetch ring lives in one buffer
   const size_t smem = sizeof(double) * 2 * (size_t)a.wcap * CK_WARPS;
   RVS_REQUIRE(smem <= 200 * 1024, RVS_E_LIMIT, "rvs_chisq_fused: window needs %zu B smem", smem);
   if (grid_f64) rc = launch_chunk_one<double, 0>(a, smem, st);
@@ -125,7 +154,7 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
     m.off = obs->d_off; m.goff = obs->d_goff; m.oix = d_oix; m.P = obs->d_P; m.npp = obs->npp;
     m.K = K; m.KS = 1; m.chisq = d_chisq; m.status = d_status;
     const GramScratch gs(K);
-    double *w = d_work + (int64_t)K * (tapcap + 1) + (K + 1) / 2;
+    double *w = d_work + fw.gram;
     m.part = w; w += gs.part();
     m.coef = w; w += gs.coef();
     m.logdet = w; w += gs.logdet();

@@ -33,7 +33,6 @@ static int launch_gram_mma_np(GramMmaArgs a, cudaStream_t st) {
               a.npp, (NP + 1) & ~1);
   const int groups = (a.K + NI - 1) / NI;
   a.KS = std::min(GM_MAX_KS, std::max(1, (512 + groups - 1) / groups));
-  RVS_CUDA_OK(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned) * groups, st));
   dim3 grid(groups, a.KS);
   gram_mma_kernel<NP, NT><<<grid, GM_THREADS, 0, st>>>(a);
   RVS_LAUNCH_OK();

@@ -216,6 +216,9 @@ __global__ void __launch_bounds__(GM_THREADS) gram_solve_kernel(GramMmaArgs a) {
   __shared__ double sM[GM_WARPS][TL::NTRI];
   __shared__ double sV[GM_WARPS][NP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // tickets of resid_mma_kernel (launched next): one per group; this grid has at
+  // least as many CTAs as there are groups
+  if (threadIdx.x == 0 && blockIdx.x * NI < a.K) a.ticket[blockIdx.x] = 0;
   const int k = blockIdx.x * GM_WARPS + wid;
   if (k >= a.K) return;
   const int obj = a.oix[k];

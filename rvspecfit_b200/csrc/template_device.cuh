@@ -66,6 +66,10 @@ struct RowLoader;
 template <>
 struct RowLoader<float> {
   static constexpr int VEC = 4;
+  using Raw = float4;
+  __device__ static void widen(const Raw &v, double out[4]) {
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  }
   __device__ static void load(const float *row, int q, double out[4]) {
     const float4 v = ldg_stream_f4(reinterpret_cast<const float4 *>(row) + q);
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
@@ -75,6 +79,10 @@ struct RowLoader<float> {
 template <>
 struct RowLoader<double> {
   static constexpr int VEC = 2;
+  using Raw = double2;
+  __device__ static void widen(const Raw &v, double out[4]) {
+    out[0] = v.x; out[1] = v.y;
+  }
   __device__ static void load(const double *row, int q, double out[4]) {
     const double2 v = __ldg(reinterpret_cast<const double2 *>(row) + q);
     out[0] = v.x; out[1] = v.y;

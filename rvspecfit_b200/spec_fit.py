@@ -54,6 +54,7 @@ class SpectrumBatch:
     def __init__(self, specdatas):
         self.n = len(specdatas)
         self.npix = np.array([len(s.lam) for s in specdatas], dtype=np.int64)
+        self.max_npix = int(self.npix.max())
         self.off = np.concatenate([[0], np.cumsum(self.npix)]).astype(np.int64)
         self.lam0 = np.array([s.lam[0] for s in specdatas])
         self.lam1 = np.array([s.lam[-1] for s in specdatas])
@@ -123,6 +124,25 @@ class SpectrumBatch:
         o.npoly, o.npp, o.nobj = int(npoly), npp, self.n
         o.shared_grid = int(len(self.grid_first) == 1)
         return o
+
+
+class PendingEval:
+    """Handle of a LikelihoodEngine.submit() call."""
+
+    def result(self):
+        eng, obj, vels, params, vs, outside_penalty, espec_systematic, raise_errors = self.args
+        if self.slot is None:
+            return eng._evaluate_general(obj, vels, params, vs, outside_penalty,
+                                         espec_systematic, False, raise_errors)
+        total, redo = eng._collect_fast(self.slot, obj, vels)
+        self.slot = None
+        if redo.any():
+            r = np.nonzero(redo)[0]
+            eng.n_eval -= len(r)
+            total[r] = eng._evaluate_general(obj[r], vels[r], params[r],
+                                             None if vs is None else vs[r], outside_penalty,
+                                             espec_systematic, False, raise_errors)
+        return total
 
 
 def _overlap_ok(t0, t1, s0, s1, vmin, vmax):
@@ -230,7 +250,7 @@ class LikelihoodEngine:
             vmax = 0.0 if vs is None else float(np.max(vs, initial=0.0))
             stride = int(batch.npix.max())
             d_tn = self._workspace(k * stride)
-            nwork = L.rvs_fused_workspace(k, bank.tapcap(vmax))
+            nwork = L.rvs_fused_workspace(k, bank.tapcap(vmax), bank.npix_t)
             if getattr(self, '_work', None) is None or self._work.numel() < nwork:
                 self._work = _dev.empty((int(nwork * 1.25) + 64,), np.float64)
             d_work = self._work
@@ -296,27 +316,57 @@ class LikelihoodEngine:
             self._buf[name] = t
         return t[:n].view(*shape)
 
-    def _evaluate_fast(self, obj, vels, params, vsini, sys_errs):
+    NSLOT = 4      # evaluations that may be in flight at once (submit without result)
+
+    def _slot(self, K, narm, nd):
+        """Pinned host staging + device input buffers of one in-flight evaluation."""
+        torch = _dev.torch_mod()
+        if not hasattr(self, '_slots'):
+            self._slots, self._slot_ix = [dict(K=0, busy=False) for _ in range(self.NSLOT)], -1
+        self._slot_ix = (self._slot_ix + 1) % self.NSLOT
+        sl = self._slots[self._slot_ix]
+        if sl['busy']:
+            raise RuntimeError(f'more than {self.NSLOT} evaluations in flight: call result() on '
+                               'the oldest PendingEval first')
+        if sl['K'] < K:
+            cap = int(K * 1.25) + 16
+            pin = dict(pin_memory=True)
+            sl.update(K=cap,
+                      h_in=torch.empty(((2 + nd) * cap,), dtype=torch.float64, **pin),
+                      h_oix=torch.empty((narm * cap,), dtype=torch.int32, **pin),
+                      h_chi=torch.empty((narm * cap,), dtype=torch.float64, **pin),
+                      h_flags=torch.empty((2 * narm * cap,), dtype=torch.int32, **pin),
+                      d_in=_dev.empty(((2 + nd) * cap,), np.float64),
+                      d_oix=_dev.empty((narm * cap,), np.int32),
+                      event=torch.cuda.Event())
+        return sl
+
+    def _submit_fast(self, obj, vels, params, vsini, sys_errs):
         """Optimiser-phase evaluation of K items at one velocity each with no
-        host work per item: one upload of (vel, vsini, mapped parameters), then
-        per arm vertex location, rotation taps, the fused template/resampling
-        kernel and the continuum solve, all stream-ordered; one download of the
-        per-arm chi-squares and flags.  Items that need anything else (off-grid
-        or missing-corner points, template not finite, normal matrix not PD,
-        velocity outside [min_vel, max_vel], template not covering the data)
-        come back flagged and are re-evaluated by the general path.
-        Returns (total (K,), redo (K,) bool)."""
+        host work per item and no host synchronisation: one asynchronous upload
+        of (vel, vsini, mapped parameters) from pinned memory, then per arm vertex
+        location, rotation taps, the fused template/resampling kernel and the
+        continuum solve, all stream-ordered; one asynchronous download of the
+        per-arm chi-squares and flags into pinned memory, and an event.  Items that
+        need anything else (off-grid or missing-corner points, template not
+        finite, normal matrix not PD, velocity outside [min_vel, max_vel],
+        template not covering the data) come back flagged and are re-evaluated by
+        the general path when the result is collected.  Returns the slot."""
         L = _cabi.lib()
         K = len(obj)
         narm = len(self.setups)
         bank0 = self.arms[self.setups[0]]['bank']
         nd = bank0.ndim
-        host_in = np.empty((2 + nd, K))
+        sl = self._slot(K, narm, nd)
+        host_in = sl['h_in'][:(2 + nd) * K].view(2 + nd, K).numpy()
         host_in[0] = vels
         host_in[1] = 0.0 if vsini is None else vsini
         host_in[2:] = spec_inter.map_params(params, bank0.log_ids).T
-        d_in = _dev.upload(host_in, np.float64)
-        d_oix = _dev.upload(self._oix[:, obj], np.int32)
+        sl['h_oix'][:narm * K].view(narm, K).numpy()[...] = self._oix[:, obj]
+        d_in = sl['d_in'][:(2 + nd) * K].view(2 + nd, K)
+        d_oix = sl['d_oix'][:narm * K].view(narm, K)
+        d_in.copy_(sl['h_in'][:(2 + nd) * K].view(2 + nd, K), non_blocking=True)
+        d_oix.copy_(sl['h_oix'][:narm * K].view(narm, K), non_blocking=True)
         vmax = 0.0 if vsini is None else float(np.max(vsini, initial=0.0))
         d_chi = self._scratch('chi', (narm, K), np.float64)
         d_flags = self._scratch('flags', (2, narm, K), np.int32)
@@ -334,9 +384,9 @@ class LikelihoodEngine:
             rc = L.rvs_locate_grid(ctypes.byref(bank.gridmap), _dev.ptr(q), K, K, _dev.ptr(d_ids),
                                    _dev.ptr(d_w), _dev.ptr(d_flags[1, a]), stream)
             _cabi.check(rc, 'rvs_locate_grid')
-            stride = int(batch.npix.max())
+            stride = batch.max_npix
             d_tn = self._scratch('tn', (K * stride,), np.float64)
-            d_work = self._scratch('work', (L.rvs_fused_workspace(K, bank.tapcap(vmax)),),
+            d_work = self._scratch('work', (L.rvs_fused_workspace(K, bank.tapcap(vmax), bank.npix_t),),
                                    np.float64)
             t0 = self.timer.start() if self.timer else None
             rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
@@ -348,12 +398,50 @@ class LikelihoodEngine:
             _cabi.check(rc, 'rvs_chisq_fused')
             if t0 is not None:
                 self.timer.stop('fused', t0, K)
-        chi = _dev.download(d_chi)
-        flags = _dev.download(d_flags)
+        sl['h_chi'][:narm * K].view(narm, K).copy_(d_chi, non_blocking=True)
+        sl['h_flags'][:2 * narm * K].view(2, narm, K).copy_(d_flags, non_blocking=True)
+        sl['event'].record()
+        sl['busy'] = True
+        return sl
+
+    def _collect_fast(self, sl, obj, vels):
+        """Wait for a submitted evaluation: (total (K,), redo (K,) bool)."""
+        K, narm = len(obj), len(self.setups)
+        sl['event'].synchronize()
+        chi = sl['h_chi'][:narm * K].view(narm, K).numpy()
+        flags = sl['h_flags'][:2 * narm * K].view(2, narm, K).numpy()
         redo = (flags != 0).any(axis=(0, 1)) | ~np.isfinite(chi).all(axis=0)
         redo |= ~self._cover0[obj] | (vels < self.config['min_vel']) | \
             (vels > self.config['max_vel'])
-        return np.add.reduce(chi, axis=0), redo
+        total = np.add.reduce(chi, axis=0)
+        sl['busy'] = False
+        return total, redo
+
+    def submit(self, obj, vels, params, vsini=None, outside_penalty=True,
+               espec_systematic=None, raise_errors=False):
+        """Asynchronous `evaluate` for one velocity per item: enqueues the work
+        and returns a PendingEval whose result() gives the chi-squares.  Up to
+        NSLOT evaluations may be in flight, so that a driver stepping several
+        groups of objects keeps the GPU busy while it digests results."""
+        obj = np.asarray(obj, dtype=np.int64)
+        params = np.array(params, dtype=np.float64, ndmin=2)
+        vels = np.asarray(vels, dtype=np.float64)
+        vs = None if vsini is None else np.asarray(vsini, dtype=np.float64)
+        fast = (vels.ndim == 1 and self.fused and self._fast_banks and len(obj) > 0
+                and (vs is None or
+                     all(self.arms[n]['bank'].tapcap(float(np.max(vs, initial=0.0)))
+                         <= _cabi.MAX_FUSED_TAPS for n in self.setups)))
+        pend = PendingEval()
+        pend.args = (self, obj, vels, params, vs, outside_penalty, espec_systematic, raise_errors)
+        pend.slot = None
+        if fast:
+            if isinstance(espec_systematic, dict):
+                sys_errs = [float(espec_systematic[n]) for n in self.setups]
+            else:
+                sys_errs = [float(espec_systematic or 0.0)] * len(self.setups)
+            self.n_eval += len(obj)
+            pend.slot = self._submit_fast(obj, vels, params, vs, sys_errs)
+        return pend
 
     def evaluate(self, obj, vels, params, vsini=None, outside_penalty=True,
                  espec_systematic=None, want_model=False, raise_errors=False):
@@ -365,24 +453,9 @@ class LikelihoodEngine:
         params = np.array(params, dtype=np.float64, ndmin=2)
         vels = np.asarray(vels, dtype=np.float64)
         flat = vels.ndim == 1
-        if (flat and self.fused and self._fast_banks and not want_model and len(obj) > 0
-                and (vsini is None or
-                     all(self.arms[n]['bank'].tapcap(float(np.max(vsini, initial=0.0)))
-                         <= _cabi.MAX_FUSED_TAPS for n in self.setups))):
-            if isinstance(espec_systematic, dict):
-                sys_errs = [float(espec_systematic[n]) for n in self.setups]
-            else:
-                sys_errs = [float(espec_systematic or 0.0)] * len(self.setups)
-            vs = None if vsini is None else np.asarray(vsini, dtype=np.float64)
-            self.n_eval += len(obj)
-            total, redo = self._evaluate_fast(obj, vels, params, vs, sys_errs)
-            if redo.any():
-                r = np.nonzero(redo)[0]
-                self.n_eval -= len(r)
-                total[r] = self._evaluate_general(
-                    obj[r], vels[r], params[r], None if vs is None else vs[r], outside_penalty,
-                    espec_systematic, False, raise_errors)
-            return total
+        if flat and not want_model:
+            return self.submit(obj, vels, params, vsini, outside_penalty, espec_systematic,
+                               raise_errors).result()
         return self._evaluate_general(obj, vels, params, vsini, outside_penalty,
                                       espec_systematic, want_model, raise_errors)
 
