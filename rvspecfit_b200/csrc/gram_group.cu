@@ -34,7 +34,8 @@ static int launch_gram_mma_np(GramMmaArgs a, cudaStream_t st) {
   const int groups = (a.K + NI - 1) / NI;
   a.KS = std::min(GM_MAX_KS, std::max(1, (512 + groups - 1) / groups));
   dim3 grid(groups, a.KS);
-  gram_mma_kernel<NP, NT><<<grid, GM_THREADS, 0, st>>>(a);
+  const size_t tile_smem = sizeof(double) * GM_WARPS * GM_TILE * a.npp;
+  gram_mma_kernel<NP, NT><<<grid, GM_THREADS, tile_smem, st>>>(a);
   RVS_LAUNCH_OK();
   gram_solve_kernel<NP, NT><<<(a.K + GM_WARPS - 1) / GM_WARPS, GM_THREADS, 0, st>>>(a);
   RVS_LAUNCH_OK();

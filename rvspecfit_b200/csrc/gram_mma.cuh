@@ -27,6 +27,7 @@ namespace rvs {
 constexpr int GM_WARPS = 4;
 constexpr int GM_THREADS = GM_WARPS * 32;
 constexpr int GM_MAX_KS = 16;
+constexpr int GM_TILE = 64;  // pixels of the basis staged per warp at a time (multiple of 8)
 
 struct GramMmaArgs {
   const double *tn;
@@ -121,7 +122,7 @@ __device__ __forceinline__ GroupGeom group_geom(const GramMmaArgs &a, int g) {
 }
 
 template <int NP, int NT>
-__global__ void __launch_bounds__(GM_THREADS) gram_mma_kernel(GramMmaArgs a) {
+__global__ void __launch_bounds__(GM_THREADS, NT == 2 ? 4 : 3) gram_mma_kernel(GramMmaArgs a) {
   using TL = GramTiles<NP>;
   constexpr int NI = 8 * NT;
   __shared__ double s_red[TL::ROWS][NI + 1];
@@ -165,37 +166,56 @@ __global__ void __launch_bounds__(GM_THREADS) gram_mma_kernel(GramMmaArgs a) {
     }
   };
   load_b(pbeg);
-  for (int p4 = pbeg; p4 < pend; p4 += 4) {
-    const int p = p4 + c;
-    const bool in = p < pend;
-    const double *Prow = Pb + (int64_t)(in ? p : 0) * a.npp;
-    double pa[TL::MT_M], pb[TL::MT_M], pv[TL::MT_V];
-#pragma unroll
-    for (int mt = 0; mt < TL::MT_M; mt++) {
-      pa[mt] = __ldg(Prow + ia[mt]);
-      pb[mt] = __ldg(Prow + ja[mt]);
+  // the basis rows of the warp's pixels go through a warp-private shared-memory
+  // tile (cp.async, 16-byte units; rows are npp = even doubles): the A fragments
+  // are then LDS with short, fixed latency instead of L1-path loads
+  extern __shared__ __align__(16) double s_tile[];
+  double *sP = s_tile + (size_t)wid * GM_TILE * a.npp;
+  const unsigned sP_s = (unsigned)__cvta_generic_to_shared(sP);
+  for (int t0 = pbeg; t0 < pend; t0 += GM_TILE) {
+    const int tile_n = min(GM_TILE, pend - t0);
+    __syncwarp();
+    {
+      const double *src = Pb + (int64_t)t0 * a.npp;
+      const int nvec = tile_n * a.npp / 2;
+      for (int v = lane; v < nvec; v += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sP_s + v * 16), "l"(src + 2 * v) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+    __syncwarp();
+    for (int p4 = t0; p4 < t0 + tile_n; p4 += 4) {
+      const int p = p4 + c;
+      const bool in = p < pend;
+      const double *Prow = sP + (in ? p - t0 : 0) * a.npp;
+      double pa[TL::MT_M], pb[TL::MT_M], pv[TL::MT_V];
 #pragma unroll
-    for (int mv = 0; mv < TL::MT_V; mv++) pv[mv] = __ldg(Prow + min(mv * 8 + r, NP - 1));
-    double bsq[NT], btd[NT];
+      for (int mt = 0; mt < TL::MT_M; mt++) {
+        pa[mt] = Prow[ia[mt]];
+        pb[mt] = Prow[ja[mt]];
+      }
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-      bsq[nt] = tq[nt] * tq[nt];
-      btd[nt] = tq[nt] * dq[nt];
-    }
-    load_b(p4 + 4);
+      for (int mv = 0; mv < TL::MT_V; mv++) pv[mv] = Prow[min(mv * 8 + r, NP - 1)];
+      double bsq[NT], btd[NT];
 #pragma unroll
-    for (int mt = 0; mt < TL::MT_M; mt++) {
-      const double av = (in && mt * 8 + r < TL::NTRI) ? pa[mt] * pb[mt] : 0.0;
+      for (int nt = 0; nt < NT; nt++) {
+        bsq[nt] = tq[nt] * tq[nt];
+        btd[nt] = tq[nt] * dq[nt];
+      }
+      load_b(p4 + 4);
 #pragma unroll
-      for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], av, bsq[nt]);
-    }
+      for (int mt = 0; mt < TL::MT_M; mt++) {
+        const double av = (in && mt * 8 + r < TL::NTRI) ? pa[mt] * pb[mt] : 0.0;
 #pragma unroll
-    for (int mv = 0; mv < TL::MT_V; mv++) {
-      const double av = (in && mv * 8 + r < NP) ? pv[mv] : 0.0;
+        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], av, bsq[nt]);
+      }
 #pragma unroll
-      for (int nt = 0; nt < NT; nt++)
-        dmma884(acc[TL::MT_M + mv][nt][0], acc[TL::MT_M + mv][nt][1], av, btd[nt]);
+      for (int mv = 0; mv < TL::MT_V; mv++) {
+        const double av = (in && mv * 8 + r < NP) ? pv[mv] : 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++)
+          dmma884(acc[TL::MT_M + mv][nt][0], acc[TL::MT_M + mv][nt][1], av, btd[nt]);
+      }
     }
   }
   // ---- cross-warp sum in fixed (warp) order, partial of this CTA to global
@@ -289,30 +309,48 @@ __global__ void __launch_bounds__(GM_THREADS) resid_mma_kernel(GramMmaArgs a) {
   const int seglen = ((npix + nseg - 1) / nseg + 7) & ~7;
   const int pbeg = (ks * GM_WARPS + wid) * seglen;
   const int pend = min(npix, pbeg + seglen);
-  for (int p8 = pbeg; p8 < pend; p8 += 8) {
+  // operands one tile (8 pixels) ahead in registers
+  double pav[KST], tv[NT][2], dv[NT][2];
+  auto load_tile = [&](int p8) {
     const int p = p8 + r;
     const bool in = p < pend;
     const double *Prow = Pb + (int64_t)(in ? p : 0) * a.npp;
-    double cont[NT][2];
-#pragma unroll
-    for (int nt = 0; nt < NT; nt++) cont[nt][0] = cont[nt][1] = 0;
 #pragma unroll
     for (int s = 0; s < KST; s++) {
       const int i = 4 * s + c;
-      const double av = (in && i < NP) ? __ldg(Prow + i) : 0.0;
-#pragma unroll
-      for (int nt = 0; nt < NT; nt++) dmma884(cont[nt][0], cont[nt][1], av, bco[s][nt]);
+      pav[s] = (in && i < NP) ? __ldg(Prow + i) : 0.0;
     }
-    if (in) {
 #pragma unroll
-      for (int nt = 0; nt < NT; nt++)
+    for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-        for (int e = 0; e < 2; e++)
-          if (tnp[nt][e]) {
-            const double res = fma(-tnp[nt][e][p], cont[nt][e], __ldg(dnp[nt][e] + p));
-            rss[nt][e] = fma(res, res, rss[nt][e]);
-          }
-    }
+      for (int e = 0; e < 2; e++) {
+        tv[nt][e] = 0;
+        dv[nt][e] = 0;
+        if (in && tnp[nt][e]) { tv[nt][e] = __ldcg(tnp[nt][e] + p); dv[nt][e] = __ldg(dnp[nt][e] + p); }
+      }
+  };
+  load_tile(pbeg);
+  for (int p8 = pbeg; p8 < pend; p8 += 8) {
+    double cont[NT][2], tc[NT][2], dc[NT][2], ac[KST];
+#pragma unroll
+    for (int s = 0; s < KST; s++) ac[s] = pav[s];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) { tc[nt][e] = tv[nt][e]; dc[nt][e] = dv[nt][e]; cont[nt][e] = 0; }
+    load_tile(p8 + 8);
+#pragma unroll
+    for (int s = 0; s < KST; s++)
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) dmma884(cont[nt][0], cont[nt][1], ac[s], bco[s][nt]);
+    // absent items / pixels past the end carry t = d = 0: no contribution
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const double res = fma(-tc[nt][e], cont[nt][e], dc[nt][e]);
+        rss[nt][e] = fma(res, res, rss[nt][e]);
+      }
   }
   // sum over the 8 pixel rows of the fragment (lanes with equal c), then warps
 #pragma unroll
