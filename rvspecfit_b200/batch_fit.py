@@ -1,9 +1,31 @@
 """Batched drivers over spec_fit.LikelihoodEngine: many objects stepped together
 so that every likelihood evaluation of a step is one kernel launch per arm.
-"""
-import numpy as np
 
-from . import _dev, spec_fit
+`process_batch` is `vel_fit.process` (reference vel_fit.py:505-737) for a list of
+objects.  Every object follows exactly the decision
+rules of the single-object path:
+  * the RV-grid scan and its refinement (`_minimum_sampler`, vel_fit.py:358-439)
+    run with all active objects' grids in one launch per round;
+  * Nelder-Mead is scipy's algorithm (scipy/optimize/_optimize.py,
+    `_minimize_neldermead`: rho, chi, psi, sigma = 1, 2, 1/2, 1/2, the same
+    termination test, the same acceptance rules, the same ordering), written for
+    a whole batch of simplices in lock-step -- each iteration needs the
+    reflection point of every active object (one launch), then the expansion /
+    contraction points of those that ask for one (one launch), then the shrunk
+    simplices (one launch);
+  * BFGS *is* scipy's `minimize(method='BFGS')`, one instance per object on its
+    own thread; every function value and every finite-difference gradient
+    (scipy's `workers` hook of approx_derivative) blocks on a coordinator that
+    gathers the requests of all live objects into one launch;
+  * the Hessian is the same central-difference routine as vel_fit, its
+    evaluation points recorded, evaluated in one launch and replayed.
+"""
+import threading
+
+import numpy as np
+import scipy.optimize
+
+from . import _dev, spec_fit, spec_inter, vel_fit
 
 
 class KernelTimer:
@@ -69,3 +91,402 @@ def scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=None, groups=2):
         best[q] = np.minimum(best[q], h.result())
     eng.timer = None
     return np.concatenate([st[:, :5], best[:, None]], axis=1)
+
+
+# ------------------------------------------------------------ batched objective
+class BatchObjective:
+    """chisq_func / chisq_func0 of vel_fit (reference vel_fit.py:210-257) for
+    many (object, parameter-vector) pairs at once.  All objects share the layout
+    of the fitted vector: [vel, (vsini), free atmospheric parameters]."""
+
+    def __init__(self, eng, specParams, paramDict0s, fixParam, fitVsini, config, priors=None):
+        self.eng = eng
+        self.specParams = list(specParams)
+        self.fix = [p in fixParam for p in self.specParams]
+        self.fitVsini = fitVsini
+        self.p0 = np.array([[d[p] for p in self.specParams] for d in paramDict0s], dtype=np.float64)
+        self.has_vsini = 'vsini' in paramDict0s[0]
+        self.vsini0 = np.array([d.get('vsini', 0.0) for d in paramDict0s], dtype=np.float64)
+        self.vsini_fixed = self.has_vsini and not fitVsini
+        self.min_vel, self.max_vel = config['min_vel'], config['max_vel']
+        self.max_vsini = config['max_vsini']
+        self.priors = priors
+        self.nfev = 0
+
+    def unpack(self, idx, X):
+        """ParamMapper.forward for a batch: vel (K,), vsini (K,) or None,
+        params (K, nspec), penalty (K,)."""
+        X = np.asarray(X, dtype=np.float64)
+        vel = X[:, 0]
+        pos = 1
+        pen = np.zeros(len(X))
+        vsini = None
+        if self.fitVsini:
+            xv = X[:, 1]
+            vsini = np.clip(xv, 0, self.max_vsini)
+            pen = (xv < 0) * (vsini - xv)**2 + (xv > self.max_vsini) * (vsini - xv)**2
+            pos = 2
+        elif self.vsini_fixed:
+            vsini = self.vsini0[idx]
+        params = np.empty((len(X), len(self.specParams)))
+        for j, fixed in enumerate(self.fix):
+            if fixed:
+                params[:, j] = self.p0[idx, j]
+            else:
+                params[:, j] = X[:, pos]
+                pos += 1
+        assert pos == X.shape[1]
+        return vel, vsini, params, pen
+
+    def prior_term(self, params):
+        tot = np.zeros(len(params))
+        if self.priors is not None:
+            for i, k in enumerate(self.specParams):
+                if k in self.priors:
+                    tot = tot + ((self.priors[k][0] - params[:, i]) / self.priors[k][1])**2
+        return tot
+
+    def chisq0(self, idx, vel, vsini, params):
+        """chisq_func0: priors + -2 log L."""
+        self.nfev += len(idx)
+        chi = self.eng.evaluate(idx, vel, params, vsini)
+        return self.prior_term(params) + chi
+
+    def __call__(self, idx, X):
+        """chisq_func for K pairs: idx (K,) object indices, X (K, N)."""
+        idx = np.asarray(idx, dtype=np.int64)
+        vel, vsini, params, pen = self.unpack(idx, X)
+        wall = (vel > self.max_vel) | (vel < self.min_vel) | ~np.isfinite(params).all(axis=1)
+        out = np.full(len(idx), 1e30)
+        ok = ~wall
+        if ok.any():
+            out[ok] = self.chisq0(idx[ok], vel[ok], None if vsini is None else vsini[ok],
+                                  params[ok]) + pen[ok]
+        return out
+
+
+# ------------------------------------------------------- lock-step Nelder-Mead
+def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000):
+    """scipy's Nelder-Mead (`_minimize_neldermead`, adaptive=False, no bounds,
+    maxfev=inf) on B simplices at once.  fbatch(idx, X) -> f for rows X (K, N)
+    belonging to problems idx (K,).  sims (B, N+1, N): initial simplices.
+    Returns dict(x (B, N), fun (B,), success (B,), final_simplex (B, N+1, N),
+    nit (B,), nfev (B,)).  Problem b visits exactly the points, in exactly the
+    order, that scipy.optimize.minimize(method='Nelder-Mead',
+    options={'initial_simplex': sims[b], ...}) would."""
+    sim = np.array(sims, dtype=np.float64)
+    B, N1, N = sim.shape
+    assert N1 == N + 1
+    rho, chi, psi, sigma = 1, 2, 0.5, 0.5
+    allb = np.arange(B)
+    fsim = fbatch(np.repeat(allb, N1), sim.reshape(B * N1, N)).reshape(B, N1)
+    nfev = np.full(B, N1)
+
+    def sort(rows):
+        ind = np.argsort(fsim[rows], axis=1, kind='stable')
+        fsim[rows] = np.take_along_axis(fsim[rows], ind, axis=1)
+        sim[rows] = np.take_along_axis(sim[rows], ind[:, :, None], axis=1)
+    sort(allb)
+    iterations = np.ones(B, dtype=np.int64)
+    active = np.ones(B, dtype=bool)
+    success = np.zeros(B, dtype=bool)
+    while active.any():
+        a = np.nonzero(active)[0]
+        # termination tests of the while-loop head and of its first statement
+        out_of_iters = iterations[a] >= maxiter
+        conv = (np.max(np.abs(sim[a, 1:] - sim[a, :1]).reshape(len(a), -1), axis=1) <= xatol) & \
+            (np.max(np.abs(fsim[a, :1] - fsim[a, 1:]), axis=1) <= fatol)
+        stop = out_of_iters | conv
+        success[a[conv & ~out_of_iters]] = True
+        active[a[stop]] = False
+        a = a[~stop]
+        if len(a) == 0:
+            break
+        xbar = np.add.reduce(sim[a, :-1], 1) / N
+        last = sim[a, -1]
+        xr = (1 + rho) * xbar - rho * last
+        fxr = fbatch(a, xr)
+        nfev[a] += 1
+        f0, fm2, fm1 = fsim[a, 0], fsim[a, -2], fsim[a, -1]
+        expand = fxr < f0
+        accept_r = ~expand & (fxr < fm2)
+        contract = ~expand & ~accept_r & (fxr < fm1)
+        inside = ~expand & ~accept_r & ~contract
+        # second point, where one is asked for
+        x2 = np.empty_like(xr)
+        x2[expand] = (1 + rho * chi) * xbar[expand] - rho * chi * last[expand]
+        x2[contract] = (1 + psi * rho) * xbar[contract] - psi * rho * last[contract]
+        x2[inside] = (1 - psi) * xbar[inside] + psi * last[inside]
+        need2 = expand | contract | inside
+        f2 = np.full(len(a), np.nan)
+        if need2.any():
+            f2[need2] = fbatch(a[need2], x2[need2])
+            nfev[a[need2]] += 1
+        new_x, new_f = xr.copy(), fxr.copy()
+        take2 = (expand & (f2 < fxr)) | (contract & (f2 <= fxr)) | (inside & (f2 < fm1))
+        new_x[take2], new_f[take2] = x2[take2], f2[take2]
+        shrink = (contract & ~(f2 <= fxr)) | (inside & ~(f2 < fm1))
+        keep = ~shrink
+        sim[a[keep], -1] = new_x[keep]
+        fsim[a[keep], -1] = new_f[keep]
+        if shrink.any():
+            s = a[shrink]
+            sim[s, 1:] = sim[s, :1] + sigma * (sim[s, 1:] - sim[s, :1])
+            fsim[s, 1:] = fbatch(np.repeat(s, N), sim[s, 1:].reshape(len(s) * N, N)).reshape(len(s), N)
+            nfev[s] += N
+        iterations[a] += 1
+        sort(a)
+    return dict(x=sim[:, 0].copy(), fun=np.min(fsim, axis=1), success=success,
+                final_simplex=sim, nit=iterations, nfev=nfev)
+
+
+# ------------------------------------------------- scipy BFGS, many at a time
+class _Coordinator:
+    """Gathers the blocking evaluation requests of many worker threads into one
+    batched call.  A round is evaluated when every live worker has a request
+    pending."""
+
+    def __init__(self, fbatch, ids):
+        self.fbatch = fbatch
+        self.lock = threading.Lock()
+        self.ready = threading.Event()
+        self.events = {i: threading.Event() for i in ids}
+        self.pending, self.results = {}, {}
+        self.live = len(ids)
+        self.rounds = 0
+
+    def request(self, wid, X):
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        with self.lock:
+            self.pending[wid] = X
+            if len(self.pending) >= self.live:
+                self.ready.set()
+        ev = self.events[wid]
+        ev.wait()
+        ev.clear()
+        return self.results.pop(wid)
+
+    def finished(self, wid):
+        with self.lock:
+            self.live -= 1
+            if self.live == 0 or len(self.pending) >= self.live:
+                self.ready.set()
+
+    def run(self):
+        while True:
+            self.ready.wait()
+            with self.lock:
+                self.ready.clear()
+                if self.live == 0 and not self.pending:
+                    return
+                if len(self.pending) < self.live:
+                    continue
+                batch, self.pending = self.pending, {}
+            wids = list(batch)
+            idx = np.concatenate([np.full(len(batch[w]), w) for w in wids])
+            vals = self.fbatch(idx, np.concatenate([batch[w] for w in wids]))
+            self.rounds += 1
+            pos = 0
+            for w in wids:
+                n = len(batch[w])
+                self.results[w] = vals[pos:pos + n]
+                pos += n
+                self.events[w].set()
+
+
+def bfgs_batch(fbatch, x0s, hess_inv0, ids=None):
+    """scipy.optimize.minimize(method='BFGS', options=dict(hess_inv0=...)) for every
+    row of x0s, the instances running concurrently and sharing launches.  Returns
+    the list of scipy OptimizeResult objects."""
+    x0s = np.asarray(x0s, dtype=np.float64)
+    ids = list(range(len(x0s))) if ids is None else list(ids)
+    coord = _Coordinator(fbatch, ids)
+    results, errors = {}, {}
+
+    def worker(wid, x0):
+        try:
+            def fun(x):
+                return float(coord.request(wid, x)[0])
+
+            def pmap(_f, it):
+                xs = [np.asarray(_) for _ in it]
+                if not xs:
+                    return []
+                return [float(_) for _ in coord.request(wid, np.array(xs))]
+            results[wid] = scipy.optimize.minimize(
+                fun, x0, method='BFGS', options=dict(hess_inv0=hess_inv0, workers=pmap))
+        except BaseException as exc:          # noqa: BLE001  (re-raised in the caller)
+            errors[wid] = exc
+        finally:
+            coord.finished(wid)
+
+    old = threading.stack_size(512 * 1024)
+    try:
+        threads = [threading.Thread(target=worker, args=(w, x0s[i]), daemon=True)
+                   for i, w in enumerate(ids)]
+        for t in threads:
+            t.start()
+    finally:
+        threading.stack_size(old)
+    coord.run()
+    for t in threads:
+        t.join()
+    if errors:
+        raise next(iter(errors.values()))
+    return [results[w] for w in ids]
+
+
+# ------------------------------------------------------------ the batched fit
+class _Replay:
+    """Records the points a routine asks for, then replays their values."""
+
+    def __init__(self):
+        self.pts, self.vals, self.i = [], None, 0
+
+    def __call__(self, x):
+        if self.vals is None:
+            self.pts.append(np.array(x, dtype=np.float64))
+            return 0.0
+        v = self.vals[self.i]
+        self.i += 1
+        return v
+
+
+def _scan_round(eng, idx, grids, params, vsini):
+    """find_best (one template per object) for ragged velocity grids: chi-squares
+    in one launch per arm, statistics on the device per distinct grid length.
+    Returns (n, 5): best_chi, best_vel, vel_err, skewness, kurtosis."""
+    nv = np.array([len(g) for g in grids])
+    V = np.stack([np.concatenate([g, np.full(nv.max() - len(g), g[-1])]) for g in grids])
+    chi = eng.evaluate(idx, V, params, vsini)
+    out = np.zeros((len(idx), 5))
+    for n in np.unique(nv):
+        sel = np.nonzero(nv == n)[0]
+        st, _ = spec_fit.scan_stats(V[sel, :n], chi[sel, None, :n])
+        out[sel] = st[:, :5]
+    return out
+
+
+def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None, priors=None):
+    """vel_fit.process for a list of objects (each a list of SpecData); same
+    arguments otherwise, paramDict0s one dictionary per object.  Returns the list
+    of result dictionaries of vel_fit.process."""
+    if config is None:
+        raise RuntimeError('Config must be provided')
+    objects = [[o] if isinstance(o, spec_fit.SpecData) else list(o) for o in objects]
+    B = len(objects)
+    options = options or {}
+    fixParam = fixParam or []
+    min_vel, max_vel = config['min_vel'], config['max_vel']
+    vel_step0, min_vel_step = config['vel_step0'], config['min_vel_step']
+    second_minimizer = config.get('second_minimizer') or False
+    eng = spec_fit.LikelihoodEngine(objects, config, options)
+    setup0 = objects[0][0].name
+    specParams = list(spec_inter.getSpecParams(setup0, config))
+    has_vsini = 'vsini' in paramDict0s[0]
+    fitVsini = has_vsini and 'vsini' not in fixParam
+    vsiniMapper = vel_fit.VSiniMapper(config['max_vsini']) if fitVsini else None
+    fobj = BatchObjective(eng, specParams, paramDict0s, fixParam, fitVsini, config, priors)
+    allb = np.arange(B)
+    # 1. RV-grid scan at the starting parameters (vel_fit.py:579-590)
+    vgrid = np.arange(min_vel, max_vel, vel_step0)
+    st = _scan_round(eng, allb, [vgrid] * B, fobj.p0,
+                     fobj.vsini0 if has_vsini else None)
+    # 2. Nelder-Mead, restarted once from its final simplex if it did not converge
+    sims = np.stack([vel_fit._get_simplex_start(
+        st[i, 1], fixParam=fixParam, specParamNames=specParams, paramDict0=paramDict0s[i],
+        vsiniMapper=vsiniMapper, fitVsini=fitVsini)[1] for i in range(B)])
+    minimize_success = np.ones(B, dtype=bool)
+    x = np.zeros((B, sims.shape[2]))
+    todo = allb
+    for attempt in range(2):
+        res = nelder_mead_lockstep(lambda i, X: fobj(todo[i], X), sims[todo])
+        x[todo] = res['x']
+        sims[todo] = res['final_simplex']
+        failed = todo[~res['success']]
+        if attempt == 1:
+            minimize_success[failed] = False
+        todo = failed
+        if len(todo) == 0:
+            break
+    # 3. BFGS polish (vel_fit.py:653-658)
+    if second_minimizer:
+        names = ['vel'] + (['vsini'] if fitVsini else []) + \
+            [p for p in specParams if p not in fixParam]
+        bres = bfgs_batch(fobj, x, vel_fit.get_hess_inv(names))
+        x = np.array([r['x'] for r in bres])
+    vel, vsini, params, _ = fobj.unpack(allb, x)
+    # 4. velocity posterior on shrinking grids (vel_fit.py:315-439), all objects per round
+    best_vel = np.clip(vel, min_vel, max_vel)
+    lo, hi = np.full(B, float(min_vel)), np.full(B, float(max_vel))
+    step = np.full(B, float(vel_step0))
+    vstat = np.zeros((B, 5))
+    active = allb
+    for _ in range(10):
+        grids = [np.arange(np.ceil((lo[i] - best_vel[i]) / step[i]) * step[i],
+                           hi[i] - best_vel[i], step[i]) + best_vel[i] for i in active]
+        s = _scan_round(eng, active, grids, params[active],
+                        None if vsini is None else vsini[active])
+        vstat[active] = s
+        best_vel[active] = s[:, 1]
+        err = s[:, 2]
+        stp = step[active]
+        done = (stp < err / 5) | (stp < min_vel_step)
+        coarse = stp > err
+        new_step = np.where(coarse, stp / 5, err / 5 * 0.8)
+        width = np.where(coarse, stp * 10, err * 10)
+        cont = ~done
+        a2 = active[cont]
+        lo[a2] = np.maximum(best_vel[a2] - width[cont], lo[a2])
+        hi[a2] = np.minimum(best_vel[a2] + width[cont], hi[a2])
+        step[a2] = new_step[cont]
+        active = a2
+        if len(active) == 0:
+            break
+    # 5. model at the best point (vel_fit.py:688-696)
+    tot, info = eng.evaluate(allb, best_vel[:, None], params, vsini, want_model=True)
+    chi_best = tot[:, 0]
+    # 6. Hessian over the atmospheric parameters at the optimiser's velocity and vsini
+    #    (vel_fit.py:698-722: hess_func keeps best_param's own velocity)
+    hsteps = [vel_fit.HESS_STEP[_] for _ in specParams]
+    recs = []
+    for i in range(B):
+        r = _Replay()
+        vel_fit.central_hessian(r, params[i], hsteps)
+        recs.append(r)
+    npts = [len(r.pts) for r in recs]
+    P = np.concatenate([np.array(r.pts) for r in recs])
+    ii = np.repeat(allb, npts)
+    vals = 0.5 * fobj.chisq0(ii, vel[ii], None if vsini is None else vsini[ii], P)
+    out, pos = [], 0
+    for i in range(B):
+        recs[i].vals = vals[pos:pos + npts[i]]
+        pos += npts[i]
+        hessian = vel_fit.central_hessian(recs[i], params[i], hsteps)
+        diag_err, covar, bad_hessian = vel_fit._uncertainties_from_hessian(hessian)
+        ret = dict(param=dict(zip(specParams, params[i])))
+        if fitVsini:
+            ret['vsini'] = vsini[i]
+        ret.update(vel=best_vel[i], vel_err=vstat[i, 2], vel_skewness=vstat[i, 3],
+                   vel_kurtosis=vstat[i, 4], param_err=dict(zip(specParams, diag_err)),
+                   param_covar=covar, minimize_success=bool(minimize_success[i]),
+                   bad_hessian=bad_hessian, chisq=float(chi_best[i]),
+                   logl=-0.5 * float(chi_best[i]), yfit=[], raw_models=[], chisq_array=[],
+                   npix_array=[])
+        for sd in objects[i]:
+            arm = info['arms'][sd.name]
+            j = int(np.nonzero(arm['sel'] == i)[0][0])
+            if arm['tbad'][j]:
+                ret['chisq_array'].append(np.nan)
+                ret['yfit'].append(np.zeros(len(sd.lam)) + np.nan)
+                continue
+            ex = arm['extras']
+            sl = slice(ex['moff'][j], ex['moff'][j + 1])
+            model, raw = ex['model'][sl], ex['raw'][sl]
+            good = ~sd.badmask
+            ret['yfit'].append(model)
+            ret['raw_models'].append(raw)
+            ret['chisq_array'].append(float(np.sum((((model - sd.spec) / sd.espec)[good])**2)))
+            ret['npix_array'].append(int(good.sum()))
+        out.append(ret)
+    return out

@@ -382,3 +382,40 @@ def test_process_matches_reference(golden):
                             vsinigrid=(None, 50))
     got = np.array([fg[k] for k in ('teff', 'logg', 'feh', 'alpha')] + [fg.get('vsini', -1)])
     close(got, g['c1_fg'], rtol=1e-12)
+
+
+def test_process_batch_matches_reference(golden):
+    """batch_fit.process_batch (lock-step Nelder-Mead, pooled scipy BFGS, batched
+    refinement scans and Hessian) against the reference's own fits of the same
+    objects, all objects in one batch."""
+    from rvspecfit_b200 import batch_fit
+    g = golden('process')
+    _register(setup('test', 'test', 3, name='test'))
+    objs = unpack_objects(g, 'c1_')
+    start = {'logg': 2, 'teff': 5000, 'feh': -0.2, 'alpha': 0.2, 'vsini': 0.1}
+    sds = [_sd(objs[0]), _sd(objs[1]), _sd(objs[0])]
+    for tag, cfg in (('bfgs', config()), ('nm', config(second_minimizer=False))):
+        res = batch_fit.process_batch(sds, [dict(start) for _ in sds], fixParam=[], config=cfg,
+                                      options={'npoly': 15})
+        for j, i in enumerate((0, 1, 0)):
+            if i == 1 and tag == 'nm':
+                continue
+            r = res[j]
+            perr = g[f'c1_{i}_{tag}_param_err']
+            par = np.array([r['param'][k] for k in ('teff', 'logg', 'feh', 'alpha')])
+            assert abs(r['vel'] - g[f'c1_{i}_{tag}_vel']) < 0.01, (i, tag)
+            assert np.all(np.abs(par - g[f'c1_{i}_{tag}_param']) < 0.01 * perr), (i, tag)
+            assert abs(r['chisq'] - g[f'c1_{i}_{tag}_chisq']) < 1e-6 * abs(r['chisq'])
+            assert np.isclose(r['vel_err'], g[f'c1_{i}_{tag}_vel_err'], rtol=1e-3)
+            close(r['yfit'][0], g[f'c1_{i}_{tag}_yfit'], rtol=1e-5)
+            assert r['minimize_success']
+        # identical objects in one batch give identical fits
+        assert res[0]['vel'] == res[2]['vel'] and res[0]['chisq'] == res[2]['chisq']
+    # against the single-object driver, including uncertainties
+    one = vel_fit.process(sds[1], dict(start), fixParam=[], config=config(second_minimizer=False),
+                          options={'npoly': 15})
+    b = res[1]
+    assert abs(one['vel'] - b['vel']) < 1e-6 and abs(one['chisq'] - b['chisq']) < 1e-7 * abs(b['chisq'])
+    for k in ('teff', 'logg', 'feh', 'alpha'):
+        assert np.isclose(one['param'][k], b['param'][k], rtol=1e-7), k
+        assert np.isclose(one['param_err'][k], b['param_err'][k], rtol=1e-3), k
