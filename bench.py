@@ -37,6 +37,9 @@ WORKLOADS = {
 # evaluations of one reference vel_fit.process call on a DESI-shaped object
 # (SURVEY.md section 6/8d probe): 2866 get_chisq, 1293 of them with a new template
 EVALS_PER_FIT = 1293
+# starting point of every fit in --mode fit (the reference starts from the CCF
+# first guess; a fixed mid-grid start exercises the optimiser at least as hard)
+FIT_START = {'teff': 5500., 'logg': 3.0, 'feh': -1.0, 'alpha': 0.2, 'vsini': 10.}
 
 
 def make_config(w):
@@ -150,7 +153,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from rvspecfit_b200 import _cabi, spec_fit, spec_inter, batch_fit
+    from rvspecfit_b200 import _cabi, spec_fit, spec_inter, batch_fit, shard
     w = WORKLOADS[args.workload]
     cfg = make_config(w)
     B = args.batch
@@ -170,18 +173,28 @@ def run_gpu(args):
 
     timer = batch_fit.KernelTimer()
 
+    starts = [dict(FIT_START) for _ in range(B)]
+
+    def fit_records(res):
+        return np.array([[r['vel'], r['vel_err'], r['chisq'], r['vsini']] +
+                         [r['param'][k] for k in synth.PARNAMES] for r in res])
+
     def hot_path(eng):
         """The step body on a ready engine; returns a small result array."""
-        res = batch_fit.scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=timer,
+        if args.mode == 'fit':
+            return fit_records(batch_fit.process_batch(None, starts, config=cfg, options=opts,
+                                                       engine=eng, timer=timer))
+        return batch_fit.scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=timer,
                                            groups=args.groups)
-        return res
 
     def step_resident(eng):
         return hot_path(eng)
 
     def step_e2e():
         eng = spec_fit.LikelihoodEngine(to_specdata(), cfg, opts)   # H2D of the spectra
-        return hot_path(eng)                                         # D2H of the results
+        rec = hot_path(eng)                                          # D2H of the results
+        # the one collective of the path: fixed-size result records of all ranks
+        return shard.gather_records(rec, B * world) if world > 1 else rec
 
     eng = spec_fit.LikelihoodEngine(to_specdata(), cfg, opts)
     L = _cabi.lib()
@@ -219,7 +232,8 @@ def run_gpu(args):
     ms_e2e, _, _, _, _ = timed(step_e2e, max(1, min(args.steps, 2)), 1)
     n_e2e = max(1, min(args.steps, 2))
     h2d = sum(3 * 8 * len(a[1]) + len(a[1]) for o in objects for a in o)
-    d2h = int(np.asarray(out).nbytes)
+    d2h = int(np.asarray(out).nbytes) * world      # whole job, like `value`
+    h2d *= world
 
     peaks = {}
     try:
@@ -244,8 +258,15 @@ def run_gpu(args):
                     items_per_launch=ksum['fused_items_per_launch'])
     nspec_total = B * world
     per_step = ms / args.steps
+    fit = args.mode == 'fit'
+    step_txt = ('per spectrum: the complete vel_fit.process fit (RV-grid scan, Nelder-Mead, '
+                'BFGS, RV refinement scans, model, Hessian) through batch_fit.process_batch'
+                if fit else
+                'per spectrum: 1 RV-grid scan + fit_evals_per_spectrum template-changing chi2 '
+                'evaluations (count of one reference process() call, SURVEY.md 8d)')
     line = {
-        'metric': 'spectra/sec (RV-grid chi2 scan + fit evaluations)',
+        'metric': 'spectra/sec (RV-grid chi2 + fit)' if fit else
+                  'spectra/sec (RV-grid chi2 scan + fit evaluations)',
         'value': nspec_total / (per_step * 1e-3), 'unit': 'spectra/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
@@ -255,16 +276,16 @@ def run_gpu(args):
                                f'({setups[0]["dats"].shape[0]} nodes, fp32), npoly {w["npoly"]}',
                    'spectra_per_gpu_per_step': B, 'rv_trials': len(vgrid),
                    'fit_evals_per_spectrum': args.evals, 'lockstep_groups': args.groups,
-                   'step': 'per spectrum: 1 RV-grid scan + fit_evals_per_spectrum '
-                           'template-changing chi2 evaluations (count of one reference '
-                           'process() call, SURVEY.md 8d)',
+                   'mode': args.mode, 'step': step_txt,
                    'l2': 'template grid (>=0.7 GB per arm) is larger than L2; rows gathered '
                          'at random per evaluation',
                    'parallelism': f'spectra sharded over {world} GPU(s), grid replicated'},
-        'chisq_evals_per_s': nspec_total * (args.evals + len(vgrid)) / (per_step * 1e-3),
+        'chisq_evals_per_s': (eng.n_eval / (args.steps + args.warmup) * world if fit else
+                              nspec_total * (args.evals + len(vgrid))) / (per_step * 1e-3),
         'e2e': {'value': nspec_total / (ms_e2e / n_e2e * 1e-3), 'unit': 'spectra/s',
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof,
+        'fit_phase_seconds': getattr(batch_fit.process_batch, 'last_phase_seconds', None),
         'kernels': ksum,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -293,9 +314,12 @@ def _cpu_worker(job):
     c = _cpu_worker.cache
     sd = [oracle.SpecData(*a) for a in c['objects'][idx]]
     opts = {'npoly': w['npoly']}
-    tp, tv, tvs = trial_points(c['pars'], c['vel'], w['layout'], nevals, 5)
+    tp, tv, tvs = trial_points(c['pars'], c['vel'], w['layout'], max(nevals, 0), 5)
     vgrid = np.arange(cfg['min_vel'], cfg['max_vel'], cfg['vel_step0'])[:nscan]
     t0 = time.time()
+    if nevals < 0:       # --mode fit: the complete fit
+        r = oracle.process(sd, dict(FIT_START), fixParam=[], options=opts, config=cfg)
+        return time.time() - t0, r['chisq']
     fb = oracle.find_best(sd, vgrid, [(5500., 3.0, -1.0, 0.2)], rot=None, options=opts,
                           config=cfg)
     acc = fb['best_chi']
@@ -327,6 +351,8 @@ def cpu_baseline(args, bounded=True):
     nevals = max(1, int(args.evals * frac))
     nscan = max(3, int(len(vg) * frac))
     nobj = 2 * cores
+    if args.mode == 'fit':
+        nevals, nscan, nobj = -1, len(vg), cores
     for k, a in enumerate(w['arms']):       # template rows shared through the page cache
         path = grid_cache_path(args.workload, a)
         if not os.path.exists(path):
@@ -342,6 +368,12 @@ def cpu_baseline(args, bounded=True):
         res = list(ex.map(_cpu_worker, jobs))
         t2 = time.time()
     wall = t2 - t1
+    if args.mode == 'fit':
+        return dict(value=nobj / wall, unit='spectra/s', cores=cores, kind='port',
+                    sample=f'{nobj} complete fits (oracle.process: scan, Nelder-Mead, BFGS, '
+                           f'refinement, Hessian) on {cores} processes, one object per task; '
+                           f'setup {t1 - t0:.1f}s excluded', wall_s=wall,
+                    per_object_s=float(np.mean([r[0] for r in res])))
     scale = (args.evals + len(vg)) / (nevals + nscan)
     return dict(value=nobj / (wall * scale), unit='spectra/s', cores=cores, kind='port',
                 sample=f'{nobj} spectra x ({nscan} RV trials + {nevals} evaluations) on {cores} '
@@ -362,12 +394,14 @@ def run_reference(args):
     v = float(np.mean([x['value'] for x in vals[args.warmup:]])) if args.steps else cb['value']
     cb['value'] = v
     setups = [a for a in w['arms']]
-    line = {'impl': 'reference', 'metric': 'spectra/sec (RV-grid chi2 scan + fit evaluations)',
+    line = {'impl': 'reference',
+            'metric': 'spectra/sec (RV-grid chi2 + fit)' if args.mode == 'fit' else
+                      'spectra/sec (RV-grid chi2 scan + fit evaluations)',
             'value': v, 'unit': 'spectra/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', 1)),
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cb['wall_s'] * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': f'{args.workload}: arms {setups}',
+            'config': {'workload': f'{args.workload}: arms {setups}', 'mode': args.mode,
                        'fit_evals_per_spectrum': args.evals},
             'cpu_baseline': cb,
             'e2e': {'value': v, 'unit': 'spectra/s', 'h2d_bytes_per_step': 0,
@@ -382,11 +416,13 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='desi', choices=list(WORKLOADS))
-    ap.add_argument('--batch', type=int, default=1024, help='spectra per GPU per step')
+    ap.add_argument('--batch', type=int, default=2048, help='spectra per GPU per step')
     ap.add_argument('--evals', type=int, default=EVALS_PER_FIT)
     ap.add_argument('--cpu-fraction', type=float, default=0.25,
                     help='fraction of the per-spectrum evaluations the CPU sample runs')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--mode', default='proxy', choices=['proxy', 'fit'],
+                    help='proxy: scan + fixed count of evaluations; fit: complete fits')
     ap.add_argument('--groups', type=int, default=2,
                     help='independent object groups stepped in ping-pong (host/GPU overlap)')
     args = ap.parse_args()

@@ -125,7 +125,9 @@ typedef struct {
   int32_t ndim;
   int32_t len[RVS_MAX_GRID_DIM];
   int32_t uoff[RVS_MAX_GRID_DIM];
-  int32_t reserved;
+  int32_t nnode;
+  const double *d_vnorm;        /* [nnode][ndim] node coordinates / ptp (the KD-tree's points) */
+  double ptp[RVS_MAX_GRID_DIM]; /* peak-to-peak of every coordinate (spec_inter.py:128) */
 } rvs_gridmap;
 
 /* ---- template evaluation ------------------------------------------------- */
@@ -133,10 +135,15 @@ typedef struct {
  * K mapped parameter vectors, coordinate i of item k at d_q[i*q_stride + k].
  * Writes the 2^ndim corner ids and weights (the d_ids / d_w of
  * rvs_template_build and rvs_chisq_fused) and d_flag[k] = 1 for the points the
- * host must resolve (off-grid, missing corner, non-finite): those get the
- * placeholder "row 0 alone". */
+ * reference resolves through its KD-tree (off-grid, missing corner) or that are
+ * non-finite: those get the placeholder "row 0 alone".  With d_outside != NULL
+ * the flagged finite points are resolved here as the reference does -- nearest
+ * node in ptp-normalised space as a single-row item, d_outside[k] = its distance
+ * (GridOutsideCheck, spec_inter.py:77-92), flag cleared; d_outside[k] = 0 for
+ * points inside, NaN (flag kept) for non-finite ones. */
 int rvs_locate_grid(const rvs_gridmap *gm, const double *d_q, int64_t q_stride, int K,
-                    int32_t *d_ids, double *d_w, int32_t *d_flag, void *stream);
+                    int32_t *d_ids, double *d_w, int32_t *d_flag, double *d_outside,
+                    void *stream);
 
 /* Host helpers (plain C, no device work).  rvs_knot_tables: h, hinv (n-1
  * each), cp, winv (n-2 each).  rvs_knot_info fills the scalar members of

@@ -42,7 +42,7 @@ class GridMap(ctypes.Structure):
     """struct rvs_gridmap"""
     _fields_ = [('d_uvec', c_dp), ('d_idgrid', c_dp), ('ndim', ctypes.c_int32),
                 ('len', ctypes.c_int32 * 5), ('uoff', ctypes.c_int32 * 5),
-                ('reserved', ctypes.c_int32)]
+                ('nnode', ctypes.c_int32), ('d_vnorm', c_dp), ('ptp', c_dbl * 5)]
 
 
 class CcfArm(ctypes.Structure):
@@ -64,7 +64,7 @@ SIGNATURES = {
     'rvs_knot_tables': (None, [c_dp, c_int, c_dp, c_dp, c_dp, c_dp]),
     'rvs_knot_info': (c_int, [c_dp, c_int, c_int, ctypes.POINTER(Knots)]),
     'rvs_locate_grid': (c_int, [ctypes.POINTER(GridMap), c_dp, c_i64, c_int, c_dp, c_dp, c_dp,
-                                c_dp]),
+                                c_dp, c_dp]),
     'rvs_template_build': (c_int, [c_dp, c_int, c_i64, ctypes.POINTER(Knots), c_dp, c_dp, c_int,
                                    c_dp, c_int, c_int, c_dp, c_i64, c_dp, c_dp]),
     'rvs_obs_prepare': (c_int, [c_dp, c_dp, c_dp, c_int, c_dbl, c_dp, c_dp, c_dp, c_dp]),

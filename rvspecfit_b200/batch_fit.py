@@ -165,8 +165,13 @@ class BatchObjective:
         return out
 
 
+# below this many active problems an iteration's candidate points go out in one call
+SPECULATE_BELOW = 640
+
+
 # ------------------------------------------------------- lock-step Nelder-Mead
-def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000):
+def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000,
+                         speculate_below=0):
     """scipy's Nelder-Mead (`_minimize_neldermead`, adaptive=False, no bounds,
     maxfev=inf) on B simplices at once.  fbatch(idx, X) -> f for rows X (K, N)
     belonging to problems idx (K,).  sims (B, N+1, N): initial simplices.
@@ -205,23 +210,43 @@ def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000):
         xbar = np.add.reduce(sim[a, :-1], 1) / N
         last = sim[a, -1]
         xr = (1 + rho) * xbar - rho * last
-        fxr = fbatch(a, xr)
-        nfev[a] += 1
         f0, fm2, fm1 = fsim[a, 0], fsim[a, -2], fsim[a, -1]
-        expand = fxr < f0
-        accept_r = ~expand & (fxr < fm2)
-        contract = ~expand & ~accept_r & (fxr < fm1)
-        inside = ~expand & ~accept_r & ~contract
-        # second point, where one is asked for
-        x2 = np.empty_like(xr)
-        x2[expand] = (1 + rho * chi) * xbar[expand] - rho * chi * last[expand]
-        x2[contract] = (1 + psi * rho) * xbar[contract] - psi * rho * last[contract]
-        x2[inside] = (1 - psi) * xbar[inside] + psi * last[inside]
-        need2 = expand | contract | inside
-        f2 = np.full(len(a), np.nan)
-        if need2.any():
-            f2[need2] = fbatch(a[need2], x2[need2])
+        if len(a) <= speculate_below:
+            # few problems left: launches are latency-bound, so the three candidate
+            # second points are evaluated together with the reflection in ONE call;
+            # each problem then uses exactly the value scipy would have computed
+            xe = (1 + rho * chi) * xbar - rho * chi * last
+            xc = (1 + psi * rho) * xbar - psi * rho * last
+            xcc = (1 - psi) * xbar + psi * last
+            fall = fbatch(np.tile(a, 4), np.concatenate([xr, xe, xc, xcc])).reshape(4, len(a))
+            fxr = fall[0]
+            nfev[a] += 1
+            expand = fxr < f0
+            accept_r = ~expand & (fxr < fm2)
+            contract = ~expand & ~accept_r & (fxr < fm1)
+            inside = ~expand & ~accept_r & ~contract
+            x2 = np.where(expand[:, None], xe, np.where(contract[:, None], xc, xcc))
+            f2 = np.where(expand, fall[1], np.where(contract, fall[2], fall[3]))
+            need2 = expand | contract | inside
+            f2[~need2] = np.nan
             nfev[a[need2]] += 1
+        else:
+            fxr = fbatch(a, xr)
+            nfev[a] += 1
+            expand = fxr < f0
+            accept_r = ~expand & (fxr < fm2)
+            contract = ~expand & ~accept_r & (fxr < fm1)
+            inside = ~expand & ~accept_r & ~contract
+            # second point, where one is asked for
+            x2 = np.empty_like(xr)
+            x2[expand] = (1 + rho * chi) * xbar[expand] - rho * chi * last[expand]
+            x2[contract] = (1 + psi * rho) * xbar[contract] - psi * rho * last[contract]
+            x2[inside] = (1 - psi) * xbar[inside] + psi * last[inside]
+            need2 = expand | contract | inside
+            f2 = np.full(len(a), np.nan)
+            if need2.any():
+                f2[need2] = fbatch(a[need2], x2[need2])
+                nfev[a[need2]] += 1
         new_x, new_f = xr.copy(), fxr.copy()
         take2 = (expand & (f2 < fxr)) | (contract & (f2 <= fxr)) | (inside & (f2 < fm1))
         new_x[take2], new_f[take2] = x2[take2], f2[take2]
@@ -336,6 +361,103 @@ def bfgs_batch(fbatch, x0s, hess_inv0, ids=None):
     return [results[w] for w in ids]
 
 
+# ---- the same, with the per-object scipy drivers spread over worker processes
+def _bfgs_process_main(conn):
+    """Worker process: runs scipy BFGS for a subset of the objects (threads +
+    coordinator as above); every evaluation round is one message to the parent,
+    which owns the GPU.  Never touches CUDA."""
+    while True:
+        try:
+            job = conn.recv()
+        except EOFError:
+            return
+        if job is None:
+            return
+        ids, x0s, hess_inv0 = job
+
+        def remote(idx, X):
+            conn.send(('req', np.asarray(idx), np.asarray(X)))
+            return conn.recv()
+        try:
+            res = bfgs_batch(remote, x0s, hess_inv0, ids=ids)
+            conn.send(('done', {w: dict(r) for w, r in zip(ids, res)}))
+        except BaseException as exc:      # noqa: BLE001
+            conn.send(('error', repr(exc)))
+
+
+class _BfgsProcessPool:
+    def __init__(self, nproc):
+        import multiprocessing as mp
+        ctx = mp.get_context('spawn')
+        self.conns, self.procs = [], []
+        for _ in range(nproc):
+            parent, child = ctx.Pipe()
+            p = ctx.Process(target=_bfgs_process_main, args=(child,), daemon=True)
+            p.start()
+            child.close()
+            self.conns.append(parent)
+            self.procs.append(p)
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(None)
+            except (OSError, ValueError):
+                pass
+        for p in self.procs:
+            p.join(timeout=2)
+
+    def run(self, fbatch, x0s, hess_inv0):
+        B = len(x0s)
+        chunks = [c for c in np.array_split(np.arange(B), len(self.conns)) if len(c)]
+        live = {}
+        for conn, ch in zip(self.conns, chunks):
+            conn.send((list(map(int, ch)), x0s[ch], hess_inv0))
+            live[conn] = True
+        results = {}
+        while live:
+            reqs = []
+            for conn in list(live):
+                msg = conn.recv()
+                if msg[0] == 'req':
+                    reqs.append((conn, msg[1], msg[2]))
+                elif msg[0] == 'done':
+                    results.update(msg[1])
+                    del live[conn]
+                else:
+                    raise RuntimeError('BFGS worker failed: ' + msg[1])
+            if reqs:
+                vals = fbatch(np.concatenate([r[1] for r in reqs]),
+                              np.concatenate([r[2] for r in reqs]))
+                pos = 0
+                for conn, idx, _ in reqs:
+                    conn.send(vals[pos:pos + len(idx)])
+                    pos += len(idx)
+        return [scipy.optimize.OptimizeResult(results[i]) for i in range(B)]
+
+
+_bfgs_pool = None
+
+
+def bfgs_many(fbatch, x0s, hess_inv0, nproc=None):
+    """bfgs_batch, with the scipy drivers (pure Python, GIL-bound) spread over a
+    persistent pool of worker processes when there are enough objects."""
+    import atexit
+    import os
+    global _bfgs_pool
+    x0s = np.asarray(x0s, dtype=np.float64)
+    if nproc is None:
+        nproc = min(os.cpu_count() or 1, 16, len(x0s) // 32)
+    if nproc < 2:
+        return bfgs_batch(fbatch, x0s, hess_inv0)
+    if _bfgs_pool is None or len(_bfgs_pool.conns) != nproc:
+        if _bfgs_pool is not None:
+            _bfgs_pool.close()
+        _bfgs_pool = _BfgsProcessPool(nproc)
+        atexit.register(_bfgs_pool.close)
+    return _bfgs_pool.run(fbatch, x0s, hess_inv0)
+
+
 # ------------------------------------------------------------ the batched fit
 class _Replay:
     """Records the points a routine asks for, then replays their values."""
@@ -367,20 +489,33 @@ def _scan_round(eng, idx, grids, params, vsini):
     return out
 
 
-def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None, priors=None):
+def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None, priors=None,
+                  engine=None, timer=None):
     """vel_fit.process for a list of objects (each a list of SpecData); same
     arguments otherwise, paramDict0s one dictionary per object.  Returns the list
-    of result dictionaries of vel_fit.process."""
+    of result dictionaries of vel_fit.process.  `engine`: a LikelihoodEngine
+    already holding the objects on the device (then `objects` may be None)."""
     if config is None:
         raise RuntimeError('Config must be provided')
-    objects = [[o] if isinstance(o, spec_fit.SpecData) else list(o) for o in objects]
-    B = len(objects)
     options = options or {}
     fixParam = fixParam or []
+    if engine is not None:
+        objects = engine.objects
+    objects = [[o] if isinstance(o, spec_fit.SpecData) else list(o) for o in objects]
+    B = len(objects)
     min_vel, max_vel = config['min_vel'], config['max_vel']
     vel_step0, min_vel_step = config['vel_step0'], config['min_vel_step']
     second_minimizer = config.get('second_minimizer') or False
-    eng = spec_fit.LikelihoodEngine(objects, config, options)
+    eng = engine if engine is not None else spec_fit.LikelihoodEngine(objects, config, options)
+    eng.timer = timer
+    import time
+    phase = {}
+    t_last = [time.time()]
+
+    def lap(name):
+        now = time.time()
+        phase[name] = phase.get(name, 0.0) + now - t_last[0]
+        t_last[0] = now
     setup0 = objects[0][0].name
     specParams = list(spec_inter.getSpecParams(setup0, config))
     has_vsini = 'vsini' in paramDict0s[0]
@@ -392,6 +527,7 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
     vgrid = np.arange(min_vel, max_vel, vel_step0)
     st = _scan_round(eng, allb, [vgrid] * B, fobj.p0,
                      fobj.vsini0 if has_vsini else None)
+    lap('scan0')
     # 2. Nelder-Mead, restarted once from its final simplex if it did not converge
     sims = np.stack([vel_fit._get_simplex_start(
         st[i, 1], fixParam=fixParam, specParamNames=specParams, paramDict0=paramDict0s[i],
@@ -400,7 +536,8 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
     x = np.zeros((B, sims.shape[2]))
     todo = allb
     for attempt in range(2):
-        res = nelder_mead_lockstep(lambda i, X: fobj(todo[i], X), sims[todo])
+        res = nelder_mead_lockstep(lambda i, X: fobj(todo[i], X), sims[todo],
+                                   speculate_below=SPECULATE_BELOW)
         x[todo] = res['x']
         sims[todo] = res['final_simplex']
         failed = todo[~res['success']]
@@ -409,12 +546,14 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
         todo = failed
         if len(todo) == 0:
             break
+    lap('nelder_mead')
     # 3. BFGS polish (vel_fit.py:653-658)
     if second_minimizer:
         names = ['vel'] + (['vsini'] if fitVsini else []) + \
             [p for p in specParams if p not in fixParam]
-        bres = bfgs_batch(fobj, x, vel_fit.get_hess_inv(names))
+        bres = bfgs_many(fobj, x, vel_fit.get_hess_inv(names))
         x = np.array([r['x'] for r in bres])
+    lap('bfgs')
     vel, vsini, params, _ = fobj.unpack(allb, x)
     # 4. velocity posterior on shrinking grids (vel_fit.py:315-439), all objects per round
     best_vel = np.clip(vel, min_vel, max_vel)
@@ -443,9 +582,11 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
         active = a2
         if len(active) == 0:
             break
+    lap('refine')
     # 5. model at the best point (vel_fit.py:688-696)
     tot, info = eng.evaluate(allb, best_vel[:, None], params, vsini, want_model=True)
     chi_best = tot[:, 0]
+    lap('model')
     # 6. Hessian over the atmospheric parameters at the optimiser's velocity and vsini
     #    (vel_fit.py:698-722: hess_func keeps best_param's own velocity)
     hsteps = [vel_fit.HESS_STEP[_] for _ in specParams]
@@ -489,4 +630,7 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
             ret['chisq_array'].append(float(np.sum((((model - sd.spec) / sd.espec)[good])**2)))
             ret['npix_array'].append(int(good.sum()))
         out.append(ret)
+    lap('hessian')
+    eng.timer = None
+    process_batch.last_phase_seconds = phase
     return out

@@ -134,7 +134,7 @@ class PendingEval:
         if self.slot is None:
             return eng._evaluate_general(obj, vels, params, vs, outside_penalty,
                                          espec_systematic, False, raise_errors)
-        total, redo = eng._collect_fast(self.slot, obj, vels)
+        total, redo = eng._collect_fast(self.slot, obj, vels, outside_penalty)
         self.slot = None
         if redo.any():
             r = np.nonzero(redo)[0]
@@ -334,7 +334,7 @@ class LikelihoodEngine:
             sl.update(K=cap,
                       h_in=torch.empty(((2 + nd) * cap,), dtype=torch.float64, **pin),
                       h_oix=torch.empty((narm * cap,), dtype=torch.int32, **pin),
-                      h_chi=torch.empty((narm * cap,), dtype=torch.float64, **pin),
+                      h_chi=torch.empty((2 * narm * cap,), dtype=torch.float64, **pin),
                       h_flags=torch.empty((2 * narm * cap,), dtype=torch.int32, **pin),
                       d_in=_dev.empty(((2 + nd) * cap,), np.float64),
                       d_oix=_dev.empty((narm * cap,), np.int32),
@@ -368,7 +368,7 @@ class LikelihoodEngine:
         d_in.copy_(sl['h_in'][:(2 + nd) * K].view(2 + nd, K), non_blocking=True)
         d_oix.copy_(sl['h_oix'][:narm * K].view(narm, K), non_blocking=True)
         vmax = 0.0 if vsini is None else float(np.max(vsini, initial=0.0))
-        d_chi = self._scratch('chi', (narm, K), np.float64)
+        d_chi = self._scratch('chi', (2, narm, K), np.float64)    # chi-square | off-grid measure
         d_flags = self._scratch('flags', (2, narm, K), np.int32)
         nvert = bank0.nvert
         d_ids = self._scratch('ids', (K, nvert), np.int32)
@@ -382,7 +382,8 @@ class LikelihoodEngine:
             if bank.log_ids != bank0.log_ids:
                 q = _dev.upload(spec_inter.map_params(params, bank.log_ids).T, np.float64)
             rc = L.rvs_locate_grid(ctypes.byref(bank.gridmap), _dev.ptr(q), K, K, _dev.ptr(d_ids),
-                                   _dev.ptr(d_w), _dev.ptr(d_flags[1, a]), stream)
+                                   _dev.ptr(d_w), _dev.ptr(d_flags[1, a]), _dev.ptr(d_chi[1, a]),
+                                   stream)
             _cabi.check(rc, 'rvs_locate_grid')
             stride = batch.max_npix
             d_tn = self._scratch('tn', (K * stride,), np.float64)
@@ -394,25 +395,30 @@ class LikelihoodEngine:
                                    bank.nvert, _dev.ptr(d_in[1]) if vmax > 0 else None, vmax,
                                    int(bank.log_spec), ctypes.byref(obs), _dev.ptr(d_oix[a]),
                                    _dev.ptr(d_in[0]), K, _dev.ptr(d_tn), stride, _dev.ptr(d_work),
-                                   _dev.ptr(d_chi[a]), _dev.ptr(d_flags[0, a]), stream)
+                                   _dev.ptr(d_chi[0, a]), _dev.ptr(d_flags[0, a]), stream)
             _cabi.check(rc, 'rvs_chisq_fused')
             if t0 is not None:
                 self.timer.stop('fused', t0, K)
-        sl['h_chi'][:narm * K].view(narm, K).copy_(d_chi, non_blocking=True)
+        sl['h_chi'][:2 * narm * K].view(2, narm, K).copy_(d_chi, non_blocking=True)
         sl['h_flags'][:2 * narm * K].view(2, narm, K).copy_(d_flags, non_blocking=True)
         sl['event'].record()
         sl['busy'] = True
         return sl
 
-    def _collect_fast(self, sl, obj, vels):
+    def _collect_fast(self, sl, obj, vels, outside_penalty=True):
         """Wait for a submitted evaluation: (total (K,), redo (K,) bool)."""
         K, narm = len(obj), len(self.setups)
         sl['event'].synchronize()
-        chi = sl['h_chi'][:narm * K].view(narm, K).numpy()
+        both = sl['h_chi'][:2 * narm * K].view(2, narm, K).numpy()
+        chi, outside = both[0], both[1]
         flags = sl['h_flags'][:2 * narm * K].view(2, narm, K).numpy()
-        redo = (flags != 0).any(axis=(0, 1)) | ~np.isfinite(chi).all(axis=0)
+        redo = (flags != 0).any(axis=(0, 1)) | ~np.isfinite(both).all(axis=(0, 1))
         redo |= ~self._cover0[obj] | (vels < self.config['min_vel']) | \
             (vels > self.config['max_vel'])
+        if outside_penalty and outside.any():
+            # off-grid points were resolved on the device (nearest node); their
+            # penalty is added per arm as get_chisq does (spec_fit.py:895-896)
+            chi = outside * self.badchi[obj][None, :] + chi
         total = np.add.reduce(chi, axis=0)
         sl['busy'] = False
         return total, redo

@@ -88,10 +88,14 @@ class TemplateBank:
             if self.ndim <= 5:      # device-side vertex location (rvs_locate_grid)
                 uoff = np.concatenate([[0], np.cumsum(self.lens)])
                 self._gm = (_dev.upload(np.concatenate(self.uvecs), np.float64),
-                            _dev.upload(self.idgrid.reshape(-1), np.int32))
+                            _dev.upload(self.idgrid.reshape(-1), np.int32),
+                            _dev.upload(vecs.T / self.ptp[None, :], np.float64))
                 gm = _cabi.GridMap()
                 gm.d_uvec, gm.d_idgrid = self._gm[0].data_ptr(), self._gm[1].data_ptr()
+                gm.d_vnorm, gm.nnode = self._gm[2].data_ptr(), vecs.shape[1]
                 gm.ndim = self.ndim
+                for i in range(self.ndim):
+                    gm.ptp[i] = float(self.ptp[i])
                 for i in range(self.ndim):
                     gm.len[i], gm.uoff[i] = int(self.lens[i]), int(uoff[i])
                 self.gridmap = gm

@@ -30,6 +30,10 @@ def test_lockstep_nelder_mead_is_scipy():
     sims = rs.normal(size=(B, N + 1, N)) * 2
     res = batch_fit.nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000)
     few = batch_fit.nelder_mead_lockstep(fbatch, sims, xatol=1e-9, fatol=1e-12, maxiter=40)
+    spec = batch_fit.nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000,
+                                          speculate_below=10)
+    for k in ('x', 'fun', 'final_simplex', 'nit', 'nfev', 'success'):
+        assert np.array_equal(spec[k], res[k]), k
     for b in range(B):
         opts = {'fatol': 1e-3, 'xatol': 1e-2, 'initial_simplex': sims[b], 'maxiter': 10000,
                 'maxfev': np.inf}
@@ -65,6 +69,10 @@ def test_threaded_bfgs_pool_is_scipy():
         assert got[b]['fun'] == want['fun'] and got[b]['nit'] == want['nit']
     # requests were gathered: far fewer batched calls than scalar evaluations
     assert len(calls) < sum(calls) / 4
+    # the same through worker processes
+    got2 = batch_fit.bfgs_many(fbatch, x0, H0, nproc=2)
+    for b in range(B):
+        assert np.array_equal(got2[b]['x'], got[b]['x']) and got2[b]['nit'] == got[b]['nit']
 
 
 def test_batch_objective_matches_scalar_rules():

@@ -304,7 +304,7 @@ def test_locate_grid_bit_identical():
     d_ids, d_w = _dev.empty((K, 16), np.int32), _dev.empty((K, 16), np.float64)
     d_flag = _dev.empty((K,), np.int32)
     rc = _cabi.lib().rvs_locate_grid(ctypes.byref(bank.gridmap), _dev.ptr(d_q), K, K,
-                                     _dev.ptr(d_ids), _dev.ptr(d_w), _dev.ptr(d_flag),
+                                     _dev.ptr(d_ids), _dev.ptr(d_w), _dev.ptr(d_flag), None,
                                      _dev.stream())
     assert rc == 0
     flag = _dev.download(d_flag).astype(bool)
@@ -313,6 +313,18 @@ def test_locate_grid_bit_identical():
     assert 100 < flag.sum() < K - 100
     assert np.array_equal(_dev.download(d_ids)[~flag], ids[~flag])
     assert np.array_equal(_dev.download(d_w)[~flag], w[~flag])
+    # with the off-grid resolution on the device: the KD-tree's node and distance
+    d_out = _dev.empty((K,), np.float64)
+    rc = _cabi.lib().rvs_locate_grid(ctypes.byref(bank.gridmap), _dev.ptr(d_q), K, K,
+                                     _dev.ptr(d_ids), _dev.ptr(d_w), _dev.ptr(d_flag),
+                                     _dev.ptr(d_out), _dev.stream())
+    assert rc == 0
+    flag2, out = _dev.download(d_flag).astype(bool), _dev.download(d_out)
+    fin = np.isfinite(qm).all(axis=1)
+    assert np.array_equal(flag2, ~fin) and np.isnan(out[~fin]).all()
+    assert np.array_equal(_dev.download(d_ids)[fin], ids[fin])
+    assert np.array_equal(_dev.download(d_w)[fin], w[fin])
+    close(out[fin], outside[fin], rtol=1e-14, atol=0, what='off-grid measure')
 
 
 def test_scan_stats_edge_cases():
