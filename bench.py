@@ -244,18 +244,20 @@ def run_gpu(args):
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else \
         'fallback 6650 GB/s (B200_PROFILING.md)'
     roof = None
-    if ksum.get('fused_ms_total'):
-        # one evaluation of one spectrum = one item in each arm's launch; the
-        # algorithmic bytes are SURVEY.md 8d's per-evaluation figure
-        narm = len(setups)
-        evals = ksum['fused_items_per_launch'] * ksum['fused_launches'] / narm
-        ach = beval * evals / (ksum['fused_ms_total'] * 1e-3) / 1e9
-        roof = dict(bound='hbm', kernel='rvs_chisq_fused: taps + chunk_kernel + gram_mma/solve/resid kernels',
+    if ksum.get('fused_eval_ms_total'):
+        # one record = one evaluation call: rvs_locate_grid + rvs_chisq_fused of every
+        # arm (the arms run concurrently on their own streams), timed with CUDA events on
+        # the stream they fork from and join to; the algorithmic bytes are SURVEY.md 8d's
+        # per-evaluation figure (all arms)
+        evals = ksum['fused_eval_items_per_launch'] * ksum['fused_eval_launches']
+        ach = beval * evals / (ksum['fused_eval_ms_total'] * 1e-3) / 1e9
+        roof = dict(bound='hbm', kernel='rvs_chisq_fused (prep + chunk_kernel + gram_mma/solve/'
+                                        'resid kernels) of the 3 arms of one evaluation call',
                     achieved=ach, peak=hbm_peak, unit='GB/s', frac=ach / hbm_peak, traffic=None,
                     peak_source=peak_src, algorithmic_bytes_per_eval=beval,
-                    evals_timed=evals, ms_total=ksum['fused_ms_total'],
-                    ms_per_launch=ksum['fused_ms_per_launch'],
-                    items_per_launch=ksum['fused_items_per_launch'])
+                    evals_timed=evals, ms_total=ksum['fused_eval_ms_total'],
+                    ms_per_call=ksum['fused_eval_ms_per_launch'],
+                    items_per_call=ksum['fused_eval_items_per_launch'])
     nspec_total = B * world
     per_step = ms / args.steps
     fit = args.mode == 'fit'

@@ -312,6 +312,8 @@ class LikelihoodEngine:
         n = int(np.prod(shape))
         t = self._buf.get(name)
         if t is None or t.numel() < n:
+            if t is not None:
+                _dev.torch_mod().cuda.synchronize()   # side streams may still read the old one
             t = _dev.empty((int(n * 1.25) + 64,), dtype)
             self._buf[name] = t
         return t[:n].view(*shape)
@@ -371,25 +373,39 @@ class LikelihoodEngine:
         d_chi = self._scratch('chi', (2, narm, K), np.float64)    # chi-square | off-grid measure
         d_flags = self._scratch('flags', (2, narm, K), np.int32)
         nvert = bank0.nvert
-        d_ids = self._scratch('ids', (K, nvert), np.int32)
-        d_w = self._scratch('w', (K, nvert), np.float64)
-        stream = _dev.stream()
+        torch = _dev.torch_mod()
+        main = torch.cuda.current_stream()
+        # the arms are independent: each runs its kernel sequence on its own stream,
+        # so the small kernels of one arm (vertex location, preparation, solves) fill
+        # the SMs left idle by the tails and launch gaps of the others
+        if not hasattr(self, '_arm_streams'):
+            self._arm_streams = [torch.cuda.Stream() for _ in self.setups]
+            self._arm_events = [torch.cuda.Event() for _ in self.setups]
+            self._fork_event = torch.cuda.Event()
+        t0 = self.timer.start() if self.timer else None
+        self._fork_event.record(main)
         for a, name in enumerate(self.setups):
             arm = self.arms[name]
             bank, batch = arm['bank'], arm['batch']
             obs = batch.obs(self.npoly, self.rbf, sys_errs[a])
+            st = self._arm_streams[a]
+            st.wait_event(self._fork_event)
+            stream = ctypes.c_void_p(st.cuda_stream)
+            d_ids = self._scratch(f'ids{a}', (K, nvert), np.int32)
+            d_w = self._scratch(f'w{a}', (K, nvert), np.float64)
             q = d_in[2:]
             if bank.log_ids != bank0.log_ids:
-                q = _dev.upload(spec_inter.map_params(params, bank.log_ids).T, np.float64)
+                with torch.cuda.stream(st):
+                    q = _dev.upload(spec_inter.map_params(params, bank.log_ids).T, np.float64)
             rc = L.rvs_locate_grid(ctypes.byref(bank.gridmap), _dev.ptr(q), K, K, _dev.ptr(d_ids),
                                    _dev.ptr(d_w), _dev.ptr(d_flags[1, a]), _dev.ptr(d_chi[1, a]),
                                    stream)
             _cabi.check(rc, 'rvs_locate_grid')
             stride = batch.max_npix
-            d_tn = self._scratch('tn', (K * stride,), np.float64)
-            d_work = self._scratch('work', (L.rvs_fused_workspace(K, bank.tapcap(vmax), bank.npix_t),),
+            d_tn = self._scratch(f'tn{a}', (K * stride,), np.float64)
+            d_work = self._scratch(f'work{a}',
+                                   (L.rvs_fused_workspace(K, bank.tapcap(vmax), bank.npix_t),),
                                    np.float64)
-            t0 = self.timer.start() if self.timer else None
             rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
                                    ctypes.byref(bank.knots), _dev.ptr(d_ids), _dev.ptr(d_w),
                                    bank.nvert, _dev.ptr(d_in[1]) if vmax > 0 else None, vmax,
@@ -397,8 +413,11 @@ class LikelihoodEngine:
                                    _dev.ptr(d_in[0]), K, _dev.ptr(d_tn), stride, _dev.ptr(d_work),
                                    _dev.ptr(d_chi[0, a]), _dev.ptr(d_flags[0, a]), stream)
             _cabi.check(rc, 'rvs_chisq_fused')
-            if t0 is not None:
-                self.timer.stop('fused', t0, K)
+            self._arm_events[a].record(st)
+        for a in range(narm):
+            main.wait_event(self._arm_events[a])
+        if t0 is not None:
+            self.timer.stop('fused_eval', t0, K)
         sl['h_chi'][:2 * narm * K].view(2, narm, K).copy_(d_chi, non_blocking=True)
         sl['h_flags'][:2 * narm * K].view(2, narm, K).copy_(d_flags, non_blocking=True)
         sl['event'].record()
