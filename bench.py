@@ -198,6 +198,27 @@ def run_gpu(args):
 
     eng = spec_fit.LikelihoodEngine(to_specdata(), cfg, opts)
     L = _cabi.lib()
+    if args.stage_profile:
+        # diagnostic run (not a bench value): arms serialised on one stream, CUDA
+        # events around every kernel of the evaluation call
+        import ctypes
+        eng.serial_arms = True
+        for _ in range(2):
+            step_resident(eng)
+        L.rvs_profile_enable(1)
+        step_resident(eng)
+        ms = (ctypes.c_double * 7)()
+        n = (ctypes.c_int64 * 7)()
+        L.rvs_profile_read(ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(n, ctypes.c_void_p), 7)
+        L.rvs_profile_enable(0)
+        names = ['locate', 'nearest', 'prep', 'chunk', 'gram_mma', 'gram_solve', 'resid_mma']
+        out = {k: dict(launches=int(c), us_per_launch=1e3 * t / max(1, c), ms_total=t)
+               for k, t, c in zip(names, ms, n)}
+        out['note'] = ('arms serialised on one stream; warm caches; per-launch = one arm, '
+                       f'{B // max(1, args.groups)} items')
+        if rank == 0:
+            print(json.dumps({'stage_profile': out}))
+        return
 
     def barrier():
         if world > 1:
@@ -420,9 +441,11 @@ def main():
     ap.add_argument('--workload', default='desi', choices=list(WORKLOADS))
     ap.add_argument('--batch', type=int, default=2048, help='spectra per GPU per step')
     ap.add_argument('--evals', type=int, default=EVALS_PER_FIT)
-    ap.add_argument('--cpu-fraction', type=float, default=0.25,
+    ap.add_argument('--cpu-fraction', type=float, default=1.0,
                     help='fraction of the per-spectrum evaluations the CPU sample runs')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--stage-profile', action='store_true',
+                    help='diagnostic: CUDA-event time of every kernel of the evaluation call')
     ap.add_argument('--mode', default='proxy', choices=['proxy', 'fit'],
                     help='proxy: scan + fixed count of evaluations; fit: complete fits')
     ap.add_argument('--groups', type=int, default=2,

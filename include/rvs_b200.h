@@ -63,6 +63,13 @@ int rvs_version(void);
 /* number of CUDA kernels this library has launched in this process (for
  * bench.py's gpu_launches) */
 int64_t rvs_launch_count(void);
+/* Optional per-stage timing of the fused evaluation (bench.py --stage-profile):
+ * when enabled, CUDA events bracket every kernel on its launching stream.
+ * rvs_profile_read synchronises the device, writes the summed milliseconds and
+ * launch counts of stages 0..nstage-1 (locate, nearest, prep, chunk, gram,
+ * solve, resid), clears the records and returns the number of stages. */
+void rvs_profile_enable(int on);
+int rvs_profile_read(double *ms_total, int64_t *launches, int nstage);
 
 /* ---- native spline: drop-in for the reference's cffi module ------------- */
 /* Host-buffer entry points with the reference's exact signatures and status
@@ -212,14 +219,32 @@ int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
  * status[K] (template bits | RVS_ST_NOT_PD | RVS_ST_RANGE | RVS_ST_LIMIT).
  * Needs knots->ratio_dev < 1e-8 (exactly uniform or log-uniform knots) and
  * tapcap <= RVS_MAX_FUSED_TAPS, else RVS_E_LIMIT: use the general path.
- * rvs_fused_chunks: how many warps share one item. */
+ * rvs_fused_chunks: how many warps share one item.
+ *
+ * box (may be NULL): TMA descriptor of a DENSE regular 4-D fp32 grid -- row id =
+ * C-order index of the node's grid position, no missing nodes (rvs_gridbox_init).
+ * With it the 16 corner rows of a polylinear item (the 2x2x2x2 box at the grid
+ * position of d_ids[k*16]) are fetched by the copy engine as two 5-D tensor
+ * tiles per block of template pixels instead of 16 per-lane row gathers; results
+ * are identical. */
+typedef struct {
+  unsigned char tmap[128]; /* CUtensorMap {ld, len[3], len[2], len[1], len[0]} fp32 */
+  int32_t len[4];          /* grid lengths, slowest dimension first */
+  int32_t cols;            /* template pixels per tile the descriptor was built for */
+  int32_t rows;            /* corner rows per tile (4 or 8) */
+} rvs_gridbox;
+/* Fills *box for the grid rows at d_grid (row stride ld floats, ld a multiple of
+ * 4, prod(len) rows).  RVS_E_ARG unless ndim == 4; RVS_E_CUDA if the driver
+ * refuses the descriptor. */
+int rvs_gridbox_init(rvs_gridbox *box, const void *d_grid, int64_t ld, int ndim,
+                     const int32_t *len);
 int rvs_fused_chunks(int npix_t, int tapcap);
 int64_t rvs_fused_workspace(int K, int tapcap, int npix_t);
 int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld, const rvs_knots *knots,
                     const int32_t *d_ids, const double *d_w, int nvert, const double *d_vsini,
                     double vsini_max, int log_spec, const rvs_obs *obs, const int32_t *d_oix,
                     const double *d_vels, int K, double *d_tn, int64_t tn_stride, double *d_work,
-                    double *d_chisq, int32_t *d_status, void *stream);
+                    double *d_chisq, int32_t *d_status, const rvs_gridbox *box, void *stream);
 
 /* RV-grid statistics of find_best for S scans: scan s has nv velocities
  * vels[s*nv..] and chi-squares chisq[(s*npar+q)*nv + j] for npar templates.

@@ -45,6 +45,12 @@ class GridMap(ctypes.Structure):
                 ('nnode', ctypes.c_int32), ('d_vnorm', c_dp), ('ptp', c_dbl * 5)]
 
 
+class GridBox(ctypes.Structure):
+    """struct rvs_gridbox"""
+    _fields_ = [('tmap', ctypes.c_ubyte * 128), ('len', ctypes.c_int32 * 4),
+                ('cols', ctypes.c_int32), ('rows', ctypes.c_int32)]
+
+
 class CcfArm(ctypes.Structure):
     """struct rvs_ccf_arm"""
     _fields_ = [('d_fft', c_dp), ('d_fft2', c_dp), ('d_lo', c_dp), ('d_hi', c_dp),
@@ -58,6 +64,8 @@ SIGNATURES = {
     'rvs_last_error': (ctypes.c_char_p, []),
     'rvs_version': (c_int, []),
     'rvs_launch_count': (c_i64, []),
+    'rvs_profile_enable': (None, [c_int]),
+    'rvs_profile_read': (c_int, [c_dp, c_dp, c_int]),
     'rvs_spline_construct': (None, [c_dp, c_dp, c_int, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'rvs_spline_eval': (c_int, [c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_int,
                                 c_dp]),
@@ -73,11 +81,12 @@ SIGNATURES = {
     'rvs_chisq_scan': (c_int, [c_dp, c_i64, c_dp, ctypes.POINTER(Knots), ctypes.POINTER(Obs),
                                c_dp, c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                c_dp]),
+    'rvs_gridbox_init': (c_int, [ctypes.POINTER(GridBox), c_dp, c_i64, c_int, c_dp]),
     'rvs_fused_chunks': (c_int, [c_int, c_int]),
     'rvs_fused_workspace': (c_i64, [c_int, c_int, c_int]),
     'rvs_chisq_fused': (c_int, [c_dp, c_int, c_i64, ctypes.POINTER(Knots), c_dp, c_dp, c_int,
                                 c_dp, c_dbl, c_int, ctypes.POINTER(Obs), c_dp, c_dp, c_int,
-                                c_dp, c_i64, c_dp, c_dp, c_dp, c_dp]),
+                                c_dp, c_i64, c_dp, c_dp, c_dp, ctypes.POINTER(GridBox), c_dp]),
     'rvs_scan_stats': (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
     'rvs_ccf_workspace': (c_i64, [ctypes.POINTER(CcfArm), c_int]),
     'rvs_ccf_accumulate': (c_int, [ctypes.POINTER(CcfArm), c_dp, c_dp, c_int, c_dp, c_dp, c_dp,
@@ -92,11 +101,12 @@ def lib():
     """Load the shared library (once).  Raises if it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get('RVS_LIB', LIB_PATH)   # tuning builds (csrc/Makefile OUT=...)
+        if not os.path.exists(path):
             raise RuntimeError(
-                f'{LIB_PATH} not found: build it with `python __graft_entry__.py build` '
+                f'{path} not found: build it with `python __graft_entry__.py build` '
                 '(make -C rvspecfit_b200/csrc).  There is no CPU fallback.')
-        L = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)      # AttributeError if the symbol is missing
             fn.restype, fn.argtypes = res, args

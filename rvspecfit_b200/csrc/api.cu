@@ -8,7 +8,19 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
+
+#ifndef RVS_TMA_COLS
+#define RVS_TMA_COLS 64
+#endif
+#define RVS_TMA_COLS_HOST RVS_TMA_COLS
+#ifndef RVS_TMA_ROWS
+#define RVS_TMA_ROWS 8
+#endif
+#define RVS_TMA_ROWS_HOST RVS_TMA_ROWS
 
 namespace rvs {
 
@@ -96,6 +108,98 @@ struct DevBuf {
 extern "C" const char *rvs_last_error(void) { return rvs::g_err; }
 extern "C" int rvs_version(void) { return 100; }
 extern "C" int64_t rvs_launch_count(void) { return rvs::g_launches.load(); }
+
+namespace rvs {
+struct ProfRec { int stage; cudaEvent_t e0, e1; };
+static bool g_prof = false;
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_rec;
+static cudaEvent_t g_prof_open[ST_COUNT][8];   // begin events by (stage, stream slot)
+static cudaStream_t g_prof_stream[ST_COUNT][8];
+bool prof_on() { return g_prof; }
+void prof_begin(int stage, cudaStream_t st) {
+  if (!g_prof) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < 8; i++)
+    if (!g_prof_open[stage][i]) { g_prof_open[stage][i] = e; g_prof_stream[stage][i] = st; return; }
+  cudaEventDestroy(e);
+}
+void prof_end(int stage, cudaStream_t st) {
+  if (!g_prof) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < 8; i++)
+    if (g_prof_open[stage][i] && g_prof_stream[stage][i] == st) {
+      cudaEvent_t e1;
+      if (cudaEventCreate(&e1) == cudaSuccess) {
+        cudaEventRecord(e1, st);
+        g_prof_rec.push_back({stage, g_prof_open[stage][i], e1});
+      }
+      g_prof_open[stage][i] = nullptr;
+      return;
+    }
+}
+}  // namespace rvs
+
+extern "C" int rvs_gridbox_init(rvs_gridbox *box, const void *d_grid, int64_t ld, int ndim,
+                                const int32_t *len) {
+  using namespace rvs;
+  RVS_REQUIRE(box && d_grid && len, RVS_E_ARG, "rvs_gridbox_init: null pointer");
+  RVS_REQUIRE(ndim == 4, RVS_E_ARG, "rvs_gridbox_init: ndim=%d (the box gather is 4-D)", ndim);
+  RVS_REQUIRE(ld > 0 && ld % 4 == 0 && ((uintptr_t)d_grid & 15) == 0, RVS_E_ARG,
+              "rvs_gridbox_init: rows must be 16-byte aligned");
+  for (int i = 0; i < 4; i++)
+    RVS_REQUIRE(len[i] >= 2, RVS_E_ARG, "rvs_gridbox_init: len[%d]=%d", i, len[i]);
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                               const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  RVS_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  RVS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, RVS_E_CUDA,
+              "rvs_gridbox_init: cuTensorMapEncodeTiled not available");
+  const cuuint64_t row = (cuuint64_t)ld * 4;
+  const cuuint64_t dims[5] = {(cuuint64_t)ld, (cuuint64_t)len[3], (cuuint64_t)len[2],
+                              (cuuint64_t)len[1], (cuuint64_t)len[0]};
+  const cuuint64_t strides[4] = {row, row * len[3], row * len[3] * len[2],
+                                 row * len[3] * len[2] * len[1]};
+  const cuuint32_t boxdim[5] = {(cuuint32_t)RVS_TMA_COLS_HOST, 2, 2, RVS_TMA_ROWS_HOST / 4, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  alignas(64) CUtensorMap tm;
+  const CUresult r = ((EncodeFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                                    const_cast<void *>(d_grid), dims, strides, boxdim, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RVS_REQUIRE(r == CUDA_SUCCESS, RVS_E_CUDA, "rvs_gridbox_init: cuTensorMapEncodeTiled -> %d",
+              (int)r);
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  memcpy(box->tmap, &tm, 128);
+  for (int i = 0; i < 4; i++) box->len[i] = len[i];
+  box->cols = RVS_TMA_COLS_HOST;
+  box->rows = RVS_TMA_ROWS_HOST;
+  return 0;
+}
+
+extern "C" void rvs_profile_enable(int on) { rvs::g_prof = on != 0; }
+extern "C" int rvs_profile_read(double *ms_total, int64_t *launches, int nstage) {
+  using namespace rvs;
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < nstage; i++) { ms_total[i] = 0; launches[i] = 0; }
+  for (auto &r : g_prof_rec) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (r.stage < nstage) { ms_total[r.stage] += ms; launches[r.stage]++; }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof_rec.clear();
+  return ST_COUNT;
+}
 
 extern "C" void rvs_spline_construct(double *xs, double *ys, int N, double *A, double *B,
                                      double *C, double *D, double *hout) {

@@ -28,6 +28,8 @@
 //     T = v y_i + u y_{i+1} + s_i (v^3 - v) + (s_{i+1}/r^2) (u^3 - u),
 // algebraically the reference's A dl^3 + B dr^3 + C dl + D dr (spliner.c:97-106).
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is resolved at run time, api.cu)
+
 #include "chisq_device.cuh"
 #include "template_device.cuh"
 
@@ -44,6 +46,28 @@ constexpr int CK_RING = RVS_CK_RING;  // slots (of 512 B) of the gather prefetch
 #define RVS_CK_MINB 6
 #endif
 constexpr int CK_MINB = RVS_CK_MINB;  // resident CTAs per SM the register budget allows
+#ifndef RVS_CK_MINB_TMA
+#define RVS_CK_MINB_TMA 6
+#endif
+constexpr int CK_MINB_TMA = RVS_CK_MINB_TMA;  // same for the TMA variant
+// TMA gather (dense regular 4-D grids, rvs_gridbox): one cp.async.bulk.tensor of a
+// [TMA_COLS px][2][2][2][1] box brings 8 of the 16 corner rows of a column block
+// into one ring stage; two stages (the two halves of the first grid dimension).
+#ifndef RVS_TMA_COLS
+#define RVS_TMA_COLS 64
+#endif
+constexpr int TMA_COLS = RVS_TMA_COLS;     // knots per column block (32 lanes x 2 or 4)
+#ifndef RVS_TMA_ROWS
+#define RVS_TMA_ROWS 8
+#endif
+constexpr int TMA_ROWS = RVS_TMA_ROWS;     // corner rows per stage: 8 (box 2x2x2x1) or 4 (2x2x1x1)
+constexpr int TMA_NQ = 16 / TMA_ROWS;      // stages per column block
+#ifndef RVS_TMA_NSTG
+#define RVS_TMA_NSTG 2
+#endif
+constexpr int TMA_NSTG = RVS_TMA_NSTG;     // ring stages per warp (NSTG - 1 in flight)
+constexpr int TMA_STG_BYTES = TMA_COLS * TMA_ROWS * 4;
+constexpr int TMA_RING_DOUBLES = TMA_NSTG * TMA_STG_BYTES / 8;
 struct TrueTag { static constexpr bool value = true; };
 struct FalseTag { static constexpr bool value = false; };
 template <int N>
@@ -62,7 +86,8 @@ struct ChunkArgs {
   int tapstride;
   // per-item records written by prep_kernel
   const double *rec;      // [K][2]  Doppler factor f, ln f (0 on linear knot grids)
-  const int32_t *irec;    // [K][4]  posmin, nk, S (chunks the item really has), kmax
+  const int32_t *irec;    // [K][8]  posmin, nk, S (chunks the item really has), kmax,
+                          //         grid position of the item's first corner (TMA gather)
   const int32_t *pbound;  // [K][nch+1] first pixel of every chunk, pbound[S] = npix
   const double *lam_t, *hinv;
   int log_spec, log_step;
@@ -79,7 +104,8 @@ struct ChunkArgs {
   double *tn;
   int64_t tn_stride;
   int32_t *status;
-  int wcap;  // doubles per smem buffer per warp
+  int wcap;   // doubles of smem buffer B0 per warp
+  int wcap1;  // doubles of smem buffer B1 per warp (>= wcap; holds the gather ring)
   int nch;   // chunks per item (upper bound; surplus chunks exit)
   int C;     // knots per chunk (upper bound)
   int K;
@@ -107,16 +133,20 @@ struct PrepArgs {
   double *rec;
   int32_t *irec, *pbound;
   int32_t *status;
+  // TMA gather: first corner id -> grid position (blen = lengths of dims 1..3)
+  const int32_t *ids;
+  int nvert, box;
+  int blen[3];
 };
 
 __global__ void __launch_bounds__(128) prep_kernel(PrepArgs a) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= a.K) return;
-  int32_t *irec = a.irec + (int64_t)k * 4;
+  int32_t *irec = a.irec + (int64_t)k * 8;
   const int obj = a.oix[k];
   if (obj < 0) {  // no spectrum in this setup: no chunks
-    if (lane < 4) irec[lane] = 0;
+    if (lane < 8) irec[lane] = 0;
     if (lane == 0) a.status[k] = 0;
     return;
   }
@@ -174,6 +204,13 @@ __global__ void __launch_bounds__(128) prep_kernel(PrepArgs a) {
     a.rec[2 * (int64_t)k] = f;
     a.rec[2 * (int64_t)k + 1] = qf;
     irec[0] = posmin; irec[1] = nk; irec[2] = S; irec[3] = kmax;
+    if (a.box) {  // C-order position of node ids[0] in the dense grid
+      int id = a.ids[(int64_t)k * a.nvert];
+      const int p3 = id % a.blen[2]; id /= a.blen[2];
+      const int p2 = id % a.blen[1]; id /= a.blen[1];
+      const int p1 = id % a.blen[0]; id /= a.blen[0];
+      irec[4] = id; irec[5] = p1; irec[6] = p2; irec[7] = p3;
+    }
   }
   // ---- first pixel of every chunk: the first pixel whose knot interval is >= c
   // (pos is non-decreasing in p).  One lane per chunk boundary: a linear guess in
@@ -251,33 +288,34 @@ __device__ __forceinline__ void prefetch_l1(const void *p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
-template <typename GT, int NV>
-__global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a) {
-  extern __shared__ __align__(16) double sm[];
+template <typename GT, int NV, bool TMA>
+__global__ void __launch_bounds__(CK_THREADS, TMA ? CK_MINB_TMA : CK_MINB)
+chunk_kernel(const ChunkArgs a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) double sm[];
   __shared__ int64_t s_off[CK_WARPS][32];  // element offset of each grid row
   __shared__ double s_w[CK_WARPS][32];
+  __shared__ __align__(8) uint64_t s_bar[CK_WARPS][TMA_NSTG];  // TMA gather: stage barriers
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t wg = (int64_t)blockIdx.x * CK_WARPS + wid;
   const int k = (int)(wg / a.nch), s = (int)(wg - (int64_t)k * a.nch);
   if (k >= a.K) return;
-  double *B0 = sm + (size_t)wid * 2 * a.wcap, *B1 = B0 + a.wcap;
+  double *B0 = sm + (size_t)wid * (a.wcap + a.wcap1), *B1 = B0 + a.wcap;
+  const unsigned bar_s = (unsigned)__cvta_generic_to_shared(&s_bar[wid][0]);
+  if (TMA && lane == 0) {  // before any load is outstanding: the fence has nothing to wait for
+#pragma unroll
+    for (int i = 0; i < TMA_NSTG; i++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8 * i) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const int n = a.npix_t;
-  const int4 ir = __ldg(reinterpret_cast<const int4 *>(a.irec) + k);  // posmin, nk, S, kmax
+  const int4 ir = __ldg(reinterpret_cast<const int4 *>(a.irec) + 2 * k);  // posmin, nk, S, kmax
+  int4 bp = make_int4(0, 0, 0, 0);  // grid position of the first corner (TMA gather)
+  if (TMA) bp = __ldg(reinterpret_cast<const int4 *>(a.irec) + 2 * k + 1);
   const int posmin = ir.x, nk = ir.y, S = ir.z;
   if (s >= S) return;
   const int c0 = posmin + (int)((int64_t)nk * s / S), c1 = posmin + (int)((int64_t)nk * (s + 1) / S);
   if (c1 <= c0) return;
   const int kmax = ir.w;
-  const int obj = a.oix[k];
-  const int64_t p0 = a.off[obj];
-  const int64_t gp0 = a.goff[obj];
-  const double *lam = a.lam + gp0, *ql = (a.log_step ? a.loglam : a.lam) + gp0;
-  const double2 fq = __ldg(reinterpret_cast<const double2 *>(a.rec) + k);
-  const double f = fq.x, qf = fq.y;
-  auto pos_q = [&](double q) -> int {
-    const int pos = (int)((q - a.q0) * a.qstep_inv);
-    return max(0, min(pos, n - 2));
-  };
   // knot windows (global indices, inclusive): Y on [ya0, ya1], raw y on [ya0-kmax, ya1+kmax]
   // which may stick out of the template: those knots are the zero padding of the
   // reference's 'same' convolution (spec_fit.py:677-680)
@@ -288,6 +326,35 @@ __global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a)
     if (lane == 0) atomicOr(a.status + k, RVS_ST_LIMIT);
     return;
   }
+  // ---- TMA gather: the first stages go out as soon as the window is known
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(B1);
+  const uint64_t tm = reinterpret_cast<uint64_t>(&tmap);
+  const int ncb = (W0 + TMA_COLS - 1) / TMA_COLS;
+  const int nstep = TMA_NQ * ncb;  // step t = (column block t / NQ, part t % NQ), stage t % NSTG
+  auto issue = [&](int t) {  // lane 0 only
+    const int slot = t % TMA_NSTG;
+    const unsigned bar = bar_s + 8 * slot, dst = ring_s + slot * TMA_STG_BYTES;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TMA_STG_BYTES) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(tm), "r"(bar),
+        "r"(w0 + (t / TMA_NQ) * TMA_COLS), "r"(bp.w), "r"(bp.z),
+        "r"(TMA_NQ == 4 ? bp.y + (t & 1) : bp.y),
+        "r"(TMA_NQ == 4 ? bp.x + ((t >> 1) & 1) : bp.x + (t & 1))
+        : "memory");
+  };
+  if (TMA && lane == 0)
+    for (int t = 0; t < TMA_NSTG - 1 && t < nstep; t++) issue(t);
+  const int obj = a.oix[k];
+  const int64_t p0 = a.off[obj];
+  const int64_t gp0 = a.goff[obj];
+  const double *lam = a.lam + gp0, *ql = (a.log_step ? a.loglam : a.lam) + gp0;
+  const double2 fq = __ldg(reinterpret_cast<const double2 *>(a.rec) + k);
+  const double f = fq.x, qf = fq.y;
+  auto pos_q = [&](double q) -> int {
+    const int pos = (int)((q - a.q0) * a.qstep_inv);
+    return max(0, min(pos, n - 2));
+  };
   if (lane < a.nvert) {
     s_off[wid][lane] = (int64_t)a.ids[(int64_t)k * a.nvert + lane] * a.ld;
     s_w[wid][lane] = a.w[(int64_t)k * a.nvert + lane];
@@ -324,7 +391,82 @@ __global__ void __launch_bounds__(CK_THREADS, CK_MINB) chunk_kernel(ChunkArgs a)
   // accumulated a slot.  Loads therefore stay in flight during the widening, the
   // FMAs and the exp, and cost no registers.  The ring lives in B1, which the
   // later stages only use after the gather.
-  {
+  if constexpr (TMA) {
+    // One elected lane issues, per column block of TMA_COLS knots, two tensor
+    // copies of 8 corner rows each ([TMA_COLS][2][2][2][1] boxes at first-dimension
+    // positions p0 and p0 + 1) into the two ring stages; the copy engine computes
+    // the 16 row addresses and zero-fills what lies outside the grid (columns
+    // before knot 0 or past the row, rows past the top edge).  A stage's mbarrier
+    // flips when its 8 x TMA_COLS x 4 bytes have landed; the lanes then read their
+    // own columns (conflict-free LDS.64/128), and a stage is re-armed as soon as the
+    // warp has consumed it, so one stage is always in flight behind the FMAs.
+    static_assert(sizeof(GT) == 4 && NV == 16, "TMA gather: fp32 grid, 16 corners");
+    constexpr int TV = TMA_COLS / 32;  // knots per lane and column block (2 or 4)
+    const bool round32 = f32row && a.log_spec;
+    auto wait = [&](int slot, unsigned parity) {
+      asm volatile(
+          "{\n\t.reg .pred P1;\n\t"
+          "LAB_WAIT:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+          "@P1 bra DONE;\n\t"
+          "bra LAB_WAIT;\n\t"
+          "DONE:\n\t}" ::"r"(bar_s + 8 * slot), "r"(parity) : "memory");
+    };
+    __syncwarp();
+    const char *ring = reinterpret_cast<const char *>(B1) + lane * (TV * 4);
+    int slot = 0;          // stage of step t
+    unsigned parity = 0;   // (t / NSTG) & 1
+    for (int cb = 0; cb < ncb; cb++) {
+      const int i0 = cb * TMA_COLS + lane * TV;
+      const int g = w0 + i0;
+      double acc[TV];
+#pragma unroll
+      for (int e = 0; e < TV; e++) acc[e] = 0;
+#pragma unroll
+      for (int hf = 0; hf < TMA_NQ; hf++) {
+        const int t = TMA_NQ * cb + hf;
+        // the stage consumed at step t - 1 is free (the __syncwarp below): re-arm it
+        if (lane == 0 && t + TMA_NSTG - 1 < nstep) issue(t + TMA_NSTG - 1);
+        wait(slot, parity);
+        const char *stg = ring + slot * TMA_STG_BYTES;
+#pragma unroll
+        for (int r = 0; r < TMA_ROWS; r++) {
+          // a single-row item uses its row alone (no 0 x neighbour products)
+          if (!f32row || (hf == 0 && r == 0)) {
+            const double wj = s_w[wid][hf * TMA_ROWS + r];
+            if constexpr (TV == 4) {
+              const float4 v = *reinterpret_cast<const float4 *>(stg + r * (TMA_COLS * 4));
+              acc[0] = fma(wj, (double)v.x, acc[0]);
+              acc[1] = fma(wj, (double)v.y, acc[1]);
+              acc[2] = fma(wj, (double)v.z, acc[2]);
+              acc[3] = fma(wj, (double)v.w, acc[3]);
+            } else {
+              const float2 v = *reinterpret_cast<const float2 *>(stg + r * (TMA_COLS * 4));
+              acc[0] = fma(wj, (double)v.x, acc[0]);
+              acc[1] = fma(wj, (double)v.y, acc[1]);
+            }
+          }
+        }
+        __syncwarp();  // every lane has read the stage: it may be overwritten
+        if (++slot == TMA_NSTG) { slot = 0; parity ^= 1; }
+      }
+      if (i0 < W0) {
+#pragma unroll
+        for (int e = 0; e < TV; e++) {
+          double y = 0;
+          if (g + e >= 0 && g + e < n) {  // else zero padding of the 'same' convolution
+            y = a.log_spec ? exp(acc[e]) : acc[e];
+            if (round32) y = (double)(float)y;
+            if (!(fabs(y) <= 1e100)) flag |= RVS_ST_TEMPLATE_BAD;
+          }
+          acc[e] = y;
+        }
+#pragma unroll
+        for (int e = 0; e < TV; e += 2)
+          *reinterpret_cast<double2 *>(B0 + i0 + e) = make_double2(acc[e], acc[e + 1]);
+      }
+    }
+  } else {
     constexpr int VEC = RowLoader<GT>::VEC;
     using Raw = typename RowLoader<GT>::Raw;
     const bool round32 = f32row && sizeof(GT) == 4 && a.log_spec;

@@ -3,6 +3,8 @@
 // stage B (gram_kernel.cuh: continuum solve -> chi-square).  The spline never
 // goes to HBM; the only intermediate is T/sigma (8 bytes per observed pixel,
 // L2-resident between the two stages).
+#include <string.h>
+
 #include <algorithm>
 
 #include "chunk_kernel.cuh"
@@ -19,14 +21,19 @@ int launch_gram_mma_group1(const GramMmaArgs &, int, cudaStream_t);
 int launch_gram_mma_group2(const GramMmaArgs &, int, cudaStream_t);
 int launch_gram_mma_group3(const GramMmaArgs &, int, cudaStream_t);
 
-template <typename GT, int NV>
-static int launch_chunk_one(const ChunkArgs &a, size_t smem, cudaStream_t st) {
-  auto kern = chunk_kernel<GT, NV>;
+template <typename GT, int NV, bool TMA = false>
+static int launch_chunk_one(const ChunkArgs &a, size_t smem, cudaStream_t st,
+                            const CUtensorMap *tm = nullptr) {
+  auto kern = chunk_kernel<GT, NV, TMA>;
+  alignas(64) CUtensorMap tmap;
+  if (tm) memcpy(&tmap, tm, sizeof(tmap)); else memset(&tmap, 0, sizeof(tmap));
   RVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t warps = (int64_t)a.K * a.nch;
   const int64_t blocks = (warps + CK_WARPS - 1) / CK_WARPS;
   RVS_REQUIRE(blocks <= 0x7fffffffLL, RVS_E_LIMIT, "rvs_chisq_fused: %lld CTAs", (long long)blocks);
-  kern<<<(unsigned)blocks, CK_THREADS, smem, st>>>(a);
+  prof_begin(ST_CHUNK, st);
+  kern<<<(unsigned)blocks, CK_THREADS, smem, st>>>(a, tmap);
+  prof_end(ST_CHUNK, st);
   RVS_LAUNCH_OK();
   return 0;
 }
@@ -34,7 +41,10 @@ static int launch_chunk_one(const ChunkArgs &a, size_t smem, cudaStream_t st) {
 // knots per chunk: long enough that the 2 x (SPL_HALO + taps) halo stays a small
 // fraction, short enough that two window buffers per warp leave room for >= 16
 // resident warps per SM
-static int chunk_knots(int tapcap) { return tapcap > 48 ? 512 : 384; }
+#ifndef RVS_CK_C
+#define RVS_CK_C 384
+#endif
+static int chunk_knots(int tapcap) { return tapcap > 48 ? 512 : RVS_CK_C; }
 }  // namespace rvs
 
 extern "C" int rvs_fused_chunks(int npix_t, int tapcap) {
@@ -53,7 +63,7 @@ struct FusedWork {
     taps = 0;
     rec = taps + even(K * (tapcap + 1));
     irec = rec + 2 * K;
-    pbound = irec + 2 * K;
+    pbound = irec + 4 * K;
     gram = pbound + even((K * (nch + 1) + 1) / 2);
     total = gram + GramScratch(K).total();
   }
@@ -69,7 +79,8 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
                                int nvert, const double *d_vsini, double vsini_max, int log_spec,
                                const rvs_obs *obs, const int32_t *d_oix, const double *d_vels,
                                int K, double *d_tn, int64_t tn_stride, double *d_work,
-                               double *d_chisq, int32_t *d_status, void *stream) {
+                               double *d_chisq, int32_t *d_status, const rvs_gridbox *box,
+                               void *stream) {
   using namespace rvs;
   if (K == 0) return 0;
   TemplateArgs ta;
@@ -95,6 +106,9 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
   RVS_REQUIRE(d_work, RVS_E_ARG, "rvs_chisq_fused: d_work is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   RVS_REQUIRE(((uintptr_t)d_work & 15) == 0, RVS_E_ARG, "rvs_chisq_fused: d_work alignment");
+  // copy-engine gather: dense 4-D fp32 grid, descriptor built for this tile width
+  const bool use_box = box && !grid_f64 && nvert == 16 && box->cols == TMA_COLS &&
+                       box->rows == TMA_ROWS;
   ChunkArgs a;
   a.C = chunk_knots(tapcap);
   a.nch = (n + a.C - 1) / a.C;
@@ -115,7 +129,11 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
     t.oix = d_oix; t.vels = d_vels; t.nch = a.nch; t.C = a.C;
     t.rec = d_work + fw.rec; t.irec = reinterpret_cast<int32_t *>(d_work + fw.irec);
     t.pbound = reinterpret_cast<int32_t *>(d_work + fw.pbound); t.status = d_status;
+    t.ids = d_ids; t.nvert = nvert; t.box = use_box ? 1 : 0;
+    for (int i = 0; i < 3; i++) t.blen[i] = use_box ? box->len[i + 1] : 1;
+    prof_begin(ST_PREP, st);
     prep_kernel<<<(K + 3) / 4, 128, 0, st>>>(t);
+    prof_end(ST_PREP, st);
     RVS_LAUNCH_OK();
   }
   a.grid = d_grid; a.ld = ld; a.npix_t = n; a.ids = d_ids; a.w = d_w; a.nvert = nvert;
@@ -139,10 +157,19 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
   a.oix = d_oix; a.vels = d_vels; a.tn = d_tn; a.tn_stride = tn_stride; a.status = d_status;
   a.K = K;
   a.wcap = (a.C + 2 * (SPL_HALO + 3 + tapcap) + 12 + 3) & ~3;
-  a.wcap = std::max(a.wcap, CK_RING * 512 / 8);  // the gather's prefetch ring lives in one buffer
-  const size_t smem = sizeof(double) * 2 * (size_t)a.wcap * CK_WARPS;
+  if (use_box) {  // TMA destinations are 128-byte aligned
+    a.wcap = (a.wcap + 15) & ~15;
+    a.wcap1 = std::max(a.wcap, TMA_RING_DOUBLES);
+  } else {
+    a.wcap = std::max(a.wcap, CK_RING * 512 / 8);  // the gather's prefetch ring lives in B1
+    a.wcap1 = a.wcap;
+  }
+  const size_t smem = sizeof(double) * (size_t)(a.wcap + a.wcap1) * CK_WARPS;
   RVS_REQUIRE(smem <= 200 * 1024, RVS_E_LIMIT, "rvs_chisq_fused: window needs %zu B smem", smem);
-  if (grid_f64) rc = launch_chunk_one<double, 0>(a, smem, st);
+  if (use_box)
+    rc = launch_chunk_one<float, 16, true>(a, smem, st,
+                                           reinterpret_cast<const CUtensorMap *>(box->tmap));
+  else if (grid_f64) rc = launch_chunk_one<double, 0>(a, smem, st);
   else if (nvert == 16) rc = launch_chunk_one<float, 16>(a, smem, st);
   else if (nvert == 5) rc = launch_chunk_one<float, 5>(a, smem, st);
   else rc = launch_chunk_one<float, 0>(a, smem, st);

@@ -35,11 +35,17 @@ static int launch_gram_mma_np(GramMmaArgs a, cudaStream_t st) {
   a.KS = std::min(GM_MAX_KS, std::max(1, (512 + groups - 1) / groups));
   dim3 grid(groups, a.KS);
   const size_t tile_smem = sizeof(double) * GM_WARPS * GM_TILE * a.npp;
+  prof_begin(ST_GRAM, st);
   gram_mma_kernel<NP, NT><<<grid, GM_THREADS, tile_smem, st>>>(a);
+  prof_end(ST_GRAM, st);
   RVS_LAUNCH_OK();
+  prof_begin(ST_SOLVE, st);
   gram_solve_kernel<NP, NT><<<(a.K + GM_WARPS - 1) / GM_WARPS, GM_THREADS, 0, st>>>(a);
+  prof_end(ST_SOLVE, st);
   RVS_LAUNCH_OK();
+  prof_begin(ST_RESID, st);
   resid_mma_kernel<NP, NT><<<grid, GM_THREADS, 0, st>>>(a);
+  prof_end(ST_RESID, st);
   RVS_LAUNCH_OK();
   return 0;
 }

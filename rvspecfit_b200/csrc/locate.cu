@@ -7,109 +7,115 @@
 // reference resolves through its KD-tree (outside the grid -- the top edge counts
 // as outside --, or a missing corner: nearest node in ptp-normalised space,
 // spec_inter.py:128-132,156-167, and its distance as the off-grid measure,
-// spec_inter.py:77-92) are flagged; nearest_node_kernel then finds that node by
-// exhaustive search, one warp per flagged point.  Non-finite coordinates stay
-// flagged for the host.
+// spec_inter.py:77-92) are resolved by the same warp with an exhaustive search
+// of the node table.  Non-finite coordinates stay flagged for the host.
 #include "common.cuh"
 
 namespace rvs {
 
+// One warp per item.  Lane i < ndim searches dimension i; lane c < 2^ndim owns
+// corner c (flat index, weight, idgrid lookup); an off-grid or missing-corner
+// point with finite coordinates is resolved in place when `outside` is given:
+// the warp scans the node table for the nearest node (ties -> lowest index, as
+// a stable argmin), writes it as a single-row item (ids = {node, -1, 0...},
+// w = {1, 0...}) with its distance as the off-grid measure and clears the flag.
+// Non-finite coordinates stay flagged for the host (outside = NaN).
 __global__ void __launch_bounds__(128) locate_grid_kernel(rvs_gridmap gm, const double *q,
                                                           int64_t qstride, int K, int32_t *ids,
-                                                          double *w, int32_t *flag) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+                                                          double *w, int32_t *flag,
+                                                          double *outside) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K) return;
   const int nd = gm.ndim, nv = 1 << nd;
-  int pos[RVS_MAX_GRID_DIM];
-  double x[RVS_MAX_GRID_DIM];
-  bool out = false;
-  for (int i = 0; i < nd; i++) {
-    const double qi = q[(int64_t)i * qstride + k];
-    const double *u = gm.d_uvec + gm.uoff[i];
-    const int n = gm.len[i];
+  int mypos = 0;
+  double myx = 0, myq = 0;
+  bool myout = false;
+  if (lane < nd) {
+    const double qi = q[(int64_t)lane * qstride + k];
+    myq = qi;
+    const double *u = gm.d_uvec + gm.uoff[lane];
+    const int n = gm.len[lane];
     int lo = 0, hi = n;  // number of nodes <= qi (digitize, increasing bins); NaN -> n
     if (!(qi == qi)) lo = n;
     else
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (u[mid] <= qi) lo = mid + 1; else hi = mid;
+        if (__ldg(u + mid) <= qi) lo = mid + 1; else hi = mid;
       }
     const int p = lo - 1;
-    if (p < 0 || p >= n - 1 || !isfinite(qi)) { out = true; pos[i] = 0; x[i] = 0; continue; }
-    pos[i] = p;
-    x[i] = (qi - u[p]) / (u[p + 1] - u[p]);
-  }
-  int32_t *idk = ids + (int64_t)k * nv;
-  double *wk = w + (int64_t)k * nv;
-  if (!out) {
-    for (int c = 0; c < nv; c++) {
-      int64_t flat = 0;
-      double wc = 1;
-      for (int i = 0; i < nd; i++) {
-        const int s = (c >> (nd - 1 - i)) & 1;
-        flat = flat * gm.len[i] + pos[i] + s;
-        const double fct = s ? x[i] : 1 - x[i];
-        wc = (i == 0) ? fct : wc * fct;
-      }
-      const int32_t id = gm.d_idgrid[flat];
-      if (id < 0) out = true;
-      idk[c] = id;
-      wk[c] = wc;
+    if (p < 0 || p >= n - 1 || !isfinite(qi)) myout = true;
+    else {
+      mypos = p;
+      myx = (qi - __ldg(u + p)) / (__ldg(u + p + 1) - __ldg(u + p));
     }
   }
-  if (out) {
-    for (int c = 0; c < nv; c++) { idk[c] = (c == 1) ? -1 : 0; wk[c] = (c == 0) ? 1.0 : 0.0; }
-  }
-  flag[k] = out ? 1 : 0;
-}
-
-// one warp per item; only flagged items with finite coordinates do any work
-__global__ void __launch_bounds__(128) nearest_node_kernel(rvs_gridmap gm, const double *q,
-                                                           int64_t qstride, int K, int32_t *ids,
-                                                           double *w, int32_t *flag,
-                                                           double *outside) {
-  const int lane = threadIdx.x & 31;
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (k >= K) return;
-  if (flag[k] == 0) {
-    if (lane == 0) outside[k] = 0.0;
-    return;
-  }
-  const int nd = gm.ndim, nv = 1 << nd;
-  double qn[RVS_MAX_GRID_DIM];
-  bool finite = true;
-  for (int i = 0; i < nd; i++) {
-    const double qi = q[(int64_t)i * qstride + k];
-    finite = finite && isfinite(qi);
-    qn[i] = qi / gm.ptp[i];
-  }
-  if (!finite) {  // the host decides (first node, no finite off-grid measure)
-    if (lane == 0) outside[k] = nan("");
-    return;
-  }
-  double best = INFINITY;
-  int bidx = 0x7fffffff;
-  for (int node = lane; node < gm.nnode; node += 32) {
-    const double *v = gm.d_vnorm + (int64_t)node * nd;
-    double d2 = 0;
+  bool out = __any_sync(0xffffffffu, myout);
+  int32_t id = 0;
+  double wc = 1;
+  {
+    int64_t flat = 0;
     for (int i = 0; i < nd; i++) {
-      const double d = qn[i] - __ldg(v + i);
-      d2 += d * d;
+      const int pi = __shfl_sync(0xffffffffu, mypos, i);
+      const double xi = __shfl_sync(0xffffffffu, myx, i);
+      const int s = (lane >> (nd - 1 - i)) & 1;
+      flat = flat * gm.len[i] + pi + s;
+      const double fct = s ? xi : 1 - xi;
+      wc = (i == 0) ? fct : wc * fct;
     }
-    if (d2 < best) { best = d2; bidx = node; }
+    if (!out && lane < nv) id = __ldg(gm.d_idgrid + flat);
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-    if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+  out = out || __any_sync(0xffffffffu, lane < nv && id < 0);
+  if (!out) {
+    if (lane < nv) {
+      ids[(int64_t)k * nv + lane] = id;
+      w[(int64_t)k * nv + lane] = wc;
+    }
+    if (lane == 0) {
+      flag[k] = 0;
+      if (outside) outside[k] = 0.0;
+    }
+    return;
   }
-  if (lane == 0) {
-    int32_t *idk = ids + (int64_t)k * nv;
-    double *wk = w + (int64_t)k * nv;
-    for (int c = 0; c < nv; c++) { idk[c] = c == 0 ? bidx : (c == 1 ? -1 : 0); wk[c] = (c == 0) ? 1.0 : 0.0; }
-    outside[k] = sqrt(best);
-    flag[k] = 0;
+  // ---- off the grid (the top edge counts as outside) or a missing corner
+  int node0 = 0, fl = 1;
+  if (outside) {
+    bool finite = true;
+    double qn[RVS_MAX_GRID_DIM];
+    for (int i = 0; i < nd; i++) {
+      const double qi = __shfl_sync(0xffffffffu, myq, i);
+      finite = finite && isfinite(qi);
+      qn[i] = qi / gm.ptp[i];
+    }
+    double res = nan("");  // the host decides (first node, no finite off-grid measure)
+    if (finite) {
+      double best = INFINITY;
+      int bidx = 0x7fffffff;
+      for (int node = lane; node < gm.nnode; node += 32) {
+        const double *v = gm.d_vnorm + (int64_t)node * nd;
+        double d2 = 0;
+        for (int i = 0; i < nd; i++) {
+          const double d = qn[i] - __ldg(v + i);
+          d2 += d * d;
+        }
+        if (d2 < best) { best = d2; bidx = node; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+      }
+      node0 = bidx;
+      res = sqrt(best);
+      fl = 0;
+    }
+    if (lane == 0) outside[k] = res;
   }
+  if (lane < nv) {
+    ids[(int64_t)k * nv + lane] = lane == 0 ? node0 : (lane == 1 ? -1 : 0);
+    w[(int64_t)k * nv + lane] = lane == 0 ? 1.0 : 0.0;
+  }
+  if (lane == 0) flag[k] = fl;
 }
 
 }  // namespace rvs
@@ -123,14 +129,12 @@ extern "C" int rvs_locate_grid(const rvs_gridmap *gm, const double *d_q, int64_t
               "rvs_locate_grid: null pointer");
   RVS_REQUIRE(gm->ndim >= 1 && gm->ndim <= RVS_MAX_GRID_DIM, RVS_E_ARG,
               "rvs_locate_grid: ndim=%d outside 1..%d", gm->ndim, RVS_MAX_GRID_DIM);
-  locate_grid_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*gm, d_q, q_stride, K,
-                                                                        d_ids, d_w, d_flag);
+  RVS_REQUIRE(!d_outside || (gm->d_vnorm && gm->nnode > 0), RVS_E_ARG,
+              "rvs_locate_grid: node table missing");
+  prof_begin(ST_LOCATE, (cudaStream_t)stream);
+  locate_grid_kernel<<<(K + 3) / 4, 128, 0, (cudaStream_t)stream>>>(*gm, d_q, q_stride, K, d_ids,
+                                                                    d_w, d_flag, d_outside);
+  prof_end(ST_LOCATE, (cudaStream_t)stream);
   RVS_LAUNCH_OK();
-  if (d_outside) {
-    RVS_REQUIRE(gm->d_vnorm && gm->nnode > 0, RVS_E_ARG, "rvs_locate_grid: node table missing");
-    nearest_node_kernel<<<(K + 3) / 4, 128, 0, (cudaStream_t)stream>>>(*gm, d_q, q_stride, K, d_ids,
-                                                                       d_w, d_flag, d_outside);
-    RVS_LAUNCH_OK();
-  }
   return 0;
 }

@@ -260,7 +260,9 @@ class LikelihoodEngine:
                                    bank.nvert, _dev.ptr(d_vs), vmax, int(bank.log_spec),
                                    ctypes.byref(obs), _dev.ptr(d_oix), _dev.ptr(d_vels), k,
                                    _dev.ptr(d_tn), stride, _dev.ptr(d_work), _dev.ptr(d_chi),
-                                   _dev.ptr(d_st), _dev.stream())
+                                   _dev.ptr(d_st),
+                                   ctypes.byref(bank.box) if bank.box is not None else None,
+                                   _dev.stream())
             _cabi.check(rc, 'rvs_chisq_fused')
             if t0 is not None:
                 self.timer.stop('fused', t0, k)
@@ -383,24 +385,39 @@ class LikelihoodEngine:
             self._arm_events = [torch.cuda.Event() for _ in self.setups]
             self._fork_event = torch.cuda.Event()
         t0 = self.timer.start() if self.timer else None
+        banks = [self.arms[name]['bank'] for name in self.setups]
+        sigs = [getattr(b, 'locate_signature', None) for b in banks]
+        shared = narm > 1 and sigs[0] is not None and all(s_ == sigs[0] for s_ in sigs)
+        sl['shared_locate'] = shared
+        if shared:      # one vertex location for all arms, before the streams fork
+            d_ids0 = self._scratch('ids0', (K, nvert), np.int32)
+            d_w0 = self._scratch('w0', (K, nvert), np.float64)
+            rc = L.rvs_locate_grid(ctypes.byref(bank0.gridmap), _dev.ptr(d_in[2:]), K, K,
+                                   _dev.ptr(d_ids0), _dev.ptr(d_w0), _dev.ptr(d_flags[1, 0]),
+                                   _dev.ptr(d_chi[1, 0]), ctypes.c_void_p(main.cuda_stream))
+            _cabi.check(rc, 'rvs_locate_grid')
         self._fork_event.record(main)
         for a, name in enumerate(self.setups):
             arm = self.arms[name]
             bank, batch = arm['bank'], arm['batch']
             obs = batch.obs(self.npoly, self.rbf, sys_errs[a])
-            st = self._arm_streams[a]
+            # serial_arms (stage profiling): every arm on the caller's stream
+            st = main if getattr(self, 'serial_arms', False) else self._arm_streams[a]
             st.wait_event(self._fork_event)
             stream = ctypes.c_void_p(st.cuda_stream)
-            d_ids = self._scratch(f'ids{a}', (K, nvert), np.int32)
-            d_w = self._scratch(f'w{a}', (K, nvert), np.float64)
-            q = d_in[2:]
-            if bank.log_ids != bank0.log_ids:
-                with torch.cuda.stream(st):
-                    q = _dev.upload(spec_inter.map_params(params, bank.log_ids).T, np.float64)
-            rc = L.rvs_locate_grid(ctypes.byref(bank.gridmap), _dev.ptr(q), K, K, _dev.ptr(d_ids),
-                                   _dev.ptr(d_w), _dev.ptr(d_flags[1, a]), _dev.ptr(d_chi[1, a]),
-                                   stream)
-            _cabi.check(rc, 'rvs_locate_grid')
+            if shared:
+                d_ids, d_w = d_ids0, d_w0
+            else:
+                d_ids = self._scratch(f'ids{a}', (K, nvert), np.int32)
+                d_w = self._scratch(f'w{a}', (K, nvert), np.float64)
+                q = d_in[2:]
+                if bank.log_ids != bank0.log_ids:
+                    with torch.cuda.stream(st):
+                        q = _dev.upload(spec_inter.map_params(params, bank.log_ids).T, np.float64)
+                rc = L.rvs_locate_grid(ctypes.byref(bank.gridmap), _dev.ptr(q), K, K,
+                                       _dev.ptr(d_ids), _dev.ptr(d_w), _dev.ptr(d_flags[1, a]),
+                                       _dev.ptr(d_chi[1, a]), stream)
+                _cabi.check(rc, 'rvs_locate_grid')
             stride = batch.max_npix
             d_tn = self._scratch(f'tn{a}', (K * stride,), np.float64)
             d_work = self._scratch(f'work{a}',
@@ -411,7 +428,9 @@ class LikelihoodEngine:
                                    bank.nvert, _dev.ptr(d_in[1]) if vmax > 0 else None, vmax,
                                    int(bank.log_spec), ctypes.byref(obs), _dev.ptr(d_oix[a]),
                                    _dev.ptr(d_in[0]), K, _dev.ptr(d_tn), stride, _dev.ptr(d_work),
-                                   _dev.ptr(d_chi[0, a]), _dev.ptr(d_flags[0, a]), stream)
+                                   _dev.ptr(d_chi[0, a]), _dev.ptr(d_flags[0, a]),
+                                   ctypes.byref(bank.box) if bank.box is not None else None,
+                                   stream)
             _cabi.check(rc, 'rvs_chisq_fused')
             self._arm_events[a].record(st)
         for a in range(narm):
@@ -431,6 +450,10 @@ class LikelihoodEngine:
         both = sl['h_chi'][:2 * narm * K].view(2, narm, K).numpy()
         chi, outside = both[0], both[1]
         flags = sl['h_flags'][:2 * narm * K].view(2, narm, K).numpy()
+        if sl.get('shared_locate'):     # located once: arm 0's rows stand for every arm
+            outside = np.broadcast_to(outside[0], outside.shape)
+            both = np.stack([chi, outside])
+            flags[1, 1:] = flags[1, 0]
         redo = (flags != 0).any(axis=(0, 1)) | ~np.isfinite(both).all(axis=(0, 1))
         redo |= ~self._cover0[obj] | (vels < self.config['min_vel']) | \
             (vels > self.config['max_vel'])

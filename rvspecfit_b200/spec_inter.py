@@ -11,6 +11,7 @@ for the Delaunay product (spec_inter.py:35-59) -- and the off-grid measure
 """
 import ctypes
 import itertools
+import os
 
 import numpy as np
 import scipy.spatial
@@ -63,6 +64,22 @@ class TemplateBank:
          self.knots.d_winv) = [t.data_ptr() for t in self._tabs]
         # grid rows, padded to a 16-byte multiple
         dats = np.asarray(dats)
+        self.box = None
+        dense = False
+        if kind == 'regulargrid':
+            # A grid without missing nodes is stored in HBM in the C order of its node
+            # table (row id = flat grid position), whatever order the product lists its
+            # nodes in: the 2^d corner rows of a cell then form a box the copy engine can
+            # fetch as one tensor tile (rvs_gridbox).  Node ids are internal to the bank,
+            # so the permutation is applied to rows, node coordinates and id table alike.
+            idg = np.asarray(idgrid)
+            flat = idg.reshape(-1)
+            dense = bool(flat.size == dats.shape[0] and (flat >= 0).all()
+                         and np.array_equal(np.sort(flat), np.arange(flat.size)))
+            if dense and not np.array_equal(flat, np.arange(flat.size)):
+                dats = dats[flat]
+                vecs = np.asarray(vecs)[:, flat]
+                idgrid = np.arange(flat.size).reshape(idg.shape)
         if dats.dtype == np.float64:
             d32 = dats.astype(np.float32)
             if np.array_equal(d32.astype(np.float64), dats):
@@ -85,6 +102,14 @@ class TemplateBank:
             self.ptp = np.ptp(vecs, axis=1)
             self.tree = scipy.spatial.cKDTree(vecs.T / self.ptp[None, :])
             self.gridmap = None
+            # banks with the same signature locate a parameter vector identically
+            # (same nodes, same id table): one rvs_locate_grid call serves them all
+            import hashlib
+            hsh = hashlib.sha1()
+            for arr in list(self.uvecs) + [np.ascontiguousarray(self.idgrid, dtype=np.int64),
+                                           np.ascontiguousarray(vecs)]:
+                hsh.update(np.ascontiguousarray(arr).tobytes())
+            self.locate_signature = (hsh.hexdigest(), self.log_ids)
             if self.ndim <= 5:      # device-side vertex location (rvs_locate_grid)
                 uoff = np.concatenate([[0], np.cumsum(self.lens)])
                 self._gm = (_dev.upload(np.concatenate(self.uvecs), np.float64),
@@ -99,6 +124,14 @@ class TemplateBank:
                 for i in range(self.ndim):
                     gm.len[i], gm.uoff[i] = int(self.lens[i]), int(uoff[i])
                 self.gridmap = gm
+            if dense and self.ndim == 4 and not self.grid_f64 and \
+                    not os.environ.get('RVS_NO_TMA'):
+                box = _cabi.GridBox()
+                lens = (ctypes.c_int32 * 4)(*[int(_) for _ in self.lens])
+                rc = L.rvs_gridbox_init(ctypes.byref(box), self.grid.data_ptr(), self.ld, 4,
+                                        ctypes.cast(lens, ctypes.c_void_p))
+                _cabi.check(rc, 'rvs_gridbox_init')
+                self.box = box
         elif kind == 'triangulation':
             self.triang = triang
             self.ndim = triang.ndim

@@ -246,6 +246,45 @@ def test_ragged_arms_in_one_launch(golden):
         assert abs(got[j] - want) < CHI_RTOL * abs(want), (i, e)
 
 
+def test_tma_box_gather_identical_to_lane_gather(golden):
+    """The copy-engine gather of the 2x2x2x2 corner box (rvs_gridbox) against the
+    per-lane row gather: same rows, same accumulation order -> identical bits.
+    Also a product whose nodes are listed in a scrambled order (the bank stores
+    its rows in C order of the node table), interior / edge / off-grid points."""
+    g = golden('chisq')
+    st = setup('test', 'tiny', 3, name='test')
+    objs = unpack_objects(g, 'one_')
+    cfg = config()
+    ev = g['one_eval']
+    K = len(ev)
+    pp = np.array(PROBE_PARAMS)
+    vel = np.concatenate([ev[:, 0], np.linspace(-300, 300, len(pp))])
+    par = np.concatenate([ev[:, 1:5], pp])
+    vs = np.concatenate([np.where(ev[:, 5] < 0, 0.0, ev[:, 5]), np.linspace(0, 80, len(pp))])
+    res = {}
+    rs = np.random.RandomState(5)
+    perm = rs.permutation(st['dats'].shape[0])
+    inv = np.argsort(perm)
+    for mode in ('box', 'lanes', 'scrambled'):
+        s2 = dict(st)
+        if mode == 'scrambled':     # node i of the product = node perm[i] of the original
+            s2['dats'] = st['dats'][perm]
+            s2['vec'] = st['vec'][:, perm]
+            s2['idgrid'] = inv[st['idgrid']]
+        bank = spec_inter.bank_from_setup(s2)
+        assert bank.box is not None
+        if mode == 'lanes':
+            bank.box = None
+        spec_inter.register_bank(bank, template_lib='synthetic/')
+        eng = spec_fit.LikelihoodEngine([_sd(o, 'test') for o in objs], cfg, {'npoly': 10})
+        res[mode] = np.array([eng.evaluate(np.full(len(vel), i), vel, par, vs)
+                              for i in range(len(objs))])
+    assert np.array_equal(res['box'], res['lanes'])
+    assert np.array_equal(res['box'], res['scrambled'])
+    want = g['one_chisq_test_15_1']
+    assert res['box'].shape[1] == K + len(pp) and want.shape[1] == K
+
+
 def test_mixed_wavelength_grids_take_per_item_solve(golden):
     """Objects on different pixel grids in one engine: the continuum solve runs
     per item (gram_kernel) instead of as the shared-basis GEMM (gram_mma_kernel);
