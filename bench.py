@@ -190,14 +190,39 @@ def run_gpu(args):
     def step_resident(eng):
         return hot_path(eng)
 
+    engines = []
+
+    def glaunch():
+        # kernels launched through CUDA-graph replays (the library counter only sees
+        # direct launches)
+        return sum(e.graph_kernel_launches for e in engines)
+
     def step_e2e():
         eng = spec_fit.LikelihoodEngine(to_specdata(), cfg, opts)   # H2D of the spectra
+        engines.append(eng)
         rec = hot_path(eng)                                          # D2H of the results
         # the one collective of the path: fixed-size result records of all ranks
         return shard.gather_records(rec, B * world) if world > 1 else rec
 
     eng = spec_fit.LikelihoodEngine(to_specdata(), cfg, opts)
+    engines.append(eng)
     L = _cabi.lib()
+    if args.timeline:
+        # diagnostic: start/end of every kernel of a few evaluation calls, concurrent
+        # streams as in the bench
+        import ctypes
+        tp2, tv2, tvs2 = tp[:args.timeline], tv[:args.timeline], tvs[:args.timeline]
+        batch_fit.scan_and_evaluate(eng, start, vgrid[:8], tp2, tv2, tvs2, groups=args.groups)
+        L.rvs_profile_enable(1)
+        batch_fit.scan_and_evaluate(eng, start, vgrid[:8], tp2, tv2, tvs2, groups=args.groups)
+        buf = (ctypes.c_double * (3 * 4096))()
+        n = L.rvs_profile_timeline(ctypes.cast(buf, ctypes.c_void_p), 4096)
+        L.rvs_profile_enable(0)
+        names = ['locate', 'nearest', 'prep', 'chunk', 'gram', 'solve', 'resid']
+        for i in range(n):
+            print(f'{names[int(buf[3 * i])]:8s} {1e3 * buf[3 * i + 1]:10.1f} {1e3 * buf[3 * i + 2]:10.1f}'
+                  f'  dur {1e3 * (buf[3 * i + 2] - buf[3 * i + 1]):8.1f} us')
+        return
     if args.stage_profile:
         # diagnostic run (not a bench value): arms serialised on one stream, CUDA
         # events around every kernel of the evaluation call
@@ -230,7 +255,7 @@ def run_gpu(args):
             fn()
         timer.reset()
         barrier()
-        l0 = L.rvs_launch_count()
+        l0 = L.rvs_launch_count() + glaunch()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clk = ClockSampler(local) if sample_clocks else None
         t0 = time.time()
@@ -246,7 +271,7 @@ def run_gpu(args):
             t = torch.tensor([ms], device='cuda', dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, L.rvs_launch_count() - l0, clocks, out, timer.summary()
+        return ms, L.rvs_launch_count() + glaunch() - l0, clocks, out, timer.summary()
 
     ms, launches, clocks, out, ksum = timed(lambda: step_resident(eng), args.steps, args.warmup,
                                             sample_clocks=True)
@@ -265,20 +290,36 @@ def run_gpu(args):
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else \
         'fallback 6650 GB/s (B200_PROFILING.md)'
     roof = None
-    if ksum.get('fused_eval_ms_total'):
-        # one record = one evaluation call: rvs_locate_grid + rvs_chisq_fused of every
-        # arm (the arms run concurrently on their own streams), timed with CUDA events on
-        # the stream they fork from and join to; the algorithmic bytes are SURVEY.md 8d's
-        # per-evaluation figure (all arms)
+    kern_txt = ('rvs_locate_grid + rvs_chisq_fused (prep_kernel, chunk_kernel [TMA gather -> exp -> '
+                'broadening -> spline -> resampling], gram_mma/gram_solve/resid_mma kernels) of the '
+                '3 arms')
+    if ksum.get('eval_phase_ms_total'):
+        # the optimiser-phase evaluations of the timed region: CUDA events bracket the
+        # whole phase (in-flight evaluations of different object groups overlap on the
+        # GPU, so per-call durations do not add up); bytes = SURVEY.md 8d's
+        # per-evaluation figure x evaluations
+        evals = ksum['eval_phase_items_per_launch'] * ksum['eval_phase_launches']
+        ach = beval * evals / (ksum['eval_phase_ms_total'] * 1e-3) / 1e9
+        ncall = max(1, ksum.get('fused_eval_launches', 1))
+        roof = dict(bound='hbm', kernel=kern_txt, achieved=ach, peak=hbm_peak, unit='GB/s',
+                    frac=ach / hbm_peak, traffic=None, peak_source=peak_src,
+                    algorithmic_bytes_per_eval=beval, evals_timed=evals,
+                    ms_total=ksum['eval_phase_ms_total'],
+                    ms_per_call=ksum['eval_phase_ms_total'] / ncall,
+                    items_per_call=ksum.get('fused_eval_items_per_launch'),
+                    timing='CUDA events around the evaluation phase of every step')
+    elif ksum.get('fused_eval_ms_total'):
+        # complete-fit mode: per evaluation call, events on the stream the arms fork
+        # from and join to (calls may overlap: the sum over-counts time)
         evals = ksum['fused_eval_items_per_launch'] * ksum['fused_eval_launches']
         ach = beval * evals / (ksum['fused_eval_ms_total'] * 1e-3) / 1e9
-        roof = dict(bound='hbm', kernel='rvs_chisq_fused (prep + chunk_kernel + gram_mma/solve/'
-                                        'resid kernels) of the 3 arms of one evaluation call',
-                    achieved=ach, peak=hbm_peak, unit='GB/s', frac=ach / hbm_peak, traffic=None,
+        roof = dict(bound='hbm', kernel=kern_txt, achieved=ach, peak=hbm_peak, unit='GB/s',
+                    frac=ach / hbm_peak, traffic=None,
                     peak_source=peak_src, algorithmic_bytes_per_eval=beval,
                     evals_timed=evals, ms_total=ksum['fused_eval_ms_total'],
                     ms_per_call=ksum['fused_eval_ms_per_launch'],
-                    items_per_call=ksum['fused_eval_items_per_launch'])
+                    items_per_call=ksum['fused_eval_items_per_launch'],
+                    timing='CUDA events around every evaluation call')
     nspec_total = B * world
     per_step = ms / args.steps
     fit = args.mode == 'fit'
@@ -444,6 +485,8 @@ def main():
     ap.add_argument('--cpu-fraction', type=float, default=1.0,
                     help='fraction of the per-spectrum evaluations the CPU sample runs')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--timeline', type=int, default=0,
+                    help='diagnostic: kernel start/end times of this many evaluation rounds')
     ap.add_argument('--stage-profile', action='store_true',
                     help='diagnostic: CUDA-event time of every kernel of the evaluation call')
     ap.add_argument('--mode', default='proxy', choices=['proxy', 'fit'],

@@ -69,7 +69,11 @@ int64_t rvs_launch_count(void);
  * launch counts of stages 0..nstage-1 (locate, nearest, prep, chunk, gram,
  * solve, resid), clears the records and returns the number of stages. */
 void rvs_profile_enable(int on);
+int rvs_profile_active(void);
 int rvs_profile_read(double *ms_total, int64_t *launches, int nstage);
+/* Same records as a timeline: out[3i..] = stage, start ms, end ms (relative to the
+ * first record's start), in launch order; returns the count and clears them. */
+int rvs_profile_timeline(double *out, int max_records);
 
 /* ---- native spline: drop-in for the reference's cffi module ------------- */
 /* Host-buffer entry points with the reference's exact signatures and status

@@ -65,7 +65,9 @@ SIGNATURES = {
     'rvs_version': (c_int, []),
     'rvs_launch_count': (c_i64, []),
     'rvs_profile_enable': (None, [c_int]),
+    'rvs_profile_active': (c_int, []),
     'rvs_profile_read': (c_int, [c_dp, c_dp, c_int]),
+    'rvs_profile_timeline': (c_int, [c_dp, c_int]),
     'rvs_spline_construct': (None, [c_dp, c_dp, c_int, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'rvs_spline_eval': (c_int, [c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_int,
                                 c_dp]),

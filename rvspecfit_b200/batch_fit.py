@@ -81,6 +81,10 @@ def scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=None, groups=2):
     best = np.full(B, np.inf)
     parts = [p for p in np.array_split(obj, max(1, min(groups, B))) if len(p)]
     pending = []
+    # device time of the whole evaluation phase: the calls of different groups
+    # overlap on the GPU (each in-flight evaluation has its own streams), so
+    # their individual durations do not add up
+    e0 = timer.start() if timer is not None else None
     for e in range(len(tp)):
         for p in parts:
             if len(pending) >= len(parts):
@@ -89,6 +93,8 @@ def scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=None, groups=2):
             pending.append((p, eng.submit(p, tv[e][p], tp[e][p], tvs[e][p])))
     for q, h in pending:
         best[q] = np.minimum(best[q], h.result())
+    if timer is not None:
+        timer.stop('eval_phase', e0, len(tp) * B)
     eng.timer = None
     return np.concatenate([st[:, :5], best[:, None]], axis=1)
 

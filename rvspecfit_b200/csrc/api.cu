@@ -143,6 +143,25 @@ void prof_end(int stage, cudaStream_t st) {
 }
 }  // namespace rvs
 
+extern "C" int rvs_profile_timeline(double *out, int max_records) {
+  using namespace rvs;
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (auto &r : g_prof_rec) {
+    if (n < max_records && !g_prof_rec.empty()) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, g_prof_rec[0].e0, r.e0);
+      cudaEventElapsedTime(&b, g_prof_rec[0].e0, r.e1);
+      out[3 * n] = r.stage; out[3 * n + 1] = a; out[3 * n + 2] = b;
+      n++;
+    }
+  }
+  for (auto &r : g_prof_rec) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof_rec.clear();
+  return n;
+}
+
 extern "C" int rvs_gridbox_init(rvs_gridbox *box, const void *d_grid, int64_t ld, int ndim,
                                 const int32_t *len) {
   using namespace rvs;
@@ -185,6 +204,7 @@ extern "C" int rvs_gridbox_init(rvs_gridbox *box, const void *d_grid, int64_t ld
 }
 
 extern "C" void rvs_profile_enable(int on) { rvs::g_prof = on != 0; }
+extern "C" int rvs_profile_active(void) { return rvs::g_prof ? 1 : 0; }
 extern "C" int rvs_profile_read(double *ms_total, int64_t *launches, int nstage) {
   using namespace rvs;
   cudaDeviceSynchronize();

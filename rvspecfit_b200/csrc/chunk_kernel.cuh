@@ -47,7 +47,7 @@ constexpr int CK_RING = RVS_CK_RING;  // slots (of 512 B) of the gather prefetch
 #endif
 constexpr int CK_MINB = RVS_CK_MINB;  // resident CTAs per SM the register budget allows
 #ifndef RVS_CK_MINB_TMA
-#define RVS_CK_MINB_TMA 6
+#define RVS_CK_MINB_TMA 7
 #endif
 constexpr int CK_MINB_TMA = RVS_CK_MINB_TMA;  // same for the TMA variant
 // TMA gather (dense regular 4-D grids, rvs_gridbox): one cp.async.bulk.tensor of a

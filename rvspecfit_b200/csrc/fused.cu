@@ -5,7 +5,12 @@
 // L2-resident between the two stages).
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "chunk_kernel.cuh"
 #include "gram_kernel.cuh"
@@ -20,6 +25,8 @@ int launch_gram_mma_group0(const GramMmaArgs &, int, cudaStream_t);
 int launch_gram_mma_group1(const GramMmaArgs &, int, cudaStream_t);
 int launch_gram_mma_group2(const GramMmaArgs &, int, cudaStream_t);
 int launch_gram_mma_group3(const GramMmaArgs &, int, cudaStream_t);
+int launch_solve(const rvs_obs *obs, const int32_t *d_oix, int K, double *d_tn, int64_t tn_stride,
+                 double *w, double *d_chisq, int32_t *d_status, cudaStream_t st);
 
 template <typename GT, int NV, bool TMA = false>
 static int launch_chunk_one(const ChunkArgs &a, size_t smem, cudaStream_t st,
@@ -27,7 +34,13 @@ static int launch_chunk_one(const ChunkArgs &a, size_t smem, cudaStream_t st,
   auto kern = chunk_kernel<GT, NV, TMA>;
   alignas(64) CUtensorMap tmap;
   if (tm) memcpy(&tmap, tm, sizeof(tmap)); else memset(&tmap, 0, sizeof(tmap));
-  RVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // once per size (per instantiation): keeps the call out of CUDA-graph captures after
+  // the first, uncaptured evaluation
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    RVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   const int64_t warps = (int64_t)a.K * a.nch;
   const int64_t blocks = (warps + CK_WARPS - 1) / CK_WARPS;
   RVS_REQUIRE(blocks <= 0x7fffffffLL, RVS_E_LIMIT, "rvs_chisq_fused: %lld CTAs", (long long)blocks);
@@ -41,6 +54,44 @@ static int launch_chunk_one(const ChunkArgs &a, size_t smem, cudaStream_t st,
 // knots per chunk: long enough that the 2 x (SPL_HALO + taps) halo stays a small
 // fraction, short enough that two window buffers per warp leave room for >= 16
 // resident warps per SM
+// The small latency-bound kernels of an evaluation (preparation, continuum solve)
+// run on a HIGH-PRIORITY helper stream forked from / joined to the caller's
+// stream.  A chunk_kernel grid keeps every SM full for ~100 us, and the block
+// scheduler serves pending grids oldest first: without priority the 13-40 us
+// solve kernels of one arm wait for slots behind the chunk grids of the other
+// arms (and of the next evaluation) and take 100-160 us each.  With it the slots
+// that finishing chunk CTAs free go to them first.  One helper stream per caller
+// stream, created on first use (RVS_NO_AUX=1 in the environment disables it).
+struct AuxStream {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+static std::mutex g_aux_mu;
+static std::map<std::pair<int, cudaStream_t>, AuxStream> g_aux;
+static AuxStream *aux_for(cudaStream_t st) {
+  static const bool off = getenv("RVS_NO_AUX") != nullptr;
+  if (off) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  auto key = std::make_pair(dev, st);
+  auto it = g_aux.find(key);
+  if (it != g_aux.end()) return &it->second;
+  AuxStream a;
+  int lo = 0, hi = 0;
+  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithPriority(&a.aux, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+  for (auto &e : a.ev)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  return &(g_aux[key] = a);
+}
+// after this, work enqueued on `to` waits for everything enqueued on `from` so far
+static void hand_over(cudaStream_t from, cudaStream_t to, cudaEvent_t ev) {
+  if (from == to) return;
+  cudaEventRecord(ev, from);
+  cudaStreamWaitEvent(to, ev, 0);
+}
+
 #ifndef RVS_CK_C
 #define RVS_CK_C 384
 #endif
@@ -105,6 +156,8 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
               "rvs_template_build + rvs_chisq_scan", vsini_max, tapcap, RVS_MAX_FUSED_TAPS);
   RVS_REQUIRE(d_work, RVS_E_ARG, "rvs_chisq_fused: d_work is NULL");
   cudaStream_t st = (cudaStream_t)stream;
+  AuxStream *ax = aux_for(st);
+  cudaStream_t s_aux = ax ? ax->aux : st;  // preparation and continuum solve
   RVS_REQUIRE(((uintptr_t)d_work & 15) == 0, RVS_E_ARG, "rvs_chisq_fused: d_work alignment");
   // copy-engine gather: dense 4-D fp32 grid, descriptor built for this tile width
   const bool use_box = box && !grid_f64 && nvert == 16 && box->cols == TMA_COLS &&
@@ -131,10 +184,12 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
     t.pbound = reinterpret_cast<int32_t *>(d_work + fw.pbound); t.status = d_status;
     t.ids = d_ids; t.nvert = nvert; t.box = use_box ? 1 : 0;
     for (int i = 0; i < 3; i++) t.blen[i] = use_box ? box->len[i + 1] : 1;
-    prof_begin(ST_PREP, st);
-    prep_kernel<<<(K + 3) / 4, 128, 0, st>>>(t);
-    prof_end(ST_PREP, st);
+    if (ax) hand_over(st, s_aux, ax->ev[0]);
+    prof_begin(ST_PREP, s_aux);
+    prep_kernel<<<(K + 3) / 4, 128, 0, s_aux>>>(t);
+    prof_end(ST_PREP, s_aux);
     RVS_LAUNCH_OK();
+    if (ax) hand_over(s_aux, st, ax->ev[1]);
   }
   a.grid = d_grid; a.ld = ld; a.npix_t = n; a.ids = d_ids; a.w = d_w; a.nvert = nvert;
   a.lam_t = knots->d_lam_t; a.hinv = knots->d_hinv; a.log_spec = log_spec;
@@ -174,6 +229,15 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
   else if (nvert == 5) rc = launch_chunk_one<float, 5>(a, smem, st);
   else rc = launch_chunk_one<float, 0>(a, smem, st);
   if (rc) return rc;
+  if (ax) hand_over(st, s_aux, ax->ev[2]);
+  rc = launch_solve(obs, d_oix, K, d_tn, tn_stride, d_work + fw.gram, d_chisq, d_status, s_aux);
+  if (ax) hand_over(s_aux, st, ax->ev[3]);
+  return rc;
+}
+
+namespace rvs {
+int launch_solve(const rvs_obs *obs, const int32_t *d_oix, int K, double *d_tn, int64_t tn_stride,
+                 double *w, double *d_chisq, int32_t *d_status, cudaStream_t st) {
   const int np = obs->npoly;
   if (obs->shared_grid) {  // one wavelength grid for all objects: Gram stage as an FP64 GEMM
     GramMmaArgs m;
@@ -181,7 +245,6 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
     m.off = obs->d_off; m.goff = obs->d_goff; m.oix = d_oix; m.P = obs->d_P; m.npp = obs->npp;
     m.K = K; m.KS = 1; m.chisq = d_chisq; m.status = d_status;
     const GramScratch gs(K);
-    double *w = d_work + fw.gram;
     m.part = w; w += gs.part();
     m.coef = w; w += gs.coef();
     m.logdet = w; w += gs.logdet();
@@ -201,3 +264,4 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
   if (np <= 13) return launch_gram_group2(g, np, K, st);
   return launch_gram_group3(g, np, K, st);
 }
+}  // namespace rvs

@@ -18,8 +18,12 @@ static int launch_gram_np(const GramArgs &a, int K, cudaStream_t st) {
   const size_t smem = sizeof(double) * GR_DEPTH * GR_THREADS * gram_slot(NP);
   RVS_REQUIRE(a.npp == ((NP + 1) & ~1), RVS_E_ARG, "gram: basis rows of %d doubles, expected %d",
               a.npp, (NP + 1) & ~1);
-  RVS_CUDA_OK(cudaFuncSetAttribute(gram_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    RVS_CUDA_OK(cudaFuncSetAttribute(gram_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    smem_set = smem;
+  }
   gram_kernel<NP><<<K, GR_THREADS, smem, st>>>(a);
   RVS_LAUNCH_OK();
   return 0;

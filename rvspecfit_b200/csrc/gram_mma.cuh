@@ -122,7 +122,11 @@ __device__ __forceinline__ GroupGeom group_geom(const GramMmaArgs &a, int g) {
 }
 
 template <int NP, int NT>
+#ifdef RVS_GM_MAXNREG
+__global__ void __maxnreg__(RVS_GM_MAXNREG) gram_mma_kernel(GramMmaArgs a) {
+#else
 __global__ void __launch_bounds__(GM_THREADS, NT == 2 ? 4 : 3) gram_mma_kernel(GramMmaArgs a) {
+#endif
   using TL = GramTiles<NP>;
   constexpr int NI = 8 * NT;
   __shared__ double s_red[TL::ROWS][NI + 1];

@@ -12,6 +12,7 @@ scan statistics -- runs in librvs_b200.so.  The host resolves grid vertices
 (spec_fit.py:863,888-896) and raises the reference's exceptions.
 """
 import ctypes
+import os
 import random
 
 import numpy as np
@@ -193,6 +194,8 @@ class LikelihoodEngine:
         self.parnames = self.arms[self.setups[0]]['bank'].parnames
         self.n_eval = 0
         self.timer = None
+        self.use_graphs = not os.environ.get('RVS_NO_GRAPHS')
+        self.graph_kernel_launches = 0      # kernels launched through graph replays
         # fast path (see _evaluate_fast): per-arm object index on the host, and
         # whether the template covers each object over [min_vel, max_vel]
         # (spec_fit.py:786-794 evaluated once instead of per call)
@@ -318,6 +321,7 @@ class LikelihoodEngine:
                 _dev.torch_mod().cuda.synchronize()   # side streams may still read the old one
             t = _dev.empty((int(n * 1.25) + 64,), dtype)
             self._buf[name] = t
+            self._graph_epoch = getattr(self, '_graph_epoch', 0) + 1   # captured pointers are stale
         return t[:n].view(*shape)
 
     NSLOT = 4      # evaluations that may be in flight at once (submit without result)
@@ -326,13 +330,14 @@ class LikelihoodEngine:
         """Pinned host staging + device input buffers of one in-flight evaluation."""
         torch = _dev.torch_mod()
         if not hasattr(self, '_slots'):
-            self._slots, self._slot_ix = [dict(K=0, busy=False) for _ in range(self.NSLOT)], -1
+            self._slots, self._slot_ix = [dict(K=0, busy=False, ix=i) for i in range(self.NSLOT)], -1
         self._slot_ix = (self._slot_ix + 1) % self.NSLOT
         sl = self._slots[self._slot_ix]
         if sl['busy']:
             raise RuntimeError(f'more than {self.NSLOT} evaluations in flight: call result() on '
                                'the oldest PendingEval first')
         if sl['K'] < K:
+            self._graph_epoch = getattr(self, '_graph_epoch', 0) + 1
             cap = int(K * 1.25) + 16
             pin = dict(pin_memory=True)
             sl.update(K=cap,
@@ -362,54 +367,120 @@ class LikelihoodEngine:
         bank0 = self.arms[self.setups[0]]['bank']
         nd = bank0.ndim
         sl = self._slot(K, narm, nd)
+        torch = _dev.torch_mod()
+        # Every in-flight evaluation has its own streams and scratch, so that the
+        # low-occupancy tail of one (continuum solves of the last arm) runs under the
+        # template kernels of the next instead of in front of them.
+        if 'stream' not in sl:
+            sl['stream'] = torch.cuda.Stream()
+            sl['ready'] = torch.cuda.Event()
+            sl['arm_streams'] = [torch.cuda.Stream() for _ in self.setups]
+            sl['arm_events'] = [torch.cuda.Event() for _ in self.setups]
+            sl['fork_event'] = torch.cuda.Event()
+        # per-arm data products are made (once) on the caller's stream
+        obs_all = [self.arms[name]['batch'].obs(self.npoly, self.rbf, sys_errs[a])
+                   for a, name in enumerate(self.setups)]
+        # inputs of this evaluation -> pinned staging (uploaded by the enqueued work)
         host_in = sl['h_in'][:(2 + nd) * K].view(2 + nd, K).numpy()
         host_in[0] = vels
         host_in[1] = 0.0 if vsini is None else vsini
         host_in[2:] = spec_inter.map_params(params, bank0.log_ids).T
         sl['h_oix'][:narm * K].view(narm, K).numpy()[...] = self._oix[:, obj]
+        # upper bound of vsini that sizes the tap buffers, in coarse steps so that
+        # consecutive evaluations share one launch configuration
+        vmax = 0.0 if vsini is None else float(np.max(vsini, initial=0.0))
+        if vmax > 0:
+            vmax = float(max(16.0, 2.0 ** np.ceil(np.log2(vmax))))
+        sl['ready'].record(torch.cuda.current_stream())
+        sl['stream'].wait_event(sl['ready'])
+        # The ~20 launches, copies and stream fork/joins of one evaluation are captured
+        # into a CUDA graph the second time a configuration (item count, tap bound,
+        # systematic error) is seen and replayed from then on: one launch per evaluation
+        # instead of a host-bound launch sequence.
+        same_maps = all(self.arms[n]['bank'].log_ids == bank0.log_ids for n in self.setups)
+        use_graph = self.use_graphs and same_maps and not getattr(self, 'serial_arms', False) \
+            and not _cabi.lib().rvs_profile_active()
+        key = (K, vmax, tuple(sys_errs))
+        epoch = getattr(self, '_graph_epoch', 0)
+        if sl.get('graph_epoch') != epoch:
+            sl['graphs'], sl['seen'], sl['graph_epoch'] = {}, {}, epoch
+        with torch.cuda.stream(sl['stream']):
+            t0 = self.timer.start() if self.timer else None
+            g = sl['graphs'].get(key) if use_graph else None
+            done = False
+            if g is None and use_graph and sl['seen'].get(key, 0) >= 1 and len(sl['graphs']) < 32:
+                # second sighting: every scratch buffer of this configuration exists already
+                l0 = L.rvs_launch_count()
+                gr = torch.cuda.CUDAGraph()
+                gr.capture_begin(capture_error_mode='thread_local')
+                try:
+                    self._enqueue_fast(sl, obs_all, params, vmax, K, narm, nd)
+                finally:
+                    gr.capture_end()
+                self.graph_kernel_launches -= L.rvs_launch_count() - l0   # captured, not run
+                if getattr(self, '_graph_epoch', 0) != epoch:   # a buffer moved while capturing
+                    sl['graphs'], sl['seen'] = {}, {}
+                    sl['graph_epoch'] = self._graph_epoch
+                    self.use_graphs = False
+                    self._enqueue_fast(sl, obs_all, params, vmax, K, narm, nd)
+                    done = True
+                else:
+                    g = sl['graphs'][key] = (gr, L.rvs_launch_count() - l0)
+            if g is not None:
+                g[0].replay()
+                self.graph_kernel_launches += g[1]
+            elif not done:
+                self._enqueue_fast(sl, obs_all, params, vmax, K, narm, nd)
+            sl['seen'][key] = sl['seen'].get(key, 0) + 1
+            if t0 is not None:
+                self.timer.stop('fused_eval', t0, K)
+            sl['event'].record()
+        sl['busy'] = True
+        return sl
+
+    def _enqueue_fast(self, sl, obs_all, params, vmax, K, narm, nd):
+        """Enqueue (or capture) the device work of one evaluation on the current
+        stream: uploads, vertex location, the arms on their own streams, downloads."""
+        L = _cabi.lib()
+        bank0 = self.arms[self.setups[0]]['bank']
+        six = sl['ix']
         d_in = sl['d_in'][:(2 + nd) * K].view(2 + nd, K)
         d_oix = sl['d_oix'][:narm * K].view(narm, K)
         d_in.copy_(sl['h_in'][:(2 + nd) * K].view(2 + nd, K), non_blocking=True)
         d_oix.copy_(sl['h_oix'][:narm * K].view(narm, K), non_blocking=True)
-        vmax = 0.0 if vsini is None else float(np.max(vsini, initial=0.0))
-        d_chi = self._scratch('chi', (2, narm, K), np.float64)    # chi-square | off-grid measure
-        d_flags = self._scratch('flags', (2, narm, K), np.int32)
+        d_chi = self._scratch(f'chi_{six}', (2, narm, K), np.float64)    # chi-square | off-grid measure
+        d_flags = self._scratch(f'flags_{six}', (2, narm, K), np.int32)
         nvert = bank0.nvert
         torch = _dev.torch_mod()
         main = torch.cuda.current_stream()
         # the arms are independent: each runs its kernel sequence on its own stream,
         # so the small kernels of one arm (vertex location, preparation, solves) fill
         # the SMs left idle by the tails and launch gaps of the others
-        if not hasattr(self, '_arm_streams'):
-            self._arm_streams = [torch.cuda.Stream() for _ in self.setups]
-            self._arm_events = [torch.cuda.Event() for _ in self.setups]
-            self._fork_event = torch.cuda.Event()
-        t0 = self.timer.start() if self.timer else None
         banks = [self.arms[name]['bank'] for name in self.setups]
         sigs = [getattr(b, 'locate_signature', None) for b in banks]
         shared = narm > 1 and sigs[0] is not None and all(s_ == sigs[0] for s_ in sigs)
         sl['shared_locate'] = shared
         if shared:      # one vertex location for all arms, before the streams fork
-            d_ids0 = self._scratch('ids0', (K, nvert), np.int32)
-            d_w0 = self._scratch('w0', (K, nvert), np.float64)
+            d_ids0 = self._scratch(f'ids0_{six}', (K, nvert), np.int32)
+            d_w0 = self._scratch(f'w0_{six}', (K, nvert), np.float64)
             rc = L.rvs_locate_grid(ctypes.byref(bank0.gridmap), _dev.ptr(d_in[2:]), K, K,
                                    _dev.ptr(d_ids0), _dev.ptr(d_w0), _dev.ptr(d_flags[1, 0]),
                                    _dev.ptr(d_chi[1, 0]), ctypes.c_void_p(main.cuda_stream))
             _cabi.check(rc, 'rvs_locate_grid')
-        self._fork_event.record(main)
+        sl['fork_event'].record(main)
         for a, name in enumerate(self.setups):
             arm = self.arms[name]
             bank, batch = arm['bank'], arm['batch']
-            obs = batch.obs(self.npoly, self.rbf, sys_errs[a])
+            obs = obs_all[a]
             # serial_arms (stage profiling): every arm on the caller's stream
-            st = main if getattr(self, 'serial_arms', False) else self._arm_streams[a]
-            st.wait_event(self._fork_event)
+            st = main if getattr(self, 'serial_arms', False) else sl['arm_streams'][a]
+            st.wait_event(sl['fork_event'])
             stream = ctypes.c_void_p(st.cuda_stream)
             if shared:
                 d_ids, d_w = d_ids0, d_w0
             else:
-                d_ids = self._scratch(f'ids{a}', (K, nvert), np.int32)
-                d_w = self._scratch(f'w{a}', (K, nvert), np.float64)
+                d_ids = self._scratch(f'ids{a}_{six}', (K, nvert), np.int32)
+                d_w = self._scratch(f'w{a}_{six}', (K, nvert), np.float64)
                 q = d_in[2:]
                 if bank.log_ids != bank0.log_ids:
                     with torch.cuda.stream(st):
@@ -419,8 +490,8 @@ class LikelihoodEngine:
                                        _dev.ptr(d_chi[1, a]), stream)
                 _cabi.check(rc, 'rvs_locate_grid')
             stride = batch.max_npix
-            d_tn = self._scratch(f'tn{a}', (K * stride,), np.float64)
-            d_work = self._scratch(f'work{a}',
+            d_tn = self._scratch(f'tn{a}_{six}', (K * stride,), np.float64)
+            d_work = self._scratch(f'work{a}_{six}',
                                    (L.rvs_fused_workspace(K, bank.tapcap(vmax), bank.npix_t),),
                                    np.float64)
             rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
@@ -432,16 +503,11 @@ class LikelihoodEngine:
                                    ctypes.byref(bank.box) if bank.box is not None else None,
                                    stream)
             _cabi.check(rc, 'rvs_chisq_fused')
-            self._arm_events[a].record(st)
+            sl['arm_events'][a].record(st)
         for a in range(narm):
-            main.wait_event(self._arm_events[a])
-        if t0 is not None:
-            self.timer.stop('fused_eval', t0, K)
+            main.wait_event(sl['arm_events'][a])
         sl['h_chi'][:2 * narm * K].view(2, narm, K).copy_(d_chi, non_blocking=True)
         sl['h_flags'][:2 * narm * K].view(2, narm, K).copy_(d_flags, non_blocking=True)
-        sl['event'].record()
-        sl['busy'] = True
-        return sl
 
     def _collect_fast(self, sl, obj, vels, outside_penalty=True):
         """Wait for a submitted evaluation: (total (K,), redo (K,) bool)."""

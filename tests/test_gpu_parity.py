@@ -285,6 +285,45 @@ def test_tma_box_gather_identical_to_lane_gather(golden):
     assert res['box'].shape[1] == K + len(pp) and want.shape[1] == K
 
 
+def test_graph_replay_identical_to_direct_launches(golden):
+    """The evaluation call is captured into a CUDA graph the second time a
+    configuration is seen and replayed afterwards: every replay must return the
+    bits of the direct launch sequence, also after scratch buffers have grown
+    (which invalidates the captured pointers) and with several evaluations in flight."""
+    g = golden('chisq')
+    for k, a in enumerate(('desi_b', 'desi_r', 'desi_z')):
+        _register(setup(a, 'tiny', 21 + k))
+    o = unpack_objects(g, 'desi_')
+    cfg = config(min_vel=-1500, max_vel=1500)
+    ev = g['desi_eval']
+    vs = np.where(ev[:, 5] < 0, 0.0, ev[:, 5])
+    sds = [_sd(x) for x in o]
+
+    def run(eng, reps):
+        obj = np.tile(np.arange(len(sds)), reps * len(ev))[:reps * len(ev)]
+        ix = np.tile(np.arange(len(ev)), reps)
+        return eng.evaluate(obj, ev[ix, 0], ev[ix, 1:5], vs[ix])
+
+    direct = spec_fit.LikelihoodEngine(sds, cfg, {'npoly': 10})
+    direct.use_graphs = False
+    eng = spec_fit.LikelihoodEngine(sds, cfg, {'npoly': 10})
+    assert eng.use_graphs
+    want1, want4 = run(direct, 1), run(direct, 4)
+    for _ in range(4):       # direct, capture + replay, replay, replay
+        assert np.array_equal(run(eng, 1), want1)
+    assert eng.graph_kernel_launches > 0
+    for _ in range(3):       # larger call: buffers grow, the old graphs are dropped
+        assert np.array_equal(run(eng, 4), want4)
+    for _ in range(3):
+        assert np.array_equal(run(eng, 1), want1)
+    # several evaluations in flight, alternating configurations
+    obj1 = np.tile(np.arange(len(sds)), len(ev))[:len(ev)]
+    for _ in range(3):
+        hs = [eng.submit(obj1, ev[:, 0], ev[:, 1:5], vs) for _ in range(3)]
+        for h in hs:
+            assert np.array_equal(h.result(), want1)
+
+
 def test_mixed_wavelength_grids_take_per_item_solve(golden):
     """Objects on different pixel grids in one engine: the continuum solve runs
     per item (gram_kernel) instead of as the shared-basis GEMM (gram_mma_kernel);

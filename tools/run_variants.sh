@@ -1,9 +1,12 @@
-# usage: tools/run_variants.sh <suffix> ...   (tuning builds rvspecfit_b200/librvs_b200<suffix>.so)
+# usage: tools/run_variants.sh "<ENV=..> <lib suffix or -> <bench args>" ...
 for v in "$@"; do
   echo "variant $v"
-  RVS_LIB=rvspecfit_b200/librvs_b200$v.so timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "tma or desi_three" 2>&1 | tail -1
-  RVS_LIB=rvspecfit_b200/librvs_b200$v.so timeout 200 python bench.py --stage-profile --evals 100 --no-cpu 2>&1 | tail -1 | python -c "
+  set -- $v
+  e=$1; shift
+  l=$1; shift
+  [ "$l" = "-" ] && l=""
+  env $e RVS_LIB=rvspecfit_b200/librvs_b200$l.so timeout 300 python bench.py --no-cpu --evals 400 "$@" 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read())['stage_profile']
-print({k:round(v['us_per_launch'],1) for k,v in d.items() if isinstance(v,dict)})"
+d=json.loads(sys.stdin.read())
+print('value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'frac', round(d['roofline']['frac'],4), 'us/call', round(1e3*d['roofline']['ms_per_call'],1))"
 done
