@@ -309,12 +309,12 @@ def test_graph_replay_identical_to_direct_launches(golden):
     eng = spec_fit.LikelihoodEngine(sds, cfg, {'npoly': 10})
     assert eng.use_graphs
     want1, want4 = run(direct, 1), run(direct, 4)
-    for _ in range(4):       # direct, capture + replay, replay, replay
+    for _ in range(5 * eng.NSLOT):   # per in-flight slot: direct (x2: buffers of the other slots appear), capture + replay, replays
         assert np.array_equal(run(eng, 1), want1)
     assert eng.graph_kernel_launches > 0
-    for _ in range(3):       # larger call: buffers grow, the old graphs are dropped
+    for _ in range(3 * eng.NSLOT):   # larger call: buffers grow, the old graphs are dropped
         assert np.array_equal(run(eng, 4), want4)
-    for _ in range(3):
+    for _ in range(3 * eng.NSLOT):
         assert np.array_equal(run(eng, 1), want1)
     # several evaluations in flight, alternating configurations
     obj1 = np.tile(np.arange(len(sds)), len(ev))[:len(ev)]
