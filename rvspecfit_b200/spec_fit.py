@@ -43,6 +43,10 @@ class SpecData:
         for a in (self.lam, self.spec, self.espec, self.badmask):
             a.setflags(write=False)
         self.objid = random.getrandbits(128)
+        # identifies the pixel grid (objects observed on the same pixels share one
+        # wavelength / basis entry on the device, SpectrumBatch)
+        self.gridkey = (len(self.lam), self.lam[:4].tobytes(), self.lam[-4:].tobytes(),
+                        float(self.lam.sum()))
 
     def __hash__(self):
         return self.objid
@@ -59,31 +63,32 @@ class SpectrumBatch:
         self.off = np.concatenate([[0], np.cumsum(self.npix)]).astype(np.int64)
         self.lam0 = np.array([s.lam[0] for s in specdatas])
         self.lam1 = np.array([s.lam[-1] for s in specdatas])
-        self.h_lam = np.concatenate([s.lam for s in specdatas])
-        self.h_spec = np.concatenate([s.spec for s in specdatas])
-        self.h_espec = np.concatenate([s.espec for s in specdatas])
+        self.h_spec, self.d_spec = _dev.upload_concat([s.spec for s in specdatas], np.float64)
+        self.h_espec, self.d_espec = _dev.upload_concat([s.espec for s in specdatas], np.float64)
         self.h_bad = np.concatenate([s.badmask for s in specdatas])
-        self.d_spec = _dev.upload(self.h_spec, np.float64)
-        self.d_espec = _dev.upload(self.h_espec, np.float64)
+        self._lams = [s.lam for s in specdatas]
         self.d_off = _dev.upload(self.off, np.int64)
         # objects observed on the same pixels share one wavelength grid: one copy
         # of lam / ln(lam) / continuum basis in the grid pools (rvs_obs)
         seen, gid, first = {}, np.zeros(self.n, dtype=np.int64), []
         for i, s in enumerate(specdatas):
-            key = (len(s.lam), s.lam[:4].tobytes(), s.lam[-4:].tobytes(),
-                   float(s.lam.sum()))
+            key = s.gridkey
             if key not in seen:
                 seen[key] = len(first)
                 first.append(i)
             gid[i] = seen[key]
         self.grid_of = gid
         self.grid_first = np.array(first, dtype=np.int64)
-        gl = [self.h_lam[self.off[i]:self.off[i + 1]] for i in self.grid_first]
+        gl = [specdatas[i].lam for i in self.grid_first]
         self.gstart = np.concatenate([[0], np.cumsum([len(_) for _ in gl])]).astype(np.int64)
         self.d_glam = _dev.upload(np.concatenate(gl), np.float64)
         self.d_gstart = _dev.upload(self.gstart, np.int64)
         self.d_goff = _dev.upload(self.gstart[:-1][gid], np.int64)
         self._prod, self._basis = {}, {}
+
+    def lam_of(self, i):
+        """Wavelengths of object i (host)."""
+        return self._lams[i]
 
     def products(self, sys_err=0.0):
         key = float(sys_err)
@@ -647,7 +652,7 @@ class LikelihoodEngine:
             es = batch.h_espec[sl]
             if sys_err:
                 es = np.sqrt(sys_err**2 + es**2)
-            polys = get_poly_basis(batch.h_lam[sl], self.npoly, self.rbf)
+            polys = get_poly_basis(batch.lam_of(o), self.npoly, self.rbf)
             chi[r, c] = _chisq0_svd(batch.h_spec[sl], ex['raw'], polys, es)[0]
         return chi
 
