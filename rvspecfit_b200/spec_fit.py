@@ -132,6 +132,11 @@ class SpectrumBatch:
         return o
 
 
+# kernels launched through CUDA-graph replays by all engines of this process
+# (rvs_launch_count only sees direct launches)
+GRAPH_LAUNCHES = [0]
+
+
 class PendingEval:
     """Handle of a LikelihoodEngine.submit() call."""
 
@@ -423,6 +428,7 @@ class LikelihoodEngine:
                 finally:
                     gr.capture_end()
                 self.graph_kernel_launches -= L.rvs_launch_count() - l0   # captured, not run
+                GRAPH_LAUNCHES[0] -= L.rvs_launch_count() - l0
                 if getattr(self, '_graph_epoch', 0) != epoch:   # a buffer moved while capturing
                     sl['graphs'], sl['seen'] = {}, {}
                     sl['graph_epoch'] = self._graph_epoch
@@ -434,6 +440,7 @@ class LikelihoodEngine:
             if g is not None:
                 g[0].replay()
                 self.graph_kernel_launches += g[1]
+                GRAPH_LAUNCHES[0] += g[1]
             elif not done:
                 self._enqueue_fast(sl, obs_all, params, vmax, K, narm, nd)
             sl['seen'][key] = sl['seen'].get(key, 0) + 1
