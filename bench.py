@@ -151,7 +151,13 @@ def run_gpu(args):
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
+    saved_stdout = None
     if world > 1:
+        # stdout carries exactly one JSON line: anything libraries write to fd 1 while the
+        # job runs (NCCL prints its version there when NCCL_DEBUG is set) goes to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from rvspecfit_b200 import _cabi, spec_fit, spec_inter, batch_fit, shard
     w = WORKLOADS[args.workload]
@@ -377,9 +383,14 @@ def run_gpu(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         line['cpu_baseline'] = cpu_baseline(args, bounded=True)
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
