@@ -341,11 +341,11 @@ class LikelihoodEngine:
         torch = _dev.torch_mod()
         if not hasattr(self, '_slots'):
             self._slots, self._slot_ix = [dict(K=0, busy=False, ix=i) for i in range(self.NSLOT)], -1
-        self._slot_ix = (self._slot_ix + 1) % self.NSLOT
-        sl = self._slots[self._slot_ix]
-        if sl['busy']:
+        free = [x for x in self._slots if not x['busy']]
+        if not free:
             raise RuntimeError(f'more than {self.NSLOT} evaluations in flight: call result() on '
                                'the oldest PendingEval first')
+        sl = free[0]    # lowest free slot: its captured graphs are the warmest
         if sl['K'] < K:
             self._graph_epoch = getattr(self, '_graph_epoch', 0) + 1
             cap = int(K * 1.25) + 16
@@ -376,7 +376,18 @@ class LikelihoodEngine:
         narm = len(self.setups)
         bank0 = self.arms[self.setups[0]]['bank']
         nd = bank0.ndim
-        sl = self._slot(K, narm, nd)
+        same_maps = all(self.arms[n]['bank'].log_ids == bank0.log_ids for n in self.setups)
+        use_graph = self.use_graphs and same_maps and not getattr(self, 'serial_arms', False) \
+            and not L.rvs_profile_active()
+        # The item count is rounded up (absent items: arm index -1 everywhere, skipped by
+        # every kernel), so that an optimiser whose active set shrinks call by call keeps
+        # hitting the same captured launch configurations.
+        Kp = K
+        if use_graph:
+            Kp = 16 if K <= 16 else (1 << int(np.ceil(np.log2(K))) if K <= 128
+                                     else (K + 127) // 128 * 128)
+        sl = self._slot(Kp, narm, nd)
+        sl['Kp'] = Kp
         torch = _dev.torch_mod()
         # Every in-flight evaluation has its own streams and scratch, so that the
         # low-occupancy tail of one (continuum solves of the last arm) runs under the
@@ -391,11 +402,17 @@ class LikelihoodEngine:
         obs_all = [self.arms[name]['batch'].obs(self.npoly, self.rbf, sys_errs[a])
                    for a, name in enumerate(self.setups)]
         # inputs of this evaluation -> pinned staging (uploaded by the enqueued work)
-        host_in = sl['h_in'][:(2 + nd) * K].view(2 + nd, K).numpy()
-        host_in[0] = vels
-        host_in[1] = 0.0 if vsini is None else vsini
-        host_in[2:] = spec_inter.map_params(params, bank0.log_ids).T
-        sl['h_oix'][:narm * K].view(narm, K).numpy()[...] = self._oix[:, obj]
+        host_in = sl['h_in'][:(2 + nd) * Kp].view(2 + nd, Kp).numpy()
+        q = spec_inter.map_params(params, bank0.log_ids).T
+        host_in[0, :K] = vels
+        host_in[1, :K] = 0.0 if vsini is None else vsini
+        host_in[2:, :K] = q
+        h_oix = sl['h_oix'][:narm * Kp].view(narm, Kp).numpy()
+        h_oix[:, :K] = self._oix[:, obj]
+        if Kp > K:
+            host_in[:2, K:] = 0.0
+            host_in[2:, K:] = q[:, :1]
+            h_oix[:, K:] = -1
         # upper bound of vsini that sizes the tap buffers, in coarse steps so that
         # consecutive evaluations share one launch configuration
         vmax = 0.0 if vsini is None else float(np.max(vsini, initial=0.0))
@@ -407,10 +424,7 @@ class LikelihoodEngine:
         # into a CUDA graph the second time a configuration (item count, tap bound,
         # systematic error) is seen and replayed from then on: one launch per evaluation
         # instead of a host-bound launch sequence.
-        same_maps = all(self.arms[n]['bank'].log_ids == bank0.log_ids for n in self.setups)
-        use_graph = self.use_graphs and same_maps and not getattr(self, 'serial_arms', False) \
-            and not _cabi.lib().rvs_profile_active()
-        key = (K, vmax, tuple(sys_errs))
+        key = (Kp, vmax, tuple(sys_errs))
         epoch = getattr(self, '_graph_epoch', 0)
         if sl.get('graph_epoch') != epoch:
             sl['graphs'], sl['seen'], sl['graph_epoch'] = {}, {}, epoch
@@ -424,7 +438,7 @@ class LikelihoodEngine:
                 gr = torch.cuda.CUDAGraph()
                 gr.capture_begin(capture_error_mode='thread_local')
                 try:
-                    self._enqueue_fast(sl, obs_all, params, vmax, K, narm, nd)
+                    self._enqueue_fast(sl, obs_all, params, vmax, Kp, narm, nd)
                 finally:
                     gr.capture_end()
                 self.graph_kernel_launches -= L.rvs_launch_count() - l0   # captured, not run
@@ -433,7 +447,7 @@ class LikelihoodEngine:
                     sl['graphs'], sl['seen'] = {}, {}
                     sl['graph_epoch'] = self._graph_epoch
                     self.use_graphs = False
-                    self._enqueue_fast(sl, obs_all, params, vmax, K, narm, nd)
+                    self._enqueue_fast(sl, obs_all, params, vmax, Kp, narm, nd)
                     done = True
                 else:
                     g = sl['graphs'][key] = (gr, L.rvs_launch_count() - l0)
@@ -442,7 +456,7 @@ class LikelihoodEngine:
                 self.graph_kernel_launches += g[1]
                 GRAPH_LAUNCHES[0] += g[1]
             elif not done:
-                self._enqueue_fast(sl, obs_all, params, vmax, K, narm, nd)
+                self._enqueue_fast(sl, obs_all, params, vmax, Kp, narm, nd)
             sl['seen'][key] = sl['seen'].get(key, 0) + 1
             if t0 is not None:
                 self.timer.stop('fused_eval', t0, K)
@@ -523,11 +537,11 @@ class LikelihoodEngine:
 
     def _collect_fast(self, sl, obj, vels, outside_penalty=True):
         """Wait for a submitted evaluation: (total (K,), redo (K,) bool)."""
-        K, narm = len(obj), len(self.setups)
+        K, narm, Kp = len(obj), len(self.setups), sl['Kp']
         sl['event'].synchronize()
-        both = sl['h_chi'][:2 * narm * K].view(2, narm, K).numpy()
+        both = sl['h_chi'][:2 * narm * Kp].view(2, narm, Kp).numpy()[:, :, :K]
         chi, outside = both[0], both[1]
-        flags = sl['h_flags'][:2 * narm * K].view(2, narm, K).numpy()
+        flags = sl['h_flags'][:2 * narm * Kp].view(2, narm, Kp).numpy()[:, :, :K]
         if sl.get('shared_locate'):     # located once: arm 0's rows stand for every arm
             outside = np.broadcast_to(outside[0], outside.shape)
             both = np.stack([chi, outside])
