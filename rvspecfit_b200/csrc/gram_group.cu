@@ -38,7 +38,14 @@ static int launch_gram_mma_np(GramMmaArgs a, cudaStream_t st) {
   const int groups = (a.K + NI - 1) / NI;
   a.KS = std::min(GM_MAX_KS, std::max(1, (512 + groups - 1) / groups));
   dim3 grid(groups, a.KS);
-  const size_t tile_smem = sizeof(double) * GM_WARPS * GM_TILE * a.npp;
+  size_t tile_smem = sizeof(double) * GM_WARPS * GM_NSTG * gm_stage_doubles(a.npp, NI);
+  tile_smem = std::max(tile_smem, sizeof(double) * GramTiles<NP>::ROWS * (NI + 1));  // s_red alias
+  static size_t smem_set = 0;
+  if (tile_smem > smem_set) {
+    RVS_CUDA_OK(cudaFuncSetAttribute(gram_mma_kernel<NP, NT>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+    smem_set = tile_smem;
+  }
   prof_begin(ST_GRAM, st);
   gram_mma_kernel<NP, NT><<<grid, GM_THREADS, tile_smem, st>>>(a);
   prof_end(ST_GRAM, st);

@@ -27,7 +27,7 @@ namespace rvs {
 constexpr int GM_WARPS = 4;
 constexpr int GM_THREADS = GM_WARPS * 32;
 constexpr int GM_MAX_KS = 16;
-constexpr int GM_TILE = 64;  // pixels of the basis staged per warp at a time (multiple of 8)
+constexpr int GM_TILE = 16;  // pixels staged per warp and stage (one 128-byte line per operand row)
 
 struct GramMmaArgs {
   const double *tn;
@@ -121,30 +121,37 @@ __device__ __forceinline__ GroupGeom group_geom(const GramMmaArgs &a, int g) {
   return gg;
 }
 
+// Shared-memory staging of gram_mma_kernel: per warp and stage a tile of GM_TILE
+// pixels of the basis [px][npp] and of the B operands T/sigma, D/sigma [item][px]
+// (rows padded by 4 doubles: the fragment reads of a half-warp then hit 16 distinct
+// 8-byte banks).
+constexpr int GM_BROW = GM_TILE + 4;
+constexpr int GM_NSTG = 2;
+__host__ __device__ constexpr int gm_stage_doubles(int npp, int ni) {
+  return GM_TILE * npp + 2 * ni * GM_BROW;
+}
+
 template <int NP, int NT>
-#ifdef RVS_GM_MAXNREG
-__global__ void __maxnreg__(RVS_GM_MAXNREG) gram_mma_kernel(GramMmaArgs a) {
-#else
 __global__ void __launch_bounds__(GM_THREADS, NT == 2 ? 4 : 3) gram_mma_kernel(GramMmaArgs a) {
-#endif
   using TL = GramTiles<NP>;
   constexpr int NI = 8 * NT;
-  __shared__ double s_red[TL::ROWS][NI + 1];
+  extern __shared__ __align__(16) double s_dyn[];
+  __shared__ int64_t s_toff[NI], s_doff[NI];  // element offsets of the items' T/sigma, D/sigma rows
+  __shared__ int s_have[NI];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = blockIdx.x, ks = blockIdx.y;
   const int r = lane >> 2, c = lane & 3;
   const GroupGeom gg = group_geom<NT>(a, g);
   const int npix = gg.npix;
   const double *Pb = a.P + gg.goff * a.npp;
-  // this thread's B columns: item r of every n-tile
-  const double *tnp[NT], *dnp[NT];
-#pragma unroll
-  for (int nt = 0; nt < NT; nt++) {
-    const int k = g * NI + nt * 8 + r;
+  if (tid < NI) {
+    const int k = g * NI + tid;
     const int obj = k < a.K ? a.oix[k] : -1;
-    tnp[nt] = obj >= 0 ? a.tn + (int64_t)k * a.tn_stride : nullptr;
-    dnp[nt] = obj >= 0 ? a.dn + a.off[obj] : nullptr;
+    s_have[tid] = obj >= 0;
+    s_toff[tid] = (int64_t)k * a.tn_stride;
+    s_doff[tid] = obj >= 0 ? a.off[obj] : 0;
   }
+  __syncthreads();
   // this thread's A rows: packed-triangle entry o = 8 mt + r  ->  (i, j), i >= j
   int ia[TL::MT_M], ja[TL::MT_M];
   tri_rows<NP>(r, ia, ja);
@@ -158,36 +165,50 @@ __global__ void __launch_bounds__(GM_THREADS, NT == 2 ? 4 : 3) gram_mma_kernel(G
   const int seglen = ((npix + nseg - 1) / nseg + 3) & ~3;
   const int pbeg = (ks * GM_WARPS + wid) * seglen;
   const int pend = min(npix, pbeg + seglen);
-  // B operands one k-step ahead (they come from L2: written by stage A)
-  double tq[NT], dq[NT];
-  auto load_b = [&](int p4) {
-    const int p = p4 + c;
-#pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-      tq[nt] = 0;
-      dq[nt] = 0;
-      if (p < pend && tnp[nt]) { tq[nt] = __ldcg(tnp[nt] + p); dq[nt] = __ldg(dnp[nt] + p); }
-    }
-  };
-  load_b(pbeg);
-  // the basis rows of the warp's pixels go through a warp-private shared-memory
-  // tile (cp.async, 16-byte units; rows are npp = even doubles): the A fragments
-  // are then LDS with short, fixed latency instead of L1-path loads
-  extern __shared__ __align__(16) double s_tile[];
-  double *sP = s_tile + (size_t)wid * GM_TILE * a.npp;
-  const unsigned sP_s = (unsigned)__cvta_generic_to_shared(sP);
-  for (int t0 = pbeg; t0 < pend; t0 += GM_TILE) {
+  // Operands go through a warp-private, double-buffered shared-memory stage filled by
+  // cp.async one tile (GM_TILE pixels = 4 k-steps) ahead: the basis rows in 16-byte
+  // units (rows are npp = even doubles), T/sigma and D/sigma in 8-byte units (object
+  // rows start at any pixel offset); the fragments are then LDS with short, fixed
+  // latency instead of L2 round trips in the dependency chain of every k-step.
+  const int stg = gm_stage_doubles(a.npp, NI);
+  double *sW = s_dyn + (size_t)wid * GM_NSTG * stg;
+  const unsigned sW_s = (unsigned)__cvta_generic_to_shared(sW);
+  // lane -> (row parity, pixel) of the B tiles: rows (lane >> 4) + 2 i, pixel lane & 15
+  const int bpx = lane & (GM_TILE - 1), brow0 = lane >> 4;
+  auto load_stage = [&](int t0, int slot) {
     const int tile_n = min(GM_TILE, pend - t0);
-    __syncwarp();
-    {
+    if (tile_n > 0) {
+      const unsigned base = sW_s + slot * stg * 8;
       const double *src = Pb + (int64_t)t0 * a.npp;
       const int nvec = tile_n * a.npp / 2;
       for (int v = lane; v < nvec; v += 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sP_s + v * 16), "l"(src + 2 * v) : "memory");
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + v * 16), "l"(src + 2 * v) : "memory");
+      double *sT = sW + slot * stg + GM_TILE * a.npp;
+      const unsigned sT_s = base + GM_TILE * a.npp * 8;
+#pragma unroll
+      for (int i = 0; i < NI / 2; i++) {
+        const int row = brow0 + 2 * i;
+        const int o = row * GM_BROW + bpx;
+        if (bpx < tile_n && s_have[row]) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sT_s + o * 8), "l"(a.tn + s_toff[row] + t0 + bpx) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sT_s + (NI * GM_BROW + o) * 8), "l"(a.dn + s_doff[row] + t0 + bpx) : "memory");
+        } else {
+          sT[o] = 0;
+          sT[NI * GM_BROW + o] = 0;
+        }
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_stage(pbeg, 0);
+  int slot = 0;
+  for (int t0 = pbeg; t0 < pend; t0 += GM_TILE, slot ^= 1) {
+    const int tile_n = min(GM_TILE, pend - t0);
+    load_stage(t0 + GM_TILE, slot ^ 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncwarp();
+    const double *sP = sW + slot * stg;
+    const double *sT = sP + GM_TILE * a.npp, *sD = sT + NI * GM_BROW;
     for (int p4 = t0; p4 < t0 + tile_n; p4 += 4) {
       const int p = p4 + c;
       const bool in = p < pend;
@@ -203,10 +224,12 @@ __global__ void __launch_bounds__(GM_THREADS, NT == 2 ? 4 : 3) gram_mma_kernel(G
       double bsq[NT], btd[NT];
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
-        bsq[nt] = tq[nt] * tq[nt];
-        btd[nt] = tq[nt] * dq[nt];
+        // pixels past the run and absent items were staged as zeros
+        const int o = (nt * 8 + r) * GM_BROW + (p4 - t0) + c;
+        const double tq = sT[o], dq = sD[o];
+        bsq[nt] = tq * tq;
+        btd[nt] = tq * dq;
       }
-      load_b(p4 + 4);
 #pragma unroll
       for (int mt = 0; mt < TL::MT_M; mt++) {
         const double av = (in && mt * 8 + r < TL::NTRI) ? pa[mt] * pb[mt] : 0.0;
@@ -221,8 +244,13 @@ __global__ void __launch_bounds__(GM_THREADS, NT == 2 ? 4 : 3) gram_mma_kernel(G
           dmma884(acc[TL::MT_M + mv][nt][0], acc[TL::MT_M + mv][nt][1], av, btd[nt]);
       }
     }
+    __syncwarp();  // every lane has read this stage: the next iteration refills it
   }
-  // ---- cross-warp sum in fixed (warp) order, partial of this CTA to global
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ---- cross-warp sum in fixed (warp) order (the staging memory is free now), partial
+  // of this CTA to global
+  double (*s_red)[NI + 1] = reinterpret_cast<double (*)[NI + 1]>(s_dyn);
   warp_ordered_sum<TL::MT, NT>(acc, s_red, wid, r, c);
   double *part = a.part + ((int64_t)g * a.KS + ks) * (TL::ROWS * NI);
   for (int e = tid; e < TL::ROWS * NI; e += GM_THREADS) {
