@@ -528,6 +528,11 @@ def main():
     ap.add_argument('--groups', type=int, default=2,
                     help='independent object groups stepped in ping-pong (host/GPU overlap)')
     args = ap.parse_args()
+    if args.stage_profile:
+        # per-kernel times are only meaningful when nothing else runs beside the kernel:
+        # one group, arms serialised, no helper stream
+        os.environ['RVS_NO_AUX'] = '1'
+        args.groups = 1
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -21,9 +21,10 @@
 //     c1 = 2 (1 + r) / r^2,  c2 = 1 / r^3,
 // whose Thomas pivots converge to a constant within ~15 rows of knot 0
 // (table wtab[] holds the exact ones there).  No per-knot tables are read.  The
-// window carries SPL_HALO extra rows on each side: the influence of the
-// artificial window ends decays as 0.268^k, below fp64 rounding after 32 rows
-// (exact natural boundary where the window touches an end of the template).
+// window carries CK_HALO extra rows on each side: the influence of the
+// artificial window ends decays as 0.268^k per row (2e-14 after 24 rows, on a
+// term that is ~1e-2 of the value: below fp64 rounding of the resampled template;
+// exact natural boundary where the window touches an end of the template).
 // Evaluation in [x_i, x_{i+1}):  u = (x - x_i)/h_i, v = (x_{i+1} - x)/h_i,
 //     T = v y_i + u y_{i+1} + s_i (v^3 - v) + (s_{i+1}/r^2) (u^3 - u),
 // algebraically the reference's A dl^3 + B dr^3 + C dl + D dr (spliner.c:97-106).
@@ -38,6 +39,13 @@ namespace rvs {
 constexpr int CK_WARPS = 4;
 constexpr int CK_THREADS = CK_WARPS * 32;
 constexpr int CK_NT = 32;  // rows next to knot 0 with tabulated pivots
+// spline halo of a chunk window: the influence of the artificial window ends decays
+// as 0.268^k per knot: 2e-14 after 24 knots, times h^2 z / y ~ 1e-2 -> below fp64
+// rounding of the resampled template
+#ifndef RVS_CK_HALO
+#define RVS_CK_HALO 24
+#endif
+constexpr int CK_HALO = RVS_CK_HALO;
 #ifndef RVS_CK_RING
 #define RVS_CK_RING 8
 #endif
@@ -319,7 +327,7 @@ chunk_kernel(const ChunkArgs a, const __grid_constant__ CUtensorMap tmap) {
   // knot windows (global indices, inclusive): Y on [ya0, ya1], raw y on [ya0-kmax, ya1+kmax]
   // which may stick out of the template: those knots are the zero padding of the
   // reference's 'same' convolution (spec_fit.py:677-680)
-  const int ya0 = max(0, c0 - SPL_HALO - 1), ya1 = min(n - 1, c1 + SPL_HALO + 2);
+  const int ya0 = max(0, c0 - CK_HALO - 1), ya1 = min(n - 1, c1 + CK_HALO + 2);
   const int w0 = (ya0 - kmax) & ~3;  // first knot of the window (multiple of 4, may be < 0)
   const int W0 = ((ya1 + kmax + 1 - w0) + 3) & ~3;
   if (W0 + 2 > a.wcap) {  // does not fit: the caller re-evaluates this item on the general path

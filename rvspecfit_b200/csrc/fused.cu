@@ -211,7 +211,7 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
   a.goff = obs->d_goff;
   a.oix = d_oix; a.vels = d_vels; a.tn = d_tn; a.tn_stride = tn_stride; a.status = d_status;
   a.K = K;
-  a.wcap = (a.C + 2 * (SPL_HALO + 3 + tapcap) + 12 + 3) & ~3;
+  a.wcap = (a.C + 2 * (CK_HALO + 3 + tapcap) + 12 + 3) & ~3;
   if (use_box) {  // TMA destinations are 128-byte aligned
     a.wcap = (a.wcap + 15) & ~15;
     a.wcap1 = std::max(a.wcap, TMA_RING_DOUBLES);
