@@ -30,8 +30,12 @@ __device__ __forceinline__ double spline_eval_uv(const ScanArgs &a, const double
   return fma(h26, cub, fma(c0.x, v, c1.x * u));
 }
 
+// resident CTAs per SM the register budget allows (tuning)
+#ifndef RVS_SCAN_MINB
+#define RVS_SCAN_MINB 4
+#endif
 template <int NP, int NT>
-__global__ void __launch_bounds__(GM_THREADS) chisq_scan_mma_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kernel(ScanArgs a) {
   using TL = GramTiles<NP>;
   constexpr int NI = 8 * NT;
   constexpr int KST = (NP + 3) / 4;
