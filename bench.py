@@ -231,7 +231,7 @@ def run_gpu(args):
         buf = (ctypes.c_double * (3 * 4096))()
         n = L.rvs_profile_timeline(ctypes.cast(buf, ctypes.c_void_p), 4096)
         L.rvs_profile_enable(0)
-        names = ['locate', 'nearest', 'prep', 'chunk', 'gram', 'solve', 'resid']
+        names = ['locate', 'prep', 'chunk', 'gram', 'solve', 'resid']
         for i in range(n):
             print(f'{names[int(buf[3 * i])]:8s} {1e3 * buf[3 * i + 1]:10.1f} {1e3 * buf[3 * i + 2]:10.1f}'
                   f'  dur {1e3 * (buf[3 * i + 2] - buf[3 * i + 1]):8.1f} us')
@@ -245,11 +245,11 @@ def run_gpu(args):
             step_resident(eng)
         L.rvs_profile_enable(1)
         step_resident(eng)
-        ms = (ctypes.c_double * 7)()
-        n = (ctypes.c_int64 * 7)()
-        L.rvs_profile_read(ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(n, ctypes.c_void_p), 7)
+        ms = (ctypes.c_double * 6)()
+        n = (ctypes.c_int64 * 6)()
+        L.rvs_profile_read(ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(n, ctypes.c_void_p), 6)
         L.rvs_profile_enable(0)
-        names = ['locate', 'nearest', 'prep', 'chunk', 'gram_mma', 'gram_solve', 'resid_mma']
+        names = ['locate', 'prep', 'chunk', 'gram_mma', 'gram_solve', 'resid_mma']
         out = {k: dict(launches=int(c), us_per_launch=1e3 * t / max(1, c), ms_total=t)
                for k, t, c in zip(names, ms, n)}
         out['note'] = ('arms serialised on one stream; warm caches; per-launch = one arm, '

@@ -66,8 +66,8 @@ int64_t rvs_launch_count(void);
 /* Optional per-stage timing of the fused evaluation (bench.py --stage-profile):
  * when enabled, CUDA events bracket every kernel on its launching stream.
  * rvs_profile_read synchronises the device, writes the summed milliseconds and
- * launch counts of stages 0..nstage-1 (locate, nearest, prep, chunk, gram,
- * solve, resid), clears the records and returns the number of stages. */
+ * launch counts of stages 0..nstage-1 (locate, prep, chunk, gram, solve,
+ * resid), clears the records and returns the number of stages. */
 void rvs_profile_enable(int on);
 int rvs_profile_active(void);
 int rvs_profile_read(double *ms_total, int64_t *launches, int nstage);

@@ -1,9 +1,10 @@
 // Fused optimiser-phase evaluation, stage A ("chunk kernel"): one WARP per
 // (item, chunk).  A chunk is a contiguous range of at most `C` template knots
 // and the observed pixels that fall on them at the item's velocity.  The warp
-//   1. gathers its window of the 2^d (or d+1) grid rows with streaming 16-byte
-//      loads, accumulates the corner-weighted sum in fp64 and exponentiates,
-//   2. applies the rotational-broadening taps (prepared by taps_kernel),
+//   1. gathers its window of the 2^d (or d+1) grid rows -- as 5-D TMA tiles of the
+//      corner box on dense regular grids, with per-lane 16-byte cp.async copies
+//      otherwise --, accumulates the corner-weighted sum in fp64 and exponentiates,
+//   2. applies the rotational-broadening taps (prepared by prep_kernel),
 //   3. solves the natural cubic spline on the window,
 //   4. resamples onto its pixels and writes T/sigma.
 // Warps never synchronise with each other (only __syncwarp / shuffles), so the

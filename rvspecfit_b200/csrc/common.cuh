@@ -15,7 +15,7 @@ void count_launch(int n = 1);
 
 // Optional per-stage timing (rvs_profile_enable): CUDA events bracket each kernel
 // of the fused evaluation on its launching stream; rvs_profile_read sums them.
-enum Stage { ST_LOCATE = 0, ST_NEAREST, ST_PREP, ST_CHUNK, ST_GRAM, ST_SOLVE, ST_RESID, ST_COUNT };
+enum Stage { ST_LOCATE = 0, ST_PREP, ST_CHUNK, ST_GRAM, ST_SOLVE, ST_RESID, ST_COUNT };
 bool prof_on();
 void prof_begin(int stage, cudaStream_t st);
 void prof_end(int stage, cudaStream_t st);

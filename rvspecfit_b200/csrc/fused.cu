@@ -1,11 +1,10 @@
-// C-ABI entry point of the fused optimiser-phase evaluation: rotation taps
-// (taps_kernel), stage A (chunk_kernel.cuh: template window -> T/sigma) and
-// stage B (gram_kernel.cuh: continuum solve -> chi-square).  The spline never
-// goes to HBM; the only intermediate is T/sigma (8 bytes per observed pixel,
-// L2-resident between the two stages).
-#include <string.h>
-
+// C-ABI entry point of the fused optimiser-phase evaluation: per-item preparation
+// (prep_kernel: rotation taps, chunk geometry), stage A (chunk_kernel.cuh: template
+// window -> T/sigma) and stage B (gram_mma.cuh / gram_kernel.cuh: continuum solve ->
+// chi-square).  The spline never goes to HBM; the only intermediate is T/sigma
+// (8 bytes per observed pixel, L2-resident between the two stages).
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <map>
