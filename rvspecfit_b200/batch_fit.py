@@ -160,37 +160,64 @@ class BatchObjective:
 
     def __call__(self, idx, X):
         """chisq_func for K pairs: idx (K,) object indices, X (K, N)."""
+        return self.submit(idx, X)()
+
+    def submit(self, idx, X):
+        """Start the evaluation of chisq_func for K pairs and return a callable that
+        waits for the values (same arithmetic as __call__: priors + -2 log L +
+        penalty, 1e30 behind the hard walls, vel_fit.py:210-257)."""
         idx = np.asarray(idx, dtype=np.int64)
         vel, vsini, params, pen = self.unpack(idx, X)
         wall = (vel > self.max_vel) | (vel < self.min_vel) | ~np.isfinite(params).all(axis=1)
-        out = np.full(len(idx), 1e30)
         ok = ~wall
+        pend = None
         if ok.any():
-            out[ok] = self.chisq0(idx[ok], vel[ok], None if vsini is None else vsini[ok],
-                                  params[ok]) + pen[ok]
-        return out
+            self.nfev += int(ok.sum())
+            if hasattr(self.eng, 'submit'):
+                pend = self.eng.submit(idx[ok], vel[ok], params[ok],
+                                       None if vsini is None else vsini[ok])
+            else:       # engines with a blocking evaluate only
+                class _Done:
+                    def __init__(self, v):
+                        self.v = v
+
+                    def result(self):
+                        return self.v
+                pend = _Done(self.eng.evaluate(idx[ok], vel[ok], params[ok],
+                                               None if vsini is None else vsini[ok]))
+
+        def wait():
+            out = np.full(len(idx), 1e30)
+            if pend is not None:
+                out[ok] = self.prior_term(params[ok]) + pend.result() + pen[ok]
+            return out
+        return wait
 
 
 # below this many active problems an iteration's candidate points go out in one call
 SPECULATE_BELOW = 640
+# smallest lock-step set worth its own evaluation calls
+NM_MIN_GROUP = 64
 
 
 # ------------------------------------------------------- lock-step Nelder-Mead
-def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000,
-                         speculate_below=0):
+def nelder_mead_steps(sims, xatol=1e-2, fatol=1e-3, maxiter=10000, speculate_below=0):
     """scipy's Nelder-Mead (`_minimize_neldermead`, adaptive=False, no bounds,
-    maxfev=inf) on B simplices at once.  fbatch(idx, X) -> f for rows X (K, N)
-    belonging to problems idx (K,).  sims (B, N+1, N): initial simplices.
-    Returns dict(x (B, N), fun (B,), success (B,), final_simplex (B, N+1, N),
-    nit (B,), nfev (B,)).  Problem b visits exactly the points, in exactly the
-    order, that scipy.optimize.minimize(method='Nelder-Mead',
-    options={'initial_simplex': sims[b], ...}) would."""
+    maxfev=inf) on B simplices at once, as a generator: it yields evaluation
+    requests (idx (K,), X (K, N)) -- rows X belonging to problems idx -- is sent
+    their function values, and returns dict(x (B, N), fun (B,), success (B,),
+    final_simplex (B, N+1, N), nit (B,), nfev (B,)).  sims (B, N+1, N): initial
+    simplices.  Problem b visits exactly the points, in exactly the order, that
+    scipy.optimize.minimize(method='Nelder-Mead', options={'initial_simplex':
+    sims[b], ...}) would.  Drivers: nelder_mead_lockstep (one generator, blocking
+    evaluations), nelder_mead_interleaved (several generators whose host work
+    overlaps each other's evaluations on the GPU)."""
     sim = np.array(sims, dtype=np.float64)
     B, N1, N = sim.shape
     assert N1 == N + 1
     rho, chi, psi, sigma = 1, 2, 0.5, 0.5
     allb = np.arange(B)
-    fsim = fbatch(np.repeat(allb, N1), sim.reshape(B * N1, N)).reshape(B, N1)
+    fsim = (yield np.repeat(allb, N1), sim.reshape(B * N1, N)).reshape(B, N1)
     nfev = np.full(B, N1)
 
     def sort(rows):
@@ -224,7 +251,7 @@ def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000,
             xe = (1 + rho * chi) * xbar - rho * chi * last
             xc = (1 + psi * rho) * xbar - psi * rho * last
             xcc = (1 - psi) * xbar + psi * last
-            fall = fbatch(np.tile(a, 4), np.concatenate([xr, xe, xc, xcc])).reshape(4, len(a))
+            fall = (yield np.tile(a, 4), np.concatenate([xr, xe, xc, xcc])).reshape(4, len(a))
             fxr = fall[0]
             nfev[a] += 1
             expand = fxr < f0
@@ -237,7 +264,7 @@ def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000,
             f2[~need2] = np.nan
             nfev[a[need2]] += 1
         else:
-            fxr = fbatch(a, xr)
+            fxr = yield a, xr
             nfev[a] += 1
             expand = fxr < f0
             accept_r = ~expand & (fxr < fm2)
@@ -251,7 +278,7 @@ def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000,
             need2 = expand | contract | inside
             f2 = np.full(len(a), np.nan)
             if need2.any():
-                f2[need2] = fbatch(a[need2], x2[need2])
+                f2[need2] = yield a[need2], x2[need2]
                 nfev[a[need2]] += 1
         new_x, new_f = xr.copy(), fxr.copy()
         take2 = (expand & (f2 < fxr)) | (contract & (f2 <= fxr)) | (inside & (f2 < fm1))
@@ -263,12 +290,56 @@ def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000,
         if shrink.any():
             s = a[shrink]
             sim[s, 1:] = sim[s, :1] + sigma * (sim[s, 1:] - sim[s, :1])
-            fsim[s, 1:] = fbatch(np.repeat(s, N), sim[s, 1:].reshape(len(s) * N, N)).reshape(len(s), N)
+            fsim[s, 1:] = (yield np.repeat(s, N), sim[s, 1:].reshape(len(s) * N, N)).reshape(len(s), N)
             nfev[s] += N
         iterations[a] += 1
         sort(a)
     return dict(x=sim[:, 0].copy(), fun=np.min(fsim, axis=1), success=success,
                 final_simplex=sim, nit=iterations, nfev=nfev)
+
+
+def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000,
+                         speculate_below=0):
+    """nelder_mead_steps driven with a blocking objective fbatch(idx, X) -> f."""
+    gen = nelder_mead_steps(sims, xatol, fatol, maxiter, speculate_below)
+    try:
+        req = next(gen)
+        while True:
+            req = gen.send(fbatch(*req))
+    except StopIteration as stop:
+        return stop.value
+
+
+def nelder_mead_interleaved(fsubmit, sims, groups=2, xatol=1e-2, fatol=1e-3, maxiter=10000,
+                            speculate_below=0):
+    """The same minimisations with the problems split into `groups` independent
+    lock-step sets.  fsubmit(idx, X) starts an evaluation and returns a callable
+    that waits for its values; while one set's request is on the GPU the host
+    advances the others, so device and host work overlap.  Every problem follows
+    its own trajectory, so the result equals nelder_mead_lockstep's."""
+    sims = np.asarray(sims, dtype=np.float64)
+    B = len(sims)
+    parts = [p for p in np.array_split(np.arange(B), max(1, min(groups, B))) if len(p)]
+    gens = [nelder_mead_steps(sims[p], xatol, fatol, maxiter, speculate_below) for p in parts]
+    out = [None] * len(parts)
+    pending = []
+    for gi, gen in enumerate(gens):
+        idx, X = next(gen)      # a generator always asks for its initial simplices
+        pending.append((gi, fsubmit(parts[gi][idx], X)))
+    while pending:
+        gi, wait = pending.pop(0)
+        try:
+            idx, X = gens[gi].send(wait())
+            pending.append((gi, fsubmit(parts[gi][idx], X)))
+        except StopIteration as stop:
+            out[gi] = stop.value
+    res = {}
+    for k in out[0]:
+        full = np.empty((B,) + out[0][k].shape[1:], dtype=out[0][k].dtype)
+        for p, o in zip(parts, out):
+            full[p] = o[k]
+        res[k] = full
+    return res
 
 
 # ------------------------------------------------- scipy BFGS, many at a time
@@ -542,8 +613,11 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
     x = np.zeros((B, sims.shape[2]))
     todo = allb
     for attempt in range(2):
-        res = nelder_mead_lockstep(lambda i, X: fobj(todo[i], X), sims[todo],
-                                   speculate_below=SPECULATE_BELOW)
+        # two independent lock-step sets: the host advances one simplex set while the
+        # other's trial points are on the GPU
+        res = nelder_mead_interleaved(lambda i, X: fobj.submit(todo[i], X), sims[todo],
+                                      groups=2 if len(todo) >= 2 * NM_MIN_GROUP else 1,
+                                      speculate_below=SPECULATE_BELOW)
         x[todo] = res['x']
         sims[todo] = res['final_simplex']
         failed = todo[~res['success']]

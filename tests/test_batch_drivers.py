@@ -34,6 +34,17 @@ def test_lockstep_nelder_mead_is_scipy():
                                           speculate_below=10)
     for k in ('x', 'fun', 'final_simplex', 'nit', 'nfev', 'success'):
         assert np.array_equal(spec[k], res[k]), k
+    # independent lock-step sets with deferred evaluation: same trajectories
+    order = []
+
+    def fsubmit(idx, X):
+        order.append(len(idx))
+        return lambda: fbatch(idx, X)
+    for groups in (1, 2, 5):
+        inter = batch_fit.nelder_mead_interleaved(fsubmit, sims, groups=groups, xatol=1e-2,
+                                                  fatol=1e-3, maxiter=10000, speculate_below=4)
+        for k in ('x', 'fun', 'final_simplex', 'nit', 'nfev', 'success'):
+            assert np.array_equal(inter[k], res[k]), (groups, k)
     for b in range(B):
         opts = {'fatol': 1e-3, 'xatol': 1e-2, 'initial_simplex': sims[b], 'maxiter': 10000,
                 'maxfev': np.inf}
