@@ -204,12 +204,14 @@ int rvs_basis_build(const double *d_lam, const int64_t *d_gstart, int G, int64_t
  * and status[k*nv+j] (RVS_ST_NOT_PD, RVS_ST_RANGE).
  * Optional outputs (may be NULL; nv must be 1): d_coeffs [K,npoly]; d_raw,
  * d_model: resampled template and continuum-multiplied model written at
- * d_moff[k] + p. */
+ * d_moff[k] + p.  fast_interp != 0: the template value at a pixel is that of the
+ * first knot >= the rest wavelength (get_chisq's fast_interp switch,
+ * spec_fit.py:913-918) instead of the spline value. */
 int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
                    const rvs_knots *knots, const rvs_obs *obs, const int32_t *d_oix,
                    const double *d_vels, int nv, int K, double *d_chisq, int32_t *d_status,
                    double *d_coeffs, double *d_raw, double *d_model, const int64_t *d_moff,
-                   void *stream);
+                   int fast_interp, void *stream);
 
 /* Fused optimiser-phase evaluation: template build (as rvs_template_build) and
  * chi-square at ONE velocity per item without the HBM round trip of the

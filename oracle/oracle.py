@@ -447,9 +447,10 @@ def resample(spl, vel, lam):
 
 
 def get_chisq(specdata, vel, atm, rot=None, options=None, config=None,
-              full_output=False, espec_systematic=None, outside_penalty=True):
-    """spec_fit.py:797-989 (without the resolution-matrix and fast_interp
-    switches)."""
+              full_output=False, espec_systematic=None, outside_penalty=True,
+              fast_interp=False):
+    """spec_fit.py:797-989 (without the resolution-matrix mode).
+    fast_interp: nearest-knot lookup instead of the spline (spec_fit.py:913-918)."""
     npoly = options.get('npoly') or 5
     rbf = options.get('rbf_continuum', True)
     acc = 0
@@ -470,9 +471,13 @@ def get_chisq(specdata, vel, atm, rot=None, options=None, config=None,
             acc += outside * bad
         check_overlap(tlam[0], tlam[-1], sd.lam[0], sd.lam[-1],
                       min(config['min_vel'], vel), max(config['max_vel'], vel))
-        if ent[4] is None:
-            ent[4] = Spline(tlam, tspec, log_step=it.log_step)
-        ev = resample(ent[4], vel, sd.lam)
+        if fast_interp:
+            beta = vel / C_KMS
+            ev = tspec[np.searchsorted(tlam, np.sqrt((1 - beta) / (1 + beta)) * sd.lam)]
+        else:
+            if ent[4] is None:
+                ent[4] = Spline(tlam, tspec, log_step=it.log_step)
+            ev = resample(ent[4], vel, sd.lam)
         polys = _basis(sd, npoly, rbf)
         if espec_systematic is not None:
             sy = espec_systematic[sd.name] if isinstance(espec_systematic, dict) \

@@ -338,6 +338,7 @@ int fill_scan_args(ScanArgs &a, const rvs_knots *kn, const rvs_obs *obs) {
   a.lam = obs->d_lam; a.loglam = obs->d_loglam; a.dn = obs->d_dn; a.einv = obs->d_einv;
   a.sumlog2 = obs->d_sumlog2; a.off = obs->d_off; a.goff = obs->d_goff; a.P = obs->d_P;
   a.npp = obs->npp;
+  a.fast_interp = 0;
   RVS_REQUIRE(obs->npp >= obs->npoly && obs->npp % 2 == 0 && ((uintptr_t)obs->d_P & 15) == 0,
               RVS_E_ARG, "chisq: basis rows must be npp = even >= npoly doubles, 16-byte aligned");
   return 0;
@@ -348,7 +349,8 @@ extern "C" int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32
                               const rvs_knots *knots, const rvs_obs *obs, const int32_t *d_oix,
                               const double *d_vels, int nv, int K, double *d_chisq,
                               int32_t *d_status, double *d_coeffs, double *d_raw,
-                              double *d_model, const int64_t *d_moff, void *stream) {
+                              double *d_model, const int64_t *d_moff, int fast_interp,
+                              void *stream) {
   using namespace rvs;
   if (K == 0 || nv == 0) return 0;
   ScanArgs a;
@@ -362,6 +364,7 @@ extern "C" int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32
   a.yz = reinterpret_cast<const double2 *>(d_yz); a.yz_stride = yz_stride; a.tix = d_tix;
   a.oix = d_oix; a.vels = d_vels; a.nv = nv; a.K = K; a.chisq = d_chisq; a.status = d_status;
   a.coeffs = d_coeffs; a.raw = d_raw; a.model = d_model; a.moff = d_moff;
+  a.fast_interp = fast_interp ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (nv >= 4 && !d_coeffs && !d_raw && !d_model) {
     // several trials per template: the trials are the columns of an FP64 GEMM (scan_mma.cuh)

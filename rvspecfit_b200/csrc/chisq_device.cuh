@@ -27,15 +27,27 @@ struct ScanArgs {
   int32_t *status;
   double *coeffs, *raw, *model;
   const int64_t *moff;
+  int fast_interp;  // 1: value of the first knot >= x instead of the spline (spec_fit.py:913-918)
 };
 
 constexpr int SCAN_WARPS = 8;
+
+// fast_interp: templ_spec[searchsorted(templ_lam, x)] (numpy 'left': first knot
+// >= x), starting from the uniform-grid interval `pos` of x
+__device__ __forceinline__ double nearest_knot_value(const ScanArgs &a, const double2 *yz, double x,
+                                                     int pos) {
+  int i = pos;
+  while (i > 0 && __ldg(a.lam_t + i - 1) >= x) i--;
+  while (i < a.npix_t - 1 && __ldg(a.lam_t + i) < x) i++;
+  return __ldg(yz + i).x;
+}
 
 // spline value at rest wavelength x (spliner.c:97-106) from (y,z) pairs
 __device__ __forceinline__ double spline_eval(const ScanArgs &a, const double2 *yz, double x,
                                               double q) {
   int pos = (int)((q - a.q0) * a.qstep_inv);
   pos = max(0, min(pos, a.npix_t - 2));
+  if (a.fast_interp) return nearest_knot_value(a, yz, x, pos);
   const double2 c0 = __ldg(yz + pos), c1 = __ldg(yz + pos + 1);
   const double xl = __ldg(a.lam_t + pos), xr = __ldg(a.lam_t + pos + 1);
   const double hh = __ldg(a.h + pos), hi = __ldg(a.hinv + pos);

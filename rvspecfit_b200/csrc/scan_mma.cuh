@@ -21,6 +21,7 @@ __device__ __forceinline__ double spline_eval_uv(const ScanArgs &a, const double
                                                  double q) {
   int pos = (int)((q - a.q0) * a.qstep_inv);
   pos = max(0, min(pos, a.npix_t - 2));
+  if (a.fast_interp) return nearest_knot_value(a, yz, x, pos);
   const double2 c0 = __ldg(yz + pos), c1 = __ldg(yz + pos + 1);
   const double xl = __ldg(a.lam_t + pos);
   const double hh = __ldg(a.h + pos), hi = __ldg(a.hinv + pos);

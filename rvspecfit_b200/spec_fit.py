@@ -239,7 +239,8 @@ class LikelihoodEngine:
         return self._ws
 
     # ------------------------------------------------------------------ core
-    def _arm_eval(self, arm, sel, obj, vels, params, vsini, sys_err, want_model):
+    def _arm_eval(self, arm, sel, obj, vels, params, vsini, sys_err, want_model,
+                  fast_interp=False):
         """chi-square of one arm for the items `sel` (indices into the call's
         item list).  vels (K, nv).  Returns chisq (k, nv), status (k, nv),
         outside (k,), tstatus (k,), extras."""
@@ -256,7 +257,8 @@ class LikelihoodEngine:
         d_st = _dev.empty((k, nv), np.int32)
         vs = None if vsini is None else np.ascontiguousarray(vsini[sel], dtype=np.float64)
         extras = None
-        if self.fused and nv == 1 and not want_model and self._fusable(bank, vs):
+        if self.fused and nv == 1 and not want_model and not fast_interp and \
+                self._fusable(bank, vs):
             d_ids = _dev.upload(ids, np.int32)
             d_w = _dev.upload(w, np.float64)
             d_vs = None if vs is None else _dev.upload(vs, np.float64)
@@ -311,7 +313,7 @@ class LikelihoodEngine:
                                   ctypes.byref(bank.knots), ctypes.byref(obs), _dev.ptr(d_oix),
                                   _dev.ptr(d_vels), nv, k, _dev.ptr(d_chi), _dev.ptr(d_st),
                                   _dev.ptr(d_co), _dev.ptr(d_raw), _dev.ptr(d_mod),
-                                  _dev.ptr(d_moff), _dev.stream())
+                                  _dev.ptr(d_moff), int(bool(fast_interp)), _dev.stream())
             _cabi.check(rc, 'rvs_chisq_scan')
             if t0 is not None:
                 self.timer.stop('scan', t0, k * nv)
@@ -584,7 +586,8 @@ class LikelihoodEngine:
         return pend
 
     def evaluate(self, obj, vels, params, vsini=None, outside_penalty=True,
-                 espec_systematic=None, want_model=False, raise_errors=False):
+                 espec_systematic=None, want_model=False, raise_errors=False,
+                 fast_interp=False):
         """-2 log L for K items.  obj (K,), vels (K,) or (K, nv), params (K, ndim),
         vsini (K,) or None.  Returns chisq with the shape of vels (plus an info
         dict when want_model).  Semantics of reference get_chisq
@@ -593,14 +596,14 @@ class LikelihoodEngine:
         params = np.array(params, dtype=np.float64, ndmin=2)
         vels = np.asarray(vels, dtype=np.float64)
         flat = vels.ndim == 1
-        if flat and not want_model:
+        if flat and not want_model and not fast_interp:
             return self.submit(obj, vels, params, vsini, outside_penalty, espec_systematic,
                                raise_errors).result()
         return self._evaluate_general(obj, vels, params, vsini, outside_penalty,
-                                      espec_systematic, want_model, raise_errors)
+                                      espec_systematic, want_model, raise_errors, fast_interp)
 
     def _evaluate_general(self, obj, vels, params, vsini, outside_penalty, espec_systematic,
-                          want_model, raise_errors):
+                          want_model, raise_errors, fast_interp=False):
         """The general path: host vertex location (any interpolator kind, off-grid
         nearest node), any number of velocities per item, model output, SVD
         rescue, the reference's exceptions."""
@@ -621,7 +624,7 @@ class LikelihoodEngine:
             else:
                 sys_err = float(espec_systematic or 0.0)
             chi, st, outside, tstatus, extras = self._arm_eval(
-                arm, sel, obj, v2, params, vsini, sys_err, want_model)
+                arm, sel, obj, v2, params, vsini, sys_err, want_model, fast_interp)
             bad = self.badchi[obj[sel]]
             # template unusable: outside not finite, or off-grid and not finite/huge
             tbad = ~np.isfinite(outside) | ((outside > 0) & ((tstatus & 1) != 0))
@@ -738,8 +741,6 @@ def get_chisq(specdata, vel, atm_params, rot_params=None, resol_params=None, opt
     `cache` is accepted and ignored (the spline never leaves the device)."""
     if resol_params is not None:
         raise NotImplementedError('resol_params: SURVEY.md section 8 row f4')
-    if fast_interp:
-        raise NotImplementedError('fast_interp is not on the GPU path')
     if isinstance(specdata, SpecData):
         specdata = [specdata]
     eng = _engine_for(specdata, config, options or {})
@@ -748,11 +749,12 @@ def get_chisq(specdata, vel, atm_params, rot_params=None, resol_params=None, opt
     if not full_output:
         return float(eng.evaluate([0], np.array([float(vel)]), par, vs,
                                   outside_penalty=outside_penalty,
-                                  espec_systematic=espec_systematic, raise_errors=True)[0])
+                                  espec_systematic=espec_systematic, raise_errors=True,
+                                  fast_interp=fast_interp)[0])
     chi, info = eng.evaluate([0], np.array([float(vel)]), par, vs,
                              outside_penalty=outside_penalty,
                              espec_systematic=espec_systematic, want_model=True,
-                             raise_errors=True)
+                             raise_errors=True, fast_interp=fast_interp)
     ret = dict(chisq=float(chi[0]), logl=-0.5 * float(chi[0]), chisq_array=[],
                red_chisq_array=[], npix_array=[], models=[], raw_models=[])
     for sd in specdata:
@@ -807,7 +809,7 @@ def get_chisq_continuum(specdata, options=None):
         rc = L.rvs_chisq_scan(_dev.ptr(yz), 4, _dev.ptr(d_z32), ctypes.byref(kn),
                               ctypes.byref(obs), _dev.ptr(d_z32), _dev.ptr(d_vel), 1, 1,
                               _dev.ptr(d_chi), _dev.ptr(d_st), _dev.ptr(d_co), _dev.ptr(d_raw),
-                              _dev.ptr(d_mod), _dev.ptr(d_moff), _dev.stream())
+                              _dev.ptr(d_mod), _dev.ptr(d_moff), 0, _dev.stream())
         _cabi.check(rc, 'rvs_chisq_scan')
         dev = (_dev.download(d_mod) - sd.spec) / sd.espec
         good = ~sd.badmask

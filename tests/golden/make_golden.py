@@ -423,8 +423,43 @@ def gold_ccf(R):
     np.savez_compressed(os.path.join(HERE, 'ccf.npz'), **out)
 
 
+def gold_switches(R):
+    """The rarely used switches of get_chisq on the objects
+    and evaluation points of chisq.npz: fast_interp (nearest-knot lookup instead of
+    the spline, spec_fit.py:913-918), espec_systematic as a scalar and as a dictionary
+    (spec_fit.py:933-940), outside_penalty=False (spec_fit.py:895-896)."""
+    out = {}
+    cfg = frozen_config(R)
+    st = synth.make_setup('test', 'tiny', seed=3)
+    inject_grid(R, st, 'test')
+    objs = make_objects([st], 'tiny', 2, 500, bad_frac=0.02)
+    prev = np.load(os.path.join(HERE, 'chisq.npz'))
+    ev = prev['one_eval']
+    opts = {'npoly': 15}
+    res = {k: np.zeros((len(objs), len(ev))) for k in ('fast', 'sys_scalar', 'sys_dict', 'nopen')}
+    for i, o in enumerate(objs):
+        sd = specdata_of(R, o)
+        assert np.array_equal(sd[0].spec, prev[f'one_{i}_0_spec'])
+        sysv = 0.05 * float(np.median(sd[0].espec)) * 20
+        out[f'sys_{i}'] = sysv
+        for j, e in enumerate(ev):
+            rot = None if e[5] < 0 else (e[5],)
+            a = (sd, e[0], tuple(e[1:5]), rot)
+            res['fast'][i, j] = R.spec_fit.get_chisq(*a, options=opts, config=cfg,
+                                                     fast_interp=True)
+            res['sys_scalar'][i, j] = R.spec_fit.get_chisq(*a, options=opts, config=cfg,
+                                                           espec_systematic=sysv)
+            res['sys_dict'][i, j] = R.spec_fit.get_chisq(*a, options=opts, config=cfg,
+                                                         espec_systematic={'test': 2 * sysv})
+            res['nopen'][i, j] = R.spec_fit.get_chisq(*a, options=opts, config=cfg,
+                                                      outside_penalty=False)
+    for k, v in res.items():
+        out[k] = v
+    np.savez_compressed(os.path.join(HERE, 'switches.npz'), **out)
+
+
 ALL = dict(kat=gold_kat, interp=gold_interp, chisq=gold_chisq, process=gold_process,
-           ccf=gold_ccf)
+           ccf=gold_ccf, switches=gold_switches)
 
 if __name__ == '__main__':
     which = sys.argv[1:] or list(ALL)

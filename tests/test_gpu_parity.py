@@ -162,6 +162,38 @@ def test_get_chisq_matches_reference(golden, fused):
     assert abs(c - g['one_chisq_test_15_1'][0, 0]) < CHI_RTOL * abs(c)
 
 
+def test_get_chisq_switches_match_reference(golden):
+    """fast_interp (nearest-knot lookup in the scan kernels), espec_systematic as a
+    scalar and as a per-setup dictionary, outside_penalty=False: reference values."""
+    g, gs = golden('chisq'), golden('switches')
+    _register(setup('test', 'tiny', 3, name='test'))
+    objs = unpack_objects(g, 'one_')
+    cfg, ev, opts = config(), g['one_eval'], {'npoly': 15}
+    K = len(ev)
+    for i, o in enumerate(objs):
+        sd = _sd(o, 'test')
+        sysv = float(gs[f'sys_{i}'])
+        for key, kw in (('fast', dict(fast_interp=True)),
+                        ('sys_scalar', dict(espec_systematic=sysv)),
+                        ('sys_dict', dict(espec_systematic={'test': 2 * sysv})),
+                        ('nopen', dict(outside_penalty=False))):
+            got = np.array([spec_fit.get_chisq(sd, e[0], tuple(e[1:5]),
+                                               None if e[5] < 0 else (e[5],), options=opts,
+                                               config=cfg, **kw) for e in ev])
+            on = np.arange(K) < K - 2       # the two off-grid points carry a float32 exp
+            assert relerr(got[on], gs[key][i][on]) < CHI_RTOL, (key, i)
+            assert relerr(got, gs[key][i]) < 1e-6, (key, i)
+    # batched form, several trials per item: the GEMM scan kernel takes the same switch
+    eng = spec_fit.LikelihoodEngine([_sd(objs[0], 'test')], cfg, opts)
+    vg = np.linspace(-300, 300, 9)
+    e = ev[1]
+    many = eng.evaluate([0], vg[None, :], e[None, 1:5], np.array([max(e[5], 0.0)]),
+                        fast_interp=True)[0]
+    one = [spec_fit.get_chisq(_sd(objs[0], 'test'), v, tuple(e[1:5]), (max(e[5], 0.0),),
+                              options=opts, config=cfg, fast_interp=True) for v in vg]
+    assert relerr(many, one) < CHI_RTOL
+
+
 def test_full_output_and_continuum(golden):
     g = golden('chisq')
     _register(setup('test', 'tiny', 3, name='test'))

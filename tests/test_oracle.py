@@ -135,6 +135,25 @@ def test_get_chisq_and_scan(golden):
         assert np.allclose(fb['best_param'], g[f'scan_{tag}_best_param'])
 
 
+def test_get_chisq_switches(golden):
+    """fast_interp, espec_systematic (scalar / per-setup dictionary) and
+    outside_penalty=False against the reference's own values."""
+    g, gs = golden('chisq'), golden('switches')
+    oracle.register_setup(setup('test', 'tiny', 3, name='test'))
+    objs = unpack_objects(g, 'one_')
+    cfg, ev, opts = config(), g['one_eval'], {'npoly': 15}
+    for i, o in enumerate(objs):
+        sd = _sd(o, 'test')
+        sysv = float(gs[f'sys_{i}'])
+        for key, kw in (('fast', dict(fast_interp=True)),
+                        ('sys_scalar', dict(espec_systematic=sysv)),
+                        ('sys_dict', dict(espec_systematic={'test': 2 * sysv})),
+                        ('nopen', dict(outside_penalty=False))):
+            got = [oracle.get_chisq(sd, e[0], tuple(e[1:5]), None if e[5] < 0 else (e[5],),
+                                    options=opts, config=cfg, **kw) for e in ev]
+            assert relerr(got, gs[key][i]) < 2e-10, (key, i)
+
+
 def test_get_chisq_desi_three_arms(golden):
     g = golden('chisq')
     for k, a in enumerate(('desi_b', 'desi_r', 'desi_z')):
