@@ -327,14 +327,57 @@ def rotational_broaden(lam_t, templ, vsini, eps=0.6):
 class SpecData:
     """spec_fit.py:70-145."""
 
-    def __init__(self, name, lam, spec, espec, badmask=None):
+    def __init__(self, name, lam, spec, espec, badmask=None, resolution=None):
         self.name = name
+        self.resolution = resolution      # ResolMatrix or None (spec_fit.py:54-67,111)
         self.lam = np.ascontiguousarray(lam, dtype=np.float64)
         self.spec = np.ascontiguousarray(spec, dtype=np.float64)
         self.espec = np.ascontiguousarray(espec, dtype=np.float64)
         self.badmask = (np.zeros(len(self.spec), dtype=bool)
                         if badmask is None else np.asarray(badmask))
         self._basis = {}
+
+
+class ResolMatrix:
+    """spec_fit.py:54-67: holder of a (sparse) resolution matrix."""
+
+    def __init__(self, mat):
+        self.mat = mat
+
+
+def construct_resol_mat(lam, resol=None, width=None):
+    """spec_fit.py:410-468: banded matrix of Gaussian line-spread functions
+    (sigma = lam/R/2.35 or `width`), truncated at 5 sigma, every COLUMN
+    normalised to unit sum, stored by diagonals."""
+    import scipy.sparse
+    assert (resol is None) != (width is None)
+    lam = np.asarray(lam, dtype=np.float64)
+    n = len(lam)
+    if resol is not None:
+        sig = lam / resol / 2.35
+    else:
+        sig = np.zeros(n) + width
+    assert np.all(np.diff(lam) > 0)
+    i1 = np.maximum(np.searchsorted(lam, lam - 5 * sig, 'left'), 0)
+    i2 = np.minimum(np.searchsorted(lam, lam + 5 * sig, 'right'), n - 1)
+    pix = np.arange(n)
+    maxl = min(n, max(np.max(i2 - pix), np.max(pix - i1)))
+    offs = np.arange(-maxl, maxl + 1)
+    nb = pix[None, :] + offs[:, None]              # neighbour of column j on diagonal row k
+    ok = (nb >= 0) & (nb < n)
+    nb[~ok] = 0
+    X = np.exp(-0.5 * ((lam[nb] - lam[None, :]) / sig[None, :])**2) * ok
+    X = X / X.sum(axis=0)[None, :]
+    # X[k, j] = weight of pixel j+offs[k] in the profile centred on j; spdiags wants
+    # data[k, c] = M[c-offs[k], c]: the reference's index shuffle (spec_fit.py:463-465)
+    yid = (pix[None, :] + (n - offs)[:, None]) % n
+    xid = yid * 0 + maxl + offs[:, None]
+    return ResolMatrix(scipy.sparse.spdiags(X[xid, yid], offs, n, n))
+
+
+def convolve_resol(spec, resol_matrix):
+    """spec_fit.py:471-489."""
+    return resol_matrix.mat @ spec
 
 
 def continuum_basis(lam, npoly, rbf=True):
@@ -448,9 +491,11 @@ def resample(spl, vel, lam):
 
 def get_chisq(specdata, vel, atm, rot=None, options=None, config=None,
               full_output=False, espec_systematic=None, outside_penalty=True,
-              fast_interp=False):
-    """spec_fit.py:797-989 (without the resolution-matrix mode).
-    fast_interp: nearest-knot lookup instead of the spline (spec_fit.py:913-918)."""
+              fast_interp=False, resol_params=None):
+    """spec_fit.py:797-989.  fast_interp: nearest-knot lookup instead of the
+    spline (spec_fit.py:913-918).  resol_params (dictionary by setup) or
+    SpecData.resolution: the resampled template is multiplied by the resolution
+    matrix before the continuum fit (spec_fit.py:922-929)."""
     npoly = options.get('npoly') or 5
     rbf = options.get('rbf_continuum', True)
     acc = 0
@@ -478,6 +523,13 @@ def get_chisq(specdata, vel, atm, rot=None, options=None, config=None,
             if ent[4] is None:
                 ent[4] = Spline(tlam, tspec, log_step=it.log_step)
             ev = resample(ent[4], vel, sd.lam)
+        if resol_params is not None:
+            ev = convolve_resol(ev, resol_params[sd.name])
+        if getattr(sd, 'resolution', None) is not None:
+            if resol_params is not None:
+                raise ValueError('You are not allowed to set resol_param together with'
+                                 'the resolution of each SpecData')
+            ev = convolve_resol(ev, sd.resolution)
         polys = _basis(sd, npoly, rbf)
         if espec_systematic is not None:
             sy = espec_systematic[sd.name] if isinstance(espec_systematic, dict) \
@@ -551,12 +603,13 @@ def scan_statistics(vel_grid, chisq, quadratic=True):
 
 
 def find_best(specdata, vel_grid, params_list, rot=None, options=None, config=None,
-              quadratic=True, return_chisq=False):
+              quadratic=True, return_chisq=False, resol_params=None):
     """spec_fit.py:1018-1092."""
     chisq = np.zeros((len(vel_grid), len(params_list)))
     for j, par in enumerate(params_list):
         for i, v in enumerate(vel_grid):
-            chisq[i, j] = get_chisq(specdata, v, par, rot, options=options, config=config)
+            chisq[i, j] = get_chisq(specdata, v, par, rot, options=options, config=config,
+                                    resol_params=resol_params)
     st = scan_statistics(np.asarray(vel_grid), chisq, quadratic)
     st['best_param'] = params_list[st.pop('ibest')]
     if return_chisq:

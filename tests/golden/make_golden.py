@@ -458,8 +458,106 @@ def gold_switches(R):
     np.savez_compressed(os.path.join(HERE, 'switches.npz'), **out)
 
 
+def gold_resol(R):
+    """Resolution-matrix mode (spec_fit.py:410-492,
+    922-929): SpecData.resolution and the resol_params dictionary, on the one-arm
+    objects / evaluation points of chisq.npz, on a three-arm DESI-shaped object with
+    an 11-diagonal matrix per arm, through find_best and through a complete process()."""
+    import scipy.sparse
+    out = {}
+    cfg = frozen_config(R)
+    st = synth.make_setup('test', 'tiny', seed=3)
+    inject_grid(R, st, 'test')
+    objs = make_objects([st], 'tiny', 2, 500, bad_frac=0.02)
+    prev = np.load(os.path.join(HERE, 'chisq.npz'))
+    ev = prev['one_eval']
+    opts = {'npoly': 15}
+    out['one_R'] = np.array([1500., 4000.])
+    chi = np.zeros((len(objs), len(ev)))
+    chi_rp = np.zeros_like(chi)
+    for i, o in enumerate(objs):
+        nm, lam, sp, es, bad = o['arms'][0]
+        assert np.array_equal(sp, prev[f'one_{i}_0_spec'])
+        rm = R.spec_fit.construct_resol_mat(lam, resol=out['one_R'][i])
+        dia = scipy.sparse.dia_matrix(rm.mat)
+        out[f'one_{i}_offsets'] = dia.offsets
+        out[f'one_{i}_data_sum'] = checksum(dia.data)
+        if i == 0:
+            out['one_0_data'] = dia.data
+        sd_res = [R.spec_fit.SpecData(nm, lam, sp, es, badmask=bad, resolution=rm)]
+        sd_plain = specdata_of(R, o)
+        for j, e in enumerate(ev):
+            rot = None if e[5] < 0 else (e[5],)
+            chi[i, j] = R.spec_fit.get_chisq(sd_res, e[0], tuple(e[1:5]), rot, options=opts,
+                                             config=cfg)
+            chi_rp[i, j] = R.spec_fit.get_chisq(sd_plain, e[0], tuple(e[1:5]), rot,
+                                                resol_params={'test': rm}, options=opts,
+                                                config=cfg)
+        e = ev[0]
+        full = R.spec_fit.get_chisq(sd_res, e[0], tuple(e[1:5]), None if e[5] < 0 else (e[5],),
+                                    options=opts, config=cfg, full_output=True)
+        out[f'one_{i}_full_chisq'] = full['chisq']
+        out[f'one_{i}_full_chisq_array'] = np.array(full['chisq_array'])
+        out[f'one_{i}_full_model'] = full['models'][0]
+        out[f'one_{i}_full_raw'] = full['raw_models'][0]
+        vg = np.arange(-400, 400, 10.)
+        plist = [tuple(o['params']), PROBE_PARAMS[1]]
+        fb = R.spec_fit.find_best(sd_res, vg, plist, rot_params=(25.,), options=opts, config=cfg)
+        for k in ('best_chi', 'best_vel', 'vel_err', 'kurtosis', 'skewness', 'probs'):
+            out[f'one_{i}_fb_{k}'] = fb[k]
+        out[f'one_{i}_fb_best_param'] = np.array(fb['best_param'])
+    out['one_chisq'], out['one_chisq_resol_params'] = chi, chi_rp
+    # three arms, fixed-width Gaussian matrices cut to 11 diagonals (the shape of DESI's
+    # resolution data, desi_fit.py:723-748)
+    arms = []
+    for k, a in enumerate(('desi_b', 'desi_r', 'desi_z')):
+        sa = synth.make_setup(a, 'tiny', seed=21 + k)
+        inject_grid(R, sa, a)
+        arms.append(sa)
+    cfgd = frozen_config(R, min_vel=-1500, max_vel=1500)
+    o = make_objects(arms, 'tiny', 1, 700, bad_frac=0.01)[0]
+    assert np.array_equal(o['arms'][0][2], prev['desi_0_0_spec'])
+    sds = []
+    for a, (nm, lam, sp, es, bad) in enumerate(o['arms']):
+        full = scipy.sparse.dia_matrix(R.spec_fit.construct_resol_mat(lam, width=0.9 + 0.2 * a).mat)
+        keep = np.abs(full.offsets) <= 5
+        m = scipy.sparse.dia_matrix((full.data[keep], full.offsets[keep]), shape=full.shape)
+        out[f'desi_{a}_offsets'] = m.offsets
+        out[f'desi_{a}_data'] = m.data.astype(np.float64)
+        sds.append(R.spec_fit.SpecData(nm, lam, sp, es, badmask=bad,
+                                       resolution=R.spec_fit.ResolMatrix(m)))
+    dev = prev['desi_eval']
+    out['desi_chisq'] = np.array([
+        R.spec_fit.get_chisq(sds, e[0], tuple(e[1:5]), None if e[5] < 0 else (e[5],),
+                             options={'npoly': 10}, config=cfgd) for e in dev])
+    vg = np.arange(-1500, 1500, 5.)[::6]
+    out['desi_scan_chisq'] = np.array([
+        R.spec_fit.get_chisq(sds, v, tuple(o['params']), (12.,), options={'npoly': 10},
+                             config=cfgd) for v in vg])
+    # a complete fit with a resolution matrix (config-1 shape, object 0 of process.npz)
+    st1 = synth.make_setup('test', 'test', seed=3)
+    inject_grid(R, st1, 'test')
+    o1 = make_objects([st1], 'test', 3, 4000, sn_range=(60, 150), vel_sig=100., bad_frac=0.0)[0]
+    pp = np.load(os.path.join(HERE, 'process.npz'))
+    nm, lam, sp, es, bad = o1['arms'][0]
+    assert np.array_equal(sp, pp['c1_0_0_spec'])
+    out['proc_R'] = 3000.
+    rm = R.spec_fit.construct_resol_mat(lam, resol=3000.)
+    sd1 = [R.spec_fit.SpecData(nm, lam, sp, es, badmask=bad, resolution=rm)]
+    start = {'logg': 2, 'teff': 5000, 'feh': -0.2, 'alpha': 0.2, 'vsini': 0.1}
+    res = R.vel_fit.process(sd1, dict(start), fixParam=[], config=cfg, options={'npoly': 15})
+    for k in ('vel', 'vel_err', 'vel_skewness', 'vel_kurtosis', 'vsini', 'chisq', 'logl'):
+        out[f'proc_{k}'] = res[k]
+    out['proc_param'] = np.array([res['param'][k] for k in synth.PARNAMES])
+    out['proc_param_err'] = np.array([res['param_err'][k] for k in synth.PARNAMES])
+    out['proc_chisq_array'] = np.array(res['chisq_array'])
+    out['proc_yfit'] = res['yfit'][0]
+    out['proc_success'] = res['minimize_success']
+    np.savez_compressed(os.path.join(HERE, 'resol.npz'), **out)
+
+
 ALL = dict(kat=gold_kat, interp=gold_interp, chisq=gold_chisq, process=gold_process,
-           ccf=gold_ccf, switches=gold_switches)
+           ccf=gold_ccf, switches=gold_switches, resol=gold_resol)
 
 if __name__ == '__main__':
     which = sys.argv[1:] or list(ALL)

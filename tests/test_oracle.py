@@ -197,6 +197,84 @@ def test_process_matches_reference(golden):
         assert np.allclose(res['yfit'][0], g[f'c1_0_{tag}_yfit'], rtol=1e-5)
 
 
+def _dia(offsets, data, n):
+    import scipy.sparse
+    return oracle.ResolMatrix(scipy.sparse.dia_matrix((data, offsets), shape=(n, n)))
+
+
+def test_resolution_matrix_mode(golden):
+    """SpecData.resolution / resol_params (spec_fit.py:410-492, 922-929; SURVEY.md 8
+    rows a18, f4) against the reference: matrix construction, get_chisq (one arm and
+    three arms with 11-diagonal matrices), full output, find_best."""
+    import scipy.sparse
+    g, gr = golden('chisq'), golden('resol')
+    oracle.register_setup(setup('test', 'tiny', 3, name='test'))
+    objs = unpack_objects(g, 'one_')
+    cfg, ev, opts = config(), g['one_eval'], {'npoly': 15}
+    for i, o in enumerate(objs):
+        nm, lam, sp, es, bad = o['arms'][0]
+        rm = oracle.construct_resol_mat(lam, resol=float(gr['one_R'][i]))
+        dia = scipy.sparse.dia_matrix(rm.mat)
+        assert np.array_equal(dia.offsets, gr[f'one_{i}_offsets'])
+        assert np.isclose(dia.data.sum(), gr[f'one_{i}_data_sum'], rtol=1e-13)
+        if i == 0:
+            assert np.allclose(dia.data, gr['one_0_data'], rtol=1e-13, atol=1e-300)
+        sd_res = [oracle.SpecData(nm, lam, sp, es, bad, resolution=rm)]
+        sd_plain = _sd(o, 'test')
+        rots = [None if e[5] < 0 else (e[5],) for e in ev]
+        got = [oracle.get_chisq(sd_res, e[0], tuple(e[1:5]), r, options=opts, config=cfg)
+               for e, r in zip(ev, rots)]
+        assert relerr(got, gr['one_chisq'][i]) < 2e-10
+        got = [oracle.get_chisq(sd_plain, e[0], tuple(e[1:5]), r, options=opts, config=cfg,
+                                resol_params={'test': rm}) for e, r in zip(ev, rots)]
+        assert relerr(got, gr['one_chisq_resol_params'][i]) < 2e-10
+        with pytest.raises(ValueError):
+            oracle.get_chisq(sd_res, 0., tuple(ev[0][1:5]), None, options=opts, config=cfg,
+                             resol_params={'test': rm})
+        full = oracle.get_chisq(sd_res, ev[0][0], tuple(ev[0][1:5]), rots[0], options=opts,
+                                config=cfg, full_output=True)
+        assert relerr(full['chisq'], gr[f'one_{i}_full_chisq']) < 2e-10
+        assert np.allclose(full['raw_models'][0], gr[f'one_{i}_full_raw'], rtol=1e-11, atol=1e-14)
+        assert np.allclose(full['models'][0], gr[f'one_{i}_full_model'], rtol=1e-8)
+        assert np.allclose(full['chisq_array'], gr[f'one_{i}_full_chisq_array'], rtol=1e-8)
+        fb = oracle.find_best(sd_res, np.arange(-400, 400, 10.),
+                              [tuple(o['params']), PROBE_PARAMS[1]], rot=(25.,), options=opts,
+                              config=cfg)
+        for k in ('best_chi', 'best_vel', 'vel_err', 'kurtosis', 'skewness'):
+            assert np.isclose(fb[k], gr[f'one_{i}_fb_{k}'], rtol=1e-7), k
+        assert np.allclose(fb['best_param'], gr[f'one_{i}_fb_best_param'])
+    for k, a in enumerate(('desi_b', 'desi_r', 'desi_z')):
+        oracle.register_setup(setup(a, 'tiny', 21 + k))
+    o = unpack_objects(g, 'desi_')[0]
+    sds = [oracle.SpecData(nm, lam, sp, es, bad,
+                           resolution=_dia(gr[f'desi_{a}_offsets'], gr[f'desi_{a}_data'], len(lam)))
+           for a, (nm, lam, sp, es, bad) in enumerate(o['arms'])]
+    cfgd = config(min_vel=-1500, max_vel=1500)
+    got = [oracle.get_chisq(sds, e[0], tuple(e[1:5]), None if e[5] < 0 else (e[5],),
+                            options={'npoly': 10}, config=cfgd) for e in g['desi_eval']]
+    assert relerr(got, gr['desi_chisq']) < 2e-10
+    vg = np.arange(-1500, 1500, 5.)[::6]
+    got = [oracle.get_chisq(sds, v, tuple(o['params']), (12.,), options={'npoly': 10},
+                            config=cfgd) for v in vg[::5]]
+    assert relerr(got, gr['desi_scan_chisq'][::5]) < 2e-10
+
+
+def test_process_with_resolution_matrix(golden):
+    g, gr = golden('process'), golden('resol')
+    oracle.register_setup(setup('test', 'test', 3, name='test'))
+    nm, lam, sp, es, bad = unpack_objects(g, 'c1_')[0]['arms'][0]
+    rm = oracle.construct_resol_mat(lam, resol=float(gr['proc_R']))
+    start = {'logg': 2, 'teff': 5000, 'feh': -0.2, 'alpha': 0.2, 'vsini': 0.1}
+    res = oracle.process([oracle.SpecData(nm, lam, sp, es, bad, resolution=rm)], dict(start),
+                         fixParam=[], config=config(), options={'npoly': 15})
+    par = np.array([res['param'][k] for k in ('teff', 'logg', 'feh', 'alpha')])
+    assert abs(res['vel'] - gr['proc_vel']) < 0.01
+    assert np.all(np.abs(par - gr['proc_param']) < 0.01 * gr['proc_param_err'])
+    assert abs(res['chisq'] - gr['proc_chisq']) < 1e-6 * abs(res['chisq'])
+    assert np.isclose(res['vel_err'], gr['proc_vel_err'], rtol=1e-3)
+    assert np.allclose(res['yfit'][0], gr['proc_yfit'], rtol=1e-5)
+
+
 def test_ccf_fit(golden):
     g = golden('ccf')
     for tag, shapes, maxvel in (('rvs', ('gaiarvs',), 600), ('two', ('desi_b', 'desi_r'), 1000)):
