@@ -123,6 +123,17 @@ typedef struct {
   int32_t nobj;
   int32_t shared_grid; /* 1: every object has the same pixels (one entry in the grid pools):
                           enables the batched GEMM form of the continuum solve */
+  /* Resolution matrices (SpecData.resolution / resol_params, spec_fit.py:410-492,
+   * 922-929; DESI's banded matrices, desi/desi_fit.py:723-748): the resampled template
+   * T of object i is replaced by R_i T before the continuum fit.  R_i is banded with
+   * the nresol diagonals d_resol_offs[] (ascending, shared by the batch), stored by
+   * OUTPUT pixel in an object pool: (R_i T)[p] = sum_k d_resol[off[i]*nresol +
+   * k*npix_i + p] * T[p + offs[k]], terms with p + offs[k] outside [0, npix_i) skipped.
+   * d_resol == NULL (nresol == 0): no resolution matrices. */
+  const double *d_resol;
+  const int32_t *d_resol_offs;
+  int32_t nresol;
+  int32_t reserved;
 } rvs_obs;
 
 /* Regular template grid in mapped parameter space (spec_inter.py:97-132):
@@ -221,7 +232,9 @@ int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
  * d_vsini (sizes the tap buffer; 0 if d_vsini is NULL).  d_tn: workspace
  * [K, tn_stride] doubles, tn_stride >= the longest object.  d_work: workspace
  * (16-byte aligned) of rvs_fused_workspace(K, tapcap, knots->npix_t) doubles, tapcap = ceil(vsini_max /
- * (c lnstep) + 1) + 1 (0 when d_vsini is NULL or vsini_max <= 0).  Outputs chisq[K],
+ * (c lnstep) + 1) + 1 (0 when d_vsini is NULL or vsini_max <= 0).  With resolution
+ * matrices (obs->d_resol) d_tn holds [2K, tn_stride] doubles: the resampled template
+ * goes to the second half and R T / sigma to the first.  Outputs chisq[K],
  * status[K] (template bits | RVS_ST_NOT_PD | RVS_ST_RANGE | RVS_ST_LIMIT).
  * Needs knots->ratio_dev < 1e-8 (exactly uniform or log-uniform knots) and
  * tapcap <= RVS_MAX_FUSED_TAPS, else RVS_E_LIMIT: use the general path.

@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) chisq_scan_kernel(ScanArgs a)
   const double *lam = a.lam + b0, *ql = (a.log_step ? a.loglam : a.lam) + b0;
   const double *Pb = a.P + b0 * a.npp;
   const double *dn = a.dn + p0, *einv = a.einv + p0;
+  const double *rb = a.resol ? a.resol + p0 * a.nresol : nullptr;
+  auto ev = [&](double x, double q) { return spline_eval(a, yz, x, q); };
 
   for (int j = blockIdx.y * SCAN_WARPS + wid; j < a.nv; j += gridDim.y * SCAN_WARPS) {
     const double beta = a.vels[(int64_t)k * a.nv + j] / RVS_C_KMS;
@@ -115,9 +117,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) chisq_scan_kernel(ScanArgs a)
 #pragma unroll
       for (int i = 0; i < NP; i++) v[i] = 0;
       for (int p = lane; p < npix; p += 32) {
-        const double x = lam[p] * f;
-        const double q = a.log_step ? ql[p] + qf : x;
-        const double tn = spline_eval(a, yz, x, q) * einv[p];
+        const double tn = template_at(a, lam, ql, rb, npix, p, f, qf, ev) * einv[p];
         double g[NP];
         load_basis<NP>(Pb + (int64_t)p * a.npp, tn, g);
         const double d = dn[p];
@@ -132,9 +132,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) chisq_scan_kernel(ScanArgs a)
       GramAcc<NP, RSPLIT, NP> acc;
       acc.zero();
       for (int p = lane; p < npix; p += 32) {
-        const double x = lam[p] * f;
-        const double q = a.log_step ? ql[p] + qf : x;
-        const double tn = spline_eval(a, yz, x, q) * einv[p];
+        const double tn = template_at(a, lam, ql, rb, npix, p, f, qf, ev) * einv[p];
         double g[NP];
         load_basis<NP>(Pb + (int64_t)p * a.npp, tn, g);
         acc.add(g);
@@ -150,9 +148,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) chisq_scan_kernel(ScanArgs a)
     double rss = 0;
     const bool want_model = (a.raw != nullptr) && j == 0;
     for (int p = lane; p < npix; p += 32) {
-      const double x = lam[p] * f;
-      const double q = a.log_step ? ql[p] + qf : x;
-      const double tv = spline_eval(a, yz, x, q);
+      const double tv = template_at(a, lam, ql, rb, npix, p, f, qf, ev);
       const double tn = tv * einv[p];
       double g[NP];
       load_basis<NP>(Pb + (int64_t)p * a.npp, tn, g);
@@ -339,6 +335,10 @@ int fill_scan_args(ScanArgs &a, const rvs_knots *kn, const rvs_obs *obs) {
   a.sumlog2 = obs->d_sumlog2; a.off = obs->d_off; a.goff = obs->d_goff; a.P = obs->d_P;
   a.npp = obs->npp;
   a.fast_interp = 0;
+  RVS_REQUIRE(obs->nresol >= 0 && (obs->nresol == 0) == (obs->d_resol == nullptr) &&
+                  (obs->nresol == 0 || obs->d_resol_offs),
+              RVS_E_ARG, "chisq: d_resol, d_resol_offs and nresol must be set together");
+  a.resol = obs->d_resol; a.resol_offs = obs->d_resol_offs; a.nresol = obs->nresol;
   RVS_REQUIRE(obs->npp >= obs->npoly && obs->npp % 2 == 0 && ((uintptr_t)obs->d_P & 15) == 0,
               RVS_E_ARG, "chisq: basis rows must be npp = even >= npoly doubles, 16-byte aligned");
   return 0;

@@ -28,6 +28,10 @@ struct ScanArgs {
   double *coeffs, *raw, *model;
   const int64_t *moff;
   int fast_interp;  // 1: value of the first knot >= x instead of the spline (spec_fit.py:913-918)
+  // resolution matrices (rvs_obs): band rows by output pixel, diagonal offsets
+  const double *resol;
+  const int32_t *resol_offs;
+  int nresol;
 };
 
 constexpr int SCAN_WARPS = 8;
@@ -56,6 +60,28 @@ __device__ __forceinline__ double spline_eval(const ScanArgs &a, const double2 *
   const double C = c1.x * hi - c1.y * t2, D = c0.x * hi - c0.y * t2;
   const double dl = x - xl, dr = xr - x;
   return A * dl * dl * dl + B * dr * dr * dr + C * dl + D * dr;
+}
+
+// Template value at observed pixel p of an object with npix pixels: the spline at the
+// Doppler-shifted wavelength, or with a resolution matrix (rb = the object's band rows)
+// row p of R times the resampled template (spec_fit.py:922-929), diagonals in ascending
+// order.  EVAL(x, q) is the spline evaluation of the calling kernel.
+template <class EVAL>
+__device__ __forceinline__ double template_at(const ScanArgs &a, const double *lam,
+                                              const double *ql, const double *rb, int npix, int p,
+                                              double f, double qf, EVAL eval) {
+  if (rb == nullptr) {
+    const double x = lam[p] * f;
+    return eval(x, a.log_step ? ql[p] + qf : x);
+  }
+  double s = 0;
+  for (int k = 0; k < a.nresol; k++) {
+    const int pp = p + __ldg(a.resol_offs + k);
+    if (pp < 0 || pp >= npix) continue;
+    const double x = lam[pp] * f;
+    s = fma(__ldg(rb + (int64_t)k * npix + p), eval(x, a.log_step ? ql[pp] + qf : x), s);
+  }
+  return s;
 }
 
 // Reduce N per-lane values over the 32 lanes of a warp with N/2+N/4+... shuffles

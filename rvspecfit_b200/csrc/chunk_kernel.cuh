@@ -118,7 +118,41 @@ struct ChunkArgs {
   int nch;   // chunks per item (upper bound; surplus chunks exit)
   int C;     // knots per chunk (upper bound)
   int K;
+  int raw_out;  // 1: write T, not T/sigma (a resolution matrix is applied next, resol_apply_kernel)
 };
+
+// Resolution-matrix stage of the fused evaluation (spec_fit.py:922-929): tn[k][p] =
+// (R_obj T_k)[p] / sigma[p] from the resampled template `raw` of item k and the
+// object's band rows (rvs_obs).  One thread per (item, pixel); the rows of T stay in L2
+// between the chunk kernel and this one.
+struct ResolArgs {
+  const double *raw;
+  double *tn;
+  int64_t tn_stride;
+  const double *resol, *einv;
+  const int32_t *resol_offs;
+  int nresol;
+  const int64_t *off;
+  const int32_t *oix;
+};
+__global__ void __launch_bounds__(256) resol_apply_kernel(ResolArgs a) {
+  const int k = blockIdx.x;
+  const int obj = a.oix[k];
+  if (obj < 0) return;
+  const int64_t p0 = a.off[obj];
+  const int npix = (int)(a.off[obj + 1] - p0);
+  const int p = blockIdx.y * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const double *raw = a.raw + (int64_t)k * a.tn_stride;
+  const double *rb = a.resol + p0 * a.nresol + p;
+  double s = 0;
+  for (int d = 0; d < a.nresol; d++) {
+    const int pp = p + __ldg(a.resol_offs + d);
+    if (pp < 0 || pp >= npix) continue;
+    s = fma(__ldg(rb + (int64_t)d * npix), raw[pp], s);
+  }
+  a.tn[(int64_t)k * a.tn_stride + p] = s * a.einv[p0 + p];
+}
 
 // Per-item preparation, one warp per item: Doppler factor, the knot range the
 // object covers at that velocity and its split into chunks, the first pixel of
@@ -697,7 +731,7 @@ chunk_kernel(const ChunkArgs a, const __grid_constant__ CUtensorMap tmap) {
     const int pbs = two ? pb : pa;
     const double la = lam[pa], lb = lam[pbs];
     const double qa = a.log_step ? ql[pa] : 0.0, qb = a.log_step ? ql[pbs] : 0.0;
-    const double ea = einv[pa], eb = einv[pbs];
+    const double ea = a.raw_out ? 1.0 : einv[pa], eb = a.raw_out ? 1.0 : einv[pbs];
     const double xa = la * f, xb = lb * f;
     const int posa = pos_q(a.log_step ? qa + qf : xa), posb = pos_q(a.log_step ? qb + qf : xb);
     const double xla = __ldg(a.lam_t + posa), xlb = __ldg(a.lam_t + posb);

@@ -208,7 +208,11 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
   }
   a.lam = obs->d_lam; a.loglam = obs->d_loglam; a.einv = obs->d_einv; a.off = obs->d_off;
   a.goff = obs->d_goff;
-  a.oix = d_oix; a.vels = d_vels; a.tn = d_tn; a.tn_stride = tn_stride; a.status = d_status;
+  // with resolution matrices the chunk kernel leaves T in the second half of d_tn
+  const bool resol = obs->d_resol != nullptr;
+  double *d_raw = d_tn + (int64_t)K * tn_stride;
+  a.oix = d_oix; a.vels = d_vels; a.tn = resol ? d_raw : d_tn; a.tn_stride = tn_stride;
+  a.status = d_status; a.raw_out = resol ? 1 : 0;
   a.K = K;
   a.wcap = (a.C + 2 * (CK_HALO + 3 + tapcap) + 12 + 3) & ~3;
   if (use_box) {  // TMA destinations are 128-byte aligned
@@ -228,6 +232,15 @@ extern "C" int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld,
   else if (nvert == 5) rc = launch_chunk_one<float, 5>(a, smem, st);
   else rc = launch_chunk_one<float, 0>(a, smem, st);
   if (rc) return rc;
+  if (resol) {
+    ResolArgs r;
+    r.raw = d_raw; r.tn = d_tn; r.tn_stride = tn_stride; r.resol = obs->d_resol;
+    r.einv = obs->d_einv; r.resol_offs = obs->d_resol_offs; r.nresol = obs->nresol;
+    r.off = obs->d_off; r.oix = d_oix;
+    dim3 grid((unsigned)K, (unsigned)((tn_stride + 255) / 256));
+    resol_apply_kernel<<<grid, 256, 0, st>>>(r);
+    RVS_LAUNCH_OK();
+  }
   if (ax) hand_over(st, s_aux, ax->ev[2]);
   rc = launch_solve(obs, d_oix, K, d_tn, tn_stride, d_work + fw.gram, d_chisq, d_status, s_aux);
   if (ax) hand_over(s_aux, st, ax->ev[3]);

@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
   const double *lam = a.lam + b0, *ql = (a.log_step ? a.loglam : a.lam) + b0;
   const double *Pb = a.P + b0 * a.npp;
   const double *dn = a.dn + p0, *einv = a.einv + p0;
+  const double *rb = a.resol ? a.resol + p0 * a.nresol : nullptr;
+  auto ev = [&](double x, double q) { return spline_eval_uv(a, yz, x, q); };
   if (tid < NI) {
     const int j = j0 + tid;
     double f = 1, qf = 0;
@@ -94,14 +96,11 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
       const bool in = p < pend;
       double bsq[NT], btd[NT];
       if (in) {
-        const double lp = lam[p], qp = ql[p], ei = einv[p], dv = dn[p];
+        const double ei = einv[p], dv = dn[p];
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
           double t = 0;
-          if (onB[nt]) {
-            const double x = lp * fB[nt];
-            t = spline_eval_uv(a, yz, x, a.log_step ? qp + qfB[nt] : x) * ei;
-          }
+          if (onB[nt]) t = template_at(a, lam, ql, rb, npix, p, fB[nt], qfB[nt], ev) * ei;
           bsq[nt] = t * t;
           btd[nt] = t * dv;
         }
@@ -183,14 +182,13 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
         for (int nt = 0; nt < NT; nt++) dmma884(cont[nt][0], cont[nt][1], av, bco[s][nt]);
       }
       if (in) {
-        const double lp = lam[p], qp = ql[p], ei = einv[p], dv = dn[p];
+        const double ei = einv[p], dv = dn[p];
 #pragma unroll
         for (int nt = 0; nt < NT; nt++)
 #pragma unroll
           for (int e = 0; e < 2; e++)
             if (onC[nt][e]) {
-              const double x = lp * fC[nt][e];
-              const double t = spline_eval_uv(a, yz, x, a.log_step ? qp + qfC[nt][e] : x) * ei;
+              const double t = template_at(a, lam, ql, rb, npix, p, fC[nt][e], qfC[nt][e], ev) * ei;
               const double res = fma(-t, cont[nt][e], dv);
               rss[nt][e] = fma(res, res, rss[nt][e]);
             }

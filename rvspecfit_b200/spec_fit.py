@@ -23,19 +23,95 @@ from . import _cabi, _dev, spec_inter
 SPEED_OF_LIGHT = 299792.458  # km/s, spec_fit.py:23
 
 
+class ResolMatrix:
+    """Holder of a resolution matrix (reference spec_fit.py:54-67): `mat` is anything
+    scipy.sparse can turn into diagonals (the reference builds scipy.sparse
+    dia matrices, spec_fit.py:466, desi/desi_fit.py:746)."""
+
+    def __init__(self, mat):
+        self.fd = {'mat': mat}
+        self.objid = random.getrandbits(128)
+
+    def __hash__(self):
+        return self.objid
+
+    @property
+    def mat(self):
+        return self.fd['mat']
+
+
+def construct_resol_mat(lam, resol=None, width=None):
+    """Resolution matrix of Gaussian line-spread functions from a resolving power
+    R = lambda/delta lambda (sigma = lam/R/2.35) or a width in Angstrom: reference
+    spec_fit.py:410-468, same arguments and result (host-side data preparation; the
+    matrix is applied on the device)."""
+    import scipy.sparse
+    assert (resol is None or width is None)
+    assert (resol is not None or width is not None)
+    lam = np.asarray(lam, dtype=np.float64)
+    n = len(lam)
+    sigs = lam / resol / 2.35 if resol is not None else np.zeros(n) + width
+    assert (np.all(np.diff(lam) > 0))
+    pix = np.arange(n)
+    left = np.maximum(np.searchsorted(lam, lam - 5 * sigs, 'left'), 0)
+    right = np.minimum(np.searchsorted(lam, lam + 5 * sigs, 'right'), n - 1)
+    half = min(n, max(np.max(right - pix), np.max(pix - left)))
+    offsets = np.arange(-half, half + 1)
+    # profile of pixel j sampled at its neighbours j + offsets, normalised per pixel j
+    nb = pix[None, :] + offsets[:, None]
+    inside = (nb >= 0) & (nb < n)
+    prof = np.exp(-0.5 * ((lam[np.where(inside, nb, 0)] - lam[None, :]) / sigs[None, :])**2)
+    prof = prof * inside
+    prof /= prof.sum(axis=0)[None, :]
+    # scipy's diagonal storage: data[k, c] = M[c - offsets[k], c], with
+    # M[r, c] = prof[offsets = c - r ... as the reference lays it out] (spec_fit.py:463-465)
+    cid = (pix[None, :] - offsets[:, None]) % n
+    kid = np.broadcast_to((half + offsets)[:, None], cid.shape)
+    return ResolMatrix(scipy.sparse.spdiags(prof[kid, cid], offsets, n, n))
+
+
+def convolve_resol(spec, resol_matrix):
+    """reference spec_fit.py:471-489 (host convenience; the likelihood applies the
+    matrix on the device)."""
+    return resol_matrix.mat @ spec
+
+
+def _band_rows(mat, n):
+    """Diagonals of a resolution matrix by OUTPUT pixel (rvs_obs.d_resol):
+    (offsets ascending int32[nd], rows f64[nd, n]) with rows[k, p] = M[p, p + offsets[k]]."""
+    import scipy.sparse
+    dia = scipy.sparse.dia_matrix(mat)
+    if dia.shape != (n, n):
+        raise ValueError(f'resolution matrix of shape {dia.shape} for a spectrum of {n} pixels')
+    offs, rows = [], []
+    for k in np.argsort(dia.offsets):
+        off = int(dia.offsets[k])
+        p = np.arange(max(0, -off), min(n, n - off))
+        p = p[p + off < dia.data.shape[1]]
+        row = np.zeros(n)
+        row[p] = dia.data[k, p + off]
+        if off == 0 or row.any():
+            offs.append(off)
+            rows.append(row)
+    if 0 not in offs:
+        offs.append(0)
+        rows.append(np.zeros(n))
+        order = np.argsort(offs)
+        offs, rows = [offs[i] for i in order], [rows[i] for i in order]
+    return np.array(offs, dtype=np.int32), np.array(rows, dtype=np.float64)
+
+
 class SpecData:
     """A single spectroscopic dataset (reference spec_fit.py:70-145)."""
 
     def __init__(self, name, lam, spec, espec, badmask=None, resolution=None,
                  dtype=np.float64):
-        if resolution is not None:
-            raise NotImplementedError('resolution matrices are not on the GPU path yet '
-                                      '(SURVEY.md section 8 row f4)')
         self.name = name
         self.lam = np.ascontiguousarray(lam, dtype=dtype)
         self.spec = np.ascontiguousarray(spec, dtype=dtype)
         self.espec = np.ascontiguousarray(espec, dtype=dtype)
-        self.resolution = None
+        self.resolution = resolution
+        self._band = None if resolution is None else _band_rows(resolution.mat, len(self.lam))
         self.spec_error_ratio = np.ascontiguousarray(spec / espec, dtype=dtype)
         if badmask is None:
             badmask = np.zeros(len(self.spec), dtype=bool)
@@ -85,6 +161,24 @@ class SpectrumBatch:
         self.d_gstart = _dev.upload(self.gstart, np.int64)
         self.d_goff = _dev.upload(self.gstart[:-1][gid], np.int64)
         self._prod, self._basis = {}, {}
+        # resolution matrices: band rows by output pixel on the diagonals any member
+        # has (a member without a matrix gets the identity), one object pool
+        self.resol_offs = self.d_resol = self.d_resol_offs = None
+        bands = [getattr(s, '_band', None) for s in specdatas]
+        if any(b is not None for b in bands):
+            offs = sorted({0}.union(*[set(b[0].tolist()) for b in bands if b is not None]))
+            pos = {o: k for k, o in enumerate(offs)}
+            blocks = []
+            for s, b in zip(specdatas, bands):
+                blk = np.zeros((len(offs), len(s.lam)))
+                if b is None:
+                    blk[pos[0]] = 1.0
+                else:
+                    blk[[pos[o] for o in b[0].tolist()]] = b[1]
+                blocks.append(blk.ravel())
+            self.resol_offs = np.array(offs, dtype=np.int32)
+            self.h_resol, self.d_resol = _dev.upload_concat(blocks, np.float64)
+            self.d_resol_offs = _dev.upload(self.resol_offs, np.int32)
 
     def lam_of(self, i):
         """Wavelengths of object i (host)."""
@@ -119,7 +213,13 @@ class SpectrumBatch:
             self._basis[key] = (loglam, P, npp)
         return self._basis[key]
 
-    def obs(self, npoly, rbf, sys_err=0.0):
+    @property
+    def tn_rows(self):
+        """Rows of the T/sigma workspace per item (rvs_chisq_fused: two with
+        resolution matrices)."""
+        return 1 if self.d_resol is None else 2
+
+    def obs(self, npoly, rbf, sys_err=0.0, resol=True):
         """struct rvs_obs (the tensors it points to stay alive in the caches)."""
         dn, einv, sumlog2 = self.products(sys_err)
         loglam, P, npp = self.basis(npoly, rbf)
@@ -129,6 +229,9 @@ class SpectrumBatch:
         o.d_sumlog2, o.d_off = sumlog2.data_ptr(), self.d_off.data_ptr()
         o.npoly, o.npp, o.nobj = int(npoly), npp, self.n
         o.shared_grid = int(len(self.grid_first) == 1)
+        if resol and self.d_resol is not None:
+            o.d_resol, o.d_resol_offs = self.d_resol.data_ptr(), self.d_resol_offs.data_ptr()
+            o.nresol = len(self.resol_offs)
         return o
 
 
@@ -264,7 +367,7 @@ class LikelihoodEngine:
             d_vs = None if vs is None else _dev.upload(vs, np.float64)
             vmax = 0.0 if vs is None else float(np.max(vs, initial=0.0))
             stride = int(batch.npix.max())
-            d_tn = self._workspace(k * stride)
+            d_tn = self._workspace(k * stride * batch.tn_rows)
             nwork = L.rvs_fused_workspace(k, bank.tapcap(vmax), bank.npix_t)
             if getattr(self, '_work', None) is None or self._work.numel() < nwork:
                 self._work = _dev.empty((int(nwork * 1.25) + 64,), np.float64)
@@ -518,7 +621,7 @@ class LikelihoodEngine:
                                        _dev.ptr(d_chi[1, a]), stream)
                 _cabi.check(rc, 'rvs_locate_grid')
             stride = batch.max_npix
-            d_tn = self._scratch(f'tn{a}_{six}', (K * stride,), np.float64)
+            d_tn = self._scratch(f'tn{a}_{six}', (K * stride * batch.tn_rows,), np.float64)
             d_work = self._scratch(f'work{a}_{six}',
                                    (L.rvs_fused_workspace(K, bank.tapcap(vmax), bank.npix_t),),
                                    np.float64)
@@ -727,6 +830,28 @@ def _engine_for(specdata, config, options):
     return _engine_cache[key]
 
 
+_resol_views = {}
+
+
+def _with_resol_params(specdata, resol_params):
+    """get_chisq's resol_params dictionary (spec_fit.py:922-929): the same data with the
+    matrix of its setup attached (cached, so that repeated calls reuse one engine)."""
+    out = []
+    for sd in specdata:
+        if sd.resolution is not None:
+            raise ValueError('You are not allowed to set resol_param together with'
+                             'the resolution of each SpecData')
+        rm = resol_params[sd.name]
+        key = (sd.objid, getattr(rm, 'objid', id(rm)))
+        if key not in _resol_views:
+            if len(_resol_views) > 64:
+                _resol_views.pop(next(iter(_resol_views)))
+            _resol_views[key] = SpecData(sd.name, sd.lam, sd.spec, sd.espec, badmask=sd.badmask,
+                                         resolution=rm)
+        out.append(_resol_views[key])
+    return out
+
+
 def param_dict_to_tuple(paramDict, setup, config):
     """spec_fit.py:730-736."""
     it = spec_inter.getInterpolator(setup, config)
@@ -739,10 +864,10 @@ def get_chisq(specdata, vel, atm_params, rot_params=None, resol_params=None, opt
     """-2 log L of the dataset at a velocity, atmospheric and rotation
     parameters: reference spec_fit.py:797-989, same arguments and returns.
     `cache` is accepted and ignored (the spline never leaves the device)."""
-    if resol_params is not None:
-        raise NotImplementedError('resol_params: SURVEY.md section 8 row f4')
     if isinstance(specdata, SpecData):
         specdata = [specdata]
+    if resol_params is not None:
+        specdata = _with_resol_params(specdata, resol_params)
     eng = _engine_for(specdata, config, options or {})
     vs = None if rot_params is None else np.array([rot_params[0]], dtype=np.float64)
     par = np.array([tuple(atm_params)], dtype=np.float64)
@@ -789,7 +914,7 @@ def get_chisq_continuum(specdata, options=None):
     ca, ra = np.zeros(len(specdata)), np.zeros(len(specdata))
     for i, sd in enumerate(specdata):
         batch = SpectrumBatch([sd])
-        obs = batch.obs(npoly, rbf)
+        obs = batch.obs(npoly, rbf, resol=False)   # spec_fit.py:739-783: no resolution matrix
         # unit template on a 4-knot linear grid covering the data: y=1, z=0
         x = np.linspace(sd.lam[0] * 0.5, sd.lam[-1] * 2, 4)
         h, hinv, cp, winv = np.zeros(3), np.zeros(3), np.zeros(2), np.zeros(2)
@@ -835,10 +960,10 @@ def find_best(specdata, vel_grid, params_list, rot_params=None, resol_params=Non
               options=None, config=None, quadratic=True):
     """Best template and velocity on a grid: reference spec_fit.py:1018-1092,
     same arguments and returned keys."""
-    if resol_params is not None:
-        raise NotImplementedError('resol_params: SURVEY.md section 8 row f4')
     if isinstance(specdata, SpecData):
         specdata = [specdata]
+    if resol_params is not None:
+        specdata = _with_resol_params(specdata, resol_params)
     eng = _engine_for(specdata, config, options or {})
     vel_grid = np.asarray(vel_grid, dtype=np.float64)
     npar, nv = len(params_list), len(vel_grid)

@@ -29,9 +29,10 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    # 5 pointers + 2 int32 + 7 doubles ; 8 pointers + 4 int32
+    # 5 pointers + 2 int32 + 7 doubles ; 8 pointers + 4 int32 + 2 pointers + 2 int32
     assert ctypes.sizeof(_cabi.Knots) == 5 * 8 + 8 + 7 * 8
-    assert ctypes.sizeof(_cabi.Obs) == 8 * 8 + 16
+    assert ctypes.sizeof(_cabi.Obs) == 8 * 8 + 16 + 2 * 8 + 8
+    assert _cabi.Obs.d_resol.offset == 80 and _cabi.Obs.nresol.offset == 96
 
 
 def test_knot_tables_match_oracle_thomas():
