@@ -174,8 +174,23 @@ def run_gpu(args):
     vgrid = np.arange(cfg['min_vel'], cfg['max_vel'], cfg['vel_step0'])
     start = np.tile(np.array([[5500., 3.0, -1.0, 0.2]]), (B, 1))
 
+    resol, nd = [None] * len(setups), 0
+    if args.resolution_matrix > 0:
+        # diagnostic workload: every spectrum carries a banded resolution matrix (Gaussian
+        # line-spread function of that sigma in Angstrom, cut to 11 diagonals like DESI's,
+        # desi/desi_fit.py:723-748); the band rows add nd x 8 B per observed pixel
+        import scipy.sparse
+        for a, arm in enumerate(objects[0]):
+            full = scipy.sparse.dia_matrix(
+                spec_fit.construct_resol_mat(arm[1], width=args.resolution_matrix).mat)
+            keep = np.abs(full.offsets) <= 5
+            resol[a] = spec_fit.ResolMatrix(scipy.sparse.dia_matrix(
+                (full.data[keep], full.offsets[keep]), shape=full.shape))
+        nd = int(keep.sum())
+        beval += nd * npo * 8
+
     def to_specdata():
-        return [[spec_fit.SpecData(*a) for a in o] for o in objects]
+        return [[spec_fit.SpecData(*a, resolution=r) for a, r in zip(o, resol)] for o in objects]
 
     timer = batch_fit.KernelTimer()
 
@@ -293,7 +308,7 @@ def run_gpu(args):
     # per step: flux and error of every spectrum (2 x 8 B per pixel), one wavelength
     # grid per arm (the objects of an arm share their pixels), offsets, and per
     # evaluation call the (vel, vsini, 4 parameters) + arm index records
-    h2d = sum(2 * 8 * len(a[1]) for o in objects for a in o) + \
+    h2d = sum((2 + nd) * 8 * len(a[1]) for o in objects for a in o) + \
         sum(8 * len(a[1]) for a in objects[0]) + \
         (0 if args.mode == 'fit' else args.evals * B * (6 * 8 + 4 * len(setups)))
     d2h = int(np.asarray(out).nbytes) * world      # whole job, like `value`
@@ -367,7 +382,7 @@ def run_gpu(args):
                                f'({setups[0]["dats"].shape[0]} nodes, fp32), npoly {w["npoly"]}',
                    'spectra_per_gpu_per_step': B, 'rv_trials': len(vgrid),
                    'fit_evals_per_spectrum': args.evals, 'lockstep_groups': args.groups,
-                   'mode': args.mode, 'step': step_txt,
+                   'mode': args.mode, 'step': step_txt, 'resolution_matrix_diagonals': nd,
                    'l2': 'template grid (>=0.7 GB per arm) is larger than L2; rows gathered '
                          'at random per evaluation',
                    'parallelism': f'spectra sharded over {world} GPU(s), grid replicated'},
@@ -519,6 +534,9 @@ def main():
     ap.add_argument('--cpu-fraction', type=float, default=1.0,
                     help='fraction of the per-spectrum evaluations the CPU sample runs')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--resolution-matrix', type=float, default=0.0, metavar='SIGMA_A',
+                    help='diagnostic: attach an 11-diagonal resolution matrix (Gaussian of this '
+                         'sigma in Angstrom) to every spectrum (SURVEY.md 8 row f4)')
     ap.add_argument('--timeline', type=int, default=0,
                     help='diagnostic: kernel start/end times of this many evaluation rounds')
     ap.add_argument('--stage-profile', action='store_true',

@@ -111,7 +111,12 @@ class SpecData:
         self.spec = np.ascontiguousarray(spec, dtype=dtype)
         self.espec = np.ascontiguousarray(espec, dtype=dtype)
         self.resolution = resolution
-        self._band = None if resolution is None else _band_rows(resolution.mat, len(self.lam))
+        self._band = None
+        if resolution is not None:      # spectra sharing one matrix object share its band rows
+            cache = resolution.__dict__.setdefault('_band_cache', {})
+            if len(self.lam) not in cache:
+                cache[len(self.lam)] = _band_rows(resolution.mat, len(self.lam))
+            self._band = cache[len(self.lam)]
         self.spec_error_ratio = np.ascontiguousarray(spec / espec, dtype=dtype)
         if badmask is None:
             badmask = np.zeros(len(self.spec), dtype=bool)

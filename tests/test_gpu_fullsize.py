@@ -117,3 +117,55 @@ def test_oracle_spot_checks_at_full_size(desi):
         want = oracle.get_chisq(osd, desi['tv'][2][i], tuple(desi['tp'][2][i]),
                                 (desi['tvs'][2][i],), options={'npoly': 10}, config=desi['cfg'])
         assert abs(got[j] - want) < CHI_RTOL * abs(want), (i, got[j], want)
+
+
+def test_resolution_matrices_at_full_size(desi):
+    """DESI-sized spectra with an 11-diagonal resolution matrix per spectrum (two
+    different widths across the batch): fused path + resol_apply == general path ==
+    oracle spot checks; linearity of the mode (identity matrices change nothing)."""
+    import oracle
+    import scipy.sparse
+    from rvspecfit_b200 import spec_fit
+    opts = {'npoly': 10}
+
+    def banded(lam, width):
+        full = scipy.sparse.dia_matrix(spec_fit.construct_resol_mat(lam, width=width).mat)
+        keep = np.abs(full.offsets) <= 5
+        return scipy.sparse.dia_matrix((full.data[keep], full.offsets[keep]), shape=full.shape)
+
+    mats = [[spec_fit.ResolMatrix(banded(a[1], wd)) for a in desi['objects'][0]]
+            for wd in (0.7, 1.1)]
+    n = 48
+    sds = [[spec_fit.SpecData(*a, resolution=mats[i % 2][k]) for k, a in enumerate(o)]
+           for i, o in enumerate(desi['objects'][:n])]
+    fused = spec_fit.LikelihoodEngine(sds, desi['cfg'], opts, fused=True)
+    general = spec_fit.LikelihoodEngine(sds, desi['cfg'], opts, fused=False)
+    obj = np.arange(n)
+    a = fused.evaluate(obj, desi['tv'][0][:n], desi['tp'][0][:n], desi['tvs'][0][:n])
+    b = general.evaluate(obj, desi['tv'][0][:n], desi['tp'][0][:n], desi['tvs'][0][:n])
+    assert np.isfinite(a).all() and _rel(a, b) < CHI_RTOL
+    plain = spec_fit.LikelihoodEngine(desi['sds'][:n], desi['cfg'], opts)
+    c = plain.evaluate(obj, desi['tv'][0][:n], desi['tp'][0][:n], desi['tvs'][0][:n])
+    assert _rel(a, c) > 1e-6          # the matrices matter
+    for st in desi['setups']:
+        oracle.register_setup(st)
+    for i in (0, 7):
+        osd = [oracle.SpecData(*arm, resolution=oracle.ResolMatrix(mats[i % 2][k].mat))
+               for k, arm in enumerate(desi['objects'][i])]
+        want = oracle.get_chisq(osd, desi['tv'][0][i], tuple(desi['tp'][0][i]),
+                                (desi['tvs'][0][i],), options=opts, config=desi['cfg'])
+        assert abs(a[i] - want) < CHI_RTOL * abs(want), (i, a[i], want)
+    # identity matrices: same chi-square as without (to rounding of 1.0 * T)
+    ident = [[spec_fit.SpecData(*arm, resolution=spec_fit.ResolMatrix(
+        scipy.sparse.identity(len(arm[1]), format='dia'))) for arm in o]
+        for o in desi['objects'][:8]]
+    e = spec_fit.LikelihoodEngine(ident, desi['cfg'], opts)
+    d = e.evaluate(obj[:8], desi['tv'][0][:8], desi['tp'][0][:8], desi['tvs'][0][:8])
+    assert _rel(d, c[:8]) < 1e-13
+    # RV scan (GEMM scan kernel) against single evaluations
+    vg = np.arange(-300, 300, 25.)
+    scan = fused.evaluate(np.arange(2), np.tile(vg, (2, 1)), desi['pars'][:2], np.array([0., 23.]))
+    for i in range(2):
+        one = fused.evaluate(np.full(len(vg), i), vg, np.tile(desi['pars'][i], (len(vg), 1)),
+                             np.full(len(vg), [0., 23.][i]))
+        assert _rel(one, scan[i]) < CHI_RTOL, i
