@@ -129,11 +129,12 @@ typedef struct {
    * the nresol diagonals d_resol_offs[] (ascending, shared by the batch), stored by
    * OUTPUT pixel in an object pool: (R_i T)[p] = sum_k d_resol[off[i]*nresol +
    * k*npix_i + p] * T[p + offs[k]], terms with p + offs[k] outside [0, npix_i) skipped.
-   * d_resol == NULL (nresol == 0): no resolution matrices. */
+   * resol_halfwidth = max |d_resol_offs[]| (selects the shared-memory staged RV-scan
+   * kernel for narrow bands).  d_resol == NULL (nresol == 0): no resolution matrices. */
   const double *d_resol;
   const int32_t *d_resol_offs;
   int32_t nresol;
-  int32_t reserved;
+  int32_t resol_halfwidth;
 } rvs_obs;
 
 /* Regular template grid in mapped parameter space (spec_inter.py:97-132):

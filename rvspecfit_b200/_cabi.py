@@ -36,7 +36,7 @@ class Obs(ctypes.Structure):
                 ('d_dn', c_dp), ('d_einv', c_dp), ('d_sumlog2', c_dp), ('d_off', c_dp),
                 ('npoly', ctypes.c_int32), ('npp', ctypes.c_int32), ('nobj', ctypes.c_int32),
                 ('shared_grid', ctypes.c_int32), ('d_resol', c_dp), ('d_resol_offs', c_dp),
-                ('nresol', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('nresol', ctypes.c_int32), ('resol_halfwidth', ctypes.c_int32)]
 
 
 class GridMap(ctypes.Structure):

@@ -339,6 +339,9 @@ int fill_scan_args(ScanArgs &a, const rvs_knots *kn, const rvs_obs *obs) {
                   (obs->nresol == 0 || obs->d_resol_offs),
               RVS_E_ARG, "chisq: d_resol, d_resol_offs and nresol must be set together");
   a.resol = obs->d_resol; a.resol_offs = obs->d_resol_offs; a.nresol = obs->nresol;
+  a.resol_hw = obs->resol_halfwidth;
+  RVS_REQUIRE(obs->nresol == 0 || obs->resol_halfwidth >= 0, RVS_E_ARG,
+              "chisq: resol_halfwidth must be max |d_resol_offs[]|");
   RVS_REQUIRE(obs->npp >= obs->npoly && obs->npp % 2 == 0 && ((uintptr_t)obs->d_P & 15) == 0,
               RVS_E_ARG, "chisq: basis rows must be npp = even >= npoly doubles, 16-byte aligned");
   return 0;

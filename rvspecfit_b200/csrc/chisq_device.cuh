@@ -32,6 +32,7 @@ struct ScanArgs {
   const double *resol;
   const int32_t *resol_offs;
   int nresol;
+  int resol_hw;  // max |resol_offs[]|
 };
 
 constexpr int SCAN_WARPS = 8;

@@ -35,11 +35,22 @@ __device__ __forceinline__ double spline_eval_uv(const ScanArgs &a, const double
 #ifndef RVS_SCAN_MINB
 #define RVS_SCAN_MINB 4
 #endif
-template <int NP, int NT>
+// Resolution matrices whose diagonals lie within RS_HW of the main one (DESI's: 5) are
+// applied from shared memory (RESOL = true): each warp resamples the template once for a
+// tile of RS_TILE of its pixels plus RS_HW neighbours on each side, for all the CTA's
+// trials, and every (pixel, trial) element of its MMA fragments is then `nresol` FMAs on
+// those values instead of `nresol` spline evaluations (template_at).  Row stride RS_W:
+// 104 words = 8 banks between trials, conflict-free for the first sweep's fragment layout.
+constexpr int RS_TILE = 32;
+constexpr int RS_HW = 10;
+constexpr int RS_W = RS_TILE + 2 * RS_HW;
+
+template <int NP, int NT, bool RESOL = false>
 __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kernel(ScanArgs a) {
   using TL = GramTiles<NP>;
   constexpr int NI = 8 * NT;
   constexpr int KST = (NP + 3) / 4;
+  __shared__ double s_raw[RESOL ? GM_WARPS : 1][RESOL ? NI : 1][RESOL ? RS_W : 1];
   __shared__ double s_red[TL::ROWS][NI + 1];
   __shared__ double sM[GM_WARPS][TL::NTRI];
   __shared__ double sV[GM_WARPS][NP];
@@ -60,6 +71,22 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
   const double *dn = a.dn + p0, *einv = a.einv + p0;
   const double *rb = a.resol ? a.resol + p0 * a.nresol : nullptr;
   auto ev = [&](double x, double q) { return spline_eval_uv(a, yz, x, q); };
+  // RESOL: resampled template of pixels [tile - RS_HW, tile + RS_TILE + RS_HW) for the
+  // CTA's trials into the warp's rows of s_raw (0 outside the spectrum / absent trials)
+  auto stage = [&](int tile) {
+    __syncwarp();
+    for (int idx = lane; idx < NI * RS_W; idx += 32) {
+      const int t = idx / RS_W, q = idx - t * RS_W;
+      const int pp = tile - RS_HW + q;
+      double v = 0;
+      if (pp >= 0 && pp < npix && j0 + t < a.nv) {
+        const double x = lam[pp] * s_f[t];
+        v = ev(x, a.log_step ? ql[pp] + s_qf[t] : x);
+      }
+      s_raw[RESOL ? wid : 0][RESOL ? t : 0][RESOL ? q : 0] = v;
+    }
+    __syncwarp();
+  };
   if (tid < NI) {
     const int j = j0 + tid;
     double f = 1, qf = 0;
@@ -94,13 +121,30 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
     for (int p4 = pbeg; p4 < pend; p4 += 4) {
       const int p = p4 + c;
       const bool in = p < pend;
+      if (RESOL && ((p4 - pbeg) & (RS_TILE - 1)) == 0) stage(p4);
       double bsq[NT], btd[NT];
       if (in) {
         const double ei = einv[p], dv = dn[p];
+        double tv[NT];
+        if constexpr (RESOL) {
+          const int col = ((p4 - pbeg) & (RS_TILE - 1)) + c + RS_HW;
+#pragma unroll
+          for (int nt = 0; nt < NT; nt++) tv[nt] = 0;
+          for (int d = 0; d < a.nresol; d++) {
+            const int o = __ldg(a.resol_offs + d);
+            if (p + o < 0 || p + o >= npix) continue;
+            const double cf = __ldg(rb + (int64_t)d * npix + p);
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) tv[nt] = fma(cf, s_raw[wid][nt * 8 + r][col + o], tv[nt]);
+          }
+        } else {
+#pragma unroll
+          for (int nt = 0; nt < NT; nt++)
+            tv[nt] = onB[nt] ? template_at(a, lam, ql, rb, npix, p, fB[nt], qfB[nt], ev) : 0.0;
+        }
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
-          double t = 0;
-          if (onB[nt]) t = template_at(a, lam, ql, rb, npix, p, fB[nt], qfB[nt], ev) * ei;
+          const double t = onB[nt] ? tv[nt] * ei : 0.0;
           bsq[nt] = t * t;
           btd[nt] = t * dv;
         }
@@ -170,6 +214,7 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
     for (int p8 = pbeg; p8 < pend; p8 += 8) {
       const int p = p8 + r;
       const bool in = p < pend;
+      if (RESOL && ((p8 - pbeg) & (RS_TILE - 1)) == 0) stage(p8);
       const double *Prow = Pb + (int64_t)(in ? p : 0) * a.npp;
       double cont[NT][2];
 #pragma unroll
@@ -183,12 +228,35 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
       }
       if (in) {
         const double ei = einv[p], dv = dn[p];
+        double tv[NT][2];
+        if constexpr (RESOL) {
+          const int col = ((p8 - pbeg) & (RS_TILE - 1)) + r + RS_HW;
+#pragma unroll
+          for (int nt = 0; nt < NT; nt++) tv[nt][0] = tv[nt][1] = 0;
+          for (int d = 0; d < a.nresol; d++) {
+            const int o = __ldg(a.resol_offs + d);
+            if (p + o < 0 || p + o >= npix) continue;
+            const double cf = __ldg(rb + (int64_t)d * npix + p);
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+              for (int e = 0; e < 2; e++)
+                tv[nt][e] = fma(cf, s_raw[wid][nt * 8 + 2 * c + e][col + o], tv[nt][e]);
+          }
+        } else {
+#pragma unroll
+          for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+              tv[nt][e] = onC[nt][e] ? template_at(a, lam, ql, rb, npix, p, fC[nt][e],
+                                                   qfC[nt][e], ev) : 0.0;
+        }
 #pragma unroll
         for (int nt = 0; nt < NT; nt++)
 #pragma unroll
           for (int e = 0; e < 2; e++)
             if (onC[nt][e]) {
-              const double t = template_at(a, lam, ql, rb, npix, p, fC[nt][e], qfC[nt][e], ev) * ei;
+              const double t = tv[nt][e] * ei;
               const double res = fma(-t, cont[nt][e], dv);
               rss[nt][e] = fma(res, res, rss[nt][e]);
             }

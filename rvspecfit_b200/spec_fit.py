@@ -237,6 +237,7 @@ class SpectrumBatch:
         if resol and self.d_resol is not None:
             o.d_resol, o.d_resol_offs = self.d_resol.data_ptr(), self.d_resol_offs.data_ptr()
             o.nresol = len(self.resol_offs)
+            o.resol_halfwidth = int(np.abs(self.resol_offs).max())
         return o
 
 

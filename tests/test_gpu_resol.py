@@ -180,3 +180,27 @@ def test_process_with_resolution_matrix_matches_reference(golden):
                           options={'npoly': 15}, resolParams={nm: rm})
     assert abs(res['vel'] - gr['proc_vel']) < 0.01
     assert abs(res['chisq'] - gr['proc_chisq']) < 1e-6 * abs(res['chisq'])
+
+
+def test_wide_band_takes_the_unstaged_scan_kernel(golden):
+    """A matrix with more than RS_HW = 10 diagonals on a side (low resolving power) is
+    applied by the scan kernel without the shared-memory staging: same values."""
+    g = golden('chisq')
+    st = setup('test', 'tiny', 3, name='test')
+    _register(st)
+    oracle.register_setup(st)
+    nm, lam, sp, es, bad = unpack_objects(g, 'one_')[0]['arms'][0]
+    rm = spec_fit.construct_resol_mat(lam, resol=500.)
+    assert np.abs(scipy.sparse.dia_matrix(rm.mat).offsets).max() > 10
+    sd = [spec_fit.SpecData('test', lam, sp, es, badmask=bad, resolution=rm)]
+    osd = [oracle.SpecData('test', lam, sp, es, bad,
+                           resolution=oracle.construct_resol_mat(lam, resol=500.))]
+    cfg, opts, e = config(), {'npoly': 15}, g['one_eval'][1]
+    eng = spec_fit.LikelihoodEngine([sd], cfg, opts)
+    vg = np.linspace(-250, 250, 21)
+    many = eng.evaluate([0], vg[None, :], e[None, 1:5], np.array([15.]))[0]
+    want = [oracle.get_chisq(osd, v, tuple(e[1:5]), (15.,), options=opts, config=cfg) for v in vg]
+    assert relerr(many, want) < CHI_RTOL
+    one = eng.evaluate(np.zeros(len(vg), dtype=int), vg, np.tile(e[1:5], (len(vg), 1)),
+                       np.full(len(vg), 15.))
+    assert relerr(one, want) < CHI_RTOL
