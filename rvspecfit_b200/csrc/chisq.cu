@@ -369,7 +369,7 @@ extern "C" int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32
   a.coeffs = d_coeffs; a.raw = d_raw; a.model = d_model; a.moff = d_moff;
   a.fast_interp = fast_interp ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (nv >= 4 && !d_coeffs && !d_raw && !d_model) {
+  if (nv >= 4 && !d_coeffs && !d_raw && !d_model && (!a.resol || a.resol_hw <= RS_HW)) {
     // several trials per template: the trials are the columns of an FP64 GEMM (scan_mma.cuh)
     const int np = obs->npoly;
     if (np <= 7) return launch_scan_mma_group0(a, np, st);

@@ -36,6 +36,9 @@ struct ScanArgs {
 };
 
 constexpr int SCAN_WARPS = 8;
+// widest half-bandwidth of a resolution matrix the GEMM scan kernel stages in shared
+// memory (scan_mma.cuh); wider ones take the per-trial scan kernel
+constexpr int RS_HW = 10;
 
 // fast_interp: templ_spec[searchsorted(templ_lam, x)] (numpy 'left': first knot
 // >= x), starting from the uniform-grid interval `pos` of x

@@ -70,7 +70,9 @@ static int launch_scan_mma_np(const ScanArgs &a, cudaStream_t st) {
   const int by = (a.nv + NI - 1) / NI;
   RVS_REQUIRE(by <= 65535, RVS_E_LIMIT, "scan: %d velocity trials per item", a.nv);
   dim3 grid(a.K, by);
-  if (a.resol && a.resol_hw <= RS_HW)  // narrow band: resampled template staged in shared memory
+  RVS_REQUIRE(!a.resol || a.resol_hw <= RS_HW, RVS_E_LIMIT,
+              "scan: resolution matrix half-bandwidth %d > %d", a.resol_hw, RS_HW);
+  if (a.resol)  // resampled template staged in shared memory
     chisq_scan_mma_kernel<NP, NT, true><<<grid, GM_THREADS, 0, st>>>(a);
   else
     chisq_scan_mma_kernel<NP, NT, false><<<grid, GM_THREADS, 0, st>>>(a);

@@ -35,14 +35,13 @@ __device__ __forceinline__ double spline_eval_uv(const ScanArgs &a, const double
 #ifndef RVS_SCAN_MINB
 #define RVS_SCAN_MINB 4
 #endif
-// Resolution matrices whose diagonals lie within RS_HW of the main one (DESI's: 5) are
-// applied from shared memory (RESOL = true): each warp resamples the template once for a
+// Resolution matrices (diagonals within RS_HW of the main one; DESI's: 5; wider bands
+// take the per-trial kernel, rvs_chisq_scan) are applied from shared memory (RESOL = true): each warp resamples the template once for a
 // tile of RS_TILE of its pixels plus RS_HW neighbours on each side, for all the CTA's
 // trials, and every (pixel, trial) element of its MMA fragments is then `nresol` FMAs on
 // those values instead of `nresol` spline evaluations (template_at).  Row stride RS_W:
 // 104 words = 8 banks between trials, conflict-free for the first sweep's fragment layout.
 constexpr int RS_TILE = 32;
-constexpr int RS_HW = 10;
 constexpr int RS_W = RS_TILE + 2 * RS_HW;
 
 template <int NP, int NT, bool RESOL = false>
@@ -138,9 +137,15 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
             for (int nt = 0; nt < NT; nt++) tv[nt] = fma(cf, s_raw[wid][nt * 8 + r][col + o], tv[nt]);
           }
         } else {
+          const double lp = lam[p], qp = ql[p];
 #pragma unroll
-          for (int nt = 0; nt < NT; nt++)
-            tv[nt] = onB[nt] ? template_at(a, lam, ql, rb, npix, p, fB[nt], qfB[nt], ev) : 0.0;
+          for (int nt = 0; nt < NT; nt++) {
+            tv[nt] = 0;
+            if (onB[nt]) {
+              const double x = lp * fB[nt];
+              tv[nt] = spline_eval_uv(a, yz, x, a.log_step ? qp + qfB[nt] : x);
+            }
+          }
         }
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
@@ -244,12 +249,17 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
                 tv[nt][e] = fma(cf, s_raw[wid][nt * 8 + 2 * c + e][col + o], tv[nt][e]);
           }
         } else {
+          const double lp = lam[p], qp = ql[p];
 #pragma unroll
           for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-            for (int e = 0; e < 2; e++)
-              tv[nt][e] = onC[nt][e] ? template_at(a, lam, ql, rb, npix, p, fC[nt][e],
-                                                   qfC[nt][e], ev) : 0.0;
+            for (int e = 0; e < 2; e++) {
+              tv[nt][e] = 0;
+              if (onC[nt][e]) {
+                const double x = lp * fC[nt][e];
+                tv[nt][e] = spline_eval_uv(a, yz, x, a.log_step ? qp + qfC[nt][e] : x);
+              }
+            }
         }
 #pragma unroll
         for (int nt = 0; nt < NT; nt++)
