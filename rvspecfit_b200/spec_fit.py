@@ -148,6 +148,7 @@ class SpectrumBatch:
         self.h_espec, self.d_espec = _dev.upload_concat([s.espec for s in specdatas], np.float64)
         self.h_bad = np.concatenate([s.badmask for s in specdatas])
         self._lams = [s.lam for s in specdatas]
+        self._gridkeys = [s.gridkey for s in specdatas]
         self.d_off = _dev.upload(self.off, np.int64)
         # objects observed on the same pixels share one wavelength grid: one copy
         # of lam / ln(lam) / continuum basis in the grid pools (rvs_obs)
@@ -172,15 +173,7 @@ class SpectrumBatch:
         bands = [getattr(s, '_band', None) for s in specdatas]
         if any(b is not None for b in bands):
             offs = sorted({0}.union(*[set(b[0].tolist()) for b in bands if b is not None]))
-            pos = {o: k for k, o in enumerate(offs)}
-            blocks = []
-            for s, b in zip(specdatas, bands):
-                blk = np.zeros((len(offs), len(s.lam)))
-                if b is None:
-                    blk[pos[0]] = 1.0
-                else:
-                    blk[[pos[o] for o in b[0].tolist()]] = b[1]
-                blocks.append(blk.ravel())
+            blocks = self._resol_blocks(specdatas, offs)
             self.resol_offs = np.array(offs, dtype=np.int32)
             self.h_resol, self.d_resol = _dev.upload_concat(blocks, np.float64)
             self.d_resol_offs = _dev.upload(self.resol_offs, np.int32)
@@ -188,6 +181,50 @@ class SpectrumBatch:
     def lam_of(self, i):
         """Wavelengths of object i (host)."""
         return self._lams[i]
+
+    def _resol_blocks(self, specdatas, offs):
+        pos = {o: k for k, o in enumerate(offs)}
+        blocks = []
+        for s in specdatas:
+            b = getattr(s, '_band', None)
+            blk = np.zeros((len(offs), len(s.lam)))
+            if b is None:
+                blk[pos[0]] = 1.0
+            else:
+                if not set(b[0].tolist()) <= set(pos):
+                    raise ValueError('resolution matrix with diagonals outside the batch\'s band')
+                blk[[pos[o] for o in b[0].tolist()]] = b[1]
+            blocks.append(blk.ravel())
+        return blocks
+
+    def reload(self, specdatas):
+        """New spectra of the SAME layout (number of objects, pixel grids, resolution
+        band) into the existing device buffers: fluxes and errors go through the pinned
+        staging buffers this batch already owns, the derived products (and band rows) are
+        recomputed in place.  Device addresses do not change, so captured CUDA graphs of
+        the engine stay valid.  Stream-ordered on the current stream."""
+        torch = _dev.torch_mod()
+        if len(specdatas) != self.n or \
+                any(len(s.lam) != n for s, n in zip(specdatas, self.npix)) or \
+                any(s.gridkey != k for s, k in zip(specdatas, self._gridkeys)):
+            raise ValueError('reload: the spectra do not have the layout of the batch')
+        if (self.d_resol is None) != all(getattr(s, '_band', None) is None for s in specdatas):
+            raise ValueError('reload: resolution matrices do not match the batch')
+        torch.cuda.current_stream().synchronize()    # the staging buffers are free again
+        np.concatenate([s.spec for s in specdatas], out=self.h_spec)
+        np.concatenate([s.espec for s in specdatas], out=self.h_espec)
+        self.d_spec.copy_(torch.from_numpy(self.h_spec), non_blocking=True)
+        self.d_espec.copy_(torch.from_numpy(self.h_espec), non_blocking=True)
+        self.h_bad = np.concatenate([s.badmask for s in specdatas])
+        if self.d_resol is not None:
+            np.concatenate(self._resol_blocks(specdatas, self.resol_offs.tolist()),
+                           out=self.h_resol)
+            self.d_resol.copy_(torch.from_numpy(self.h_resol), non_blocking=True)
+        for key, (dn, einv, sumlog2) in self._prod.items():
+            rc = _cabi.lib().rvs_obs_prepare(
+                _dev.ptr(self.d_spec), _dev.ptr(self.d_espec), _dev.ptr(self.d_off), self.n, key,
+                _dev.ptr(dn), _dev.ptr(einv), _dev.ptr(sumlog2), _dev.stream())
+            _cabi.check(rc, 'rvs_obs_prepare')
 
     def products(self, sys_err=0.0):
         key = float(sys_err)
@@ -332,6 +369,23 @@ class LikelihoodEngine:
             self.arms[n]['bank'].kind == 'regulargrid' and self.arms[n]['bank'].gridmap is not None
             and self.arms[n]['bank'].knots.ratio_dev < 1e-8 for n in self.setups)
         self._buf = {}
+
+    def reload(self, objects):
+        """Replace the spectra by new ones of the same layout (same arms per object, same
+        pixel grids): SpectrumBatch.reload for every arm.  The engine, its device buffers
+        and its captured CUDA graphs stay -- the streaming pattern of a survey driver that
+        pushes exposure after exposure of one instrument through one engine."""
+        objects = [[o] if isinstance(o, SpecData) else list(o) for o in objects]
+        if len(objects) != self.nobj or any(
+                [sd.name for sd in a] != [sd.name for sd in b]
+                for a, b in zip(objects, self.objects)):
+            raise ValueError('reload: the objects do not have the layout of the engine')
+        if any(sl['busy'] for sl in getattr(self, '_slots', [])):
+            raise RuntimeError('reload with evaluations in flight: collect their results first')
+        for name in self.setups:
+            arm = self.arms[name]
+            arm['batch'].reload([sd for o in objects for sd in o if sd.name == name])
+        self.objects = objects
 
     @staticmethod
     def _fusable(bank, vs):

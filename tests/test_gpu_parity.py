@@ -541,3 +541,37 @@ def test_process_batch_matches_reference(golden):
     for k in ('teff', 'logg', 'feh', 'alpha'):
         assert np.isclose(one['param'][k], b['param'][k], rtol=1e-7), k
         assert np.isclose(one['param_err'][k], b['param_err'][k], rtol=1e-3), k
+
+
+def test_engine_reload_equals_fresh_engine(golden):
+    """LikelihoodEngine.reload (new spectra of the same layout into the existing device
+    buffers, captured graphs kept): identical bits to an engine built from scratch."""
+    g = golden('chisq')
+    _register(setup('test', 'tiny', 3, name='test'))
+    objs = unpack_objects(g, 'one_')
+    cfg, ev, opts = config(), g['one_eval'][:6], {'npoly': 15}
+    a, b = _sd(objs[0], 'test'), _sd(objs[1], 'test')
+    obj = np.repeat([0, 1], len(ev))
+    par = np.tile(ev, (2, 1))
+    vs = np.where(par[:, 5] < 0, 0.0, par[:, 5])
+    eng = spec_fit.LikelihoodEngine([a, b], cfg, opts)
+    for _ in range(3):          # captures the graphs
+        first = eng.evaluate(obj, par[:, 0], par[:, 1:5], vs)
+    eng.reload([b, a])
+    swapped = eng.evaluate(obj, par[:, 0], par[:, 1:5], vs)
+    fresh = spec_fit.LikelihoodEngine([b, a], cfg, opts).evaluate(obj, par[:, 0], par[:, 1:5], vs)
+    assert np.array_equal(swapped, fresh)
+    assert not np.array_equal(swapped, first)
+    n = len(ev)
+    assert np.array_equal(swapped[:n], first[n:]) and np.array_equal(swapped[n:], first[:n])
+    # the scan and model-output paths see the new data too
+    vg = np.linspace(-200, 200, 9)
+    s1 = eng.evaluate([0], vg[None, :], ev[None, 1, 1:5], np.array([10.]))
+    s2 = spec_fit.LikelihoodEngine([b], cfg, opts).evaluate([0], vg[None, :], ev[None, 1, 1:5],
+                                                            np.array([10.]))
+    assert np.array_equal(s1, s2)
+    with pytest.raises(ValueError):
+        eng.reload([a])
+    short = [spec_fit.SpecData('test', a[0].lam[:-3], a[0].spec[:-3], a[0].espec[:-3])]
+    with pytest.raises(ValueError):
+        eng.reload([short, a])
