@@ -113,7 +113,7 @@ class SpecData:
         self.resolution = resolution
         self._band = None
         if resolution is not None:      # spectra sharing one matrix object share its band rows
-            cache = resolution.__dict__.setdefault('_band_cache', {})
+            cache = getattr(resolution, '__dict__', {}).setdefault('_band_cache', {})
             if len(self.lam) not in cache:
                 cache[len(self.lam)] = _band_rows(resolution.mat, len(self.lam))
             self._band = cache[len(self.lam)]
