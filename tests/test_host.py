@@ -87,3 +87,54 @@ def test_simplex_and_hessian_helpers():
     assert np.allclose(H, [[3, 0.5], [0.5, 2]], atol=1e-8)
     err, cov, bad = vel_fit._uncertainties_from_hessian(np.array([[4., 0.], [0., -1.]]))
     assert bad and err[0] == 0.5
+
+
+def test_resolution_matrix_host_side(golden):
+    """Host part of the resolution-matrix mode (no GPU): construct_resol_mat against the
+    reference's matrices (tests/golden/resol.npz), the band-row layout of rvs_obs.d_resol,
+    matrices stored with descending offsets (desi_fit.py:746), the resol_params views."""
+    import pytest
+    import scipy.sparse
+    from rvspecfit_b200 import spec_fit
+    g, gr = golden('chisq'), golden('resol')
+    objs = unpack_objects(g, 'one_')
+    for i, o in enumerate(objs):
+        lam = o['arms'][0][1]
+        rm = spec_fit.construct_resol_mat(lam, resol=float(gr['one_R'][i]))
+        dia = scipy.sparse.dia_matrix(rm.mat)
+        assert np.array_equal(dia.offsets, gr[f'one_{i}_offsets'])
+        assert np.isclose(dia.data.sum(), gr[f'one_{i}_data_sum'], rtol=1e-13)
+        if i == 0:
+            close(dia.data, gr['one_0_data'], rtol=1e-13)
+        # band rows by OUTPUT pixel reproduce the matrix product
+        n = len(lam)
+        offs, rows = spec_fit._band_rows(rm.mat, n)
+        assert offs.dtype == np.int32 and np.all(np.diff(offs) > 0) and 0 in offs
+        x = np.random.RandomState(i).normal(size=n)
+        y = np.zeros(n)
+        for k, off in enumerate(offs):
+            p = np.arange(max(0, -off), min(n, n - off))
+            y[p] += rows[k, p] * x[p + off]
+        close(y, rm.mat @ x, rtol=1e-12, atol=1e-14)
+        close(spec_fit.convolve_resol(x, rm), rm.mat @ x, rtol=0, atol=0)
+    # DESI's storage order: offsets w2 .. -w2
+    nm, lam, sp, es, bad = unpack_objects(g, 'desi_')[0]['arms'][0]
+    offs, data = gr['desi_0_offsets'], gr['desi_0_data']
+    up = scipy.sparse.dia_matrix((data, offs), shape=(len(lam), len(lam)))
+    down = scipy.sparse.dia_matrix((data[::-1], offs[::-1]), shape=(len(lam), len(lam)))
+    a, b = spec_fit._band_rows(up, len(lam)), spec_fit._band_rows(down, len(lam))
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and len(a[0]) == 11
+    with pytest.raises(ValueError):
+        spec_fit._band_rows(up, len(lam) - 1)
+    # SpecData carries the matrix; resol_params makes cached views and refuses both
+    rm = spec_fit.ResolMatrix(up)
+    sd = spec_fit.SpecData(nm, lam, sp, es, badmask=bad)
+    v1 = spec_fit._with_resol_params([sd], {nm: rm})
+    v2 = spec_fit._with_resol_params([sd], {nm: rm})
+    assert v1[0] is v2[0] and v1[0].resolution is rm and v1[0]._band is not None
+    assert sd.resolution is None
+    with pytest.raises(ValueError):
+        spec_fit._with_resol_params(v1, {nm: rm})
+    # spectra sharing one matrix object share its band rows
+    sd2 = spec_fit.SpecData(nm, lam, sp * 2, es, badmask=bad, resolution=rm)
+    assert sd2._band is v1[0]._band
