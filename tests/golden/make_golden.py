@@ -474,7 +474,8 @@ def gold_resol(R):
     opts = {'npoly': 15}
     out['one_R'] = np.array([1500., 4000.])
     chi = np.zeros((len(objs), len(ev)))
-    chi_rp = np.zeros_like(chi)
+    chi_rp, chi_fast, chi_sys = np.zeros_like(chi), np.zeros_like(chi), np.zeros_like(chi)
+    out['one_sys'] = np.zeros(len(objs))
     for i, o in enumerate(objs):
         nm, lam, sp, es, bad = o['arms'][0]
         assert np.array_equal(sp, prev[f'one_{i}_0_spec'])
@@ -493,6 +494,13 @@ def gold_resol(R):
             chi_rp[i, j] = R.spec_fit.get_chisq(sd_plain, e[0], tuple(e[1:5]), rot,
                                                 resol_params={'test': rm}, options=opts,
                                                 config=cfg)
+            # the matrix combined with the other switches of row a18
+            out['one_sys'][i] = 0.05 * float(np.median(es)) * 20
+            chi_fast[i, j] = R.spec_fit.get_chisq(sd_res, e[0], tuple(e[1:5]), rot, options=opts,
+                                                  config=cfg, fast_interp=True)
+            chi_sys[i, j] = R.spec_fit.get_chisq(sd_res, e[0], tuple(e[1:5]), rot, options=opts,
+                                                 config=cfg, espec_systematic=out['one_sys'][i],
+                                                 outside_penalty=False)
         e = ev[0]
         full = R.spec_fit.get_chisq(sd_res, e[0], tuple(e[1:5]), None if e[5] < 0 else (e[5],),
                                     options=opts, config=cfg, full_output=True)
@@ -507,6 +515,7 @@ def gold_resol(R):
             out[f'one_{i}_fb_{k}'] = fb[k]
         out[f'one_{i}_fb_best_param'] = np.array(fb['best_param'])
     out['one_chisq'], out['one_chisq_resol_params'] = chi, chi_rp
+    out['one_chisq_fast'], out['one_chisq_sys_nopen'] = chi_fast, chi_sys
     # three arms, fixed-width Gaussian matrices cut to 11 diagonals (the shape of DESI's
     # resolution data, desi_fit.py:723-748)
     arms = []

@@ -67,6 +67,24 @@ def test_get_chisq_with_resolution_matches_reference(golden):
         with pytest.raises(ValueError):
             spec_fit.get_chisq(sd_res, 0., tuple(ev[0][1:5]), None, options=opts, config=cfg,
                                resol_params={'test': rm})
+        # the matrix together with the other switches of row a18: nearest-knot lookup
+        # (per-trial kernel), systematic error + no off-grid penalty (fused path)
+        got = np.array([spec_fit.get_chisq(sd_res, e[0], tuple(e[1:5]), r, options=opts,
+                                           config=cfg, fast_interp=True)
+                        for e, r in zip(ev, rots)])
+        assert relerr(got[on], gr['one_chisq_fast'][i][on]) < CHI_RTOL
+        got = np.array([spec_fit.get_chisq(sd_res, e[0], tuple(e[1:5]), r, options=opts,
+                                           config=cfg, espec_systematic=float(gr['one_sys'][i]),
+                                           outside_penalty=False) for e, r in zip(ev, rots)])
+        assert relerr(got[on], gr['one_chisq_sys_nopen'][i][on]) < CHI_RTOL
+        # nearest-knot lookup in the staged GEMM scan kernel == single evaluations
+        eng = spec_fit.LikelihoodEngine([sd_res], cfg, opts)
+        vg9 = np.linspace(-300, 300, 9)
+        many = eng.evaluate([0], vg9[None, :], ev[None, 1, 1:5], np.array([max(ev[1, 5], 0.0)]),
+                            fast_interp=True)[0]
+        one = [spec_fit.get_chisq(sd_res, v, tuple(ev[1, 1:5]), (max(ev[1, 5], 0.0),),
+                                  options=opts, config=cfg, fast_interp=True) for v in vg9]
+        assert relerr(many, one) < CHI_RTOL
         # batched, fused and general path
         for fused in (True, False):
             eng = spec_fit.LikelihoodEngine([sd_res], cfg, opts, fused=fused)

@@ -231,6 +231,14 @@ def test_resolution_matrix_mode(golden):
         with pytest.raises(ValueError):
             oracle.get_chisq(sd_res, 0., tuple(ev[0][1:5]), None, options=opts, config=cfg,
                              resol_params={'test': rm})
+        # the matrix together with the other switches of row a18
+        got = [oracle.get_chisq(sd_res, e[0], tuple(e[1:5]), r, options=opts, config=cfg,
+                                fast_interp=True) for e, r in zip(ev, rots)]
+        assert relerr(got, gr['one_chisq_fast'][i]) < 2e-10
+        got = [oracle.get_chisq(sd_res, e[0], tuple(e[1:5]), r, options=opts, config=cfg,
+                                espec_systematic=float(gr['one_sys'][i]), outside_penalty=False)
+               for e, r in zip(ev, rots)]
+        assert relerr(got, gr['one_chisq_sys_nopen'][i]) < 2e-10
         full = oracle.get_chisq(sd_res, ev[0][0], tuple(ev[0][1:5]), rots[0], options=opts,
                                 config=cfg, full_output=True)
         assert relerr(full['chisq'], gr[f'one_{i}_full_chisq']) < 2e-10
