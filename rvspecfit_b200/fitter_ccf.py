@@ -121,7 +121,7 @@ def _workspace(nbytes):
     return _ws[key]
 
 
-def fit_batch(objects, config, preprocessed=None, raise_errors=True):
+def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=None):
     """fitter_ccf.fit for many objects.  objects: list of lists of SpecData.
     preprocessed: optional list (per object) of dicts setup -> (proc_spec,
     proc_ivar) that bypasses the host-side continuum fit.  Returns a list of the
@@ -144,18 +144,20 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True):
             if b.ntempl != ref.ntempl:
                 raise RuntimeError('CCF template counts are inconsistent across setups')
     ntempl = next(iter(banks.values())).ntempl
-    # host preprocessing (row f3): proc[i][a] = (proc_spec, proc_ivar)
-    proc = []
+    # host preprocessing (row f3): proc[i][a] = (proc_spec, proc_ivar); the continuum fits
+    # of a batch run in a pool of host processes (make_ccf.preprocess_many)
+    jobs, where = [], []
+    proc = [[None] * len(o) for o in objects]
     for i, o in enumerate(objects):
-        cur = []
-        for sd in o:
+        for a, sd in enumerate(o):
             if preprocessed is not None:
-                cur.append(tuple(np.asarray(_, dtype=np.float64) for _ in preprocessed[i][sd.name]))
+                proc[i][a] = tuple(np.asarray(_, dtype=np.float64)
+                                   for _ in preprocessed[i][sd.name])
             else:
-                cur.append(make_ccf.preprocess_data(sd.lam, sd.spec, sd.espec,
-                                                    badmask=sd.badmask,
-                                                    ccfconf=banks[sd.name].ccfconf))
-        proc.append(cur)
+                jobs.append((sd.lam, sd.spec, sd.espec, sd.badmask, banks[sd.name].ccfconf))
+                where.append((i, a))
+    for (i, a), res in zip(where, make_ccf.preprocess_many(jobs, workers)):
+        proc[i][a] = res
     d_vg = _dev.upload(vel_grid, np.float64)
     block = max(1, int(CHISQ_BLOCK_BYTES // (ntempl * nvel * 8)))
     results = [None] * nobj

@@ -8,7 +8,9 @@ SURVEY.md section 8 row f3 ("next"): they stay on the host (numpy / scipy, as in
 the reference) and feed the device path in fitter_ccf.py with the
 continuum-normalised spectrum and inverse variance on the CCF pixel grid.
 """
+import atexit
 import logging
+import os
 
 import numpy as np
 import scipy.interpolate
@@ -109,6 +111,53 @@ def preprocess_data(lam, spec0, espec, ccfconf=None, badmask=None, maxerr=10):
     il, ir = ivar[li], ivar[ri]
     out_ivar[inside] = il * ir / (wl**2 * ir + wr**2 * il + ((il * ir) == 0).astype(int))
     return out_spec, out_ivar
+
+
+# ---- many spectra: the continuum fit is ~40 ms of scipy per arm, so a batch of survey
+# size is preprocessed by a pool of host processes, one (object, arm) per task -- what the
+# reference's drivers do with whole objects (desi/desi_fit.py:1475-1479, OMP_NUM_THREADS=1)
+_pool = None
+
+
+def _pool_init():
+    try:
+        import threadpoolctl
+        _pool_init.limit = threadpoolctl.threadpool_limits(1)
+    except ImportError:
+        pass
+
+
+def _preprocess_job(job):
+    lam, spec, espec, badmask, ccfconf = job
+    return preprocess_data(lam, spec, espec, ccfconf=ccfconf, badmask=badmask)
+
+
+def _close_pool():
+    global _pool
+    if _pool is not None:
+        _pool[1].shutdown(wait=False, cancel_futures=True)
+        _pool = None
+
+
+def preprocess_many(jobs, workers=None):
+    """preprocess_data for a list of (lam, spec, espec, badmask, ccfconf) in a persistent
+    pool of `workers` spawned processes (default: the host's cores, at most 32; serial
+    below 16 jobs).  Same values as the serial loop, in job order."""
+    jobs = list(jobs)
+    if workers is None:
+        workers = min(os.cpu_count() or 1, 32) if len(jobs) >= 16 else 1
+    if workers <= 1 or len(jobs) < 2:
+        return [_preprocess_job(j) for j in jobs]
+    global _pool
+    if _pool is None or _pool[0] != workers:
+        import concurrent.futures as cf
+        import multiprocessing as mp
+        _close_pool()
+        _pool = (workers, cf.ProcessPoolExecutor(workers, mp_context=mp.get_context('spawn'),
+                                                 initializer=_pool_init))
+        atexit.register(_close_pool)
+    chunk = max(1, len(jobs) // (8 * workers))
+    return list(_pool[1].map(_preprocess_job, jobs, chunksize=chunk))
 
 
 def preprocess_model(logl, lammodel, model0, vsini=None, ccfconf=None, broaden=None):

@@ -138,3 +138,22 @@ def test_resolution_matrix_host_side(golden):
     # spectra sharing one matrix object share its band rows
     sd2 = spec_fit.SpecData(nm, lam, sp * 2, es, badmask=bad, resolution=rm)
     assert sd2._band is v1[0]._band
+
+
+def test_preprocess_many_pool_equals_serial(golden):
+    """The pool of host processes returns exactly what the serial loop does, in order."""
+    g = golden('ccf')
+    jobs = []
+    for tag in ('rvs', 'two'):
+        for o in unpack_objects(g, tag + '_'):
+            for nm, lam, sp, es, bad in o['arms']:
+                c = g[f'{tag}_{nm}_conf']
+                jobs.append((lam, sp, es, bad, make_ccf.get_ccf_config(c[0], c[1], int(c[2]))))
+    jobs = (jobs * 3)[:8]
+    serial = make_ccf.preprocess_many(jobs, workers=1)
+    pooled = make_ccf.preprocess_many(jobs, workers=2)
+    again = make_ccf.preprocess_many(jobs[::-1], workers=2)[::-1]     # persistent pool
+    make_ccf._close_pool()
+    for a, b, c in zip(serial, pooled, again):
+        for k in range(2):
+            assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k])
