@@ -331,15 +331,6 @@ __device__ __forceinline__ void prefetch_l1(const void *p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
-// grid values of one 16-byte load as the doubles the (scaled) weights multiply
-__device__ __forceinline__ void widen_row(const float4 &v, double out[4]) {
-  out[0] = widen_f32_scaled(v.x); out[1] = widen_f32_scaled(v.y);
-  out[2] = widen_f32_scaled(v.z); out[3] = widen_f32_scaled(v.w);
-}
-__device__ __forceinline__ void widen_row(const double2 &v, double out[4]) {
-  out[0] = v.x; out[1] = v.y;
-}
-
 template <typename GT, int NV, bool TMA>
 __global__ void __launch_bounds__(CK_THREADS, TMA ? CK_MINB_TMA : CK_MINB)
 chunk_kernel(const ChunkArgs a, const __grid_constant__ CUtensorMap tmap) {
@@ -407,11 +398,9 @@ chunk_kernel(const ChunkArgs a, const __grid_constant__ CUtensorMap tmap) {
     const int pos = (int)((q - a.q0) * a.qstep_inv);
     return max(0, min(pos, n - 2));
   };
-  // fp32 grids: the weights carry the 2^896 of widen_f32_scaled (exact: they are <= 1)
-  constexpr double WSC = sizeof(GT) == 4 ? WIDEN_SCALE : 1.0;
   if (lane < a.nvert) {
     s_off[wid][lane] = (int64_t)a.ids[(int64_t)k * a.nvert + lane] * a.ld;
-    s_w[wid][lane] = a.w[(int64_t)k * a.nvert + lane] * WSC;
+    s_w[wid][lane] = a.w[(int64_t)k * a.nvert + lane];
   }
   __syncwarp();
   // single-row item (off-grid nearest node): exp rounded to the row's precision
@@ -483,25 +472,23 @@ chunk_kernel(const ChunkArgs a, const __grid_constant__ CUtensorMap tmap) {
         if (lane == 0 && t + TMA_NSTG - 1 < nstep) issue(t + TMA_NSTG - 1);
         wait(slot, parity);
         const char *stg = ring + slot * TMA_STG_BYTES;
-        auto add_row = [&](int r) {
-          const double wj = s_w[wid][hf * TMA_ROWS + r];
-          if constexpr (TV == 4) {
-            const float4 v = *reinterpret_cast<const float4 *>(stg + r * (TMA_COLS * 4));
-            acc[0] = fma(wj, widen_f32_scaled(v.x), acc[0]);
-            acc[1] = fma(wj, widen_f32_scaled(v.y), acc[1]);
-            acc[2] = fma(wj, widen_f32_scaled(v.z), acc[2]);
-            acc[3] = fma(wj, widen_f32_scaled(v.w), acc[3]);
-          } else {
-            const float2 v = *reinterpret_cast<const float2 *>(stg + r * (TMA_COLS * 4));
-            acc[0] = fma(wj, widen_f32_scaled(v.x), acc[0]);
-            acc[1] = fma(wj, widen_f32_scaled(v.y), acc[1]);
-          }
-        };
-        if (!f32row) {  // one (warp-uniform) branch per stage, not per row
 #pragma unroll
-          for (int r = 0; r < TMA_ROWS; r++) add_row(r);
-        } else if (hf == 0) {
-          add_row(0);  // a single-row item uses its row alone (no 0 x neighbour products)
+        for (int r = 0; r < TMA_ROWS; r++) {
+          // a single-row item uses its row alone (no 0 x neighbour products)
+          if (!f32row || (hf == 0 && r == 0)) {
+            const double wj = s_w[wid][hf * TMA_ROWS + r];
+            if constexpr (TV == 4) {
+              const float4 v = *reinterpret_cast<const float4 *>(stg + r * (TMA_COLS * 4));
+              acc[0] = fma(wj, (double)v.x, acc[0]);
+              acc[1] = fma(wj, (double)v.y, acc[1]);
+              acc[2] = fma(wj, (double)v.z, acc[2]);
+              acc[3] = fma(wj, (double)v.w, acc[3]);
+            } else {
+              const float2 v = *reinterpret_cast<const float2 *>(stg + r * (TMA_COLS * 4));
+              acc[0] = fma(wj, (double)v.x, acc[0]);
+              acc[1] = fma(wj, (double)v.y, acc[1]);
+            }
+          }
         }
         __syncwarp();  // every lane has read the stage: it may be overwritten
         if (++slot == TMA_NSTG) { slot = 0; parity ^= 1; }
@@ -586,7 +573,7 @@ chunk_kernel(const ChunkArgs a, const __grid_constant__ CUtensorMap tmap) {
           if (have) {
             const Raw v = *reinterpret_cast<const Raw *>(ring + (row % RG) * 512);
             double r[4];
-            widen_row(v, r);
+            RowLoader<GT>::widen(v, r);
             const double wj = s_w[wid][row];
 #pragma unroll
             for (int e = 0; e < VEC; e++) acc[e] = fma(wj, r[e], acc[e]);
@@ -616,7 +603,7 @@ chunk_kernel(const ChunkArgs a, const __grid_constant__ CUtensorMap tmap) {
           if (have) {
             const Raw v = *reinterpret_cast<const Raw *>(ring + slot * 512);
             double r[4];
-            widen_row(v, r);
+            RowLoader<GT>::widen(v, r);
             const double wj = s_w[wid][row];
 #pragma unroll
             for (int e = 0; e < VEC; e++) acc[e] = fma(wj, r[e], acc[e]);

@@ -61,31 +61,6 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
-// Grid float -> double without the conversion unit.  F2F.F64.F32 issues on the XU pipe
-// (about 4 lanes per clock and SM for 64-bit results) and the template gather needs one
-// per grid value, 16 per knot: ncu shows that pipe saturated in chunk_kernel
-// (sm__inst_executed_pipe_xu).  widen_f32_scaled returns x * 2^-896 EXACTLY, built on the
-// integer pipes: the double with the float's sign, its exponent FIELD unchanged (so the
-// value is scaled by 2^(127-1023)) and its mantissa moved up 29 bits -- zero stays zero,
-// float subnormals become double subnormals of the same scaled value.  The caller folds
-// the factor 2^896 into the (double) weight it multiplies with: fma(w * 2^896, x * 2^-896,
-// acc) forms the same exact product as fma(w, x, acc) and rounds once, so results are
-// bit-identical to the conversion instruction.  (Infinities / NaN in a grid row, which
-// only a broken product contains, come out as huge finite numbers: the template is then
-// flagged bad through its magnitude instead of its non-finiteness.)
-// -DRVS_F2F_XU restores the plain conversion (A/B measurements).
-#ifdef RVS_F2F_XU
-constexpr double WIDEN_SCALE = 1.0;
-__device__ __forceinline__ double widen_f32_scaled(float x) { return (double)x; }
-#else
-constexpr double WIDEN_SCALE = 0x1p896;
-__device__ __forceinline__ double widen_f32_scaled(float x) {
-  const uint32_t u = __float_as_uint(x);
-  const uint64_t b = (uint64_t)(u & 0x7fffffffu) << 29;
-  return __hiloint2double((int)((uint32_t)(b >> 32) | (u & 0x80000000u)), (int)(uint32_t)b);
-}
-#endif
-
 // read-only, L1-allocating global loads
 template <typename T>
 __device__ __forceinline__ T ldg(const T *p) {
