@@ -218,7 +218,10 @@ int rvs_basis_build(const double *d_lam, const int64_t *d_gstart, int G, int64_t
  * d_model: resampled template and continuum-multiplied model written at
  * d_moff[k] + p.  fast_interp != 0: the template value at a pixel is that of the
  * first knot >= the rest wavelength (get_chisq's fast_interp switch,
- * spec_fit.py:913-918) instead of the spline value. */
+ * spec_fit.py:913-918) instead of the spline value.  With resolution matrices
+ * (obs->d_resol) the resampled template T of every (item, trial) is replaced by
+ * R_obj T before the continuum fit (spec_fit.py:922-929); d_raw then receives R T,
+ * the reference's raw_models. */
 int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
                    const rvs_knots *knots, const rvs_obs *obs, const int32_t *d_oix,
                    const double *d_vels, int nv, int K, double *d_chisq, int32_t *d_status,
