@@ -314,11 +314,12 @@ def run_gpu(args):
     ms_e2e, _, _, _, _ = timed(step_e2e, max(1, min(args.steps, 2)), 2)
     e2e_eng.clear()
     n_e2e = max(1, min(args.steps, 2))
-    # per step: flux and error of every spectrum (2 x 8 B per pixel), one wavelength
-    # grid per arm (the objects of an arm share their pixels), offsets, and per
-    # evaluation call the (vel, vsini, 4 parameters) + arm index records
+    # per timed step (LikelihoodEngine.reload + hot path): flux and error of every spectrum
+    # (2 x 8 B per pixel, + the band rows of resolution matrices), the scan's velocity grids
+    # and start parameters, and per evaluation call the (vel, vsini, 4 parameters) + arm
+    # index records; wavelength grids and offsets went up with the engine (untimed first step)
     h2d = sum((2 + nd) * 8 * len(a[1]) for o in objects for a in o) + \
-        sum(8 * len(a[1]) for a in objects[0]) + \
+        B * (len(vgrid) * 8 + 6 * 8) + \
         (0 if args.mode == 'fit' else args.evals * B * (6 * 8 + 4 * len(setups)))
     d2h = int(np.asarray(out).nbytes) * world      # whole job, like `value`
     h2d *= world
