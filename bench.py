@@ -48,6 +48,15 @@ def make_config(w):
                 template_lib='synthetic/')
 
 
+def workload_string(wname):
+    """config.workload of both arms (GPU and --impl reference): the same string."""
+    w = WORKLOADS[wname]
+    g = synth.GRIDS[w['layout']]
+    nodes = int(np.prod([len(g[k]) for k in synth.PARNAMES]))
+    return (f'{wname}: arms {list(w["arms"])}, grid {w["layout"]} ({nodes} nodes, fp32), '
+            f'npoly {w["npoly"]}, RV grid [{w["min_vel"]}, {w["max_vel"]}) step 5 km/s')
+
+
 def grid_cache_path(wname, arm):
     d = '/dev/shm' if os.path.isdir('/dev/shm') else '/tmp'
     return os.path.join(d, f'rvs_bench_grid_{wname}_{arm}.npy')
@@ -159,7 +168,7 @@ def run_gpu(args):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from rvspecfit_b200 import _cabi, spec_fit, spec_inter, batch_fit, shard
+    from rvspecfit_b200 import _cabi, _dev, spec_fit, spec_inter, batch_fit, shard
     w = WORKLOADS[args.workload]
     cfg = make_config(w)
     B = args.batch
@@ -204,9 +213,10 @@ def run_gpu(args):
         """The step body on a ready engine; returns a small result array."""
         if args.mode == 'fit':
             return fit_records(batch_fit.process_batch(None, starts, config=cfg, options=opts,
-                                                       engine=eng, timer=timer))
+                                                       engine=eng, timer=timer,
+                                                       groups=args.groups or None))
         return batch_fit.scan_and_evaluate(eng, start, vgrid, tp, tv, tvs, timer=timer,
-                                           groups=args.groups)
+                                           groups=args.groups or 2)
 
     def step_resident(eng):
         return hot_path(eng)
@@ -238,8 +248,19 @@ def run_gpu(args):
         rec = hot_path(eng)                                          # D2H of the results
         e2e_parts['engine_load_s'].append(t1 - t0)
         e2e_parts['hot_path_s'].append(time.time() - t1)
-        # the one collective of the path: fixed-size result records of all ranks
-        return shard.gather_records(rec, B * world) if world > 1 else rec
+        e2e_recs.append(rec)
+        return rec
+
+    e2e_recs = []
+
+    def e2e_finish():
+        # the one collective of the path: the fixed-size result records of all ranks,
+        # gathered ONCE after the last step (inside the timed region) -- the ranks never
+        # wait for each other while they fit
+        if world > 1 and e2e_recs:
+            allrec = np.concatenate(e2e_recs)
+            return shard.gather_records(allrec, len(allrec) * world)
+        return None
 
     eng = spec_fit.LikelihoodEngine(host_objects, cfg, opts)
     L = _cabi.lib()
@@ -248,9 +269,9 @@ def run_gpu(args):
         # streams as in the bench
         import ctypes
         tp2, tv2, tvs2 = tp[:args.timeline], tv[:args.timeline], tvs[:args.timeline]
-        batch_fit.scan_and_evaluate(eng, start, vgrid[:8], tp2, tv2, tvs2, groups=args.groups)
+        batch_fit.scan_and_evaluate(eng, start, vgrid[:8], tp2, tv2, tvs2, groups=args.groups or 2)
         L.rvs_profile_enable(1)
-        batch_fit.scan_and_evaluate(eng, start, vgrid[:8], tp2, tv2, tvs2, groups=args.groups)
+        batch_fit.scan_and_evaluate(eng, start, vgrid[:8], tp2, tv2, tvs2, groups=args.groups or 2)
         buf = (ctypes.c_double * (3 * 4096))()
         n = L.rvs_profile_timeline(ctypes.cast(buf, ctypes.c_void_p), 4096)
         L.rvs_profile_enable(0)
@@ -276,7 +297,7 @@ def run_gpu(args):
         out = {k: dict(launches=int(c), us_per_launch=1e3 * t / max(1, c), ms_total=t)
                for k, t, c in zip(names, ms, n)}
         out['note'] = ('arms serialised on one stream; warm caches; per-launch = one arm, '
-                       f'{B // max(1, args.groups)} items')
+                       f'{B // max(1, args.groups or 2)} items')
         if rank == 0:
             print(json.dumps({'stage_profile': out}))
         return
@@ -286,11 +307,13 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, nsteps, nwarm, sample_clocks=False):
+    def timed(fn, nsteps, nwarm, sample_clocks=False, finish=None):
         for _ in range(nwarm):
             fn()
         timer.reset()
+        e2e_recs.clear()
         barrier()
+        io0 = list(_dev.IO_BYTES)
         l0 = L.rvs_launch_count() + glaunch()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clk = ClockSampler(local) if sample_clocks else None
@@ -298,9 +321,12 @@ def run_gpu(args):
         e0.record()
         for _ in range(nsteps):
             out = fn()
+        if finish is not None:
+            finish()
         e1.record()
         barrier()
         t1 = time.time()
+        timed.io = [(b - a) / nsteps for a, b in zip(io0, _dev.IO_BYTES)]
         ms = e0.elapsed_time(e1)
         clocks = clk.stop(t0, t1) if clk else None
         if world > 1:
@@ -311,18 +337,17 @@ def run_gpu(args):
 
     ms, launches, clocks, out, ksum = timed(lambda: step_resident(eng), args.steps, args.warmup,
                                             sample_clocks=True)
-    ms_e2e, _, _, _, _ = timed(step_e2e, max(1, min(args.steps, 2)), 2)
+    # end to end: every requested step again, from host arrays (the first warm-up step
+    # builds the persistent engine)
+    n_e2e = args.steps
+    ms_e2e, _, _, _, _ = timed(step_e2e, n_e2e, max(2, min(args.warmup, 3)), finish=e2e_finish)
     e2e_eng.clear()
-    n_e2e = max(1, min(args.steps, 2))
-    # per timed step (LikelihoodEngine.reload + hot path): flux and error of every spectrum
-    # (2 x 8 B per pixel, + the band rows of resolution matrices), the scan's velocity grids
-    # and start parameters, and per evaluation call the (vel, vsini, 4 parameters) + arm
-    # index records; wavelength grids and offsets went up with the engine (untimed first step)
-    h2d = sum((2 + nd) * 8 * len(a[1]) for o in objects for a in o) + \
-        B * (len(vgrid) * 8 + 6 * 8) + \
-        (0 if args.mode == 'fit' else args.evals * B * (6 * 8 + 4 * len(setups)))
-    d2h = int(np.asarray(out).nbytes) * world      # whole job, like `value`
-    h2d *= world
+    # bytes per timed step, counted where the copies are made (_dev.IO_BYTES): flux and
+    # error of every spectrum through LikelihoodEngine.reload (+ band rows of resolution
+    # matrices), the velocity grids / parameters / arm indices of every scan and evaluation
+    # call, and back the chi-squares, flags, scan statistics and best-fit models; whole job
+    h2d = int(timed.io[0]) * world
+    d2h = int(timed.io[1]) * world
 
     peaks = {}
     try:
@@ -353,25 +378,38 @@ def run_gpu(args):
         ncall = max(1, ksum.get('fused_eval_launches', 1))
         roof = dict(bound='hbm', kernel=kern_txt, achieved=ach, peak=hbm_peak, unit='GB/s',
                     frac=ach / hbm_peak,
-                    traffic=None if traffic is None else traffic * (B // max(1, args.groups)),
-                    traffic_bytes_per_eval=traffic, peak_source=peak_src,
+                    traffic=None if traffic is None else traffic * (B // max(1, args.groups or 2)),
+                    traffic_bytes_per_eval=traffic,
+                    traffic_source='static: ncu --set full capture of a 1024-item call, '
+                                   'profiles/r1w_traffic.json (not re-measured in this run)',
+                    peak_source=peak_src,
                     algorithmic_bytes_per_eval=beval, evals_timed=evals,
                     ms_total=ksum['eval_phase_ms_total'],
                     ms_per_call=ksum['eval_phase_ms_total'] / ncall,
                     items_per_call=ksum.get('fused_eval_items_per_launch'),
                     timing='CUDA events around the evaluation phase of every step')
     elif ksum.get('fused_eval_ms_total'):
-        # complete-fit mode: per evaluation call, events on the stream the arms fork
-        # from and join to (calls may overlap: the sum over-counts time)
+        # complete-fit mode: CUDA events around every evaluation call, on the stream its
+        # arms fork from and join to.  The lock-step sets of a step keep several calls in
+        # flight at once, so the time the evaluation kernels had the device is the UNION of
+        # the calls' [start, end] intervals, not their sum; RV scans of other sets that run
+        # inside those intervals are not subtracted (their time counts against the figure)
         evals = ksum['fused_eval_items_per_launch'] * ksum['fused_eval_launches']
-        ach = beval * evals / (ksum['fused_eval_ms_total'] * 1e-3) / 1e9
+        ach = beval * evals / (ksum['fused_eval_ms_busy'] * 1e-3) / 1e9
         roof = dict(bound='hbm', kernel=kern_txt, achieved=ach, peak=hbm_peak, unit='GB/s',
-                    frac=ach / hbm_peak, traffic=None,
+                    frac=ach / hbm_peak,
+                    traffic=None if traffic is None else traffic * ksum['fused_eval_items_per_launch'],
+                    traffic_bytes_per_eval=traffic,
+                    traffic_source='static: ncu --set full capture of a 1024-item call, '
+                                   'profiles/r1w_traffic.json (not re-measured in this run)',
                     peak_source=peak_src, algorithmic_bytes_per_eval=beval,
-                    evals_timed=evals, ms_total=ksum['fused_eval_ms_total'],
+                    evals_timed=evals, ms_busy=ksum['fused_eval_ms_busy'],
+                    ms_sum_of_calls=ksum['fused_eval_ms_total'],
                     ms_per_call=ksum['fused_eval_ms_per_launch'],
                     items_per_call=ksum['fused_eval_items_per_launch'],
-                    timing='CUDA events around every evaluation call')
+                    share_of_step=ksum['fused_eval_ms_busy'] / ms,
+                    timing='CUDA events around every evaluation call; busy time = union '
+                           'of the call intervals over the timed steps')
     nspec_total = B * world
     per_step = ms / args.steps
     fit = args.mode == 'fit'
@@ -387,11 +425,12 @@ def run_gpu(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: arms {list(w["arms"])}, {npo} obs px, '
-                               f'{npt} template px, grid {w["layout"]} '
-                               f'({setups[0]["dats"].shape[0]} nodes, fp32), npoly {w["npoly"]}',
+        'config': {'workload': workload_string(args.workload),
+                   'obs_px': npo, 'template_px': npt,
                    'spectra_per_gpu_per_step': B, 'rv_trials': len(vgrid),
-                   'fit_evals_per_spectrum': args.evals, 'lockstep_groups': args.groups,
+                   'fit_evals_per_spectrum': (eng.n_eval / (args.steps + args.warmup) / B
+                                              if fit else args.evals),
+                   'lockstep_groups': (args.groups if args.groups else 'auto'),
                    'mode': args.mode, 'step': step_txt, 'resolution_matrix_diagonals': nd,
                    'l2': 'template grid (>=0.7 GB per arm) is larger than L2; rows gathered '
                          'at random per evaluation',
@@ -523,8 +562,7 @@ def run_reference(args):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cb['wall_s'] * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': f'{args.workload}: arms {setups}', 'mode': args.mode,
-                       'fit_evals_per_spectrum': args.evals},
+            'config': {'workload': workload_string(args.workload), 'mode': args.mode},
             'cpu_baseline': cb,
             'e2e': {'value': v, 'unit': 'spectra/s', 'h2d_bytes_per_step': 0,
                     'd2h_bytes_per_step': 0}}
@@ -550,10 +588,11 @@ def main():
                     help='diagnostic: kernel start/end times of this many evaluation rounds')
     ap.add_argument('--stage-profile', action='store_true',
                     help='diagnostic: CUDA-event time of every kernel of the evaluation call')
-    ap.add_argument('--mode', default='proxy', choices=['proxy', 'fit'],
-                    help='proxy: scan + fixed count of evaluations; fit: complete fits')
-    ap.add_argument('--groups', type=int, default=2,
-                    help='independent object groups stepped in ping-pong (host/GPU overlap)')
+    ap.add_argument('--mode', default='fit', choices=['fit', 'proxy'],
+                    help='fit: complete vel_fit.process fits (the headline); proxy: one RV scan '
+                         '+ a fixed count of evaluations at pre-generated points (kernel study)')
+    ap.add_argument('--groups', type=int, default=0,
+                    help='independent lock-step sets of objects in flight (0: automatic)')
     args = ap.parse_args()
     if args.stage_profile:
         # per-kernel times are only meaningful when nothing else runs beside the kernel:

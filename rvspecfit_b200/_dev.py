@@ -7,6 +7,11 @@ import numpy as np
 from . import _cabi
 
 
+# bytes moved between host and device by this process: [host->device, device->host]
+# (bench.py reports them per step for the end-to-end figure)
+IO_BYTES = [0, 0]
+
+
 def torch_mod():
     return _cabi.require_cuda()
 
@@ -20,6 +25,7 @@ def upload(a, dtype):
     """numpy -> device tensor (contiguous, given numpy dtype)."""
     torch = torch_mod()
     a = np.ascontiguousarray(a, dtype=dtype)
+    IO_BYTES[0] += a.nbytes
     return torch.from_numpy(a).to(device(), non_blocking=False)
 
 
@@ -34,6 +40,7 @@ def upload_concat(arrays, dtype):
     host = pin.numpy()
     if n:
         np.concatenate(arrays, out=host)
+    IO_BYTES[0] += host.nbytes
     return host, pin.to(device(), non_blocking=True)
 
 
@@ -68,4 +75,5 @@ def stream():
 
 
 def download(t):
+    IO_BYTES[1] += t.numel() * t.element_size()
     return t.detach().cpu().numpy()

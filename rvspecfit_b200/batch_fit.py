@@ -13,19 +13,19 @@ rules of the single-object path:
     reflection point of every active object (one launch), then the expansion /
     contraction points of those that ask for one (one launch), then the shrunk
     simplices (one launch);
-  * BFGS *is* scipy's `minimize(method='BFGS')`, one instance per object on its
-    own thread; every function value and every finite-difference gradient
-    (scipy's `workers` hook of approx_derivative) blocks on a coordinator that
-    gathers the requests of all live objects into one launch;
-  * the Hessian is the same central-difference routine as vel_fit, its
-    evaluation points recorded, evaluated in one launch and replayed.
+  * BFGS is scipy's `_minimize_bfgs` with its MINPACK line search, restated
+    over arrays of problems (batch_bfgs.bfgs_steps): one function value and one
+    forward-difference gradient per live problem and round, in one launch;
+  * the Hessian is the same central-difference stencil as vel_fit's, all
+    objects' points in one launch.
+The objects are split into a few lock-step sets, each a coroutine that yields
+its evaluation requests (fit_steps); run_pipeline keeps one request of every
+set in flight, so the host logic of one set and the latency-bound tail of
+another (few live problems) hide under the device work of the rest.
 """
-import threading
-
 import numpy as np
-import scipy.optimize
 
-from . import _dev, spec_fit, spec_inter, vel_fit
+from . import _dev, batch_bfgs, spec_fit, spec_inter, vel_fit
 
 
 class KernelTimer:
@@ -61,6 +61,16 @@ class KernelTimer:
             out[name + '_ms_total'] = float(np.sum(ms))
             out[name + '_ms_per_launch'] = float(np.mean(ms))
             out[name + '_items_per_launch'] = float(np.mean([r[3] for r in rs]))
+            # launches of concurrent lock-step sets overlap on the device: the time
+            # during which at least one of them was running
+            t0 = rs[0][1]
+            iv = sorted((t0.elapsed_time(r[1]), t0.elapsed_time(r[2])) for r in rs)
+            busy, end = 0.0, -np.inf
+            for a, b in iv:
+                if b > end:
+                    busy += b - max(a, end)
+                    end = b
+            out[name + '_ms_busy'] = float(busy)
         return out
 
 
@@ -154,44 +164,72 @@ class BatchObjective:
 
     def chisq0(self, idx, vel, vsini, params):
         """chisq_func0: priors + -2 log L."""
+        return self.submit0(idx, vel, vsini, params)()
+
+    def submit0(self, idx, vel, vsini, params):
+        """Start chisq_func0 (vel_fit.py:210-230) for K (object, point) pairs; returns
+        a waiter."""
+        idx = np.asarray(idx, dtype=np.int64)
         self.nfev += len(idx)
-        chi = self.eng.evaluate(idx, vel, params, vsini)
-        return self.prior_term(params) + chi
+        return _Waiter(self._start(idx, vel, params, vsini), None, self.prior_term(params), 0.0,
+                       len(idx))
 
     def __call__(self, idx, X):
         """chisq_func for K pairs: idx (K,) object indices, X (K, N)."""
         return self.submit(idx, X)()
 
+    def _start(self, idx, vel, params, vsini):
+        if hasattr(self.eng, 'submit'):
+            return self.eng.submit(idx, vel, params, vsini)
+        return _Done(self.eng.evaluate(idx, vel, params, vsini))    # blocking engines
+
     def submit(self, idx, X):
-        """Start the evaluation of chisq_func for K pairs and return a callable that
-        waits for the values (same arithmetic as __call__: priors + -2 log L +
-        penalty, 1e30 behind the hard walls, vel_fit.py:210-257)."""
+        """Start the evaluation of chisq_func for K pairs and return a waiter: a
+        callable that gives the values (priors + -2 log L + penalty, 1e30 behind the
+        hard walls, vel_fit.py:210-257), with ready() telling whether it would block."""
         idx = np.asarray(idx, dtype=np.int64)
         vel, vsini, params, pen = self.unpack(idx, X)
         wall = (vel > self.max_vel) | (vel < self.min_vel) | ~np.isfinite(params).all(axis=1)
         ok = ~wall
+        if ok.all():
+            self.nfev += len(idx)
+            return _Waiter(self._start(idx, vel, params, vsini), None, self.prior_term(params),
+                           pen, len(idx))
         pend = None
         if ok.any():
             self.nfev += int(ok.sum())
-            if hasattr(self.eng, 'submit'):
-                pend = self.eng.submit(idx[ok], vel[ok], params[ok],
-                                       None if vsini is None else vsini[ok])
-            else:       # engines with a blocking evaluate only
-                class _Done:
-                    def __init__(self, v):
-                        self.v = v
+            pend = self._start(idx[ok], vel[ok], params[ok], None if vsini is None else vsini[ok])
+        return _Waiter(pend, ok, self.prior_term(params[ok]), pen[ok], len(idx))
 
-                    def result(self):
-                        return self.v
-                pend = _Done(self.eng.evaluate(idx[ok], vel[ok], params[ok],
-                                               None if vsini is None else vsini[ok]))
 
-        def wait():
-            out = np.full(len(idx), 1e30)
-            if pend is not None:
-                out[ok] = self.prior_term(params[ok]) + pend.result() + pen[ok]
-            return out
-        return wait
+class _Done:
+    def __init__(self, v):
+        self.v = v
+
+    def result(self):
+        return self.v
+
+    def ready(self):
+        return True
+
+
+class _Waiter:
+    """Values of a started objective evaluation: 1e30 behind the walls (`ok` False),
+    additive host terms + the engine's -2 log L elsewhere."""
+
+    def __init__(self, pend, ok, prior, pen, n):
+        self.pend, self.ok, self.prior, self.pen, self.n = pend, ok, prior, pen, n
+
+    def ready(self):
+        return self.pend is None or self.pend.ready()
+
+    def __call__(self):
+        if self.ok is None:
+            return self.prior + self.pend.result() + self.pen
+        out = np.full(self.n, 1e30)
+        if self.pend is not None:
+            out[self.ok] = self.prior + self.pend.result() + self.pen
+        return out
 
 
 # below this many active problems an iteration's candidate points go out in one call
@@ -342,215 +380,60 @@ def nelder_mead_interleaved(fsubmit, sims, groups=2, xatol=1e-2, fatol=1e-3, max
     return res
 
 
-# ------------------------------------------------- scipy BFGS, many at a time
-class _Coordinator:
-    """Gathers the blocking evaluation requests of many worker threads into one
-    batched call.  A round is evaluated when every live worker has a request
-    pending."""
+# ------------------------------------------------------------ pipeline driver
+class _Ready:
+    """Waiter of a request that was served when it was made."""
 
-    def __init__(self, fbatch, ids):
-        self.fbatch = fbatch
-        self.lock = threading.Lock()
-        self.ready = threading.Event()
-        self.events = {i: threading.Event() for i in ids}
-        self.pending, self.results = {}, {}
-        self.live = len(ids)
-        self.rounds = 0
+    def __init__(self, value):
+        self.value = value
 
-    def request(self, wid, X):
-        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
-        with self.lock:
-            self.pending[wid] = X
-            if len(self.pending) >= self.live:
-                self.ready.set()
-        ev = self.events[wid]
-        ev.wait()
-        ev.clear()
-        return self.results.pop(wid)
+    def ready(self):
+        return True
 
-    def finished(self, wid):
-        with self.lock:
-            self.live -= 1
-            if self.live == 0 or len(self.pending) >= self.live:
-                self.ready.set()
-
-    def run(self):
-        while True:
-            self.ready.wait()
-            with self.lock:
-                self.ready.clear()
-                if self.live == 0 and not self.pending:
-                    return
-                if len(self.pending) < self.live:
-                    continue
-                batch, self.pending = self.pending, {}
-            wids = list(batch)
-            idx = np.concatenate([np.full(len(batch[w]), w) for w in wids])
-            vals = self.fbatch(idx, np.concatenate([batch[w] for w in wids]))
-            self.rounds += 1
-            pos = 0
-            for w in wids:
-                n = len(batch[w])
-                self.results[w] = vals[pos:pos + n]
-                pos += n
-                self.events[w].set()
+    def __call__(self):
+        return self.value
 
 
-def bfgs_batch(fbatch, x0s, hess_inv0, ids=None):
-    """scipy.optimize.minimize(method='BFGS', options=dict(hess_inv0=...)) for every
-    row of x0s, the instances running concurrently and sharing launches.  Returns
-    the list of scipy OptimizeResult objects."""
-    x0s = np.asarray(x0s, dtype=np.float64)
-    ids = list(range(len(x0s))) if ids is None else list(ids)
-    coord = _Coordinator(fbatch, ids)
-    results, errors = {}, {}
-
-    def worker(wid, x0):
+def run_pipeline(gens, start):
+    """Advance several request-yielding coroutines, keeping one request of each
+    in flight.  `start(request)` begins serving a request and returns a waiter
+    (callable giving the answer, with ready() telling whether it would block).
+    Whichever coroutine's answer is ready first is advanced first, so host work
+    of one lock-step set overlaps the device work of the others.  Returns the
+    coroutines' return values in order."""
+    out = [None] * len(gens)
+    pending = []
+    for gi, gen in enumerate(gens):
         try:
-            def fun(x):
-                return float(coord.request(wid, x)[0])
+            pending.append((gi, start(next(gen))))
+        except StopIteration as stop:
+            out[gi] = stop.value
+    while pending:
+        pick = 0
+        for j, (_, w) in enumerate(pending):
+            if w.ready():
+                pick = j
+                break
+        gi, wait = pending.pop(pick)
+        try:
+            pending.append((gi, start(gens[gi].send(wait()))))
+        except StopIteration as stop:
+            out[gi] = stop.value
+    return out
 
-            def pmap(_f, it):
-                xs = [np.asarray(_) for _ in it]
-                if not xs:
-                    return []
-                return [float(_) for _ in coord.request(wid, np.array(xs))]
-            results[wid] = scipy.optimize.minimize(
-                fun, x0, method='BFGS', options=dict(hess_inv0=hess_inv0, workers=pmap))
-        except BaseException as exc:          # noqa: BLE001  (re-raised in the caller)
-            errors[wid] = exc
-        finally:
-            coord.finished(wid)
 
-    old = threading.stack_size(512 * 1024)
+def _drive(gen, sel):
+    """Run an optimiser coroutine (requests (idx, X) in its own problem numbers)
+    inside a fit coroutine: requests become ('f', objects, X)."""
     try:
-        threads = [threading.Thread(target=worker, args=(w, x0s[i]), daemon=True)
-                   for i, w in enumerate(ids)]
-        for t in threads:
-            t.start()
-    finally:
-        threading.stack_size(old)
-    coord.run()
-    for t in threads:
-        t.join()
-    if errors:
-        raise next(iter(errors.values()))
-    return [results[w] for w in ids]
-
-
-# ---- the same, with the per-object scipy drivers spread over worker processes
-def _bfgs_process_main(conn):
-    """Worker process: runs scipy BFGS for a subset of the objects (threads +
-    coordinator as above); every evaluation round is one message to the parent,
-    which owns the GPU.  Never touches CUDA."""
-    while True:
-        try:
-            job = conn.recv()
-        except EOFError:
-            return
-        if job is None:
-            return
-        ids, x0s, hess_inv0 = job
-
-        def remote(idx, X):
-            conn.send(('req', np.asarray(idx), np.asarray(X)))
-            return conn.recv()
-        try:
-            res = bfgs_batch(remote, x0s, hess_inv0, ids=ids)
-            conn.send(('done', {w: dict(r) for w, r in zip(ids, res)}))
-        except BaseException as exc:      # noqa: BLE001
-            conn.send(('error', repr(exc)))
-
-
-class _BfgsProcessPool:
-    def __init__(self, nproc):
-        import multiprocessing as mp
-        ctx = mp.get_context('spawn')
-        self.conns, self.procs = [], []
-        for _ in range(nproc):
-            parent, child = ctx.Pipe()
-            p = ctx.Process(target=_bfgs_process_main, args=(child,), daemon=True)
-            p.start()
-            child.close()
-            self.conns.append(parent)
-            self.procs.append(p)
-
-    def close(self):
-        for c in self.conns:
-            try:
-                c.send(None)
-            except (OSError, ValueError):
-                pass
-        for p in self.procs:
-            p.join(timeout=2)
-
-    def run(self, fbatch, x0s, hess_inv0):
-        B = len(x0s)
-        chunks = [c for c in np.array_split(np.arange(B), len(self.conns)) if len(c)]
-        live = {}
-        for conn, ch in zip(self.conns, chunks):
-            conn.send((list(map(int, ch)), x0s[ch], hess_inv0))
-            live[conn] = True
-        results = {}
-        while live:
-            reqs = []
-            for conn in list(live):
-                msg = conn.recv()
-                if msg[0] == 'req':
-                    reqs.append((conn, msg[1], msg[2]))
-                elif msg[0] == 'done':
-                    results.update(msg[1])
-                    del live[conn]
-                else:
-                    raise RuntimeError('BFGS worker failed: ' + msg[1])
-            if reqs:
-                vals = fbatch(np.concatenate([r[1] for r in reqs]),
-                              np.concatenate([r[2] for r in reqs]))
-                pos = 0
-                for conn, idx, _ in reqs:
-                    conn.send(vals[pos:pos + len(idx)])
-                    pos += len(idx)
-        return [scipy.optimize.OptimizeResult(results[i]) for i in range(B)]
-
-
-_bfgs_pool = None
-
-
-def bfgs_many(fbatch, x0s, hess_inv0, nproc=None):
-    """bfgs_batch, with the scipy drivers (pure Python, GIL-bound) spread over a
-    persistent pool of worker processes when there are enough objects."""
-    import atexit
-    import os
-    global _bfgs_pool
-    x0s = np.asarray(x0s, dtype=np.float64)
-    if nproc is None:
-        nproc = min(os.cpu_count() or 1, 16, len(x0s) // 32)
-    if nproc < 2:
-        return bfgs_batch(fbatch, x0s, hess_inv0)
-    if _bfgs_pool is None or len(_bfgs_pool.conns) != nproc:
-        if _bfgs_pool is not None:
-            _bfgs_pool.close()
-        _bfgs_pool = _BfgsProcessPool(nproc)
-        atexit.register(_bfgs_pool.close)
-    return _bfgs_pool.run(fbatch, x0s, hess_inv0)
+        idx, X = next(gen)
+        while True:
+            idx, X = gen.send((yield ('f', sel[idx], X)))
+    except StopIteration as stop:
+        return stop.value
 
 
 # ------------------------------------------------------------ the batched fit
-class _Replay:
-    """Records the points a routine asks for, then replays their values."""
-
-    def __init__(self):
-        self.pts, self.vals, self.i = [], None, 0
-
-    def __call__(self, x):
-        if self.vals is None:
-            self.pts.append(np.array(x, dtype=np.float64))
-            return 0.0
-        v = self.vals[self.i]
-        self.i += 1
-        return v
-
-
 def _scan_round(eng, idx, grids, params, vsini):
     """find_best (one template per object) for ragged velocity grids: chi-squares
     in one launch per arm, statistics on the device per distinct grid length.
@@ -566,58 +449,114 @@ def _scan_round(eng, idx, grids, params, vsini):
     return out
 
 
-def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None, priors=None,
-                  engine=None, timer=None):
-    """vel_fit.process for a list of objects (each a list of SpecData); same
-    arguments otherwise, paramDict0s one dictionary per object.  Returns the list
-    of result dictionaries of vel_fit.process.  `engine`: a LikelihoodEngine
-    already holding the objects on the device (then `objects` may be None)."""
-    if config is None:
-        raise RuntimeError('Config must be provided')
-    options = options or {}
-    fixParam = fixParam or []
-    if engine is not None:
-        objects = engine.objects
-    objects = [[o] if isinstance(o, spec_fit.SpecData) else list(o) for o in objects]
-    B = len(objects)
-    min_vel, max_vel = config['min_vel'], config['max_vel']
-    vel_step0, min_vel_step = config['vel_step0'], config['min_vel_step']
-    second_minimizer = config.get('second_minimizer') or False
-    eng = engine if engine is not None else spec_fit.LikelihoodEngine(objects, config, options)
-    eng.timer = timer
+def hessian_points(x, hs):
+    """Evaluation points of vel_fit.central_hessian for every row of x (B, n):
+    (B, npts, n), the centre first, then for the step sets hs and hs/2 the
+    +-e_i pairs and the four (+-e_i, +-e_j) corners of every j < i, in the
+    order that routine asks for them."""
+    x = np.asarray(x, dtype=np.float64)
+    B, n = x.shape
+    hs = np.asarray(hs, dtype=np.float64)
+    pts = [x]
+    for h in (hs / 2, hs):
+        for i in range(n):
+            for si in (1, -1):
+                p = x.copy()
+                p[:, i] = x[:, i] + si * h[i]
+                pts.append(p)
+            for j in range(i):
+                for si, sj in ((1, 1), (1, -1), (-1, 1), (-1, -1)):
+                    p = x.copy()
+                    p[:, i] = x[:, i] + si * h[i]
+                    p[:, j] = x[:, j] + sj * h[j]
+                    pts.append(p)
+    return np.stack(pts, axis=1)
+
+
+def hessian_from_values(vals, hs):
+    """vel_fit.central_hessian's arithmetic on the values at hessian_points:
+    vals (B, npts) -> (B, n, n)."""
+    hs = np.asarray(hs, dtype=np.float64)
+    n = len(hs)
+    B = len(vals)
+    f0 = vals[:, 0]
+    pos = 1
+    both = []
+    for h in (hs / 2, hs):
+        H = np.zeros((B, n, n))
+        for i in range(n):
+            fp, fm = vals[:, pos], vals[:, pos + 1]
+            pos += 2
+            H[:, i, i] = (fp - 2 * f0 + fm) / h[i]**2
+            for j in range(i):
+                fpp, fpm, fmp, fmm = (vals[:, pos + k] for k in range(4))
+                pos += 4
+                H[:, i, j] = H[:, j, i] = (fpp - fpm - fmp + fmm) / (4 * h[i] * h[j])
+        both.append(H)
+    return (4 * both[0] - both[1]) / 3
+
+
+def simplex_starts(best_vel, fobj, specParams, fixParam, fitVsini, max_vsini):
+    """vel_fit._get_simplex_start for every object: (B, N + 1, N)."""
+    cols, std = [best_vel], [5]
+    if fitVsini:
+        cols.append(np.clip(fobj.vsini0, 0, max_vsini))
+        std.append(3)
+    for j, name in enumerate(specParams):
+        if name not in fixParam:
+            cols.append(fobj.p0[:, j])
+            std.append(vel_fit.SIMPLEX_STD.get(name) or 0.5)
+    cur = np.stack(cols, axis=1)
+    std = np.array(std)
+    ndim = cur.shape[1]
+    R = np.random.RandomState(43434)        # the reference's fixed seed, vel_fit.py:306
+    noise = std[None, :] * R.normal(size=(ndim, ndim))
+    sims = np.empty((len(cur), ndim + 1, ndim))
+    sims[:, 0] = cur
+    sims[:, 1:] = cur[:, None, :] + noise[None]
+    return sims
+
+
+def fit_steps(sel, fobj, specParams, fixParam, fitVsini, has_vsini, config, phase):
+    """vel_fit.process (reference vel_fit.py:505-737) for the objects `sel` of
+    the engine as ONE coroutine: it yields requests
+        ('scan', objects, grids, params, vsini)   find_best on ragged RV grids
+        ('f', objects, X)                         chisq_func at fitted vectors X
+        ('f0', objects, vel, vsini, params)       chisq_func0 (priors + -2 log L)
+        ('model', objects, vel, params, vsini)    get_chisq(full_output=True)
+    is sent their answers, and returns a dict of per-object arrays.  Every object
+    follows the decision rules of the single-object path (see the module
+    docstring)."""
     import time
-    phase = {}
     t_last = [time.time()]
 
     def lap(name):
         now = time.time()
         phase[name] = phase.get(name, 0.0) + now - t_last[0]
         t_last[0] = now
-    setup0 = objects[0][0].name
-    specParams = list(spec_inter.getSpecParams(setup0, config))
-    has_vsini = 'vsini' in paramDict0s[0]
-    fitVsini = has_vsini and 'vsini' not in fixParam
-    vsiniMapper = vel_fit.VSiniMapper(config['max_vsini']) if fitVsini else None
-    fobj = BatchObjective(eng, specParams, paramDict0s, fixParam, fitVsini, config, priors)
-    allb = np.arange(B)
-    # 1. RV-grid scan at the starting parameters (vel_fit.py:579-590)
+    n = len(sel)
+    loc = np.arange(n)
+    min_vel, max_vel = config['min_vel'], config['max_vel']
+    vel_step0, min_vel_step = config['vel_step0'], config['min_vel_step']
+    p0 = fobj.p0[sel]
+    vs0 = fobj.vsini0[sel] if has_vsini else None
+    # 1. RV-grid scan at the starting parameters (vel_fit.py:579-602)
     vgrid = np.arange(min_vel, max_vel, vel_step0)
-    st = _scan_round(eng, allb, [vgrid] * B, fobj.p0,
-                     fobj.vsini0 if has_vsini else None)
+    st = yield ('scan', sel, [vgrid] * n, p0, vs0)
+    if not np.isfinite(st[:, :2]).all():
+        raise RuntimeError('The log(likelihood) value is not finite in the initial RV scan of '
+                           f'object(s) {sel[~np.isfinite(st[:, :2]).all(axis=1)].tolist()}')
     lap('scan0')
     # 2. Nelder-Mead, restarted once from its final simplex if it did not converge
-    sims = np.stack([vel_fit._get_simplex_start(
-        st[i, 1], fixParam=fixParam, specParamNames=specParams, paramDict0=paramDict0s[i],
-        vsiniMapper=vsiniMapper, fitVsini=fitVsini)[1] for i in range(B)])
-    minimize_success = np.ones(B, dtype=bool)
-    x = np.zeros((B, sims.shape[2]))
-    todo = allb
+    #    (vel_fit.py:628-650)
+    sims = simplex_starts(st[:, 1], _Sub(fobj, sel), specParams, fixParam, fitVsini,
+                          config['max_vsini'])
+    minimize_success = np.ones(n, dtype=bool)
+    x = np.zeros((n, sims.shape[2]))
+    todo = loc
     for attempt in range(2):
-        # two independent lock-step sets: the host advances one simplex set while the
-        # other's trial points are on the GPU
-        res = nelder_mead_interleaved(lambda i, X: fobj.submit(todo[i], X), sims[todo],
-                                      groups=2 if len(todo) >= 2 * NM_MIN_GROUP else 1,
-                                      speculate_below=SPECULATE_BELOW)
+        res = yield from _drive(nelder_mead_steps(sims[todo], speculate_below=SPECULATE_BELOW),
+                                sel[todo])
         x[todo] = res['x']
         sims[todo] = res['final_simplex']
         failed = todo[~res['success']]
@@ -628,24 +567,27 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
             break
     lap('nelder_mead')
     # 3. BFGS polish (vel_fit.py:653-658)
-    if second_minimizer:
+    if config.get('second_minimizer'):
         names = ['vel'] + (['vsini'] if fitVsini else []) + \
             [p for p in specParams if p not in fixParam]
-        bres = bfgs_many(fobj, x, vel_fit.get_hess_inv(names))
-        x = np.array([r['x'] for r in bres])
+        res = yield from _drive(batch_bfgs.bfgs_steps(x, vel_fit.get_hess_inv(names)), sel)
+        x = res['x']
     lap('bfgs')
-    vel, vsini, params, _ = fobj.unpack(allb, x)
+    vel, vsini, params, _ = fobj.unpack(sel, x)
     # 4. velocity posterior on shrinking grids (vel_fit.py:315-439), all objects per round
     best_vel = np.clip(vel, min_vel, max_vel)
-    lo, hi = np.full(B, float(min_vel)), np.full(B, float(max_vel))
-    step = np.full(B, float(vel_step0))
-    vstat = np.zeros((B, 5))
-    active = allb
+    lo, hi = np.full(n, float(min_vel)), np.full(n, float(max_vel))
+    step = np.full(n, float(vel_step0))
+    vstat = np.zeros((n, 5))
+    active = loc
     for _ in range(10):
         grids = [np.arange(np.ceil((lo[i] - best_vel[i]) / step[i]) * step[i],
                            hi[i] - best_vel[i], step[i]) + best_vel[i] for i in active]
-        s = _scan_round(eng, active, grids, params[active],
-                        None if vsini is None else vsini[active])
+        s = yield ('scan', sel[active], grids, params[active],
+                   None if vsini is None else vsini[active])
+        if not np.isfinite(s[:, :3]).all():
+            raise RuntimeError('RV refinement scan without a finite minimum for object(s) '
+                               f'{sel[active][~np.isfinite(s[:, :3]).all(axis=1)].tolist()}')
         vstat[active] = s
         best_vel[active] = s[:, 1]
         err = s[:, 2]
@@ -664,53 +606,120 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
             break
     lap('refine')
     # 5. model at the best point (vel_fit.py:688-696)
-    tot, info = eng.evaluate(allb, best_vel[:, None], params, vsini, want_model=True)
-    chi_best = tot[:, 0]
+    tot, info = yield ('model', sel, best_vel, params, vsini)
+    if not np.isfinite(tot).all():
+        raise RuntimeError('The log(likelihood) value is not finite at the best-fit point of '
+                           f'object(s) {sel[~np.isfinite(tot)].tolist()}')
     lap('model')
     # 6. Hessian over the atmospheric parameters at the optimiser's velocity and vsini
     #    (vel_fit.py:698-722: hess_func keeps best_param's own velocity)
     hsteps = [vel_fit.HESS_STEP[_] for _ in specParams]
-    recs = []
-    for i in range(B):
-        r = _Replay()
-        vel_fit.central_hessian(r, params[i], hsteps)
-        recs.append(r)
-    npts = [len(r.pts) for r in recs]
-    P = np.concatenate([np.array(r.pts) for r in recs])
-    ii = np.repeat(allb, npts)
-    vals = 0.5 * fobj.chisq0(ii, vel[ii], None if vsini is None else vsini[ii], P)
-    out, pos = [], 0
-    for i in range(B):
-        recs[i].vals = vals[pos:pos + npts[i]]
-        pos += npts[i]
-        hessian = vel_fit.central_hessian(recs[i], params[i], hsteps)
-        diag_err, covar, bad_hessian = vel_fit._uncertainties_from_hessian(hessian)
-        ret = dict(param=dict(zip(specParams, params[i])))
-        if fitVsini:
-            ret['vsini'] = vsini[i]
-        ret.update(vel=best_vel[i], vel_err=vstat[i, 2], vel_skewness=vstat[i, 3],
-                   vel_kurtosis=vstat[i, 4], param_err=dict(zip(specParams, diag_err)),
-                   param_covar=covar, minimize_success=bool(minimize_success[i]),
-                   bad_hessian=bad_hessian, chisq=float(chi_best[i]),
-                   logl=-0.5 * float(chi_best[i]), yfit=[], raw_models=[], chisq_array=[],
-                   npix_array=[])
-        for sd in objects[i]:
-            arm = info['arms'][sd.name]
-            j = int(np.nonzero(arm['sel'] == i)[0][0])
-            if arm['tbad'][j]:
-                ret['chisq_array'].append(np.nan)
-                ret['yfit'].append(np.zeros(len(sd.lam)) + np.nan)
-                continue
-            ex = arm['extras']
-            sl = slice(ex['moff'][j], ex['moff'][j + 1])
-            model, raw = ex['model'][sl], ex['raw'][sl]
-            good = ~sd.badmask
-            ret['yfit'].append(model)
-            ret['raw_models'].append(raw)
-            ret['chisq_array'].append(float(np.sum((((model - sd.spec) / sd.espec)[good])**2)))
-            ret['npix_array'].append(int(good.sum()))
-        out.append(ret)
+    P = hessian_points(params, hsteps)
+    npts = P.shape[1]
+    ii = np.repeat(loc, npts)
+    vals = yield ('f0', sel[ii], vel[ii], None if vsini is None else vsini[ii],
+                  P.reshape(n * npts, -1))
+    hess = hessian_from_values(0.5 * vals.reshape(n, npts), hsteps)
     lap('hessian')
-    eng.timer = None
+    return dict(sel=sel, x=x, vel=vel, vsini=vsini, params=params, best_vel=best_vel,
+                vstat=vstat, minimize_success=minimize_success, chisq=tot, info=info,
+                hessian=hess)
+
+
+class _Sub:
+    """The rows `sel` of a BatchObjective's per-object start values."""
+
+    def __init__(self, fobj, sel):
+        self.p0 = fobj.p0[sel]
+        self.vsini0 = fobj.vsini0[sel]
+
+
+# objects per lock-step set and sets in flight: enough sets that the tail of one (few
+# live problems, latency-bound calls) runs under the bulk of the others
+FIT_GROUP = 512
+FIT_MAX_GROUPS = 6
+
+
+def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None, priors=None,
+                  engine=None, timer=None, groups=None):
+    """vel_fit.process for a list of objects (each a list of SpecData); same
+    arguments otherwise, paramDict0s one dictionary per object.  Returns the list
+    of result dictionaries of vel_fit.process.  `engine`: a LikelihoodEngine
+    already holding the objects on the device (then `objects` may be None).
+    The objects are fitted as `groups` independent lock-step sets whose phases
+    interleave on the GPU (run_pipeline)."""
+    if config is None:
+        raise RuntimeError('Config must be provided')
+    options = options or {}
+    fixParam = fixParam or []
+    if engine is not None:
+        objects = engine.objects
+    objects = [[o] if isinstance(o, spec_fit.SpecData) else list(o) for o in objects]
+    B = len(objects)
+    eng = engine if engine is not None else spec_fit.LikelihoodEngine(objects, config, options)
+    eng.timer = timer
+    setup0 = objects[0][0].name
+    specParams = list(spec_inter.getSpecParams(setup0, config))
+    has_vsini = 'vsini' in paramDict0s[0]
+    fitVsini = has_vsini and 'vsini' not in fixParam
+    fobj = BatchObjective(eng, specParams, paramDict0s, fixParam, fitVsini, config, priors)
+    if groups is None:
+        groups = int(np.clip(B // FIT_GROUP, 1, FIT_MAX_GROUPS))
+    groups = max(1, min(groups, B, eng.NSLOT))
+    phase = {}
+    parts = [p for p in np.array_split(np.arange(B), groups) if len(p)]
+    gens = [fit_steps(p, fobj, specParams, fixParam, fitVsini, has_vsini, config, phase)
+            for p in parts]
+
+    def start(req):
+        kind = req[0]
+        if kind == 'f':
+            return fobj.submit(req[1], req[2])
+        if kind == 'f0':
+            return fobj.submit0(*req[1:])
+        if kind == 'scan':
+            return _Ready(_scan_round(eng, *req[1:]))
+        if kind == 'model':
+            _, idx, vel, params, vsini = req
+            return _Ready(eng.evaluate(idx, vel[:, None], params, vsini, want_model=True))
+        raise ValueError(kind)
+    try:
+        results = run_pipeline(gens, start)
+    finally:
+        eng.timer = None
+        eng.drain()
+    out = [None] * B
+    for r in results:
+        info = r['info']
+        tot = r['chisq'][:, 0]
+        rows = {name: {int(o): j for j, o in enumerate(arm['sel'])}
+                for name, arm in info['arms'].items()}
+        for k, i in enumerate(r['sel']):
+            diag_err, covar, bad_hessian = vel_fit._uncertainties_from_hessian(r['hessian'][k])
+            ret = dict(param=dict(zip(specParams, r['params'][k])))
+            if fitVsini:
+                ret['vsini'] = r['vsini'][k]
+            ret.update(vel=r['best_vel'][k], vel_err=r['vstat'][k, 2],
+                       vel_skewness=r['vstat'][k, 3], vel_kurtosis=r['vstat'][k, 4],
+                       param_err=dict(zip(specParams, diag_err)), param_covar=covar,
+                       minimize_success=bool(r['minimize_success'][k]),
+                       bad_hessian=bad_hessian, chisq=float(tot[k]), logl=-0.5 * float(tot[k]),
+                       yfit=[], raw_models=[], chisq_array=[], npix_array=[])
+            for sd in objects[i]:
+                arm = info['arms'][sd.name]
+                j = rows[sd.name][k]
+                if arm['tbad'][j]:
+                    ret['chisq_array'].append(np.nan)
+                    ret['yfit'].append(np.zeros(len(sd.lam)) + np.nan)
+                    continue
+                ex = arm['extras']
+                sl = slice(ex['moff'][j], ex['moff'][j + 1])
+                model, raw = ex['model'][sl], ex['raw'][sl]
+                good = ~sd.badmask
+                ret['yfit'].append(model)
+                ret['raw_models'].append(raw)
+                ret['chisq_array'].append(float(np.sum((((model - sd.spec) / sd.espec)[good])**2)))
+                ret['npix_array'].append(int(good.sum()))
+            out[i] = ret
     process_batch.last_phase_seconds = phase
     return out

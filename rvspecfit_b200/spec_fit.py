@@ -215,11 +215,13 @@ class SpectrumBatch:
         np.concatenate([s.espec for s in specdatas], out=self.h_espec)
         self.d_spec.copy_(torch.from_numpy(self.h_spec), non_blocking=True)
         self.d_espec.copy_(torch.from_numpy(self.h_espec), non_blocking=True)
+        _dev.IO_BYTES[0] += self.h_spec.nbytes + self.h_espec.nbytes
         self.h_bad = np.concatenate([s.badmask for s in specdatas])
         if self.d_resol is not None:
             np.concatenate(self._resol_blocks(specdatas, self.resol_offs.tolist()),
                            out=self.h_resol)
             self.d_resol.copy_(torch.from_numpy(self.h_resol), non_blocking=True)
+            _dev.IO_BYTES[0] += self.h_resol.nbytes
         for key, (dn, einv, sumlog2) in self._prod.items():
             rc = _cabi.lib().rvs_obs_prepare(
                 _dev.ptr(self.d_spec), _dev.ptr(self.d_espec), _dev.ptr(self.d_off), self.n, key,
@@ -285,6 +287,10 @@ GRAPH_LAUNCHES = [0]
 
 class PendingEval:
     """Handle of a LikelihoodEngine.submit() call."""
+
+    def ready(self):
+        """True when result() would not wait for the device."""
+        return self.slot is None or self.slot['event'].query()
 
     def result(self):
         eng, obj, vels, params, vs, outside_penalty, espec_systematic, raise_errors = self.args
@@ -396,6 +402,29 @@ class LikelihoodEngine:
         vmax = 0.0 if vs is None else float(np.max(vs, initial=0.0))
         return bank.tapcap(vmax) <= _cabi.MAX_FUSED_TAPS
 
+    def _tap_bound(self, vsini):
+        """Upper bound of vsini that sizes the tap buffers of a fused call, in coarse
+        steps (powers of two from 16 km/s) so that consecutive evaluations share one
+        launch configuration.  The rounded value is clamped to the largest one whose
+        rotation kernel still fits the fused path wherever the actual maximum does, so
+        that submit()'s gate and rvs_chisq_fused agree."""
+        vmax = 0.0 if vsini is None else float(np.max(vsini, initial=0.0))
+        if not vmax > 0:
+            return 0.0
+        rounded = float(max(16.0, 2.0 ** np.ceil(np.log2(vmax))))
+        banks = [self.arms[n]['bank'] for n in self.setups]
+        if all(b.tapcap(rounded) <= _cabi.MAX_FUSED_TAPS for b in banks):
+            return rounded
+        return vmax
+
+    def drain(self):
+        """Wait for every evaluation in flight and free its slot (used when a driver
+        stops early, e.g. on an exception, with submitted work it will not collect)."""
+        for sl in getattr(self, '_slots', []):
+            if sl['busy']:
+                sl['event'].synchronize()
+                sl['busy'] = False
+
     def _workspace(self, n):
         if getattr(self, '_ws', None) is None or self._ws.numel() < n:
             self._ws = _dev.empty((int(n * 1.25) + 1024,), np.float64)
@@ -499,7 +528,7 @@ class LikelihoodEngine:
             self._graph_epoch = getattr(self, '_graph_epoch', 0) + 1   # captured pointers are stale
         return t[:n].view(*shape)
 
-    NSLOT = 4      # evaluations that may be in flight at once (submit without result)
+    NSLOT = 8      # evaluations that may be in flight at once (submit without result)
 
     def _slot(self, K, narm, nd):
         """Pinned host staging + device input buffers of one in-flight evaluation."""
@@ -580,9 +609,7 @@ class LikelihoodEngine:
             h_oix[:, K:] = -1
         # upper bound of vsini that sizes the tap buffers, in coarse steps so that
         # consecutive evaluations share one launch configuration
-        vmax = 0.0 if vsini is None else float(np.max(vsini, initial=0.0))
-        if vmax > 0:
-            vmax = float(max(16.0, 2.0 ** np.ceil(np.log2(vmax))))
+        vmax = self._tap_bound(vsini)
         sl['ready'].record(torch.cuda.current_stream())
         sl['stream'].wait_event(sl['ready'])
         # The ~20 launches, copies and stream fork/joins of one evaluation are captured
@@ -623,6 +650,8 @@ class LikelihoodEngine:
             elif not done:
                 self._enqueue_fast(sl, obs_all, params, vmax, Kp, narm, nd)
             sl['seen'][key] = sl['seen'].get(key, 0) + 1
+            _dev.IO_BYTES[0] += (2 + nd) * Kp * 8 + narm * Kp * 4
+            _dev.IO_BYTES[1] += 2 * narm * Kp * (8 + 4)
             if t0 is not None:
                 self.timer.stop('fused_eval', t0, K)
             sl['event'].record()
@@ -716,8 +745,10 @@ class LikelihoodEngine:
             (vels > self.config['max_vel'])
         if outside_penalty and outside.any():
             # off-grid points were resolved on the device (nearest node); their
-            # penalty is added per arm as get_chisq does (spec_fit.py:895-896)
-            chi = outside * self.badchi[obj][None, :] + chi
+            # penalty is added once per arm the object HAS, as get_chisq does
+            # (spec_fit.py:879,895-896: one term per SpecData of the object)
+            present = self._oix[:, obj] >= 0
+            chi = np.where(present, outside * self.badchi[obj][None, :], 0.0) + chi
         total = np.add.reduce(chi, axis=0)
         sl['busy'] = False
         return total, redo
@@ -734,7 +765,7 @@ class LikelihoodEngine:
         vs = None if vsini is None else np.asarray(vsini, dtype=np.float64)
         fast = (vels.ndim == 1 and self.fused and self._fast_banks and len(obj) > 0
                 and (vs is None or
-                     all(self.arms[n]['bank'].tapcap(float(np.max(vs, initial=0.0)))
+                     all(self.arms[n]['bank'].tapcap(self._tap_bound(vs))
                          <= _cabi.MAX_FUSED_TAPS for n in self.setups)))
         pend = PendingEval()
         pend.args = (self, obj, vels, params, vs, outside_penalty, espec_systematic, raise_errors)

@@ -1,6 +1,7 @@
 """Host logic of the batched drivers, no GPU: the lock-step Nelder-Mead and the
-threaded BFGS pool must follow scipy's own trajectories bit for bit on an
-objective that is cheap to evaluate on the CPU."""
+lock-step BFGS must follow scipy's own trajectories bit for bit on objectives
+that are cheap to evaluate on the CPU, and the pipelined process_batch must
+reproduce vel_fit.process object by object."""
 import numpy as np
 import scipy.optimize
 
@@ -61,29 +62,200 @@ def test_lockstep_nelder_mead_is_scipy():
         assert np.array_equal(few['final_simplex'][b], want['final_simplex'][0])
 
 
-def test_threaded_bfgs_pool_is_scipy():
-    B, N = 16, 4
-    f_one, fbatch = _problems(B, N, 11)
-    rs = np.random.RandomState(5)
-    x0 = rs.normal(size=(B, N))
-    H0 = np.diag([1.0, 25.0, 0.01, 4.0])
-    calls = []
+def _noisy_problems(B, N, seed, noise):
+    """Smooth problems with values ~1e4 plus a rapidly varying term of the given
+    amplitude: the forward-difference gradient (step 1.5e-8) sees it as noise, which
+    drives scipy's BFGS through the fallback line search and the precision-loss exit
+    the way chi-square surfaces do."""
+    f_smooth, _ = _problems(B, N, seed)
 
-    def counted(idx, X):
-        calls.append(len(idx))
-        return fbatch(idx, X)
-    got = batch_fit.bfgs_batch(counted, x0, H0)
+    def f_one(b, x):
+        return 1e4 + f_smooth(b, x) + noise * np.sin(1e9 * x[0] + 3e8 * x[-1])
+
+    def fbatch(idx, X):
+        return np.array([f_one(int(b), x) for b, x in zip(idx, X)])
+    return f_one, fbatch
+
+
+def test_lockstep_bfgs_is_scipy():
+    import warnings
+    from rvspecfit_b200 import batch_bfgs
+    seen = set()
+    for B, N, seed, noise in ((24, 4, 11, 0.0), (24, 6, 5, 1e-7), (16, 6, 6, 1e-9),
+                              (16, 3, 7, 1e-5), (8, 6, 8, 1e-3), (8, 2, 9, 0.0)):
+        f_one, fbatch = _noisy_problems(B, N, seed, noise)
+        rs = np.random.RandomState(seed + 1)
+        x0 = rs.normal(size=(B, N))
+        H0 = np.diag(np.exp(rs.normal(size=N) * 2))
+        calls = []
+
+        def counted(idx, X):
+            calls.append(len(idx))
+            assert len(idx) % (N + 1) == 0
+            return fbatch(idx, X)
+        got = batch_bfgs.bfgs_lockstep(counted, x0, H0)
+        for b in range(B):
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                want = scipy.optimize.minimize(lambda x: f_one(b, x), x0[b], method='BFGS',
+                                               options=dict(hess_inv0=H0))
+            assert np.array_equal(got['x'][b], want['x']), (noise, b)
+            assert got['fun'][b] == want['fun'] and got['nit'][b] == want['nit']
+            assert got['status'][b] == want['status']
+            seen.add(int(want['status']))
+        # requests were gathered: far fewer batched calls than scalar evaluations
+        assert len(calls) == got['rounds'] and len(calls) < sum(calls) / 4
+    assert seen == {0, 2}      # both the converged and the precision-loss exit were met
+
+
+def test_hessian_points_replay_central_hessian():
+    """The vectorised Hessian stencil asks for exactly the points of
+    vel_fit.central_hessian and combines their values with its arithmetic."""
+    from rvspecfit_b200 import vel_fit
+    rs = np.random.RandomState(2)
+    B, n = 5, 4
+    x = rs.normal(size=(B, n)) * [300, 1, 1, 0.3] + [5000, 3, -1, 0.2]
+    hs = [vel_fit.HESS_STEP[k] for k in ('teff', 'logg', 'feh', 'alpha')]
+    A = rs.normal(size=(B, n, n))
+
+    def f(b, p):
+        d = (p - x[b]) / [100, 0.3, 0.2, 0.1] + 0.3
+        return float(d @ (A[b] @ A[b].T) @ d + np.sum(np.cos(d)))
+    P = batch_fit.hessian_points(x, hs)
+    vals = np.array([[f(b, p) for p in P[b]] for b in range(B)])
+    H = batch_fit.hessian_from_values(vals, hs)
     for b in range(B):
-        want = scipy.optimize.minimize(lambda x: f_one(b, x), x0[b], method='BFGS',
-                                       options=dict(hess_inv0=H0))
-        assert np.array_equal(got[b]['x'], want['x']), b
-        assert got[b]['fun'] == want['fun'] and got[b]['nit'] == want['nit']
-    # requests were gathered: far fewer batched calls than scalar evaluations
-    assert len(calls) < sum(calls) / 4
-    # the same through worker processes
-    got2 = batch_fit.bfgs_many(fbatch, x0, H0, nproc=2)
-    for b in range(B):
-        assert np.array_equal(got2[b]['x'], got[b]['x']) and got2[b]['nit'] == got[b]['nit']
+        asked = []
+
+        def rec(p):
+            asked.append(np.array(p))
+            return f(b, p)
+        want = vel_fit.central_hessian(rec, x[b], hs)
+        assert np.array_equal(H[b], want), b
+        uniq = {p.tobytes() for p in asked}
+        assert uniq == {p.tobytes() for p in P[b]}
+
+
+class _AnalyticEngine:
+    """Stand-in for LikelihoodEngine on the CPU: a smooth -2 log L per object."""
+    NSLOT = 8
+
+    def __init__(self, nobj, seed):
+        rs = np.random.RandomState(seed)
+        self.nobj = nobj
+        self.objects = [[_Arm()] for _ in range(nobj)]
+        self.truth = np.column_stack([rs.normal(0, 100, nobj), rs.uniform(3, 30, nobj),
+                                      rs.uniform(4500, 6500, nobj), rs.uniform(1, 4.5, nobj),
+                                      rs.uniform(-2, 0, nobj), rs.uniform(0, 0.4, nobj)])
+        self.scale = np.array([3.0, 4.0, 80.0, 0.2, 0.1, 0.08])
+        self.timer = None
+        self.calls = []
+
+    def chi(self, obj, vel, params, vsini):
+        vel = np.asarray(vel, dtype=np.float64)
+        z = [(vel - self.truth[obj, 0].reshape((-1,) + (1,) * (vel.ndim - 1))) / self.scale[0]]
+        v = np.zeros(len(obj)) if vsini is None else np.asarray(vsini)
+        z.append(((v - self.truth[obj, 1]) / self.scale[1]).reshape((-1,) + (1,) * (vel.ndim - 1)))
+        for j in range(4):
+            z.append(((params[:, j] - self.truth[obj, 2 + j]) / self.scale[2 + j]).reshape(
+                (-1,) + (1,) * (vel.ndim - 1)))
+        tot = 7000.0 + 40 * obj.reshape((-1,) + (1,) * (vel.ndim - 1))
+        tot = tot + 300 * (1 - 1 / (1 + z[0]**2 / 300)) * 300
+        for a, zz in enumerate(z[1:]):
+            tot = tot + zz**2 + 0.1 * np.cos(zz + a) + 0.05 * zz * z[(a + 2) % 6]
+        return tot
+
+    def evaluate(self, obj, vels, params, vsini=None, want_model=False, **kw):
+        obj = np.asarray(obj, dtype=np.int64)
+        params = np.array(params, dtype=np.float64, ndmin=2)
+        self.calls.append(len(obj))
+        out = self.chi(obj, vels, params, vsini)
+        if want_model:
+            n = len(obj)
+            ex = dict(moff=np.arange(n + 1) * 3, model=np.ones(3 * n), raw=np.ones(3 * n))
+            return out, dict(arms={'fake': dict(sel=np.arange(n), extras=ex,
+                                                tbad=np.zeros(n, dtype=bool))})
+        return out
+
+    def drain(self):
+        pass
+
+
+class _Arm:
+    name = 'fake'
+    lam = np.arange(3.0)
+    spec = np.ones(3)
+    espec = np.ones(3)
+    badmask = np.zeros(3, dtype=bool)
+
+
+def _host_scan_stats(vel_grid, chisq, quadratic=True):
+    """spec_fit.scan_stats on the host (the oracle's restatement of find_best's tail)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), 'oracle'))
+    import oracle
+    out = np.zeros((len(vel_grid), 8))
+    for s in range(len(vel_grid)):
+        r = oracle.scan_statistics(vel_grid[s], chisq[s].T, quadratic)
+        out[s, :5] = r['best_chi'], r['best_vel'], r['vel_err'], r['skewness'], r['kurtosis']
+    return out, None
+
+
+def test_process_batch_pipeline_equals_single_object_rules(monkeypatch):
+    """process_batch (grouped coroutines, lock-step NM and BFGS, vectorised stencils)
+    against vel_fit.process driven by scipy, on an analytic likelihood: every number
+    of every object identical, whatever the grouping."""
+    from rvspecfit_b200 import spec_fit, spec_inter, vel_fit
+    B = 7
+    eng = _AnalyticEngine(B, 4)
+    names = ('teff', 'logg', 'feh', 'alpha')
+    cfg = dict(min_vel=-1000, max_vel=1000, vel_step0=5, max_vsini=500, min_vsini=0.1,
+               min_vel_step=0.2, second_minimizer=True, template_lib='none/')
+    monkeypatch.setattr(spec_inter, 'getSpecParams', lambda setup, config: names)
+    monkeypatch.setattr(spec_fit, 'scan_stats', _host_scan_stats)
+    starts = [dict(teff=5500., logg=3., feh=-1., alpha=0.2, vsini=10.) for _ in range(B)]
+    priors = {'teff': (5600., 400.)}
+    res = {g: batch_fit.process_batch(None, starts, config=cfg, options={}, engine=eng,
+                                      priors=priors, groups=g) for g in (1, 3)}
+
+    # the single-object path with the same likelihood behind the reference-shaped calls
+    def get_chisq(specdata, vel, atm, rot=None, resol=None, options=None, config=None,
+                  full_output=False, outside_penalty=True):
+        i = np.array([specdata[0].index])
+        c = float(eng.chi(i, np.array([float(vel)]), np.array([atm], dtype=np.float64),
+                          None if rot is None else np.array([rot[0]]))[0])
+        if full_output:
+            return dict(chisq=c, logl=-0.5 * c, chisq_array=[0.0], npix_array=[3],
+                        models=[np.ones(3)], raw_models=[np.ones(3)])
+        return c
+
+    def find_best(specdata, vel_grid, params_list, rot_params=None, resol_params=None,
+                  options=None, config=None, quadratic=True):
+        i = np.array([specdata[0].index])
+        chi = eng.chi(i, np.asarray(vel_grid)[None, :], np.array(params_list, dtype=np.float64),
+                      None if rot_params is None else np.array([rot_params[0]]))
+        o = _host_scan_stats(np.asarray(vel_grid)[None], chi[None])[0][0]
+        return dict(best_chi=o[0], best_vel=o[1], vel_err=o[2], skewness=o[3], kurtosis=o[4],
+                    best_param=params_list[0])
+    monkeypatch.setattr(spec_fit, 'get_chisq', get_chisq)
+    monkeypatch.setattr(spec_fit, 'find_best', find_best)
+    monkeypatch.setattr(spec_fit, 'param_dict_to_tuple',
+                        lambda d, setup, config: tuple(d[k] for k in names))
+    for i in range(B):
+        sd = spec_fit.SpecData('fake', np.arange(3.0) + 1, np.ones(3), np.ones(3))
+        sd.index = i
+        want = vel_fit.process([sd], dict(starts[i]), config=cfg, options={}, priors=priors)
+        for g in res:
+            got = res[g][i]
+            for k in ('vel', 'vel_err', 'vel_skewness', 'vel_kurtosis', 'vsini', 'chisq',
+                      'minimize_success', 'bad_hessian'):
+                assert got[k] == want[k], (g, i, k, got[k], want[k])
+            for k in names:
+                assert got['param'][k] == want['param'][k], (g, i, k)
+                assert got['param_err'][k] == want['param_err'][k] or \
+                    (np.isnan(got['param_err'][k]) and np.isnan(want['param_err'][k])), (g, i, k)
+            assert np.array_equal(got['param_covar'], want['param_covar'])
 
 
 def test_batch_objective_matches_scalar_rules():
