@@ -314,6 +314,73 @@ int rvs_ccf_accumulate(const rvs_ccf_arm *arm, const double *d_pspec, const doub
 int rvs_ccf_best(const double *d_chisq, const double *d_sse, const double *d_velgrid, int nrow,
                  int ntempl, int nvel, double *d_out, double *d_best_ccf, void *stream);
 
+/* ---- host-side lock-step Nelder-Mead stepper (nm_host.cpp; no device work) ----
+ * The optimiser loop of vel_fit.process (reference vel_fit.py:628-650:
+ * scipy.optimize.minimize(method='Nelder-Mead', options={initial_simplex, xatol, fatol,
+ * maxiter, maxfev=inf})) for B simplices at once, scipy's decision rules and
+ * floating-point expressions.  Protocol: n = rvs_nm_request(...) writes the problem
+ * index and the coordinates of the next n trial points (n > cap: nothing beyond cap was
+ * written, call again with larger buffers is NOT possible -- size them B * max(N + 1, 4));
+ * the caller evaluates them and passes the n values to rvs_nm_feed; n == 0 means every
+ * problem has stopped and rvs_nm_result may be read.  With at most `speculate_below`
+ * live problems a round asks for the reflection AND the three candidate second points
+ * of every problem (one round per iteration instead of two; each problem still uses
+ * exactly the values scipy would have computed). */
+void *rvs_nm_create(int B, int N, const double *h_sims /* [B][N+1][N] */, double xatol,
+                    double fatol, int64_t maxiter);
+void rvs_nm_destroy(void *nm);
+int64_t rvs_nm_request(void *nm, int speculate_below, int32_t *h_idx, double *h_X, int64_t cap);
+int rvs_nm_feed(void *nm, const double *h_f, int64_t n);
+int rvs_nm_result(void *nm, double *h_x /* [B][N] */, double *h_fun, uint8_t *h_success,
+                  double *h_final_simplex, int64_t *h_nit, int64_t *h_nfev);
+
+/* ---- host side of an optimiser-phase evaluation call of the batched fit (fit_host.cpp) --
+ * Layout of the fitted vector and the per-object constants of a batch_fit.BatchObjective:
+ * vector = [vel, (vsini if fit_vsini), free atmospheric parameters in grid order]
+ * (reference vel_fit.py:119-207 ParamMapper). */
+typedef struct {
+  int32_t nfit;      /* length of the fitted vector */
+  int32_t nspec;     /* atmospheric parameters of the grid */
+  int32_t fit_vsini; /* 1: vector[1] is vsini (clipped to [0, max_vsini], quadratic penalty) */
+  int32_t has_vsini; /* 1 (and !fit_vsini): vsini fixed at h_vsini0[object] */
+  int32_t fixmask;   /* bit j: parameter j is fixed at h_p0[object][j] */
+  int32_t logmask;   /* bit j: parameter j enters the grid as log10 (read_grid.py:127-145) */
+  int32_t priormask; /* bit j: Gaussian prior (h_prior_mu[j], h_prior_sig[j]) on parameter j */
+  int32_t narm, nobj;
+  int32_t pad_;
+  double min_vel, max_vel, max_vsini;
+  const double *h_p0;        /* [nobj][nspec] start / fixed values */
+  const double *h_q0;        /* [nobj][nspec] the same, grid-mapped (log10 where logmask) */
+  const double *h_vsini0;    /* [nobj] or NULL */
+  const double *h_prior_mu;  /* [nspec] */
+  const double *h_prior_sig; /* [nspec] */
+  const int32_t *h_oix;      /* [narm][nobj] row of the object in each arm's batch, -1 absent */
+  const double *h_badchi;    /* [nobj] 10 x total pixels (spec_fit.py:863) */
+  const uint8_t *h_cover;    /* [nobj] template covers the object over [min_vel, max_vel] */
+} rvs_fit_layout;
+/* K fitted vectors h_X[K][nfit] of objects h_obj[K] -> rows (vel, vsini, q_0..) of
+ * h_in[2+nspec][Kp] and arm rows h_oix[narm][Kp] (the call's pinned upload buffers; items
+ * K..Kp-1 are padding, absent on every arm), the additive host terms h_prior[K], h_pen[K],
+ * and h_wall[K] = 1 for vectors behind the hard walls (vel outside [min_vel, max_vel] or a
+ * non-finite parameter: not evaluated, value 1e30, vel_fit.py:252-254).  h_logvals
+ * [nlog][K]: log10 of the FITTED log-mapped parameters, in parameter order, computed by
+ * the caller (numpy's log10, so that every path of the package maps identically).
+ * *h_vsini_max = largest vsini of an evaluated item. */
+int rvs_fit_pack(const rvs_fit_layout *L, int64_t K, int64_t Kp, const int32_t *h_obj,
+                 const double *h_X, const double *h_logvals, double *h_in, int32_t *h_oix,
+                 double *h_prior, double *h_pen, uint8_t *h_wall, double *h_vsini_max);
+/* The call's downloads h_chi[2][narm][Kp] (chi-square | off-grid measure) and
+ * h_flags[2][narm][Kp] (evaluation | location status) -> objective values h_out[K] =
+ * prior + sum over arms (chi-square + off-grid penalty) + penalty, 1e30 behind the walls;
+ * h_redo[K] = 1 where the fused path could not settle the item (any flag, a non-finite
+ * value, template not covering the object): the caller re-evaluates those through the
+ * general path.  Returns the number of such items (negative: RVS_E_*). */
+int64_t rvs_fit_collect(const rvs_fit_layout *L, int64_t K, int64_t Kp, const int32_t *h_obj,
+                        const double *h_in, const double *h_chi, const int32_t *h_flags,
+                        int shared_locate, int outside_penalty, const double *h_prior,
+                        const double *h_pen, const uint8_t *h_wall, double *h_out,
+                        uint8_t *h_redo);
+
 #ifdef __cplusplus
 }
 #endif

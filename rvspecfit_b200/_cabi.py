@@ -60,6 +60,17 @@ class CcfArm(ctypes.Structure):
                 ('nvel', ctypes.c_int32)]
 
 
+class FitLayout(ctypes.Structure):
+    """struct rvs_fit_layout"""
+    _fields_ = [('nfit', ctypes.c_int32), ('nspec', ctypes.c_int32), ('fit_vsini', ctypes.c_int32),
+                ('has_vsini', ctypes.c_int32), ('fixmask', ctypes.c_int32),
+                ('logmask', ctypes.c_int32), ('priormask', ctypes.c_int32),
+                ('narm', ctypes.c_int32), ('nobj', ctypes.c_int32), ('pad_', ctypes.c_int32),
+                ('min_vel', c_dbl), ('max_vel', c_dbl), ('max_vsini', c_dbl),
+                ('h_p0', c_dp), ('h_q0', c_dp), ('h_vsini0', c_dp), ('h_prior_mu', c_dp),
+                ('h_prior_sig', c_dp), ('h_oix', c_dp), ('h_badchi', c_dp), ('h_cover', c_dp)]
+
+
 # name -> (restype, argtypes); every symbol include/rvs_b200.h declares
 SIGNATURES = {
     'rvs_last_error': (ctypes.c_char_p, []),
@@ -94,6 +105,15 @@ SIGNATURES = {
     'rvs_ccf_workspace': (c_i64, [ctypes.POINTER(CcfArm), c_int]),
     'rvs_ccf_accumulate': (c_int, [ctypes.POINTER(CcfArm), c_dp, c_dp, c_int, c_dp, c_dp, c_dp,
                                    c_dp, c_i64, c_dp]),
+    'rvs_nm_create': (ctypes.c_void_p, [c_int, c_int, c_dp, c_dbl, c_dbl, c_i64]),
+    'rvs_nm_destroy': (None, [ctypes.c_void_p]),
+    'rvs_nm_request': (c_i64, [ctypes.c_void_p, c_int, c_dp, c_dp, c_i64]),
+    'rvs_nm_feed': (c_int, [ctypes.c_void_p, c_dp, c_i64]),
+    'rvs_nm_result': (c_int, [ctypes.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    'rvs_fit_pack': (c_int, [ctypes.POINTER(FitLayout), c_i64, c_i64, c_dp, c_dp, c_dp, c_dp, c_dp,
+                             c_dp, c_dp, c_dp, c_dp]),
+    'rvs_fit_collect': (c_i64, [ctypes.POINTER(FitLayout), c_i64, c_i64, c_dp, c_dp, c_dp, c_dp,
+                                c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'rvs_ccf_best': (c_int, [c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
 }
 

@@ -128,6 +128,54 @@ class BatchObjective:
         self.max_vsini = config['max_vsini']
         self.priors = priors
         self.nfev = 0
+        self._lay = None
+
+    def layout(self):
+        """struct rvs_fit_layout of this objective (the arrays it points to are kept
+        alive here), or False when the engine has no packed fast path."""
+        if self._lay is None:
+            eng = self.eng
+            self._lay = False
+            if hasattr(eng, 'submit_fit') and len(self.specParams) <= 30:
+                from . import _cabi
+                bank0 = eng.arms[eng.setups[0]]['bank']
+                ns = len(self.specParams)
+                lay = _cabi.FitLayout()
+                lay.nfit = 1 + int(self.fitVsini) + sum(not f for f in self.fix)
+                lay.nspec, lay.fit_vsini = ns, int(self.fitVsini)
+                lay.has_vsini = int(self.has_vsini)
+                lay.fixmask = sum(1 << j for j, f in enumerate(self.fix) if f)
+                lay.logmask = sum(1 << j for j in bank0.log_ids)
+                pri = self.priors or {}
+                lay.priormask = sum(1 << j for j, k in enumerate(self.specParams) if k in pri)
+                lay.narm, lay.nobj = len(eng.setups), eng.nobj
+                lay.min_vel, lay.max_vel = float(self.min_vel), float(self.max_vel)
+                lay.max_vsini = float(self.max_vsini)
+                keep = dict(
+                    p0=np.ascontiguousarray(self.p0),
+                    q0=np.ascontiguousarray(spec_inter.map_params(self.p0, bank0.log_ids)),
+                    vs0=np.ascontiguousarray(self.vsini0),
+                    mu=np.array([pri[k][0] if k in pri else 0.0 for k in self.specParams],
+                                dtype=np.float64),
+                    sig=np.array([pri[k][1] if k in pri else 1.0 for k in self.specParams],
+                                 dtype=np.float64),
+                    oix=np.ascontiguousarray(eng._oix, dtype=np.int32),
+                    badchi=np.ascontiguousarray(eng.badchi, dtype=np.float64),
+                    cover=np.ascontiguousarray(eng._cover0, dtype=np.uint8))
+                lay.h_p0, lay.h_q0 = keep['p0'].ctypes.data, keep['q0'].ctypes.data
+                lay.h_vsini0 = keep['vs0'].ctypes.data
+                lay.h_prior_mu, lay.h_prior_sig = keep['mu'].ctypes.data, keep['sig'].ctypes.data
+                lay.h_oix, lay.h_badchi = keep['oix'].ctypes.data, keep['badchi'].ctypes.data
+                lay.h_cover = keep['cover'].ctypes.data
+                # fitted columns of the log-mapped parameters, in parameter order
+                cols, pos = [], 1 + int(self.fitVsini)
+                for j, fixed in enumerate(self.fix):
+                    if not fixed:
+                        if j in bank0.log_ids:
+                            cols.append(pos)
+                        pos += 1
+                self._lay, self._lay_keep, self._logcols = lay, keep, cols
+        return self._lay
 
     def unpack(self, idx, X):
         """ParamMapper.forward for a batch: vel (K,), vsini (K,) or None,
@@ -187,6 +235,17 @@ class BatchObjective:
         """Start the evaluation of chisq_func for K pairs and return a waiter: a
         callable that gives the values (priors + -2 log L + penalty, 1e30 behind the
         hard walls, vel_fit.py:210-257), with ready() telling whether it would block."""
+        lay = self.layout()
+        if lay:
+            obj32 = np.ascontiguousarray(idx, dtype=np.int32)
+            X = np.ascontiguousarray(X, dtype=np.float64)
+            with np.errstate(all='ignore'):
+                logvals = np.log10(X[:, self._logcols].T) if self._logcols else None
+            pend = self.eng.submit_fit(lay, obj32, X,
+                                       None if logvals is None else np.ascontiguousarray(logvals))
+            if pend is not None:
+                self.nfev += len(obj32)
+                return _FitWaiter(self, pend, obj32, X)
         idx = np.asarray(idx, dtype=np.int64)
         vel, vsini, params, pen = self.unpack(idx, X)
         wall = (vel > self.max_vel) | (vel < self.min_vel) | ~np.isfinite(params).all(axis=1)
@@ -211,6 +270,31 @@ class _Done:
 
     def ready(self):
         return True
+
+
+class _FitWaiter:
+    """Values of an evaluation started through LikelihoodEngine.submit_fit; the items
+    the fused path could not settle go through the general path here."""
+
+    def __init__(self, fobj, pend, obj32, X):
+        self.fobj, self.pend, self.obj32, self.X = fobj, pend, obj32, X
+
+    def ready(self):
+        return self.pend.ready()
+
+    def __call__(self):
+        out, redo = self.pend.result()
+        if redo is not None:
+            r = np.nonzero(redo)[0]
+            fobj = self.fobj
+            idx = self.obj32[r].astype(np.int64)
+            vel, vsini, params, pen = fobj.unpack(idx, self.X[r])
+            eng = fobj.eng
+            eng.n_eval -= len(r)
+            with eng._general_lock:
+                chi = eng._evaluate_general(idx, vel, params, vsini, True, None, False, False)
+            out[r] = fobj.prior_term(params) + chi + pen
+        return out
 
 
 class _Waiter:
@@ -336,10 +420,52 @@ def nelder_mead_steps(sims, xatol=1e-2, fatol=1e-3, maxiter=10000, speculate_bel
                 final_simplex=sim, nit=iterations, nfev=nfev)
 
 
+def nelder_mead_native(sims, xatol=1e-2, fatol=1e-3, maxiter=10000, speculate_below=0):
+    """nelder_mead_steps with the stepping done by the library's host-side stepper
+    (csrc/nm_host.cpp, rvs_nm_*): the same generator protocol, the same trajectories
+    (tests/test_batch_drivers.py compares both with scipy), a fraction of the host
+    time per round.  `speculate_below` may be a callable giving the threshold for the
+    coming round."""
+    import ctypes
+    from . import _cabi
+    L = _cabi.lib()
+    sim = np.array(sims, dtype=np.float64, order='C')     # own copy: receives the final simplices
+    B, N1, N = sim.shape
+    assert N1 == N + 1
+    h = L.rvs_nm_create(B, N, _dev.hptr(sim), float(xatol), float(fatol), int(maxiter))
+    if not h:
+        raise _cabi.RvsError('rvs_nm_create failed')
+    h = ctypes.c_void_p(h)
+    try:
+        cap = B * max(N1, 4)
+        idx = np.empty(cap, dtype=np.int32)
+        X = np.empty((cap, N), dtype=np.float64)
+        while True:
+            sb = speculate_below() if callable(speculate_below) else speculate_below
+            n = L.rvs_nm_request(h, int(sb), _dev.hptr(idx), _dev.hptr(X), cap)
+            if n == 0:
+                break
+            assert n <= cap
+            f = np.ascontiguousarray((yield idx[:n], X[:n]), dtype=np.float64)
+            _cabi.check(L.rvs_nm_feed(h, _dev.hptr(f), n), 'rvs_nm_feed')
+        x, fun = np.empty((B, N)), np.empty(B)
+        success = np.empty(B, dtype=np.uint8)
+        nit, nfev = np.empty(B, dtype=np.int64), np.empty(B, dtype=np.int64)
+        _cabi.check(L.rvs_nm_result(h, _dev.hptr(x), _dev.hptr(fun), _dev.hptr(success),
+                                    _dev.hptr(sim), _dev.hptr(nit), _dev.hptr(nfev)),
+                    'rvs_nm_result')
+        return dict(x=x, fun=fun, success=success.astype(bool), final_simplex=sim, nit=nit,
+                    nfev=nfev)
+    finally:
+        L.rvs_nm_destroy(h)
+
+
 def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000,
-                         speculate_below=0):
-    """nelder_mead_steps driven with a blocking objective fbatch(idx, X) -> f."""
-    gen = nelder_mead_steps(sims, xatol, fatol, maxiter, speculate_below)
+                         speculate_below=0, native=False):
+    """nelder_mead_steps (or its native sibling) driven with a blocking objective
+    fbatch(idx, X) -> f."""
+    gen = (nelder_mead_native if native else nelder_mead_steps)(sims, xatol, fatol, maxiter,
+                                                                speculate_below)
     try:
         req = next(gen)
         while True:
@@ -419,6 +545,39 @@ def run_pipeline(gens, start):
             pending.append((gi, start(gens[gi].send(wait()))))
         except StopIteration as stop:
             out[gi] = stop.value
+    return out
+
+
+def run_threads(gens, start, device=None):
+    """run_pipeline with one host thread per coroutine.  The per-round host work of a
+    lock-step set is library calls that release the interpreter lock (the optimiser
+    stepper rvs_nm_*, rvs_fit_pack / rvs_fit_collect, graph launches, event waits), so
+    the sets' host work runs on different cores instead of queueing behind each other.
+    `device`: CUDA device index the threads make current (a new thread starts on
+    device 0)."""
+    import threading
+    out = [None] * len(gens)
+    errors = []
+
+    def work(gi):
+        try:
+            if device is not None:
+                _dev.torch_mod().cuda.set_device(device)
+            gen = gens[gi]
+            req = next(gen)
+            while not errors:
+                req = gen.send(start(req)())
+        except StopIteration as stop:
+            out[gi] = stop.value
+        except BaseException as exc:          # noqa: BLE001  (re-raised by the caller)
+            errors.append(exc)
+    threads = [threading.Thread(target=work, args=(gi,), daemon=True) for gi in range(len(gens))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
     return out
 
 
@@ -555,7 +714,8 @@ def fit_steps(sel, fobj, specParams, fixParam, fitVsini, has_vsini, config, phas
     x = np.zeros((n, sims.shape[2]))
     todo = loc
     for attempt in range(2):
-        res = yield from _drive(nelder_mead_steps(sims[todo], speculate_below=SPECULATE_BELOW),
+        res = yield from _drive(nelder_mead_native(sims[todo],
+                                                   speculate_below=lambda: SPECULATE_BELOW),
                                 sel[todo])
         x[todo] = res['x']
         sims[todo] = res['final_simplex']
@@ -636,18 +796,20 @@ class _Sub:
 
 # objects per lock-step set and sets in flight: enough sets that the tail of one (few
 # live problems, latency-bound calls) runs under the bulk of the others
-FIT_GROUP = 512
-FIT_MAX_GROUPS = 6
+FIT_GROUP = 1024
+FIT_MAX_GROUPS = 4
+THREADS = True
 
 
 def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None, priors=None,
-                  engine=None, timer=None, groups=None):
+                  engine=None, timer=None, groups=None, threads=None):
     """vel_fit.process for a list of objects (each a list of SpecData); same
     arguments otherwise, paramDict0s one dictionary per object.  Returns the list
     of result dictionaries of vel_fit.process.  `engine`: a LikelihoodEngine
     already holding the objects on the device (then `objects` may be None).
     The objects are fitted as `groups` independent lock-step sets whose phases
-    interleave on the GPU (run_pipeline)."""
+    interleave on the GPU: one host thread per set (run_threads; `threads=False`:
+    all sets advanced by the calling thread, run_pipeline)."""
     if config is None:
         raise RuntimeError('Config must be provided')
     options = options or {}
@@ -678,13 +840,22 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
         if kind == 'f0':
             return fobj.submit0(*req[1:])
         if kind == 'scan':
-            return _Ready(_scan_round(eng, *req[1:]))
+            with general_lock:
+                return _Ready(_scan_round(eng, *req[1:]))
         if kind == 'model':
             _, idx, vel, params, vsini = req
-            return _Ready(eng.evaluate(idx, vel[:, None], params, vsini, want_model=True))
+            with general_lock:
+                return _Ready(eng.evaluate(idx, vel[:, None], params, vsini, want_model=True))
         raise ValueError(kind)
+    import contextlib
+    general_lock = getattr(eng, '_general_lock', contextlib.nullcontext())
+    if threads is None:
+        threads = THREADS and len(gens) > 1 and hasattr(eng, 'submit_fit')
     try:
-        results = run_pipeline(gens, start)
+        if threads:
+            results = run_threads(gens, start, _dev.torch_mod().cuda.current_device())
+        else:
+            results = run_pipeline(gens, start)
     finally:
         eng.timer = None
         eng.drain()

@@ -14,6 +14,7 @@ scan statistics -- runs in librvs_b200.so.  The host resolves grid vertices
 import ctypes
 import os
 import random
+import threading
 
 import numpy as np
 import scipy.linalg
@@ -308,6 +309,33 @@ class PendingEval:
         return total
 
 
+class PendingFit:
+    """Handle of a LikelihoodEngine.submit_fit() call."""
+
+    def ready(self):
+        return self.slot['event'].query()
+
+    def result(self):
+        """(values (K,), redo (K,) bool): objective values (1e30 behind the walls) and
+        the items the fused path could not settle."""
+        sl, eng, K = self.slot, self.eng, self.K
+        sl['event'].synchronize()
+        eng._account(sl)
+        narm = len(eng.setups)
+        n = _cabi.lib().rvs_fit_collect(
+            ctypes.byref(self.lay), K, sl['Kp'], _dev.hptr(self.obj32),
+            ctypes.c_void_p(sl['h_in'].data_ptr()), ctypes.c_void_p(sl['h_chi'].data_ptr()),
+            ctypes.c_void_p(sl['h_flags'].data_ptr()), int(bool(sl.get('shared_locate'))), 1,
+            _dev.hptr(sl['f_prior']), _dev.hptr(sl['f_pen']), _dev.hptr(sl['f_wall']),
+            _dev.hptr(sl['f_out']), _dev.hptr(sl['f_redo']))
+        out = sl['f_out'][:K].copy()
+        redo = sl['f_redo'][:K].astype(bool) if n else None
+        sl['busy'] = False
+        if n < 0:
+            _cabi.check(int(n), 'rvs_fit_collect')
+        return out, redo
+
+
 def _overlap_ok(t0, t1, s0, s1, vmin, vmax):
     """spec_fit.py:786-794, vectorised; True where the template covers the data."""
     ok = np.ones(np.broadcast(s0, vmin).shape, dtype=bool)
@@ -375,6 +403,16 @@ class LikelihoodEngine:
             self.arms[n]['bank'].kind == 'regulargrid' and self.arms[n]['bank'].gridmap is not None
             and self.arms[n]['bank'].knots.ratio_dev < 1e-8 for n in self.setups)
         self._buf = {}
+        self._obs_cache = {}
+        self._data_epoch, self._data_event = 0, None    # see _launch
+        self._lock = threading.RLock()      # slots, scratch buffers, captures, counters
+        self._general_lock = threading.RLock()   # the general path's shared workspaces
+        self._launch_skew = 0
+        # largest vsini whose rotation kernel fits the fused path on every arm
+        # (tapcap = ceil(v / c / lnstep + 1) + 1 <= MAX_FUSED_TAPS)
+        self._fused_vmax = min(
+            (_cabi.MAX_FUSED_TAPS - 2) * 299792.458 * self.arms[n]['bank'].knots.lnstep
+            for n in self.setups) * (1 - 1e-12)
 
     def reload(self, objects):
         """Replace the spectra by new ones of the same layout (same arms per object, same
@@ -392,6 +430,8 @@ class LikelihoodEngine:
             arm = self.arms[name]
             arm['batch'].reload([sd for o in objects for sd in o if sd.name == name])
         self.objects = objects
+        self._data_epoch += 1
+        self._data_event = None
 
     @staticmethod
     def _fusable(bank, vs):
@@ -408,14 +448,11 @@ class LikelihoodEngine:
         launch configuration.  The rounded value is clamped to the largest one whose
         rotation kernel still fits the fused path wherever the actual maximum does, so
         that submit()'s gate and rvs_chisq_fused agree."""
-        vmax = 0.0 if vsini is None else float(np.max(vsini, initial=0.0))
+        vmax = 0.0 if vsini is None else float(vsini.max(initial=0.0))
         if not vmax > 0:
             return 0.0
         rounded = float(max(16.0, 2.0 ** np.ceil(np.log2(vmax))))
-        banks = [self.arms[n]['bank'] for n in self.setups]
-        if all(b.tapcap(rounded) <= _cabi.MAX_FUSED_TAPS for b in banks):
-            return rounded
-        return vmax
+        return rounded if rounded <= self._fused_vmax else vmax
 
     def drain(self):
         """Wait for every evaluation in flight and free its slot (used when a driver
@@ -554,7 +591,42 @@ class LikelihoodEngine:
                       event=torch.cuda.Event())
         return sl
 
-    def _submit_fast(self, obj, vels, params, vsini, sys_errs):
+    def _acquire(self, K):
+        """Round the item count up to a launch configuration and take a free slot
+        (pinned staging, device inputs, streams) for it: (slot, Kp)."""
+        L = _cabi.lib()
+        narm = len(self.setups)
+        bank0 = self.arms[self.setups[0]]['bank']
+        nd = bank0.ndim
+        if not hasattr(self, '_same_maps'):
+            self._same_maps = all(self.arms[n]['bank'].log_ids == bank0.log_ids
+                                  for n in self.setups)
+        use_graph = self.use_graphs and self._same_maps and \
+            not getattr(self, 'serial_arms', False) and not L.rvs_profile_active()
+        # The item count is rounded up (absent items: arm index -1 everywhere, skipped by
+        # every kernel), so that an optimiser whose active set shrinks call by call keeps
+        # hitting the same captured launch configurations.
+        Kp = K
+        if use_graph:
+            Kp = 16 if K <= 16 else (1 << int(np.ceil(np.log2(K))) if K <= 128
+                                     else (K + 127) // 128 * 128)
+        torch = _dev.torch_mod()
+        with self._lock:
+            sl = self._slot(Kp, narm, nd)
+            sl['busy'] = True
+        sl['Kp'], sl['use_graph'] = Kp, use_graph
+        # Every in-flight evaluation has its own streams and scratch, so that the
+        # low-occupancy tail of one (continuum solves of the last arm) runs under the
+        # template kernels of the next instead of in front of them.
+        if 'stream' not in sl:
+            sl['stream'] = torch.cuda.Stream()
+            sl['ready'] = torch.cuda.Event()
+            sl['arm_streams'] = [torch.cuda.Stream() for _ in self.setups]
+            sl['arm_events'] = [torch.cuda.Event() for _ in self.setups]
+            sl['fork_event'] = torch.cuda.Event()
+        return sl, Kp
+
+    def _submit_fast(self, obj, vels, params, vsini, sys_errs, vmax):
         """Optimiser-phase evaluation of K items at one velocity each with no
         host work per item and no host synchronisation: one asynchronous upload
         of (vel, vsini, mapped parameters) from pinned memory, then per arm vertex
@@ -565,36 +637,11 @@ class LikelihoodEngine:
         finite, normal matrix not PD, velocity outside [min_vel, max_vel],
         template not covering the data) come back flagged and are re-evaluated by
         the general path when the result is collected.  Returns the slot."""
-        L = _cabi.lib()
         K = len(obj)
         narm = len(self.setups)
         bank0 = self.arms[self.setups[0]]['bank']
         nd = bank0.ndim
-        same_maps = all(self.arms[n]['bank'].log_ids == bank0.log_ids for n in self.setups)
-        use_graph = self.use_graphs and same_maps and not getattr(self, 'serial_arms', False) \
-            and not L.rvs_profile_active()
-        # The item count is rounded up (absent items: arm index -1 everywhere, skipped by
-        # every kernel), so that an optimiser whose active set shrinks call by call keeps
-        # hitting the same captured launch configurations.
-        Kp = K
-        if use_graph:
-            Kp = 16 if K <= 16 else (1 << int(np.ceil(np.log2(K))) if K <= 128
-                                     else (K + 127) // 128 * 128)
-        sl = self._slot(Kp, narm, nd)
-        sl['Kp'] = Kp
-        torch = _dev.torch_mod()
-        # Every in-flight evaluation has its own streams and scratch, so that the
-        # low-occupancy tail of one (continuum solves of the last arm) runs under the
-        # template kernels of the next instead of in front of them.
-        if 'stream' not in sl:
-            sl['stream'] = torch.cuda.Stream()
-            sl['ready'] = torch.cuda.Event()
-            sl['arm_streams'] = [torch.cuda.Stream() for _ in self.setups]
-            sl['arm_events'] = [torch.cuda.Event() for _ in self.setups]
-            sl['fork_event'] = torch.cuda.Event()
-        # per-arm data products are made (once) on the caller's stream
-        obs_all = [self.arms[name]['batch'].obs(self.npoly, self.rbf, sys_errs[a])
-                   for a, name in enumerate(self.setups)]
+        sl, Kp = self._acquire(K)
         # inputs of this evaluation -> pinned staging (uploaded by the enqueued work)
         host_in = sl['h_in'][:(2 + nd) * Kp].view(2 + nd, Kp).numpy()
         q = spec_inter.map_params(params, bank0.log_ids).T
@@ -607,56 +654,98 @@ class LikelihoodEngine:
             host_in[:2, K:] = 0.0
             host_in[2:, K:] = q[:, :1]
             h_oix[:, K:] = -1
-        # upper bound of vsini that sizes the tap buffers, in coarse steps so that
-        # consecutive evaluations share one launch configuration
-        vmax = self._tap_bound(vsini)
-        sl['ready'].record(torch.cuda.current_stream())
-        sl['stream'].wait_event(sl['ready'])
+        self._launch(sl, K, Kp, vmax, sys_errs, params)
+        return sl
+
+    def _launch(self, sl, K, Kp, vmax, sys_errs, params):
+        """Start the device work of the evaluation whose inputs are in the slot's pinned
+        buffers; records the slot's event behind it."""
+        L = _cabi.lib()
+        torch = _dev.torch_mod()
+        narm = len(self.setups)
+        nd = self.arms[self.setups[0]]['bank'].ndim
+        use_graph = sl['use_graph']
+        # per-arm data products are made (once) on the caller's stream
+        okey = tuple(sys_errs)
+        obs_all = self._obs_cache.get(okey)
+        if obs_all is None:
+            with self._lock:
+                obs_all = self._obs_cache[okey] = [
+                    self.arms[name]['batch'].obs(self.npoly, self.rbf, sys_errs[a])
+                    for a, name in enumerate(self.setups)]
+                self._data_epoch += 1
+                self._data_event = None
+        # The slot's stream waits for the spectra and their derived products (uploaded /
+        # computed on the caller's stream by the constructor, reload() or the first obs()
+        # of a systematic error) once per such change -- not for whatever else the
+        # caller's stream carries (another lock-step set's RV scan, say)
+        if sl.get('data_epoch') != self._data_epoch:
+            with self._lock:
+                if self._data_event is None:
+                    self._data_event = torch.cuda.Event()
+                    self._data_event.record(torch.cuda.current_stream())
+                sl['stream'].wait_event(self._data_event)
+                sl['data_epoch'] = self._data_epoch
         # The ~20 launches, copies and stream fork/joins of one evaluation are captured
         # into a CUDA graph the second time a configuration (item count, tap bound,
         # systematic error) is seen and replayed from then on: one launch per evaluation
         # instead of a host-bound launch sequence.
-        key = (Kp, vmax, tuple(sys_errs))
+        key = (Kp, vmax, okey)
         epoch = getattr(self, '_graph_epoch', 0)
         if sl.get('graph_epoch') != epoch:
             sl['graphs'], sl['seen'], sl['graph_epoch'] = {}, {}, epoch
+        g = sl['graphs'].get(key) if use_graph else None
         with torch.cuda.stream(sl['stream']):
             t0 = self.timer.start() if self.timer else None
-            g = sl['graphs'].get(key) if use_graph else None
-            done = False
-            if g is None and use_graph and sl['seen'].get(key, 0) >= 1 and len(sl['graphs']) < 32:
-                # second sighting: every scratch buffer of this configuration exists already
-                l0 = L.rvs_launch_count()
-                gr = torch.cuda.CUDAGraph()
-                gr.capture_begin(capture_error_mode='thread_local')
-                try:
-                    self._enqueue_fast(sl, obs_all, params, vmax, Kp, narm, nd)
-                finally:
-                    gr.capture_end()
-                self.graph_kernel_launches -= L.rvs_launch_count() - l0   # captured, not run
-                GRAPH_LAUNCHES[0] -= L.rvs_launch_count() - l0
-                if getattr(self, '_graph_epoch', 0) != epoch:   # a buffer moved while capturing
-                    sl['graphs'], sl['seen'] = {}, {}
-                    sl['graph_epoch'] = self._graph_epoch
-                    self.use_graphs = False
-                    self._enqueue_fast(sl, obs_all, params, vmax, Kp, narm, nd)
-                    done = True
-                else:
-                    g = sl['graphs'][key] = (gr, L.rvs_launch_count() - l0)
             if g is not None:
                 g[0].replay()
-                self.graph_kernel_launches += g[1]
-                GRAPH_LAUNCHES[0] += g[1]
-            elif not done:
-                self._enqueue_fast(sl, obs_all, params, vmax, Kp, narm, nd)
-            sl['seen'][key] = sl['seen'].get(key, 0) + 1
-            _dev.IO_BYTES[0] += (2 + nd) * Kp * 8 + narm * Kp * 4
-            _dev.IO_BYTES[1] += 2 * narm * Kp * (8 + 4)
+                nk = g[1]
+            else:
+                # direct launches and graph captures: one thread at a time (scratch buffers
+                # may grow, which moves the graph epoch)
+                with self._lock:
+                    nk, done = 0, False
+                    if use_graph and sl['seen'].get(key, 0) >= 1 and len(sl['graphs']) < 32:
+                        # second sighting: every scratch buffer of this configuration exists
+                        l0 = L.rvs_launch_count()
+                        gr = torch.cuda.CUDAGraph()
+                        gr.capture_begin(capture_error_mode='thread_local')
+                        try:
+                            self._enqueue_fast(sl, obs_all, params, vmax, Kp, narm, nd)
+                        finally:
+                            gr.capture_end()
+                        nk = L.rvs_launch_count() - l0
+                        self._launch_skew -= nk                 # captured, not run
+                        if getattr(self, '_graph_epoch', 0) != epoch:   # a buffer moved
+                            sl['graphs'], sl['seen'] = {}, {}
+                            sl['graph_epoch'] = self._graph_epoch
+                            self.use_graphs = False
+                            nk = 0
+                        else:
+                            sl['graphs'][key] = (gr, nk)
+                            gr.replay()
+                            done = True
+                    if not done:
+                        self._enqueue_fast(sl, obs_all, params, vmax, Kp, narm, nd)
+                        nk = 0      # counted by the library
+                    sl['seen'][key] = sl['seen'].get(key, 0) + 1
             if t0 is not None:
                 self.timer.stop('fused_eval', t0, K)
             sl['event'].record()
-        sl['busy'] = True
-        return sl
+        sl['graph_kernels'] = nk
+
+    def _account(self, sl):
+        """Counters of a finished evaluation (kernels launched through graph replays,
+        bytes moved)."""
+        narm, Kp = len(self.setups), sl['Kp']
+        nd = self.arms[self.setups[0]]['bank'].ndim
+        nk = sl.get('graph_kernels', 0)
+        with self._lock:
+            self.graph_kernel_launches += nk
+            GRAPH_LAUNCHES[0] += nk + self._launch_skew
+            self._launch_skew = 0
+            _dev.IO_BYTES[0] += (2 + nd) * Kp * 8 + narm * Kp * 4
+            _dev.IO_BYTES[1] += 2 * narm * Kp * (8 + 4)
 
     def _enqueue_fast(self, sl, obs_all, params, vmax, K, narm, nd):
         """Enqueue (or capture) the device work of one evaluation on the current
@@ -733,6 +822,7 @@ class LikelihoodEngine:
         """Wait for a submitted evaluation: (total (K,), redo (K,) bool)."""
         K, narm, Kp = len(obj), len(self.setups), sl['Kp']
         sl['event'].synchronize()
+        self._account(sl)
         both = sl['h_chi'][:2 * narm * Kp].view(2, narm, Kp).numpy()[:, :, :K]
         chi, outside = both[0], both[1]
         flags = sl['h_flags'][:2 * narm * Kp].view(2, narm, Kp).numpy()[:, :, :K]
@@ -753,6 +843,51 @@ class LikelihoodEngine:
         sl['busy'] = False
         return total, redo
 
+    def submit_fit(self, lay, obj32, X, logvals):
+        """Optimiser-phase evaluation of the batched fit's objective for K (object,
+        fitted vector) pairs: rvs_fit_pack turns the vectors straight into the call's
+        pinned upload buffers (no per-item numpy), the captured graph of the call is
+        launched, and PendingFit.result() reduces the downloads with rvs_fit_collect.
+        `lay`: _cabi.FitLayout of the objective (batch_fit.BatchObjective.layout()).
+        Returns None when the fused path does not apply (the caller then uses submit)."""
+        if not (self.fused and self._fast_banks):
+            return None
+        L = _cabi.lib()
+        K = len(obj32)
+        narm = len(self.setups)
+        nd = lay.nspec
+        sl, Kp = self._acquire(K)
+        if not self._same_maps:
+            sl['busy'] = False
+            return None
+        if sl.get('fit_cap', 0) < Kp:
+            cap = sl['K']
+            sl.update(fit_cap=cap, f_prior=np.empty(cap), f_pen=np.empty(cap),
+                      f_wall=np.empty(cap, dtype=np.uint8), f_out=np.empty(cap),
+                      f_redo=np.empty(cap, dtype=np.uint8))
+        vsmax = ctypes.c_double(0.0)
+        rc = L.rvs_fit_pack(ctypes.byref(lay), K, Kp, _dev.hptr(obj32), _dev.hptr(X),
+                            None if logvals is None else _dev.hptr(logvals),
+                            ctypes.c_void_p(sl['h_in'].data_ptr()),
+                            ctypes.c_void_p(sl['h_oix'].data_ptr()), _dev.hptr(sl['f_prior']),
+                            _dev.hptr(sl['f_pen']), _dev.hptr(sl['f_wall']), ctypes.byref(vsmax))
+        if rc:
+            sl['busy'] = False
+            _cabi.check(rc, 'rvs_fit_pack')
+        vmax = vsmax.value
+        if vmax > 0:
+            rounded = float(max(16.0, 2.0 ** np.ceil(np.log2(vmax))))
+            vmax = rounded if rounded <= self._fused_vmax else vmax
+        if vmax > self._fused_vmax:
+            sl['busy'] = False
+            return None
+        with self._lock:
+            self.n_eval += K
+        self._launch(sl, K, Kp, vmax, (0.0,) * narm, None)
+        pend = PendingFit()
+        pend.eng, pend.slot, pend.lay, pend.obj32, pend.K = self, sl, lay, obj32, K
+        return pend
+
     def submit(self, obj, vels, params, vsini=None, outside_penalty=True,
                espec_systematic=None, raise_errors=False):
         """Asynchronous `evaluate` for one velocity per item: enqueues the work
@@ -763,10 +898,10 @@ class LikelihoodEngine:
         params = np.array(params, dtype=np.float64, ndmin=2)
         vels = np.asarray(vels, dtype=np.float64)
         vs = None if vsini is None else np.asarray(vsini, dtype=np.float64)
-        fast = (vels.ndim == 1 and self.fused and self._fast_banks and len(obj) > 0
-                and (vs is None or
-                     all(self.arms[n]['bank'].tapcap(self._tap_bound(vs))
-                         <= _cabi.MAX_FUSED_TAPS for n in self.setups)))
+        fast = vels.ndim == 1 and self.fused and self._fast_banks and len(obj) > 0
+        if fast:
+            vmax = self._tap_bound(vs)
+            fast = vmax <= self._fused_vmax
         pend = PendingEval()
         pend.args = (self, obj, vels, params, vs, outside_penalty, espec_systematic, raise_errors)
         pend.slot = None
@@ -776,7 +911,7 @@ class LikelihoodEngine:
             else:
                 sys_errs = [float(espec_systematic or 0.0)] * len(self.setups)
             self.n_eval += len(obj)
-            pend.slot = self._submit_fast(obj, vels, params, vs, sys_errs)
+            pend.slot = self._submit_fast(obj, vels, params, vs, sys_errs, vmax)
         return pend
 
     def evaluate(self, obj, vels, params, vsini=None, outside_penalty=True,
@@ -798,6 +933,14 @@ class LikelihoodEngine:
 
     def _evaluate_general(self, obj, vels, params, vsini, outside_penalty, espec_systematic,
                           want_model, raise_errors, fast_interp=False):
+        """The general path, one thread at a time (it shares workspaces)."""
+        with self._general_lock:
+            return self._evaluate_general_impl(obj, vels, params, vsini, outside_penalty,
+                                               espec_systematic, want_model, raise_errors,
+                                               fast_interp)
+
+    def _evaluate_general_impl(self, obj, vels, params, vsini, outside_penalty,
+                               espec_systematic, want_model, raise_errors, fast_interp=False):
         """The general path: host vertex location (any interpolator kind, off-grid
         nearest node), any number of velocities per item, model output, SVD
         rescue, the reference's exceptions."""

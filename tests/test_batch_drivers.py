@@ -46,6 +46,13 @@ def test_lockstep_nelder_mead_is_scipy():
                                                   fatol=1e-3, maxiter=10000, speculate_below=4)
         for k in ('x', 'fun', 'final_simplex', 'nit', 'nfev', 'success'):
             assert np.array_equal(inter[k], res[k]), (groups, k)
+    # the library's host-side stepper (csrc/nm_host.cpp): the same trajectories
+    for kw, ref in ((dict(), res), (dict(speculate_below=10), res), (dict(speculate_below=10**6), res),
+                    (dict(xatol=1e-9, fatol=1e-12, maxiter=40), few)):
+        nat = batch_fit.nelder_mead_lockstep(fbatch, sims, native=True,
+                                             **{**dict(xatol=1e-2, fatol=1e-3, maxiter=10000), **kw})
+        for k in ('x', 'fun', 'final_simplex', 'nit', 'nfev', 'success'):
+            assert np.array_equal(nat[k], ref[k]), (kw, k)
     for b in range(B):
         opts = {'fatol': 1e-3, 'xatol': 1e-2, 'initial_simplex': sims[b], 'maxiter': 10000,
                 'maxfev': np.inf}
@@ -286,3 +293,96 @@ def test_batch_objective_matches_scalar_rules():
             want = ((5100. - par[0]) / 200.)**2 + \
                 (pd['vel'] * 1e-3 + par.sum() + 10 * pd['vsini'] + idx[k]) + pd['penalty']
         assert got[k] == want, k
+
+
+def test_fit_pack_collect_equal_numpy_rules():
+    """rvs_fit_pack / rvs_fit_collect (csrc/fit_host.cpp) against the numpy restatement of
+    the same rules (BatchObjective.unpack / prior_term, LikelihoodEngine._collect_fast):
+    identical bits for every fitted-vector layout."""
+    import ctypes
+    from rvspecfit_b200 import _cabi, _dev, spec_inter
+    L = _cabi.lib()
+    rs = np.random.RandomState(0)
+    nobj, ns, narm = 9, 4, 3
+
+    class Bank:
+        log_ids = [0]
+        ndim = 4
+
+    class Eng:
+        setups = ['a', 'b', 'c']
+        arms = {'a': {'bank': Bank()}}
+
+        def submit_fit(self, *a):
+            return None
+    eng = Eng()
+    eng.nobj = nobj
+    eng._oix = rs.randint(-1, 5, size=(narm, nobj)).astype(np.int32)
+    eng.badchi = rs.uniform(100, 1000, nobj)
+    eng._cover0 = rs.rand(nobj) > 0.2
+    names = ['teff', 'logg', 'feh', 'alpha']
+    p0 = [dict(teff=5000. + 100 * i, logg=2. + .1 * i, feh=-1., alpha=0.2, vsini=3. + i)
+          for i in range(nobj)]
+    cfg = dict(min_vel=-1000, max_vel=1000, max_vsini=500)
+    hp = _dev.hptr
+    for fix, fitv, pri in ((['alpha'], True, {'teff': (5100., 200.), 'feh': (-1., .3)}),
+                           ([], True, None), (['teff'], False, {'logg': (2., 1.)}),
+                           ([], False, None)):
+        fobj = batch_fit.BatchObjective(eng, names, [dict(d) for d in p0],
+                                        fix + ([] if fitv else ['vsini']), fitv, cfg, pri)
+        lay = fobj.layout()
+        assert lay
+        K, Kp = 50, 64
+        idx = rs.randint(0, nobj, K).astype(np.int32)
+        cols = [rs.normal(0, 600, K)] + ([rs.normal(100, 300, K)] if fitv else []) + \
+            [rs.uniform(4000, 7000, K) if n == 'teff' else rs.normal(0, 1, K)
+             for n in names if n not in fix]
+        X = np.ascontiguousarray(np.column_stack(cols))
+        assert X.shape[1] == lay.nfit
+        X[3, -1] = np.nan
+        logvals = np.ascontiguousarray(np.log10(X[:, fobj._logcols].T)) if fobj._logcols else None
+        h_in = np.zeros((2 + ns, Kp))
+        h_oix = np.zeros((narm, Kp), dtype=np.int32)
+        prior, pen, wall = np.zeros(K), np.zeros(K), np.zeros(K, dtype=np.uint8)
+        vm = ctypes.c_double()
+        rc = L.rvs_fit_pack(ctypes.byref(lay), K, Kp, hp(idx), hp(X),
+                            None if logvals is None else hp(logvals), hp(h_in), hp(h_oix),
+                            hp(prior), hp(pen), hp(wall), ctypes.byref(vm))
+        assert rc == 0
+        vel, vsini, params, pen2 = fobj.unpack(idx.astype(np.int64), X)
+        wall2 = (vel > 1000) | (vel < -1000) | ~np.isfinite(params).all(axis=1)
+        assert wall2.any() and np.array_equal(wall.astype(bool), wall2)
+        ok = ~wall2
+        assert np.array_equal(h_in[0, :K][ok], vel[ok])
+        if vsini is not None:
+            assert np.array_equal(h_in[1, :K][ok], vsini[ok]) and vm.value == vsini[ok].max()
+        assert np.array_equal(h_in[2:, :K].T[ok], spec_inter.map_params(params, [0])[ok])
+        assert np.array_equal(prior[ok], fobj.prior_term(params)[ok])
+        assert np.array_equal(pen, pen2)
+        assert np.array_equal(h_oix[:, :K][:, ok], eng._oix[:, idx][:, ok])
+        assert (h_oix[:, :K][:, ~ok] == -1).all() and (h_oix[:, K:] == -1).all()
+        chi = rs.normal(1000, 100, size=(2, narm, Kp))
+        chi[1] = 0
+        chi[1, :, 5:9] = rs.uniform(0, .1, size=(narm, 4))
+        flags = np.zeros((2, narm, Kp), dtype=np.int32)
+        flags[0, 1, 7] = 2
+        chi[0, 2, 11] = np.nan
+        for shared in (0, 1):
+            out, redo = np.zeros(K), np.zeros(K, dtype=np.uint8)
+            n = L.rvs_fit_collect(ctypes.byref(lay), K, Kp, hp(idx), hp(h_in), hp(chi), hp(flags),
+                                  shared, 1, hp(prior), hp(pen), hp(wall), hp(out), hp(redo))
+            c, o = chi[0, :, :K], chi[1, :, :K]
+            fl = flags[:, :, :K].copy()
+            if shared:
+                o = np.broadcast_to(o[0], o.shape)
+                fl[1, 1:] = fl[1, 0]
+            r2 = (fl != 0).any(axis=(0, 1)) | ~np.isfinite(np.stack([c, o])).all(axis=(0, 1))
+            r2 |= ~eng._cover0[idx] | (h_in[0, :K] < -1000) | (h_in[0, :K] > 1000)
+            present = eng._oix[:, idx] >= 0
+            tot = np.add.reduce(np.where(present, o * eng.badchi[idx][None, :], 0.0) + c, axis=0)
+            want = prior + tot + pen
+            want[wall2] = 1e30
+            r2[wall2] = False
+            assert n == r2.sum() and np.array_equal(redo.astype(bool), r2)
+            fin = np.isfinite(want)
+            assert np.array_equal(out[fin], want[fin])
