@@ -458,36 +458,59 @@ def run_gpu(args):
 
 
 # ------------------------------------------------------------------ CPU arm
+def _reference_available():
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import ref_loader
+    return ref_loader.available()
+
+
 def _cpu_worker(job):
-    """One object through the oracle: the same step body as the GPU arm."""
+    """One object through the CPU implementation of the path -- the reference package
+    itself when baseline/_ref holds it (baseline/install_ref.py), else the oracle port:
+    the same step body as the GPU arm."""
     wname, seed, idx, nevals, nscan = job
     os.environ['OMP_NUM_THREADS'] = '1'
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import oracle
     w = WORKLOADS[wname]
     cfg = make_config(w)
     key = (wname, seed)
     if _cpu_worker.cache.get('key') != key:
         setups, objects, pars, vel = make_inputs(wname, _cpu_worker.nspec, seed, mmap_grids=True)
-        for st in setups:
-            oracle.register_setup(st)
-        _cpu_worker.cache = dict(key=key, objects=objects, pars=pars, vel=vel)
+        if _reference_available():
+            import ref_loader
+            R = ref_loader.load()
+            for st in setups:
+                ref_loader.inject_grid(R, st)
+            api = dict(SpecData=R.spec_fit.SpecData, process=R.vel_fit.process,
+                       find_best=R.spec_fit.find_best, get_chisq=R.spec_fit.get_chisq,
+                       config=R.utils.freezeDict(cfg), kind='reference')
+        else:
+            sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+            import oracle
+            for st in setups:
+                oracle.register_setup(st)
+            api = dict(SpecData=oracle.SpecData, process=oracle.process,
+                       find_best=lambda sd, vg, pl, rot_params=None, **kw:
+                       oracle.find_best(sd, vg, pl, rot=rot_params, **kw),
+                       get_chisq=oracle.get_chisq, config=cfg, kind='port')
+        _cpu_worker.cache = dict(key=key, objects=objects, pars=pars, vel=vel, api=api)
     c = _cpu_worker.cache
-    sd = [oracle.SpecData(*a) for a in c['objects'][idx]]
+    api = c['api']
+    cfg = api['config']
+    sd = [api['SpecData'](a[0], a[1], a[2], a[3], badmask=a[4]) for a in c['objects'][idx]]
     opts = {'npoly': w['npoly']}
     tp, tv, tvs = trial_points(c['pars'], c['vel'], w['layout'], max(nevals, 0), 5)
-    vgrid = np.arange(cfg['min_vel'], cfg['max_vel'], cfg['vel_step0'])[:nscan]
+    vgrid = np.arange(w['min_vel'], w['max_vel'], 5)[:nscan]
     t0 = time.time()
     if nevals < 0:       # --mode fit: the complete fit
-        r = oracle.process(sd, dict(FIT_START), fixParam=[], options=opts, config=cfg)
-        return time.time() - t0, r['chisq']
-    fb = oracle.find_best(sd, vgrid, [(5500., 3.0, -1.0, 0.2)], rot=None, options=opts,
+        r = api['process'](sd, dict(FIT_START), fixParam=[], options=opts, config=cfg)
+        return time.time() - t0, r['chisq'], api['kind']
+    fb = api['find_best'](sd, vgrid, [(5500., 3.0, -1.0, 0.2)], rot_params=None, options=opts,
                           config=cfg)
     acc = fb['best_chi']
     for e in range(nevals):
-        acc += oracle.get_chisq(sd, tv[e, idx], tuple(tp[e, idx]), (tvs[e, idx],),
+        acc += api['get_chisq'](sd, tv[e, idx], tuple(tp[e, idx]), (tvs[e, idx],),
                                 options=opts, config=cfg)
-    return time.time() - t0, acc
+    return time.time() - t0, acc, api['kind']
 
 
 _cpu_worker.cache = {}
@@ -496,13 +519,16 @@ _cpu_worker.nspec = 0
 
 def _cpu_init(nspec):
     _cpu_worker.nspec = nspec
+    import logging
+    import warnings
+    warnings.simplefilter('ignore')
+    logging.disable(logging.WARNING)     # the reference logs a line per ill-conditioned Hessian
 
 
 def cpu_baseline(args, bounded=True):
-    """The oracle port on all host cores, one object per task in a spawn pool
-    (the reference's own pattern, desi_fit.py:1475-1479), on a bounded sample
-    of the same workload: `cores` objects, a fraction of the evaluations, scaled
-    linearly to the full per-spectrum count."""
+    """The reference's own CPU implementation (baseline/_ref; the oracle port if that
+    is absent) on all host cores, one object per task in a spawn pool (the reference's
+    own pattern, desi_fit.py:1475-1479), on a bounded sample of the same workload."""
     import concurrent.futures as cf
     import multiprocessing as mp
     cores = os.cpu_count() or 1
@@ -529,14 +555,17 @@ def cpu_baseline(args, bounded=True):
         res = list(ex.map(_cpu_worker, jobs))
         t2 = time.time()
     wall = t2 - t1
+    kind = res[0][2]
+    impl = ('the reference package (baseline/_ref, vel_fit.process)' if kind == 'reference'
+            else 'the oracle port (oracle.process)')
     if args.mode == 'fit':
-        return dict(value=nobj / wall, unit='spectra/s', cores=cores, kind='port',
-                    sample=f'{nobj} complete fits (oracle.process: scan, Nelder-Mead, BFGS, '
-                           f'refinement, Hessian) on {cores} processes, one object per task; '
+        return dict(value=nobj / wall, unit='spectra/s', cores=cores, kind=kind,
+                    sample=f'{nobj} complete fits by {impl}: scan, Nelder-Mead, BFGS, '
+                           f'refinement, Hessian; {cores} processes, one object per task; '
                            f'setup {t1 - t0:.1f}s excluded', wall_s=wall,
                     per_object_s=float(np.mean([r[0] for r in res])))
     scale = (args.evals + len(vg)) / (nevals + nscan)
-    return dict(value=nobj / (wall * scale), unit='spectra/s', cores=cores, kind='port',
+    return dict(value=nobj / (wall * scale), unit='spectra/s', cores=cores, kind=kind,
                 sample=f'{nobj} spectra x ({nscan} RV trials + {nevals} evaluations) on {cores} '
                        f'processes, scaled x{scale:.1f} to the full per-spectrum count; '
                        f'setup {t1 - t0:.1f}s excluded', wall_s=wall,
@@ -576,7 +605,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='desi', choices=list(WORKLOADS))
-    ap.add_argument('--batch', type=int, default=2048, help='spectra per GPU per step')
+    ap.add_argument('--batch', type=int, default=4096, help='spectra per GPU per step')
     ap.add_argument('--evals', type=int, default=EVALS_PER_FIT)
     ap.add_argument('--cpu-fraction', type=float, default=1.0,
                     help='fraction of the per-spectrum evaluations the CPU sample runs')

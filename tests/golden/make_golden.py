@@ -1,10 +1,11 @@
 """Generate tests/golden/*.npz by running the REFERENCE package itself.
 
-Runs only in the build container (needs /root/reference).  It copies the
-reference's python package to a scratch directory (nothing is copied into this
-repo), builds its cffi spline exactly as the reference does
-(`python rvspecfit/ffibuilder.py`), stubs the absent third-party imports
-(h5py, astropy, numdifftools, matplotlib), injects seeded synthetic template
+Runs only in the build container (needs /root/reference).  It installs the
+reference into the git-ignored baseline/_ref/ (baseline/install_ref.py: pip
+install of a scratch copy, which builds its cffi spline as the reference's own
+setup.py does; nothing enters this repository's history), stubs the absent
+third-party imports (h5py, astropy, numdifftools, matplotlib --
+baseline/ref_loader.py), injects seeded synthetic template
 banks (rvspecfit_b200/synth.py) straight into the reference's caches
 (spec_inter.interp_cache, fitter_ccf.CCFCache -- SURVEY.md §8c) and records what
 the reference computes.  The resulting fixtures travel to the GPU box; the
@@ -18,10 +19,7 @@ ndf.Hessian replaced by oracle.central_hessian: param_err / param_covar /
 bad_hessian in those fixtures are NOT reference outputs ("parity unpinned").
 """
 import os
-import shutil
-import subprocess
 import sys
-import tempfile
 import types
 
 import numpy as np
@@ -37,59 +35,18 @@ REF_SRC = '/root/reference/py/rvspecfit'
 
 
 def load_reference():
-    work = os.environ.get('RVS_REF_WORK') or os.path.join(tempfile.gettempdir(), 'rvs_ref_work')
-    pkg = os.path.join(work, 'rvspecfit')
-    if not os.path.exists(os.path.join(pkg, '_version.py')):
-        if os.path.exists(work):
-            shutil.rmtree(work)
-        os.makedirs(work)
-        shutil.copytree(REF_SRC, pkg)
-        with open(os.path.join(pkg, '_version.py'), 'w') as fp:
-            fp.write("version = '0+golden'\n__version__ = version\n")
-        subprocess.check_call([sys.executable, 'rvspecfit/ffibuilder.py'], cwd=work,
-                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    for m in ['h5py', 'astropy', 'astropy.io', 'astropy.io.fits', 'numdifftools',
-              'matplotlib', 'matplotlib.pyplot']:
-        sys.modules.setdefault(m, types.ModuleType(m))
-    sys.path.insert(0, work)
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import oracle
-    ndf = sys.modules['numdifftools']
-
-    class MinStepGenerator:
-        def __init__(self, base_step=None):
-            self.base_step = base_step
-
-    class Hessian:
-        def __init__(self, f, step=None):
-            self.f, self.step = f, step
-
-        def __call__(self, x):
-            steps = self.step.base_step if self.step is not None else \
-                [oracle.HESS_STEP[k] for k in synth.PARNAMES]
-            return oracle.central_hessian(self.f, x, steps)
-    ndf.MinStepGenerator, ndf.Hessian = MinStepGenerator, Hessian
-    import rvspecfit  # noqa: F401
-    from rvspecfit import (spec_fit, spec_inter, vel_fit, fitter_ccf, make_ccf,
-                           read_grid, utils, spliner, make_nd)
-    return types.SimpleNamespace(spec_fit=spec_fit, spec_inter=spec_inter,
-                                 vel_fit=vel_fit, fitter_ccf=fitter_ccf,
-                                 make_ccf=make_ccf, read_grid=read_grid, utils=utils,
-                                 spliner=spliner, make_nd=make_nd, oracle=oracle)
+    """The reference package as installed by baseline/install_ref.py (the same copy
+    bench.py's reference arm times), third-party stubs from baseline/ref_loader.py."""
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import install_ref
+    import ref_loader
+    install_ref.install()
+    return ref_loader.load(synth.PARNAMES)
 
 
 def inject_grid(R, setup, name=None):
-    name = name or setup['name']
-    si = R.spec_inter
-    si.interp_cache.template_lib = 'synthetic/'
-    it = si.SpecInterpolator(
-        name, si.GridInterp(setup['uvecs'], setup['idgrid'], setup['vec'],
-                            setup['dats'], exp=True),
-        si.GridOutsideCheck(setup['uvecs'], setup['vec'], setup['idgrid']),
-        setup['lam'], R.read_grid.LogParamMapper([0]), setup['parnames'],
-        log_step=True)
-    si.interp_cache.interps[name] = it
-    return it
+    import ref_loader
+    return ref_loader.inject_grid(R, setup, name)
 
 
 def inject_tri(R, setup, name):
