@@ -340,7 +340,11 @@ def run_gpu(args):
     # end to end: every requested step again, from host arrays (the first warm-up step
     # builds the persistent engine)
     n_e2e = args.steps
-    ms_e2e, _, _, _, _ = timed(step_e2e, n_e2e, max(2, min(args.warmup, 3)), finish=e2e_finish)
+    if args.no_e2e:         # profiler runs only: the line then carries no end-to-end figure
+        ms_e2e, timed.io = float('nan'), [0, 0]
+    else:
+        ms_e2e, _, _, _, _ = timed(step_e2e, n_e2e, max(2, min(args.warmup, 3)),
+                                   finish=e2e_finish)
     e2e_eng.clear()
     # bytes per timed step, counted where the copies are made (_dev.IO_BYTES): flux and
     # error of every spectrum through LikelihoodEngine.reload (+ band rows of resolution
@@ -610,6 +614,8 @@ def main():
     ap.add_argument('--cpu-fraction', type=float, default=1.0,
                     help='fraction of the per-spectrum evaluations the CPU sample runs')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true',
+                    help='diagnostic (profiler runs): skip the end-to-end leg')
     ap.add_argument('--resolution-matrix', type=float, default=0.0, metavar='SIGMA_A',
                     help='diagnostic: attach an 11-diagonal resolution matrix (Gaussian of this '
                          'sigma in Angstrom) to every spectrum (SURVEY.md 8 row f4)')

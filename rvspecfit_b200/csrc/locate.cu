@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128) locate_grid_kernel(rvs_gridmap gm, const 
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K) return;
   const int nd = gm.ndim, nv = 1 << nd;
-  int mypos = 0;
+  int mypos = 0, mynear = 0;
   double myx = 0, myq = 0;
   bool myout = false;
   if (lane < nd) {
@@ -44,6 +44,14 @@ __global__ void __launch_bounds__(128) locate_grid_kernel(rvs_gridmap gm, const 
         if (__ldg(u + mid) <= qi) lo = mid + 1; else hi = mid;
       }
     const int p = lo - 1;
+    {  // nearest grid coordinate of this dimension in the KD-tree's normalised metric
+       // (lower index on a tie): used when the point turns out to be off the grid
+      const int ka = min(max(p, 0), n - 1), kb = min(max(p + 1, 0), n - 1);
+      const double qn = qi / gm.ptp[lane];
+      const double da = fabs(qn - __ldg(u + ka) / gm.ptp[lane]);
+      const double db = fabs(qn - __ldg(u + kb) / gm.ptp[lane]);
+      mynear = db < da ? kb : ka;
+    }
     if (p < 0 || p >= n - 1 || !isfinite(qi)) myout = true;
     else {
       mypos = p;
@@ -89,21 +97,39 @@ __global__ void __launch_bounds__(128) locate_grid_kernel(rvs_gridmap gm, const 
     }
     double res = nan("");  // the host decides (first node, no finite off-grid measure)
     if (finite) {
+      // The squared distance is separable over the dimensions, so the nearest point of
+      // the FULL regular grid is the per-dimension nearest coordinate; if a template
+      // exists there it is the nearest node (an optimiser walking along a grid edge asks
+      // for this on most of its calls).  Otherwise (hole) search the node table.
+      int64_t flat = 0;
+      for (int i = 0; i < nd; i++) flat = flat * gm.len[i] + __shfl_sync(0xffffffffu, mynear, i);
+      const int cand = __ldg(gm.d_idgrid + flat);
       double best = INFINITY;
       int bidx = 0x7fffffff;
-      for (int node = lane; node < gm.nnode; node += 32) {
-        const double *v = gm.d_vnorm + (int64_t)node * nd;
+      if (cand >= 0) {
+        const double *v = gm.d_vnorm + (int64_t)cand * nd;
         double d2 = 0;
         for (int i = 0; i < nd; i++) {
           const double d = qn[i] - __ldg(v + i);
-          d2 += d * d;
+          d2 = fma(d, d, d2);
         }
-        if (d2 < best) { best = d2; bidx = node; }
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        best = d2;
+        bidx = cand;
+      } else {
+        for (int node = lane; node < gm.nnode; node += 32) {
+          const double *v = gm.d_vnorm + (int64_t)node * nd;
+          double d2 = 0;
+          for (int i = 0; i < nd; i++) {
+            const double d = qn[i] - __ldg(v + i);
+            d2 = fma(d, d, d2);
+          }
+          if (d2 < best) { best = d2; bidx = node; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+          if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
       }
       node0 = bidx;
       res = sqrt(best);
