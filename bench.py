@@ -31,6 +31,10 @@ WORKLOADS = {
                  min_vel=-1500, max_vel=1500),
     # config 2: SDSS/BOSS single arm, 24x9x9x4 grid
     'sdss': dict(arms=('sdss',), layout='sdss', npoly=10, min_vel=-1500, max_vel=1500),
+    # config 4: Gaia RVS window, FFT cross-correlation first guess over a (template x
+    # vsini) bank at npoints 8192 (gaia_rvs/make_gaia.sh:5-11, make_ccf.py:496-497,556)
+    'gaia_rvs': dict(arms=('gaiarvs',), layout='small', npoly=10, min_vel=-1000, max_vel=1000,
+                     ccf=dict(npoints=8192, every=7, vsinis=(0., 10., 30., 100., 300.))),
     # config 1 shape (correctness-sized; fits L2, not a roofline workload)
     'test': dict(arms=('test',), layout='test', npoly=15, min_vel=-1000, max_vel=1000),
 }
@@ -150,6 +154,109 @@ class ClockSampler:
             return None
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons),
                     samples=len(sm))
+
+
+# ------------------------------------------------------------------ CCF workload
+def ccf_bank_path(wname):
+    d = '/dev/shm' if os.path.isdir('/dev/shm') else '/tmp'
+    return os.path.join(d, f'rvs_bench_ccfbank_{wname}.npz')
+
+
+def ccf_bank(wname, setup):
+    """The CCF template bank of the workload (built once per box with the device routines
+    of this package, kept in /dev/shm so that the CPU arm's processes map the same arrays)."""
+    from rvspecfit_b200 import make_ccf, spec_inter
+    w = WORKLOADS[wname]
+    c = w['ccf']
+    sh = synth.SHAPES[setup['shape']]
+    conf = make_ccf.get_ccf_config(np.log(sh['t_lo']), np.log(sh['t_hi']), c['npoints'])
+    path = ccf_bank_path(wname)
+    if not os.path.exists(path):
+        bank = spec_inter.getInterpolator(setup['name'], make_config(w)).bank
+        nodes = setup['vec'].T.copy()
+        nodes[:, 0] = 10**nodes[:, 0]
+        b = make_ccf.build_bank(bank, nodes, conf, every=c['every'], vsinis=c['vsinis'])
+        np.savez(path + '.tmp.npz', models=b['models'], params=b['params'],
+                 vsinis=np.array(b['vsinis']))
+        os.replace(path + '.tmp.npz', path)
+    z = np.load(path)
+    return conf, z['models'], z['params'], list(z['vsinis'])
+
+
+def run_gpu_ccf(args):
+    """--mode ccf: one step = fitter_ccf.fit_batch over the batch (device preprocessing,
+    cuFFT, fused product / window / argmin kernels), host arrays in, first guesses out --
+    this path has no resident variant (its inputs are the spectra), so `value` and `e2e`
+    are the same measurement."""
+    import torch
+    from rvspecfit_b200 import _cabi, _dev, fitter_ccf, spec_fit, spec_inter
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
+    w = WORKLOADS[args.workload]
+    cfg = make_config(w)
+    B = args.batch
+    setups, objects, pars, vel = make_inputs(args.workload, B, 1000)
+    for st in setups:
+        spec_inter.register_bank(spec_inter.bank_from_setup(st), template_lib='synthetic/')
+    conf, models, params, vsinis = ccf_bank(args.workload, setups[0])
+    name = setups[0]['name']
+    fitter_ccf.register_ccf_bank(name, np.fft.rfft(models, axis=1), np.fft.rfft(models**2, axis=1),
+                                 models, params, vsinis, list(setups[0]['parnames']), conf)
+    sds = [[spec_fit.SpecData(*a) for a in o] for o in objects]
+    L = _cabi.lib()
+
+    def step():
+        res = fitter_ccf.fit_batch(sds, cfg, want_proc_spec=False)
+        return np.array([[r['best_vel'], r['best_vsini'], r['best_id']] for r in res])
+    for _ in range(args.warmup):
+        out = step()
+    torch.cuda.synchronize()
+    l0 = L.rvs_launch_count()
+    io0 = list(_dev.IO_BYTES)
+    clk = ClockSampler(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1) / args.steps
+    ntempl, npts = len(models), conf['npoints']
+    # algorithmic bytes per (object, template): the two template transforms read and the
+    # inverse transform's output (SURVEY.md section 8d / DESIGN.md 3.3)
+    bytes_step = B * ntempl * 3 * (npts // 2 + 1) * 16
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    dv = out[:, 0] - vel
+    line = {'metric': 'spectra/sec (CCF first guess)', 'value': B / (ms * 1e-3),
+            'unit': 'spectra/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64 / c128', 'data': 'synthetic',
+            'config': {'workload': workload_string(args.workload), 'mode': 'ccf',
+                       'spectra_per_gpu_per_step': B, 'ccf_templates': ntempl,
+                       'ccf_npoints': npts, 'obs_px': len(objects[0][0][1]),
+                       'step': 'fitter_ccf.fit_batch: device preprocessing (masks, soft-L1 '
+                               'continuum, resampling), rfft of the data, product + inverse '
+                               'transform per template, lag window, argmin + parabola'},
+            'e2e': {'value': B / (ms * 1e-3), 'unit': 'spectra/s',
+                    'h2d_bytes_per_step': int((_dev.IO_BYTES[0] - io0[0]) / args.steps),
+                    'd2h_bytes_per_step': int((_dev.IO_BYTES[1] - io0[1]) / args.steps)},
+            'gpu_launches': int(L.rvs_launch_count() - l0), 'clocks': clk.stop(t0, t1),
+            'roofline': {'bound': 'hbm', 'kernel': 'rvs_ccf_accumulate (cuFFT Z2D + ccf_mult / '
+                         'ccf_gather kernels) over the whole step, host work included',
+                         'achieved': bytes_step / (ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                         'frac': bytes_step / (ms * 1e-3) / 1e9 / hbm, 'traffic': None,
+                         'algorithmic_bytes_per_object_template': 3 * (npts // 2 + 1) * 16},
+            'first_guess_rms_kms': float(np.sqrt(np.mean(dv**2))),
+            'first_guess_median_abs_kms': float(np.median(np.abs(dv)))}
+    if not args.no_cpu:
+        line['cpu_baseline'] = cpu_baseline(args)
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -501,6 +608,34 @@ def _cpu_worker(job):
     api = c['api']
     cfg = api['config']
     sd = [api['SpecData'](a[0], a[1], a[2], a[3], badmask=a[4]) for a in c['objects'][idx]]
+    if nevals == -2:     # --mode ccf: the cross-correlation first guess
+        if 'ccf' not in c:
+            z = np.load(ccf_bank_path(wname))
+            sh = synth.SHAPES[WORKLOADS[wname]['arms'][0]]
+            if api['kind'] == 'reference':
+                import ref_loader
+                R = ref_loader.load()
+                conf = R.make_ccf.get_ccf_config(logl0=np.log(sh['t_lo']), logl1=np.log(sh['t_hi']),
+                                                 npoints=w['ccf']['npoints'])
+                CC = R.fitter_ccf.CCFCache
+                nm = w['arms'][0]
+                CC.ccfs[nm] = np.fft.rfft(z['models'], axis=1)
+                CC.ccf2s[nm] = np.fft.rfft(z['models']**2, axis=1)
+                CC.ccf_models[nm] = z['models']
+                CC.ccf_info[nm] = dict(params=z['params'], ccfconf=conf, vsinis=list(z['vsinis']),
+                                       parnames=list(synth.PARNAMES))
+                c['ccf'] = lambda s: R.fitter_ccf.fit(s, cfg)
+            else:
+                import oracle
+                conf = oracle.ccf_config(np.log(sh['t_lo']), np.log(sh['t_hi']), w['ccf']['npoints'])
+                bank = {w['arms'][0]: dict(
+                    fft=np.fft.rfft(z['models'], axis=1), fft2=np.fft.rfft(z['models']**2, axis=1),
+                    models=z['models'], params=z['params'], vsinis=list(z['vsinis']),
+                    parnames=list(synth.PARNAMES), ccfconf=conf)}
+                c['ccf'] = lambda s: oracle.ccf_fit(s, cfg, bank)
+        t0 = time.time()
+        r = c['ccf'](sd)
+        return time.time() - t0, r['best_vel'], api['kind']
     opts = {'npoly': w['npoly']}
     tp, tv, tvs = trial_points(c['pars'], c['vel'], w['layout'], max(nevals, 0), 5)
     vgrid = np.arange(w['min_vel'], w['max_vel'], 5)[:nscan]
@@ -544,6 +679,11 @@ def cpu_baseline(args, bounded=True):
     nobj = 2 * cores
     if args.mode == 'fit':
         nevals, nscan, nobj = -1, len(vg), cores
+    if args.mode == 'ccf':
+        nevals, nscan, nobj = -2, 0, 4 * cores
+        if not os.path.exists(ccf_bank_path(args.workload)):
+            raise RuntimeError('the CCF bank of the workload has not been built: run the GPU '
+                               'arm of --mode ccf once on this box first')
     for k, a in enumerate(w['arms']):       # template rows shared through the page cache
         path = grid_cache_path(args.workload, a)
         if not os.path.exists(path):
@@ -554,7 +694,8 @@ def cpu_baseline(args, bounded=True):
     t0 = time.time()
     with cf.ProcessPoolExecutor(cores, mp_context=mp.get_context('spawn'),
                                 initializer=_cpu_init, initargs=(nobj,)) as ex:
-        list(ex.map(_cpu_worker, [(j[0], j[1], j[2], 1, 3) for j in jobs[:cores]]))  # warm-up: per-worker banks
+        list(ex.map(_cpu_worker, [(j[0], j[1], j[2], -2 if args.mode == 'ccf' else 1, 3)
+                                  for j in jobs[:cores]]))       # warm-up: per-worker banks
         t1 = time.time()
         res = list(ex.map(_cpu_worker, jobs))
         t2 = time.time()
@@ -562,6 +703,13 @@ def cpu_baseline(args, bounded=True):
     kind = res[0][2]
     impl = ('the reference package (baseline/_ref, vel_fit.process)' if kind == 'reference'
             else 'the oracle port (oracle.process)')
+    if args.mode == 'ccf':
+        return dict(value=nobj / wall, unit='spectra/s', cores=cores, kind=kind,
+                    sample=f'{nobj} first guesses by '
+                           f'{"the reference package (fitter_ccf.fit)" if kind == "reference" else "the oracle port (oracle.ccf_fit)"}'
+                           f' on {cores} processes, one object per task; setup {t1 - t0:.1f}s '
+                           'excluded', wall_s=wall,
+                    per_object_s=float(np.mean([r[0] for r in res])))
     if args.mode == 'fit':
         return dict(value=nobj / wall, unit='spectra/s', cores=cores, kind=kind,
                     sample=f'{nobj} complete fits by {impl}: scan, Nelder-Mead, BFGS, '
@@ -589,8 +737,9 @@ def run_reference(args):
     cb['value'] = v
     setups = [a for a in w['arms']]
     line = {'impl': 'reference',
-            'metric': 'spectra/sec (RV-grid chi2 + fit)' if args.mode == 'fit' else
-                      'spectra/sec (RV-grid chi2 scan + fit evaluations)',
+            'metric': {'fit': 'spectra/sec (RV-grid chi2 + fit)',
+                       'ccf': 'spectra/sec (CCF first guess)'}.get(
+                           args.mode, 'spectra/sec (RV-grid chi2 scan + fit evaluations)'),
             'value': v, 'unit': 'spectra/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', 1)),
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cb['wall_s'] * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
@@ -623,7 +772,7 @@ def main():
                     help='diagnostic: kernel start/end times of this many evaluation rounds')
     ap.add_argument('--stage-profile', action='store_true',
                     help='diagnostic: CUDA-event time of every kernel of the evaluation call')
-    ap.add_argument('--mode', default='fit', choices=['fit', 'proxy'],
+    ap.add_argument('--mode', default='fit', choices=['fit', 'proxy', 'ccf'],
                     help='fit: complete vel_fit.process fits (the headline); proxy: one RV scan '
                          '+ a fixed count of evaluations at pre-generated points (kernel study)')
     ap.add_argument('--groups', type=int, default=0,
@@ -636,6 +785,8 @@ def main():
         args.groups = 1
     if args.impl == 'reference':
         run_reference(args)
+    elif args.mode == 'ccf':
+        run_gpu_ccf(args)
     else:
         run_gpu(args)
 

@@ -314,6 +314,26 @@ int rvs_ccf_accumulate(const rvs_ccf_arm *arm, const double *d_pspec, const doub
 int rvs_ccf_best(const double *d_chisq, const double *d_sse, const double *d_velgrid, int nrow,
                  int ntempl, int nvel, double *d_out, double *d_best_ccf, void *stream);
 
+/* Data preparation in front of the CCF, on the device: make_ccf.preprocess_data
+ * (reference make_ccf.py:330-414, with interp_masker :287-327 and get_continuum
+ * :105-164) for n spectra observed on ONE pixel grid d_lam[npix] (increasing).
+ * d_spec, d_espec: [n][npix]; d_bad: [n][npix] bytes or NULL.  Host-built tables of the
+ * pixel grid (rvspecfit_b200/make_ccf.py DevicePrep): d_basis[npix][nn] = value at every
+ * pixel of the quadratic interpolating spline through unit node values (the continuum is
+ * exp(d_basis . p)), d_bin[nn+1] = pixel ranges whose medians start the node values,
+ * d_left[npoints] / d_wr[npoints] = left bracketing pixel (-1: outside the spectrum) and
+ * right-hand weight of every CCF pixel.  continuum = 0 skips the continuum (ccfconf
+ * without splinestep).  Outputs d_pspec, d_pivar [n][npoints] (what rvs_ccf_accumulate
+ * takes), optionally d_cont [n][npix] and d_info [n][2] (solver iterations, 1 = every
+ * pixel was masked).  rvs_ccf_prep_smem: bytes of shared memory a spectrum of npix pixels
+ * needs (RVS_E_LIMIT above ~220 kB: preprocess such spectra on the host). */
+int64_t rvs_ccf_prep_smem(int npix, int nn);
+int rvs_ccf_preprocess(const double *d_lam, const double *d_spec, const double *d_espec,
+                       const uint8_t *d_bad, int n, int npix, const double *d_basis, int nn,
+                       const int32_t *d_bin, const int32_t *d_left, const double *d_wr,
+                       int npoints, int continuum, double maxerr, double *d_pspec,
+                       double *d_pivar, double *d_cont, int32_t *d_info, void *stream);
+
 /* ---- host-side lock-step Nelder-Mead stepper (nm_host.cpp; no device work) ----
  * The optimiser loop of vel_fit.process (reference vel_fit.py:628-650:
  * scipy.optimize.minimize(method='Nelder-Mead', options={initial_simplex, xatol, fatol,

@@ -105,6 +105,9 @@ SIGNATURES = {
     'rvs_ccf_workspace': (c_i64, [ctypes.POINTER(CcfArm), c_int]),
     'rvs_ccf_accumulate': (c_int, [ctypes.POINTER(CcfArm), c_dp, c_dp, c_int, c_dp, c_dp, c_dp,
                                    c_dp, c_i64, c_dp]),
+    'rvs_ccf_prep_smem': (c_i64, [c_int, c_int]),
+    'rvs_ccf_preprocess': (c_int, [c_dp, c_dp, c_dp, c_dp, c_int, c_int, c_dp, c_int, c_dp, c_dp,
+                                   c_dp, c_int, c_int, c_dbl, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'rvs_nm_create': (ctypes.c_void_p, [c_int, c_int, c_dp, c_dbl, c_dbl, c_i64]),
     'rvs_nm_destroy': (None, [ctypes.c_void_p]),
     'rvs_nm_request': (c_i64, [ctypes.c_void_p, c_int, c_dp, c_dp, c_i64]),

@@ -121,11 +121,31 @@ def _workspace(nbytes):
     return _ws[key]
 
 
-def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=None):
+def _stack_rows(pairs):
+    """[(proc_spec, proc_ivar)] rows, host arrays or device rows -> two (n, npoints)
+    device tensors."""
+    torch = _dev.torch_mod()
+    if all(isinstance(p[0], np.ndarray) for p in pairs):
+        return (_dev.upload(np.stack([p[0] for p in pairs]), np.float64),
+                _dev.upload(np.stack([p[1] for p in pairs]), np.float64))
+    cols = []
+    for k in (0, 1):
+        cols.append(torch.stack([p[k] if not isinstance(p[k], np.ndarray)
+                                 else _dev.upload(p[k], np.float64) for p in pairs]))
+    return cols[0].contiguous(), cols[1].contiguous()
+
+
+def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=None,
+              preprocess='device', want_proc_spec=True):
     """fitter_ccf.fit for many objects.  objects: list of lists of SpecData.
     preprocessed: optional list (per object) of dicts setup -> (proc_spec,
-    proc_ivar) that bypasses the host-side continuum fit.  Returns a list of the
-    reference's result dictionaries (plus 'best_id')."""
+    proc_ivar) that bypasses the preprocessing.  preprocess: 'device' -- masks, gap
+    bridging, continuum fit and resampling on the GPU for the spectra of every pixel grid
+    in one launch (make_ccf.DevicePrep; spectra it does not take go to the host route);
+    'host' -- the reference's own steps (make_ccf.preprocess_data) in a pool of host
+    processes.  want_proc_spec=False leaves 'proc_spec' out of the results (saves the
+    download in throughput runs).  Returns a list of the reference's result dictionaries
+    (plus 'best_id')."""
     L = _cabi.lib()
     objects = [[o] if isinstance(o, SpecData) else list(o) for o in objects]
     nobj = len(objects)
@@ -148,16 +168,28 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=Non
     # of a batch run in a pool of host processes (make_ccf.preprocess_many)
     jobs, where = [], []
     proc = [[None] * len(o) for o in objects]
+    dev_groups = {}     # (setup, pixel grid) -> [(i, a)] for the device route
     for i, o in enumerate(objects):
         for a, sd in enumerate(o):
             if preprocessed is not None:
                 proc[i][a] = tuple(np.asarray(_, dtype=np.float64)
                                    for _ in preprocessed[i][sd.name])
+            elif preprocess == 'device' and np.isfinite(sd.spec).all() and \
+                    make_ccf.device_prep(sd.lam, sd.gridkey, banks[sd.name].ccfconf).ok:
+                dev_groups.setdefault((sd.name, sd.gridkey), []).append((i, a))
             else:
                 jobs.append((sd.lam, sd.spec, sd.espec, sd.badmask, banks[sd.name].ccfconf))
                 where.append((i, a))
     for (i, a), res in zip(where, make_ccf.preprocess_many(jobs, workers)):
         proc[i][a] = res
+    for (name, gkey), members in dev_groups.items():
+        first = objects[members[0][0]][members[0][1]]
+        prep = make_ccf.device_prep(first.lam, gkey, banks[name].ccfconf)
+        sds = [objects[i][a] for i, a in members]
+        d_ps, d_pi = prep(np.stack([s.spec for s in sds]), np.stack([s.espec for s in sds]),
+                          np.stack([s.badmask for s in sds]))
+        for r, (i, a) in enumerate(members):
+            proc[i][a] = (d_ps[r], d_pi[r])          # device rows
     d_vg = _dev.upload(vel_grid, np.float64)
     block = max(1, int(CHISQ_BLOCK_BYTES // (ntempl * nvel * 8)))
     results = [None] * nobj
@@ -176,9 +208,7 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=Non
             for name, rows in groups.items():
                 bank = banks[name]
                 tab = bank.lag_table(maxvel, vel_grid)
-                ps = np.stack([proc[i0 + r][a][0] for r in rows])
-                pi = np.stack([proc[i0 + r][a][1] for r in rows])
-                d_ps, d_pi = _dev.upload(ps, np.float64), _dev.upload(pi, np.float64)
+                d_ps, d_pi = _stack_rows([proc[i0 + r][a] for r in rows])
                 d_row = _dev.upload(np.asarray(rows), np.int32)
                 arm = tab['arm']
                 need = L.rvs_ccf_workspace(ctypes.byref(arm), len(rows))
@@ -209,8 +239,12 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=Non
                 best_model={sd.name: np.roll(banks[sd.name].models[bid],
                                              int(bvel / banks[sd.name].velstep))
                             for sd in objects[i]},
-                proc_spec={sd.name: proc[i][a][0] for a, sd in enumerate(objects[i])},
                 vel_grid=vel_grid, best_id=bid)
+            if want_proc_spec:
+                results[i]['proc_spec'] = {
+                    sd.name: (proc[i][a][0] if isinstance(proc[i][a][0], np.ndarray)
+                              else _dev.download(proc[i][a][0]))
+                    for a, sd in enumerate(objects[i])}
     return results
 
 
@@ -219,4 +253,4 @@ def fit(specdata, config):
     fitter_ccf.py:62-253, same arguments and returned keys."""
     if isinstance(specdata, SpecData):
         specdata = [specdata]
-    return fit_batch([list(specdata)], config)[0]
+    return fit_batch([list(specdata)], config, preprocess='host')[0]
