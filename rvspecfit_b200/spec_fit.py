@@ -1148,7 +1148,9 @@ def get_chisq_continuum(specdata, options=None):
     ca, ra = np.zeros(len(specdata)), np.zeros(len(specdata))
     for i, sd in enumerate(specdata):
         batch = SpectrumBatch([sd])
-        obs = batch.obs(npoly, rbf, resol=False)   # spec_fit.py:739-783: no resolution matrix
+        # a SpecData with a resolution matrix gets it applied to the unit template, as the
+        # reference does (spec_fit.py:765-767): the rows of the matrix do not sum to exactly 1
+        obs = batch.obs(npoly, rbf)
         # unit template on a 4-knot linear grid covering the data: y=1, z=0
         x = np.linspace(sd.lam[0] * 0.5, sd.lam[-1] * 2, 4)
         h, hinv, cp, winv = np.zeros(3), np.zeros(3), np.zeros(2), np.zeros(2)

@@ -522,8 +522,145 @@ def gold_resol(R):
     np.savez_compressed(os.path.join(HERE, 'resol.npz'), **out)
 
 
+def gold_branches(R):
+    """Branches the other fixtures do not reach:
+      * a Gaia-RVS-shaped arm (0.05 A template sampling: 1.75 km/s per knot) evaluated at
+        vsini up to 450 km/s -- rotation kernels of up to ~260 one-sided taps, beyond
+        the fused path's limit of 128, and in between the case where only the ROUNDED
+        tap bound exceeds it -- with find_best at vsini 300;
+      * an object with RAGGED arms (one of three arms missing) at off-grid parameter
+        vectors: the off-grid penalty is added once per arm the object has;
+      * a complete vel_fit.process on a three-arm DESI-shaped object;
+      * get_chisq on the FULL 28 600-node DESI layout (the bench's banks) at six points;
+      * get_chisq_continuum for SpecData carrying a resolution matrix;
+      * fitter_ccf.fit at npoints 8192 (make_ccf.preprocess_data outputs + first guess)."""
+    import scipy.sparse
+    out = {}
+    cfg = frozen_config(R)
+    # ---- Gaia-RVS, high vsini
+    st = synth.make_setup('gaiarvs', 'tiny', seed=41)
+    inject_grid(R, st, 'gaiarvs')
+    out['gaia_dats_sum'] = checksum(st['dats'])
+    objs = make_objects([st], 'tiny', 2, 9100, sn_range=(40, 120), vel_sig=60.)
+    pack_objects(objs, out, 'gaia_')
+    rs = np.random.RandomState(8)
+    ev = []
+    for k, vs in enumerate([-1, 5., 60., 150., 215., 300., 450., 300.]):
+        p = synth.random_params('tiny', 1, 9200 + k)[0]
+        ev.append([rs.uniform(-150, 150), *p, vs])
+    ev = np.array(ev)
+    out['gaia_eval'] = ev
+    res = np.zeros((len(objs), len(ev)))
+    for i, o in enumerate(objs):
+        sd = specdata_of(R, o)
+        for j, e in enumerate(ev):
+            rot = None if e[5] < 0 else (e[5],)
+            res[i, j] = R.spec_fit.get_chisq(sd, e[0], tuple(e[1:5]), rot,
+                                             options={'npoly': 10}, config=cfg)
+    out['gaia_chisq'] = res
+    vg = np.arange(-500, 500, 5.)
+    sd = specdata_of(R, objs[0])
+    fb = R.spec_fit.find_best(sd, vg, [tuple(objs[0]['params'])], rot_params=(300.,),
+                              options={'npoly': 10}, config=cfg)
+    out['gaia_scan_grid'] = vg
+    for k in ('best_chi', 'best_vel', 'vel_err', 'kurtosis', 'skewness'):
+        out[f'gaia_scan_{k}'] = fb[k]
+    # ---- CCF at 8192 points: preprocessing outputs and the first guess (the bank is
+    # rebuilt by the test from the same seeds with this package's builder; its
+    # continuum-normalised models are pinned by ccf.npz at smaller sizes)
+    sh = synth.SHAPES['gaiarvs']
+    conf = R.make_ccf.get_ccf_config(logl0=np.log(sh['t_lo']), logl1=np.log(sh['t_hi']),
+                                     npoints=8192)
+    out['gaia_ccf_conf'] = np.array([conf['logl0'], conf['logl1'], conf['npoints'],
+                                     conf['splinestep']])
+    inds = np.arange(0, st['dats'].shape[0], 3)
+    specs = np.exp(st['dats'][inds].astype(np.float64))
+    vec = st['vec'].T[inds].copy()
+    vec[:, 0] = 10**vec[:, 0]
+    models, params, vs = R.make_ccf.preprocess_model_list(st['lam'], specs, vec, conf,
+                                                          vsinis=[0., 100., 300.])
+    CC = R.fitter_ccf.CCFCache
+    CC.ccfs['gaiarvs'] = np.fft.rfft(models, axis=1)
+    CC.ccf2s['gaiarvs'] = np.fft.rfft(models**2, axis=1)
+    CC.ccf_models['gaiarvs'] = models
+    CC.ccf_info['gaiarvs'] = dict(params=params, ccfconf=conf, vsinis=vs,
+                                  parnames=st['parnames'])
+    out['gaia_ccf_params'], out['gaia_ccf_vsinis'] = params, np.array(vs)
+    out['gaia_ccf_models_sum'] = models.sum(axis=1)
+    ccfg = frozen_config(R, max_vel=600, vel_step0=2.5)
+    for i, o in enumerate(objs):
+        sd = specdata_of(R, o)
+        ps, pi = R.make_ccf.preprocess_data(sd[0].lam, sd[0].spec, sd[0].espec,
+                                            badmask=sd[0].badmask, ccfconf=conf)
+        out[f'gaia_ccf_{i}_proc_spec'], out[f'gaia_ccf_{i}_proc_ivar'] = ps, pi
+        r = R.fitter_ccf.fit(sd, ccfg)
+        out[f'gaia_ccf_{i}_best_vel'] = r['best_vel']
+        out[f'gaia_ccf_{i}_best_vsini'] = r['best_vsini']
+        out[f'gaia_ccf_{i}_best_par'] = np.array([r['best_par'][k] for k in synth.PARNAMES])
+        out[f'gaia_ccf_{i}_best_ccf_min'] = float(np.min(r['best_ccf']))
+    # ---- three DESI arms (tiny layout): ragged arms off the grid, and a complete fit
+    names = ('desi_b', 'desi_r', 'desi_z')
+    arms = [synth.make_setup(s, 'tiny', seed=21 + k) for k, s in enumerate(names)]
+    for a in arms:
+        inject_grid(R, a)
+    out['desi_dats_sum'] = np.array([checksum(a['dats']) for a in arms])
+    objs3 = make_objects(arms, 'tiny', 2, 7300, sn_range=(30, 90), vel_sig=120.)
+    pack_objects(objs3, out, 'd3_')
+    offgrid = np.array([[35., 9500., 2.0, -1.0, 0.2, 8.],      # teff above the grid
+                        [-20., 5000., 2.0, -2.4, 0.2, -1],      # feh below
+                        [5., 5000., 5.4, -1.0, 1.3, 20.],       # logg and alpha above
+                        [60., 4800., 2.2, -0.8, 0.4, 12.]])     # inside
+    out['d3_offgrid_eval'] = offgrid
+    rag = np.zeros((3, len(offgrid)))
+    sd_all = specdata_of(R, objs3[0])
+    for r, keep in enumerate(((0, 1, 2), (0, 2), (1,))):
+        sd = [sd_all[k] for k in keep]
+        for j, e in enumerate(offgrid):
+            rot = None if e[5] < 0 else (e[5],)
+            rag[r, j] = R.spec_fit.get_chisq(sd, e[0], tuple(e[1:5]), rot,
+                                             options={'npoly': 10}, config=cfg)
+    out['d3_ragged_chisq'] = rag
+    start = {'teff': 5500., 'logg': 3.0, 'feh': -1.0, 'alpha': 0.3, 'vsini': 10.}
+    keys = ('vel', 'vel_err', 'vel_skewness', 'vel_kurtosis', 'vsini', 'chisq')
+    for i, o in enumerate(objs3):
+        res3 = R.vel_fit.process(specdata_of(R, o), dict(start), fixParam=[], config=cfg,
+                                 options={'npoly': 10})
+        for k in keys:
+            out[f'd3_{i}_{k}'] = res3[k]
+        out[f'd3_{i}_param'] = np.array([res3['param'][k] for k in synth.PARNAMES])
+        out[f'd3_{i}_param_err'] = np.array([res3['param_err'][k] for k in synth.PARNAMES])
+        out[f'd3_{i}_chisq_array'] = np.array(res3['chisq_array'])
+        out[f'd3_{i}_success'] = res3['minimize_success']
+    # ---- continuum-only fit with a resolution matrix (spec_fit.py:739-783)
+    sd0 = sd_all[0]
+    rm = R.spec_fit.construct_resol_mat(sd0.lam, width=1.1)
+    sdr = R.spec_fit.SpecData(sd0.name, sd0.lam, sd0.spec, sd0.espec, badmask=sd0.badmask,
+                              resolution=rm)
+    cc = R.spec_fit.get_chisq_continuum([sdr, sd_all[1]], options={'npoly': 10})
+    out['cont_resol_chisq'] = np.array(cc['chisq_array'])
+    out['cont_resol_redchisq'] = np.array(cc['redchisq_array'])
+    # ---- the full DESI layout (28 600 nodes): the banks of bench.py
+    sys.path.insert(0, ROOT)
+    import bench
+    setups, objects, pars, vel = bench.make_inputs('desi', 4, 4242)
+    out['full_dats_sum'] = np.array([checksum(s['dats'][::97]) for s in setups])
+    for s in setups:
+        inject_grid(R, s)
+    tp, tv, tvs = bench.trial_points(pars, vel, 'desi', 3, 77)
+    cfgd = R.utils.freezeDict(bench.make_config(bench.WORKLOADS['desi']))
+    full = np.zeros((2, 3))
+    for i in range(2):
+        sd = [R.spec_fit.SpecData(a[0], a[1], a[2], a[3], badmask=a[4]) for a in objects[i]]
+        for e in range(3):
+            full[i, e] = R.spec_fit.get_chisq(sd, tv[e, i], tuple(tp[e, i]), (tvs[e, i],),
+                                              options={'npoly': 10}, config=cfgd)
+    out['full_chisq'] = full
+    np.savez_compressed(os.path.join(HERE, 'branches.npz'), **out)
+
+
 ALL = dict(kat=gold_kat, interp=gold_interp, chisq=gold_chisq, process=gold_process,
-           ccf=gold_ccf, switches=gold_switches, resol=gold_resol)
+           ccf=gold_ccf, switches=gold_switches, resol=gold_resol, branches=gold_branches)
+
 
 if __name__ == '__main__':
     which = sys.argv[1:] or list(ALL)

