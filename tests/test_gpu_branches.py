@@ -84,22 +84,42 @@ def test_offgrid_penalty_counts_present_arms_only(golden):
     ev = g['d3_offgrid_eval']
     objects = [_sd(o, keep) for keep in ((0, 1, 2), (0, 2), (1,))]
     vs = np.where(ev[:, 5] < 0, 0.0, ev[:, 5])
+    idx = np.repeat(np.arange(3), len(ev))
+    rows = np.tile(np.arange(len(ev)), 3)
+    want = g['d3_ragged_chisq']
+    inside = np.array([False, False, False, True])
+
+    def check(got, what):
+        # Off the grid the reference's template is exp() of ONE float32 row, which numpy
+        # evaluates in float32 with its SIMD expf (spec_inter.py:160,167).  That routine is
+        # not correctly rounded: on this fixture's rows 40 % of its values differ from the
+        # correctly rounded float32 exp (up to 1.6e-7 relative; checked on the host with
+        # the oracle, which calls the same numpy routine and matches the fixture to 1e-10),
+        # which moves -2 log L by ~1e-7 of its size (measured <= 3.5e-3 on ~3e4).  The
+        # device rounds exp() correctly to float32; a penalty counted for a missing arm
+        # would be off by 1e3 or more.  Inside the grid the usual 1e-9 holds.
+        got = got.reshape(3, -1)
+        close(got[:, inside], want[:, inside], rtol=CHI_RTOL, what=what + ', inside')
+        close(got[:, ~inside], want[:, ~inside], rtol=0, atol=3e-7 * np.abs(want).max(),
+              what=what + ', off the grid')
+        return got
+    res = {}
     for fused in (True, False):
         eng = spec_fit.LikelihoodEngine(objects, cfg, opts, fused=fused)
-        idx = np.repeat(np.arange(3), len(ev))
-        rows = np.tile(np.arange(len(ev)), 3)
         # vsini -1 in the fixture means rot_params=None; a zero vsini is the same template
-        got = eng.evaluate(idx, ev[rows, 0], ev[rows, 1:5], vs[rows])
-        close(got.reshape(3, -1), g['d3_ragged_chisq'], rtol=CHI_RTOL,
-              what=f'ragged arms off the grid (fused={fused})')
+        res[fused] = check(eng.evaluate(idx, ev[rows, 0], ev[rows, 1:5], vs[rows]),
+                           f'ragged arms (fused={fused})')
+    # the two kernel sets round identically, so they must agree to 1e-9 off the grid too:
+    # the fused path counts the penalty exactly as the general path does
+    close(res[True], res[False], rtol=CHI_RTOL, what='fused vs general path')
     # and through the packed objective of the batched fit (rvs_fit_pack / rvs_fit_collect)
     eng = spec_fit.LikelihoodEngine(objects, cfg, opts)
     names = list(spec_inter.getSpecParams('desi_b', cfg))
     start = [dict(zip(names, ev[3, 1:5]), vsini=10.) for _ in objects]
     fobj = batch_fit.BatchObjective(eng, names, start, [], True, cfg, None)
     X = np.column_stack([ev[rows, 0], vs[rows], ev[rows, 1:5]])
-    close(fobj(idx, X).reshape(3, -1), g['d3_ragged_chisq'], rtol=CHI_RTOL,
-          what='ragged arms off the grid (packed objective)')
+    packed = check(fobj(idx, X), 'ragged arms (packed objective)')
+    close(packed, res[True], rtol=1e-12, what='packed objective vs engine')
 
 
 def test_three_arm_process_matches_reference(golden):
