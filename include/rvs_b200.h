@@ -271,10 +271,16 @@ int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld, const rvs_knot
 
 /* RV-grid statistics of find_best for S scans: scan s has nv velocities
  * vels[s*nv..] and chi-squares chisq[(s*npar+q)*nv + j] for npar templates.
- * out[s*8..] = best_chi, best_vel, vel_err, skewness, kurtosis, i_vel, i_par, 0;
- * probs (may be NULL) [S,nv]. */
+ * out[s*8..] = best_chi, best_vel, vel_err, skewness, kurtosis, i_vel, i_par, flags
+ * (bit 0: the parabola vertex is not strictly inside its bracket -- the reference's
+ * assertion spec_fit.py:1014 would fail; bit 1: a chi-square is NaN); probs (may be NULL)
+ * [S,nv].  rvs_scan_stats_ragged: scan s uses only its first d_nv[s] velocities; rows keep
+ * the stride nv_stride (refinement scans of many objects, vel_fit.py:358-439). */
 int rvs_scan_stats(const double *d_vels, const double *d_chisq, int S, int npar, int nv,
                    int quadratic, double *d_out, double *d_probs, void *stream);
+int rvs_scan_stats_ragged(const double *d_vels, const double *d_chisq, int S, int npar,
+                          int nv_stride, const int32_t *d_nv, int quadratic, double *d_out,
+                          double *d_probs, void *stream);
 
 /* ---- cross-correlation first guess (fitter_ccf.py:126-232) ---------------- */
 /* One arm's CCF template bank and the lag -> velocity-grid table.  d_fft,

@@ -102,6 +102,8 @@ SIGNATURES = {
                                 c_dp, c_dbl, c_int, ctypes.POINTER(Obs), c_dp, c_dp, c_int,
                                 c_dp, c_i64, c_dp, c_dp, c_dp, ctypes.POINTER(GridBox), c_dp]),
     'rvs_scan_stats': (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
+    'rvs_scan_stats_ragged': (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_dp, c_int, c_dp, c_dp,
+                                      c_dp]),
     'rvs_ccf_workspace': (c_i64, [ctypes.POINTER(CcfArm), c_int]),
     'rvs_ccf_accumulate': (c_int, [ctypes.POINTER(CcfArm), c_dp, c_dp, c_int, c_dp, c_dp, c_dp,
                                    c_dp, c_i64, c_dp]),

@@ -598,14 +598,24 @@ def _scan_round(eng, idx, grids, params, vsini):
     in one launch per arm, statistics on the device per distinct grid length.
     Returns (n, 5): best_chi, best_vel, vel_err, skewness, kurtosis."""
     nv = np.array([len(g) for g in grids])
-    V = np.stack([np.concatenate([g, np.full(nv.max() - len(g), g[-1])]) for g in grids])
+    nmax = int(nv.max())
+    if (nv == nmax).all():
+        V = np.stack(grids)
+    else:
+        V = np.empty((len(grids), nmax))
+        for i, g in enumerate(grids):
+            V[i, :nv[i]] = g
+            V[i, nv[i]:] = g[-1]
     chi = eng.evaluate(idx, V, params, vsini)
-    out = np.zeros((len(idx), 5))
-    for n in np.unique(nv):
-        sel = np.nonzero(nv == n)[0]
-        st, _ = spec_fit.scan_stats(V[sel, :n], chi[sel, None, :n])
-        out[sel] = st[:, :5]
-    return out
+    st, _ = spec_fit.scan_stats(V, chi[:, None, :], nv=None if (nv == nmax).all() else nv,
+                                want_probs=False)
+    # the reference's find_best would trip its assertion / propagate the NaN here
+    # (spec_fit.py:1014, 1072-1092); vel_fit.process raises, and so does the batch
+    bad = st[:, 7] != 0
+    if bad.any():
+        raise RuntimeError('RV scan without a usable minimum (flat or non-finite chi-square '
+                           f'around it) for object(s) {np.asarray(idx)[bad].tolist()}')
+    return st[:, :5]
 
 
 def hessian_points(x, hs):

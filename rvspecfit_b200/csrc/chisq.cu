@@ -193,11 +193,15 @@ static int launch_scan(const ScanArgs &a, cudaStream_t st) {
 
 // ------------------------------------------------------------ scan statistics
 // One CTA per scan.  spec_fit.py:1072-1092.
-__global__ void scan_stats_kernel(const double *vels, const double *chisq, int npar, int nv,
-                                  int quadratic, double *out, double *probs) {
+// Ragged form: `nvs` (may be NULL) gives the number of velocities of every scan; rows of
+// vels / chisq / probs keep the stride nv_stride.
+__global__ void scan_stats_kernel(const double *vels, const double *chisq, int npar,
+                                  int nv_stride, const int32_t *nvs, int quadratic, double *out,
+                                  double *probs) {
   const int s = blockIdx.x;
-  const double *v = vels + (int64_t)s * nv;
-  const double *c = chisq + (int64_t)s * npar * nv;
+  const int nv = nvs ? nvs[s] : nv_stride;
+  const double *v = vels + (int64_t)s * nv_stride;
+  const double *c = chisq + (int64_t)s * npar * nv_stride;
   __shared__ double sval[32];
   __shared__ int sidx[32];
   __shared__ double sred[4][32];
@@ -209,7 +213,7 @@ __global__ void scan_stats_kernel(const double *vels, const double *chisq, int n
   bool anynan = false;
   for (int t = threadIdx.x; t < npar * nv; t += blockDim.x) {
     const int q = t / nv, i = t - q * nv;
-    const double x = c[t];
+    const double x = c[(int64_t)q * nv_stride + i];
     const int flat = i * npar + q;
     if (isnan(x)) anynan = true;
     if (x < best || (x == best && flat < bidx)) { best = x; bidx = flat; }
@@ -229,12 +233,13 @@ __global__ void scan_stats_kernel(const double *vels, const double *chisq, int n
     if (sidx[0] == 0x7fffffff) sidx[0] = 0;
   }
   __syncthreads();
-  (void)anynan;
+  anynan = __syncthreads_or(anynan);
   const int i1 = sidx[0] / npar, i2 = sidx[0] % npar;
-  const double *col = c + (int64_t)i2 * nv;
+  const double *col = c + (int64_t)i2 * nv_stride;
   const double cmin = col[i1];
   // parabola vertex through the three points around the minimum
   double bv = v[i1];
+  int vertex_bad = 0;
   if (quadratic && i1 > 0 && i1 < nv - 1) {
     const double x0 = v[i1 - 1] - v[i1], x2 = v[i1 + 1] - v[i1];
     const double y0 = col[i1 - 1] - cmin, y2 = col[i1 + 1] - cmin;
@@ -243,7 +248,11 @@ __global__ void scan_stats_kernel(const double *vels, const double *chisq, int n
     const double a2 = (y0 * x2 - y2 * x0) / den;
     const double a1 = (y2 * x0 * x0 - y0 * x2 * x2) / den;
     bv = v[i1] - a1 / (2 * a2);
+    // the reference asserts that the vertex lies strictly inside the bracket
+    // (spec_fit.py:1014); a flat or non-finite triple fails it -- reported in out[7]
+    if (!(bv > v[i1 - 1] && bv < v[i1 + 1])) vertex_bad = 1;
   }
+  if (anynan) vertex_bad |= 2;
   // moments
   auto block4 = [&](double e0, double e1, double e2, double e3) {
     e0 = warp_sum(e0); e1 = warp_sum(e1); e2 = warp_sum(e2); e3 = warp_sum(e3);
@@ -264,7 +273,7 @@ __global__ void scan_stats_kernel(const double *vels, const double *chisq, int n
   double m2 = 0, m3 = 0, m4 = 0;
   for (int i = threadIdx.x; i < nv; i += blockDim.x) {
     const double pr = exp(-0.5 * (col[i] - cmin)) / tot;
-    if (probs) probs[(int64_t)s * nv + i] = pr;
+    if (probs) probs[(int64_t)s * nv_stride + i] = pr;
     const double dv = v[i] - bv;
     m2 += pr * dv * dv;
     m3 += pr * dv * dv * dv;
@@ -279,7 +288,7 @@ __global__ void scan_stats_kernel(const double *vels, const double *chisq, int n
       sk = bc[1] / (err * err * err);
     }
     double *o = out + (int64_t)s * 8;
-    o[0] = cmin; o[1] = bv; o[2] = err; o[3] = sk; o[4] = ku; o[5] = i1; o[6] = i2; o[7] = 0;
+    o[0] = cmin; o[1] = bv; o[2] = err; o[3] = sk; o[4] = ku; o[5] = i1; o[6] = i2; o[7] = vertex_bad;
   }
 }
 
@@ -394,8 +403,21 @@ extern "C" int rvs_scan_stats(const double *d_vels, const double *d_chisq, int S
   if (S == 0) return 0;
   RVS_REQUIRE(d_vels && d_chisq && d_out && npar >= 1 && nv >= 1, RVS_E_ARG,
               "rvs_scan_stats: bad arguments");
-  scan_stats_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(d_vels, d_chisq, npar, nv, quadratic,
-                                                         d_out, d_probs);
+  scan_stats_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(d_vels, d_chisq, npar, nv, nullptr,
+                                                         quadratic, d_out, d_probs);
+  RVS_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int rvs_scan_stats_ragged(const double *d_vels, const double *d_chisq, int S, int npar,
+                                     int nv_stride, const int32_t *d_nv, int quadratic,
+                                     double *d_out, double *d_probs, void *stream) {
+  using namespace rvs;
+  if (S == 0) return 0;
+  RVS_REQUIRE(d_vels && d_chisq && d_out && d_nv && npar >= 1 && nv_stride >= 1, RVS_E_ARG,
+              "rvs_scan_stats_ragged: bad arguments");
+  scan_stats_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(d_vels, d_chisq, npar, nv_stride, d_nv,
+                                                         quadratic, d_out, d_probs);
   RVS_LAUNCH_OK();
   return 0;
 }

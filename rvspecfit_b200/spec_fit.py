@@ -1179,17 +1179,26 @@ def get_chisq_continuum(specdata, options=None):
     return dict(chisq_array=ca, redchisq_array=ra)
 
 
-def scan_stats(vel_grid, chisq, quadratic=True):
+def scan_stats(vel_grid, chisq, quadratic=True, nv=None, want_probs=True):
     """find_best tail (spec_fit.py:1072-1092) on the device.  vel_grid (S, nv),
-    chisq (S, npar, nv).  Returns (out (S, 8), probs (S, nv))."""
+    chisq (S, npar, nv); `nv` (S,) optional: scan s uses its first nv[s] velocities
+    only (ragged refinement grids).  Returns (out (S, 8), probs (S, nv) or None)."""
     vel_grid = np.asarray(vel_grid, dtype=np.float64)
-    S, npar, nv = chisq.shape
+    S, npar, nvmax = chisq.shape
     d_v, d_c = _dev.upload(vel_grid, np.float64), _dev.upload(chisq, np.float64)
-    d_out, d_pr = _dev.empty((S, 8), np.float64), _dev.empty((S, nv), np.float64)
-    rc = _cabi.lib().rvs_scan_stats(_dev.ptr(d_v), _dev.ptr(d_c), S, npar, nv, int(quadratic),
-                                    _dev.ptr(d_out), _dev.ptr(d_pr), _dev.stream())
+    d_out = _dev.empty((S, 8), np.float64)
+    d_pr = _dev.empty((S, nvmax), np.float64) if want_probs else None
+    if nv is None:
+        rc = _cabi.lib().rvs_scan_stats(_dev.ptr(d_v), _dev.ptr(d_c), S, npar, nvmax,
+                                        int(quadratic), _dev.ptr(d_out), _dev.ptr(d_pr),
+                                        _dev.stream())
+    else:
+        d_nv = _dev.upload(np.asarray(nv), np.int32)
+        rc = _cabi.lib().rvs_scan_stats_ragged(_dev.ptr(d_v), _dev.ptr(d_c), S, npar, nvmax,
+                                               _dev.ptr(d_nv), int(quadratic), _dev.ptr(d_out),
+                                               _dev.ptr(d_pr), _dev.stream())
     _cabi.check(rc, 'rvs_scan_stats')
-    return _dev.download(d_out), _dev.download(d_pr)
+    return _dev.download(d_out), (_dev.download(d_pr) if want_probs else None)
 
 
 def find_best(specdata, vel_grid, params_list, rot_params=None, resol_params=None,

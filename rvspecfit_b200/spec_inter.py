@@ -276,6 +276,18 @@ class interp_cache:
     template_lib = None
 
 
+def clear_caches():
+    """Forget every cached interpolator, CCF bank and likelihood engine."""
+    import sys
+    interp_cache.interps.clear()
+    interp_cache.template_lib = None
+    for mod, attr in (('fitter_ccf', 'CCFCache'), ('spec_fit', '_engine_cache')):
+        m = sys.modules.get(__package__ + '.' + mod)
+        if m is not None:
+            obj = getattr(m, attr)
+            (obj.banks if attr == 'CCFCache' else obj).clear()
+
+
 def register_bank(bank, template_lib=None):
     """Put an in-memory bank into the registry `getInterpolator` serves."""
     if template_lib is not None:
@@ -325,6 +337,13 @@ def getInterpolator(HR, config, warmup_cache=False, cache=None):
     as is; otherwise the reference's on-disk products are loaded (needs h5py)."""
     if cache is None:
         cache = interp_cache.interps
+        lib = config['template_lib']
+        if interp_cache.template_lib is not None and lib != interp_cache.template_lib:
+            # another template library: nothing cached for the old one may be served
+            # (reference spec_inter.py:321-324) -- interpolators, CCF banks and the
+            # engines that captured them
+            clear_caches()
+            interp_cache.template_lib = lib
     if HR not in cache:
         from . import bank_io
         cache[HR] = SpecInterpolator(bank_io.load_bank(HR, config))

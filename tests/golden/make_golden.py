@@ -23,6 +23,7 @@ import sys
 import types
 
 import numpy as np
+import scipy.sparse
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
@@ -658,7 +659,64 @@ def gold_branches(R):
     np.savez_compressed(os.path.join(HERE, 'branches.npz'), **out)
 
 
-ALL = dict(kat=gold_kat, interp=gold_interp, chisq=gold_chisq, process=gold_process,
+def gold_specdata(R):
+    """desi_fit.get_specdata (desi/desi_fit.py:781-888): masking, bridging, error clamp,
+    dichroic mask, and the deconvolved resolution matrices, on synthetic DESI-like frames
+    with zero / negative / non-finite inverse variances, masked runs at the ends and in
+    the middle, an all-masked arm and a zero-median arm."""
+    import importlib
+    for m in ('astropy.table', 'astropy.units'):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    desi_fit = importlib.import_module('rvspecfit.desi.desi_fit')
+    out = {}
+    rs = np.random.RandomState(12)
+    setups = ['b', 'r', 'z']
+    waves = {'b': np.arange(4000., 4700.1, 0.8), 'r': np.arange(6000., 6400.1, 0.8),
+             'z': np.arange(8000., 8400.1, 0.8)}
+    nfib, width = 5, 11
+    fluxes, ivars, masks, resol = {}, {}, {}, {}
+    for s in setups:
+        n = len(waves[s])
+        fl = 20 * (1 + 0.3 * np.sin(waves[s] / 200.))[None, :] + rs.normal(size=(nfib, n))
+        iv = 1. / (0.5 + rs.uniform(size=(nfib, n)))**2
+        mk = np.zeros((nfib, n), dtype=int)
+        iv[0, 100:130] = 0
+        iv[0, 400] = -1
+        iv[1, :12] = 0
+        iv[1, -7:] = 0
+        fl[1, 250] = np.nan
+        iv[2, 300] = np.inf
+        mk[2, 330:360] = 4
+        iv[3, rs.choice(n, 30, replace=False)] = 1e6         # errors to be clamped
+        xs = np.arange(width) - width // 2
+        sig = 1.2 + 0.3 * np.sin(np.arange(n) / 300.)
+        band = np.exp(-0.5 * (xs[:, None] / sig[None, :])**2)
+        resol[s] = np.tile((band / band.sum(axis=0))[None], (nfib, 1, 1))
+        out[f'resol_{s}'] = resol[s][0]                     # the same band for every fibre
+        fluxes[s], ivars[s], masks[s] = fl, iv, mk
+    masks['r'][4, :] = 1                                    # arm dropped
+    fluxes['z'][4] = np.where(rs.uniform(size=len(waves['z'])) < 0.6, 0.0, fluxes['z'][4])
+    for s in setups:
+        out[f'wave_{s}'], out[f'flux_{s}'], out[f'ivar_{s}'] = waves[s], fluxes[s], ivars[s]
+        out[f'mask_{s}'] = masks[s]
+    sig0 = {'b': 0.5, 'r': 0.45, 'z': 0.4}
+    for mode, kw in (('plain', {}), ('resol', dict(use_resolution_matrix=True,
+                                                      lsf_sigma0_angstrom=sig0))):
+        for f in range(nfib):
+            sds = desi_fit.get_specdata(waves, fluxes, ivars, masks, resol, f, setups, **kw)
+            out[f'{mode}_{f}_names'] = np.array([sd.name for sd in sds] if sds else [])
+            for sd in sds or ():
+                out[f'{mode}_{f}_{sd.name}_spec'] = sd.spec
+                out[f'{mode}_{f}_{sd.name}_espec'] = sd.espec
+                out[f'{mode}_{f}_{sd.name}_bad'] = sd.badmask
+                if sd.resolution is not None and f in (0, 3):
+                    dia = scipy.sparse.dia_matrix(sd.resolution.mat)
+                    out[f'{mode}_{f}_{sd.name}_resol_offsets'] = dia.offsets
+                    out[f'{mode}_{f}_{sd.name}_resol_data'] = dia.data
+    np.savez_compressed(os.path.join(HERE, 'specdata.npz'), **out)
+
+
+ALL = dict(specdata=gold_specdata, kat=gold_kat, interp=gold_interp, chisq=gold_chisq, process=gold_process,
            ccf=gold_ccf, switches=gold_switches, resol=gold_resol, branches=gold_branches)
 
 

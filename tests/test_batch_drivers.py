@@ -196,7 +196,7 @@ class _Arm:
     badmask = np.zeros(3, dtype=bool)
 
 
-def _host_scan_stats(vel_grid, chisq, quadratic=True):
+def _host_scan_stats(vel_grid, chisq, quadratic=True, nv=None, want_probs=True):
     """spec_fit.scan_stats on the host (the oracle's restatement of find_best's tail)."""
     import os
     import sys
@@ -204,7 +204,8 @@ def _host_scan_stats(vel_grid, chisq, quadratic=True):
     import oracle
     out = np.zeros((len(vel_grid), 8))
     for s in range(len(vel_grid)):
-        r = oracle.scan_statistics(vel_grid[s], chisq[s].T, quadratic)
+        n = len(vel_grid[s]) if nv is None else int(nv[s])
+        r = oracle.scan_statistics(vel_grid[s][:n], chisq[s][:, :n].T, quadratic)
         out[s, :5] = r['best_chi'], r['best_vel'], r['vel_err'], r['skewness'], r['kurtosis']
     return out, None
 

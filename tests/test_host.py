@@ -3,6 +3,7 @@ the reference's own outputs, the HDF5 dictionary decoder, optimiser helpers."""
 import types
 
 import numpy as np
+import pytest
 
 from helpers import close, unpack_objects
 from rvspecfit_b200 import bank_io, make_ccf, vel_fit
@@ -157,3 +158,70 @@ def test_preprocess_many_pool_equals_serial(golden):
     for a, b, c in zip(serial, pooled, again):
         for k in range(2):
             assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k])
+
+
+def test_get_specdata_matches_reference(golden):
+    """desi_data.get_specdata against the reference's desi_fit.get_specdata
+    (desi/desi_fit.py:781-888) on synthetic frames with zero / negative / non-finite
+    inverse variances, masked runs, clamped errors, a dropped arm and a zero-median arm,
+    with and without resolution matrices (fixture specdata.npz)."""
+    import scipy.sparse
+    from rvspecfit_b200 import desi_data
+    g = golden('specdata')
+    setups = ['b', 'r', 'z']
+    waves = {s: g[f'wave_{s}'] for s in setups}
+    fluxes = {s: g[f'flux_{s}'] for s in setups}
+    ivars = {s: g[f'ivar_{s}'] for s in setups}
+    masks = {s: g[f'mask_{s}'] for s in setups}
+    nfib = len(fluxes['b'])
+    resol = {s: np.tile(g[f'resol_{s}'][None], (nfib, 1, 1)) for s in setups}
+    sig0 = {'b': 0.5, 'r': 0.45, 'z': 0.4}
+    ncmp = 0
+    for mode, kw in (('plain', {}), ('resol', dict(use_resolution_matrix=True,
+                                                      lsf_sigma0_angstrom=sig0))):
+        for f in range(nfib):
+            sds = desi_data.get_specdata(waves, fluxes, ivars, masks, resol, f, setups, **kw)
+            want = [str(_) for _ in g[f'{mode}_{f}_names']]
+            assert [sd.name for sd in sds or ()] == want, (mode, f)
+            for sd in sds or ():
+                assert np.array_equal(sd.spec, g[f'{mode}_{f}_{sd.name}_spec'], equal_nan=True)
+                assert np.array_equal(sd.espec, g[f'{mode}_{f}_{sd.name}_espec'])
+                assert np.array_equal(sd.badmask, g[f'{mode}_{f}_{sd.name}_bad'])
+                key = f'{mode}_{f}_{sd.name}_resol_data'
+                if key in g:
+                    dia = scipy.sparse.dia_matrix(sd.resolution.mat)
+                    assert np.array_equal(dia.offsets, g[f'{mode}_{f}_{sd.name}_resol_offsets'])
+                    assert np.allclose(dia.data, g[key], rtol=1e-13, atol=1e-15)
+                    ncmp += 1
+    assert ncmp >= 4
+    # arm 'r' of the last fibre is entirely masked -> dropped, as in the reference
+    assert 'desi_r' not in [str(_) for _ in g[f'plain_{nfib - 1}_names']]
+
+
+def test_template_library_change_clears_caches():
+    """a config pointing at another template library must not be served
+    the first library's banks (reference spec_inter.py:321-324)."""
+    from rvspecfit_b200 import fitter_ccf, spec_fit, spec_inter
+    ic = spec_inter.interp_cache
+    saved = (dict(ic.interps), ic.template_lib, dict(fitter_ccf.CCFCache.banks),
+             dict(spec_fit._engine_cache))
+    try:
+        ic.interps.clear()
+        ic.interps['arm'] = 'interpolator of library A'
+        ic.template_lib = 'libA/'
+        fitter_ccf.CCFCache.banks['arm'] = 'ccf bank of library A'
+        spec_fit._engine_cache['k'] = 'engine of library A'
+        assert spec_inter.getInterpolator('arm', {'template_lib': 'libA/'}) == \
+            'interpolator of library A'
+        with pytest.raises(Exception):      # library B has no files: the old bank is NOT served
+            spec_inter.getInterpolator('arm', {'template_lib': 'libB/'})
+        assert 'arm' not in ic.interps and not fitter_ccf.CCFCache.banks
+        assert not spec_fit._engine_cache
+    finally:
+        ic.interps.clear()
+        ic.interps.update(saved[0])
+        ic.template_lib = saved[1]
+        fitter_ccf.CCFCache.banks.clear()
+        fitter_ccf.CCFCache.banks.update(saved[2])
+        spec_fit._engine_cache.clear()
+        spec_fit._engine_cache.update(saved[3])
