@@ -278,10 +278,28 @@ def run_gpu(args):
     from rvspecfit_b200 import _cabi, _dev, spec_fit, spec_inter, batch_fit, shard
     w = WORKLOADS[args.workload]
     cfg = make_config(w)
-    B = args.batch
-    # weak scaling: every rank owns its own B spectra; the template grid is
-    # replicated in each GPU's HBM; no data-path collective
-    setups, objects, pars, vel = make_inputs(args.workload, B, 1000 + 7919 * rank)
+    if world > 1 and hasattr(os, 'sched_setaffinity'):
+        # every rank (its interpreter and the host threads of its lock-step sets) on its
+        # own block of cores, so that the ranks do not migrate over each other
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // world)
+        mine = cores[local * per:(local + 1) * per] or cores
+        try:
+            os.sched_setaffinity(0, mine)
+        except OSError:
+            pass
+    if args.total_spectra:
+        # strong scaling: a fixed set of spectra, rank r fits its contiguous block
+        # (shard.block_range); the set is generated whole so that every N fits the same objects
+        lo, hi = shard.block_range(args.total_spectra, rank, world)
+        B = hi - lo
+        setups, objects, pars, vel = make_inputs(args.workload, args.total_spectra, 1000)
+        objects, pars, vel = objects[lo:hi], pars[lo:hi], vel[lo:hi]
+    else:
+        # weak scaling: every rank owns its own B spectra; the template grid is
+        # replicated in each GPU's HBM; no data-path collective
+        B = args.batch
+        setups, objects, pars, vel = make_inputs(args.workload, B, 1000 + 7919 * rank)
     for st in setups:
         spec_inter.register_bank(spec_inter.bank_from_setup(st), template_lib='synthetic/')
     opts = {'npoly': w['npoly']}
@@ -521,7 +539,7 @@ def run_gpu(args):
                     share_of_step=ksum['fused_eval_ms_busy'] / ms,
                     timing='CUDA events around every evaluation call; busy time = union '
                            'of the call intervals over the timed steps')
-    nspec_total = B * world
+    nspec_total = args.total_spectra or B * world
     per_step = ms / args.steps
     fit = args.mode == 'fit'
     step_txt = ('per spectrum: the complete vel_fit.process fit (RV-grid scan, Nelder-Mead, '
@@ -534,8 +552,8 @@ def run_gpu(args):
                   'spectra/sec (RV-grid chi2 scan + fit evaluations)',
         'value': nspec_total / (per_step * 1e-3), 'unit': 'spectra/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic',
+        'higher_is_better': True, 'scaling': 'strong' if args.total_spectra else 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_string(args.workload),
                    'obs_px': npo, 'template_px': npt,
                    'spectra_per_gpu_per_step': B, 'rv_trials': len(vgrid),
@@ -759,6 +777,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='desi', choices=list(WORKLOADS))
     ap.add_argument('--batch', type=int, default=4096, help='spectra per GPU per step')
+    ap.add_argument('--total-spectra', type=int, default=0,
+                    help='strong scaling: this many spectra in total, split over the ranks in '
+                         'contiguous blocks (default: weak scaling, --batch per GPU)')
     ap.add_argument('--evals', type=int, default=EVALS_PER_FIT)
     ap.add_argument('--cpu-fraction', type=float, default=1.0,
                     help='fraction of the per-spectrum evaluations the CPU sample runs')

@@ -269,6 +269,32 @@ int rvs_chisq_fused(const void *d_grid, int grid_f64, int64_t ld, const rvs_knot
                     const double *d_vels, int K, double *d_tn, int64_t tn_stride, double *d_work,
                     double *d_chisq, int32_t *d_status, const rvs_gridbox *box, void *stream);
 
+/* One arm (spectral setup) of a multi-arm evaluation call: the per-arm arguments of
+ * rvs_chisq_fused. */
+typedef struct {
+  const void *d_grid;
+  int32_t grid_f64, log_spec;
+  int64_t ld;
+  const rvs_knots *knots;
+  const rvs_obs *obs;
+  const int32_t *d_oix;
+  double *d_tn;
+  int64_t tn_stride;
+  double *d_work;
+  double *d_chisq;
+  int32_t *d_status;
+  const rvs_gridbox *box;
+} rvs_fused_arm;
+/* rvs_chisq_fused for the narm (<= 4) arms of a call whose items share vertex ids and
+ * weights (banks with one node table, located once), rotation and velocity: when the arms
+ * run the same kernel instantiations (same grid kind, npoly, all on shared pixel grids, no
+ * resolution matrices) every kernel of the call is launched ONCE for all arms -- 6 launches
+ * per call instead of 5 per arm, the small latency-bound kernels paid once; otherwise the
+ * arms are enqueued one after the other.  Values are identical to per-arm calls. */
+int rvs_chisq_fused_multi(const rvs_fused_arm *arms, int narm, const int32_t *d_ids,
+                          const double *d_w, int nvert, const double *d_vsini, double vsini_max,
+                          const double *d_vels, int K, void *stream);
+
 /* RV-grid statistics of find_best for S scans: scan s has nv velocities
  * vels[s*nv..] and chi-squares chisq[(s*npar+q)*nv + j] for npar templates.
  * out[s*8..] = best_chi, best_vel, vel_err, skewness, kurtosis, i_vel, i_par, flags

@@ -20,6 +20,7 @@ c_dbl = ctypes.c_double
 ST_OK, ST_TEMPLATE_BAD, ST_NOT_PD, ST_RANGE, ST_TAPS, ST_LIMIT = 0, 1, 2, 4, 8, 16
 MAX_NPOLY = 16
 MAX_FUSED_TAPS = 128
+MAX_ARMS = 4
 
 
 class Knots(ctypes.Structure):
@@ -58,6 +59,14 @@ class CcfArm(ctypes.Structure):
                 ('d_dxn', c_dp), ('d_dx', c_dp), ('npoints', ctypes.c_int32),
                 ('ntempl', ctypes.c_int32), ('continuum', ctypes.c_int32),
                 ('nvel', ctypes.c_int32)]
+
+
+class FusedArm(ctypes.Structure):
+    """struct rvs_fused_arm"""
+    _fields_ = [('d_grid', c_dp), ('grid_f64', ctypes.c_int32), ('log_spec', ctypes.c_int32),
+                ('ld', c_i64), ('knots', ctypes.POINTER(Knots)), ('obs', ctypes.POINTER(Obs)),
+                ('d_oix', c_dp), ('d_tn', c_dp), ('tn_stride', c_i64), ('d_work', c_dp),
+                ('d_chisq', c_dp), ('d_status', c_dp), ('box', ctypes.POINTER(GridBox))]
 
 
 class FitLayout(ctypes.Structure):
@@ -101,6 +110,8 @@ SIGNATURES = {
     'rvs_chisq_fused': (c_int, [c_dp, c_int, c_i64, ctypes.POINTER(Knots), c_dp, c_dp, c_int,
                                 c_dp, c_dbl, c_int, ctypes.POINTER(Obs), c_dp, c_dp, c_int,
                                 c_dp, c_i64, c_dp, c_dp, c_dp, ctypes.POINTER(GridBox), c_dp]),
+    'rvs_chisq_fused_multi': (c_int, [ctypes.POINTER(FusedArm), c_int, c_dp, c_dp, c_int, c_dp, c_dbl,
+                                      c_dp, c_int, c_dp]),
     'rvs_scan_stats': (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
     'rvs_scan_stats_ragged': (c_int, [c_dp, c_dp, c_int, c_int, c_int, c_dp, c_int, c_dp, c_dp,
                                       c_dp]),

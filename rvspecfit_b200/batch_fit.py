@@ -317,7 +317,7 @@ class _Waiter:
 
 
 # below this many active problems an iteration's candidate points go out in one call
-SPECULATE_BELOW = 640
+SPECULATE_BELOW = 256
 # smallest lock-step set worth its own evaluation calls
 NM_MIN_GROUP = 64
 
@@ -548,13 +548,14 @@ def run_pipeline(gens, start):
     return out
 
 
-def run_threads(gens, start, device=None):
+def run_threads(gens, start, device=None, post=None):
     """run_pipeline with one host thread per coroutine.  The per-round host work of a
     lock-step set is library calls that release the interpreter lock (the optimiser
     stepper rvs_nm_*, rvs_fit_pack / rvs_fit_collect, graph launches, event waits), so
     the sets' host work runs on different cores instead of queueing behind each other.
     `device`: CUDA device index the threads make current (a new thread starts on
-    device 0)."""
+    device 0).  `post`: applied to every coroutine's return value on its own thread (the
+    result assembly of one set then runs under the device work of the others)."""
     import threading
     out = [None] * len(gens)
     errors = []
@@ -568,7 +569,10 @@ def run_threads(gens, start, device=None):
             while not errors:
                 req = gen.send(start(req)())
         except StopIteration as stop:
-            out[gi] = stop.value
+            try:
+                out[gi] = stop.value if post is None else post(stop.value)
+            except BaseException as exc:      # noqa: BLE001
+                errors.append(exc)
         except BaseException as exc:          # noqa: BLE001  (re-raised by the caller)
             errors.append(exc)
     threads = [threading.Thread(target=work, args=(gi,), daemon=True) for gi in range(len(gens))]
@@ -806,8 +810,8 @@ class _Sub:
 
 # objects per lock-step set and sets in flight: enough sets that the tail of one (few
 # live problems, latency-bound calls) runs under the bulk of the others
-FIT_GROUP = 1024
-FIT_MAX_GROUPS = 4
+FIT_GROUP = 256
+FIT_MAX_GROUPS = 2
 THREADS = True
 
 
@@ -857,20 +861,9 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
             with general_lock:
                 return _Ready(eng.evaluate(idx, vel[:, None], params, vsini, want_model=True))
         raise ValueError(kind)
-    import contextlib
-    general_lock = getattr(eng, '_general_lock', contextlib.nullcontext())
-    if threads is None:
-        threads = THREADS and len(gens) > 1 and hasattr(eng, 'submit_fit')
-    try:
-        if threads:
-            results = run_threads(gens, start, _dev.torch_mod().cuda.current_device())
-        else:
-            results = run_pipeline(gens, start)
-    finally:
-        eng.timer = None
-        eng.drain()
-    out = [None] * B
-    for r in results:
+    def assemble(r):
+        """Result dictionaries of one set: [(object index, dict)]."""
+        rows_out = []
         info = r['info']
         tot = r['chisq'][:, 0]
         rows = {name: {int(o): j for j, o in enumerate(arm['sel'])}
@@ -901,6 +894,24 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
                 ret['raw_models'].append(raw)
                 ret['chisq_array'].append(float(np.sum((((model - sd.spec) / sd.espec)[good])**2)))
                 ret['npix_array'].append(int(good.sum()))
+            rows_out.append((int(i), ret))
+        return rows_out
+    import contextlib
+    general_lock = getattr(eng, '_general_lock', contextlib.nullcontext())
+    if threads is None:
+        threads = THREADS and len(gens) > 1 and hasattr(eng, 'submit_fit')
+    try:
+        if threads:
+            results = run_threads(gens, start, _dev.torch_mod().cuda.current_device(),
+                                  post=assemble)
+        else:
+            results = [assemble(r) for r in run_pipeline(gens, start)]
+    finally:
+        eng.timer = None
+        eng.drain()
+    out = [None] * B
+    for rows in results:
+        for i, ret in rows:
             out[i] = ret
     process_batch.last_phase_seconds = phase
     return out

@@ -182,7 +182,18 @@ struct PrepArgs {
   int blen[3];
 };
 
-__global__ void __launch_bounds__(128) prep_kernel(PrepArgs a) {
+// The arms of an evaluation call (the setups of a multi-arm object: three for DESI) go
+// through ONE launch of every kernel of the call: blockIdx.y (.z for the Gram kernels)
+// selects the arm's argument record in the launch's constant parameter block.  A call is
+// then 6 kernels instead of 16, its small fixed-latency kernels are paid once instead of
+// once per arm, and the tail of one arm's grid is filled by the others.
+constexpr int RVS_MAX_ARMS = 4;
+struct PrepArgsM {
+  PrepArgs a[RVS_MAX_ARMS];
+};
+
+__global__ void __launch_bounds__(128) prep_kernel(const __grid_constant__ PrepArgsM m) {
+  const PrepArgs &a = m.a[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= a.K) return;
@@ -331,9 +342,16 @@ __device__ __forceinline__ void prefetch_l1(const void *p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
+struct ChunkArgsM {
+  ChunkArgs a[RVS_MAX_ARMS];
+  alignas(64) CUtensorMap tmap[RVS_MAX_ARMS];
+};
+
 template <typename GT, int NV, bool TMA>
 __global__ void __launch_bounds__(CK_THREADS, TMA ? CK_MINB_TMA : CK_MINB)
-chunk_kernel(const ChunkArgs a, const __grid_constant__ CUtensorMap tmap) {
+chunk_kernel(const __grid_constant__ ChunkArgsM arms) {
+  const ChunkArgs &a = arms.a[blockIdx.y];
+  const CUtensorMap &tmap = arms.tmap[blockIdx.y];
   extern __shared__ __align__(128) double sm[];
   __shared__ int64_t s_off[CK_WARPS][32];  // element offset of each grid row
   __shared__ double s_w[CK_WARPS][32];

@@ -30,14 +30,18 @@ static int launch_gram_np(const GramArgs &a, int K, cudaStream_t st) {
 }
 
 template <int NP>
-static int launch_gram_mma_np(GramMmaArgs a, cudaStream_t st) {
+static int launch_gram_mma_np(GramMmaArgsM m, int narm, cudaStream_t st) {
   constexpr int NT = NP <= 10 ? 2 : 1;
   constexpr int NI = 8 * NT;
+  const GramMmaArgs &a = m.a[0];      // K and the basis layout are the same for every arm
   RVS_REQUIRE(a.npp == ((NP + 1) & ~1), RVS_E_ARG, "gram: basis rows of %d doubles, expected %d",
               a.npp, (NP + 1) & ~1);
   const int groups = (a.K + NI - 1) / NI;
-  a.KS = std::min(GM_MAX_KS, std::max(1, (512 + groups - 1) / groups));
-  dim3 grid(groups, a.KS);
+  // pixel splits: a function of the item count only, so that an arm's partial sums are
+  // taken in the same order whether it is launched alone or with the other arms
+  const int KS = std::min(GM_MAX_KS, std::max(1, (512 + groups - 1) / groups));
+  for (int i = 0; i < narm; i++) m.a[i].KS = KS;
+  dim3 grid(groups, KS, narm);
   size_t tile_smem = sizeof(double) * GM_WARPS * GM_NSTG * gm_stage_doubles(a.npp, NI);
   tile_smem = std::max(tile_smem, sizeof(double) * GramTiles<NP>::ROWS * (NI + 1));  // s_red alias
   static size_t smem_set = 0;
@@ -47,15 +51,15 @@ static int launch_gram_mma_np(GramMmaArgs a, cudaStream_t st) {
     smem_set = tile_smem;
   }
   prof_begin(ST_GRAM, st);
-  gram_mma_kernel<NP, NT><<<grid, GM_THREADS, tile_smem, st>>>(a);
+  gram_mma_kernel<NP, NT><<<grid, GM_THREADS, tile_smem, st>>>(m);
   prof_end(ST_GRAM, st);
   RVS_LAUNCH_OK();
   prof_begin(ST_SOLVE, st);
-  gram_solve_kernel<NP, NT><<<(a.K + GM_WARPS - 1) / GM_WARPS, GM_THREADS, 0, st>>>(a);
+  gram_solve_kernel<NP, NT><<<dim3((a.K + GM_WARPS - 1) / GM_WARPS, narm), GM_THREADS, 0, st>>>(m);
   prof_end(ST_SOLVE, st);
   RVS_LAUNCH_OK();
   prof_begin(ST_RESID, st);
-  resid_mma_kernel<NP, NT><<<grid, GM_THREADS, 0, st>>>(a);
+  resid_mma_kernel<NP, NT><<<grid, GM_THREADS, 0, st>>>(m);
   prof_end(ST_RESID, st);
   RVS_LAUNCH_OK();
   return 0;
@@ -97,9 +101,10 @@ int RVS_CAT(launch_scan_mma_group, RVS_NP_GROUP)(const ScanArgs &a, int npoly, c
   return RVS_E_ARG;
 }
 
-int RVS_CAT(launch_gram_mma_group, RVS_NP_GROUP)(const GramMmaArgs &a, int npoly, cudaStream_t st) {
+int RVS_CAT(launch_gram_mma_group, RVS_NP_GROUP)(const GramMmaArgsM &m, int narm, int npoly,
+                                                 cudaStream_t st) {
   switch (npoly) {
-#define RVS_CASE(N) case N: return launch_gram_mma_np<N>(a, st);
+#define RVS_CASE(N) case N: return launch_gram_mma_np<N>(m, narm, st);
 #if RVS_NP_GROUP == 0
     RVS_CASE(1) RVS_CASE(2) RVS_CASE(3) RVS_CASE(4) RVS_CASE(5) RVS_CASE(6) RVS_CASE(7)
 #elif RVS_NP_GROUP == 1

@@ -48,6 +48,10 @@ struct GramMmaArgs {
   int32_t *status;
 };
 
+struct GramMmaArgsM {     // one record per arm of the call (chunk_kernel.cuh: RVS_MAX_ARMS)
+  GramMmaArgs a[4];
+};
+
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1)
@@ -132,7 +136,9 @@ __host__ __device__ constexpr int gm_stage_doubles(int npp, int ni) {
 }
 
 template <int NP, int NT>
-__global__ void __launch_bounds__(GM_THREADS, NT == 2 ? 4 : 3) gram_mma_kernel(GramMmaArgs a) {
+__global__ void __launch_bounds__(GM_THREADS, NT == 2 ? 4 : 3)
+gram_mma_kernel(const __grid_constant__ GramMmaArgsM m) {
+  const GramMmaArgs &a = m.a[blockIdx.z];
   using TL = GramTiles<NP>;
   constexpr int NI = 8 * NT;
   extern __shared__ __align__(16) double s_dyn[];
@@ -262,7 +268,9 @@ __global__ void __launch_bounds__(GM_THREADS, NT == 2 ? 4 : 3) gram_mma_kernel(G
 // One warp per item: total of the pixel-split partials in fixed order, Cholesky
 // solve (spec_fit.py:236-241), coefficients and log-determinant to global.
 template <int NP, int NT>
-__global__ void __launch_bounds__(GM_THREADS) gram_solve_kernel(GramMmaArgs a) {
+__global__ void __launch_bounds__(GM_THREADS)
+gram_solve_kernel(const __grid_constant__ GramMmaArgsM m) {
+  const GramMmaArgs &a = m.a[blockIdx.y];
   using TL = GramTiles<NP>;
   constexpr int NI = 8 * NT;
   __shared__ double sM[GM_WARPS][TL::NTRI];
@@ -300,7 +308,9 @@ __global__ void __launch_bounds__(GM_THREADS) gram_solve_kernel(GramMmaArgs a) {
 }
 
 template <int NP, int NT>
-__global__ void __launch_bounds__(GM_THREADS) resid_mma_kernel(GramMmaArgs a) {
+__global__ void __launch_bounds__(GM_THREADS)
+resid_mma_kernel(const __grid_constant__ GramMmaArgsM m) {
+  const GramMmaArgs &a = m.a[blockIdx.z];
   constexpr int NI = 8 * NT;
   constexpr int KST = (NP + 3) / 4;  // k-steps over the basis index
   __shared__ double s_red[GM_WARPS][NI];

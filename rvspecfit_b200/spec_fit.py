@@ -776,6 +776,52 @@ class LikelihoodEngine:
                                    _dev.ptr(d_ids0), _dev.ptr(d_w0), _dev.ptr(d_flags[1, 0]),
                                    _dev.ptr(d_chi[1, 0]), ctypes.c_void_p(main.cuda_stream))
             _cabi.check(rc, 'rvs_locate_grid')
+        if shared and narm <= _cabi.MAX_ARMS and not getattr(self, 'serial_arms', False) \
+                and not os.environ.get('RVS_NO_MERGE'):
+            # all arms in ONE launch of every kernel of the call (rvs_chisq_fused_multi)
+            arms = (_cabi.FusedArm * narm)()
+            keep = []
+            for a, name in enumerate(self.setups):
+                arm = self.arms[name]
+                bank, batch = arm['bank'], arm['batch']
+                stride = batch.max_npix
+                d_tn = self._scratch(f'tn{a}_{six}', (K * stride * batch.tn_rows,), np.float64)
+                d_work = self._scratch(
+                    f'work{a}_{six}',
+                    (L.rvs_fused_workspace(K, bank.tapcap(vmax), bank.npix_t),), np.float64)
+                fa = arms[a]
+                fa.d_grid, fa.grid_f64, fa.log_spec = bank.grid.data_ptr(), bank.grid_f64, \
+                    int(bank.log_spec)
+                fa.ld = bank.ld
+                fa.knots = ctypes.pointer(bank.knots)
+                fa.obs = ctypes.pointer(obs_all[a])
+                fa.d_oix, fa.d_tn, fa.tn_stride = d_oix[a].data_ptr(), d_tn.data_ptr(), stride
+                fa.d_work = d_work.data_ptr()
+                fa.d_chisq, fa.d_status = d_chi[0, a].data_ptr(), d_flags[0, a].data_ptr()
+                if bank.box is not None:
+                    fa.box = ctypes.pointer(bank.box)
+                keep.append((d_tn, d_work))
+            rc = L.rvs_chisq_fused_multi(arms, narm, _dev.ptr(d_ids0), _dev.ptr(d_w0), nvert,
+                                         _dev.ptr(d_in[1]) if vmax > 0 else None, vmax,
+                                         _dev.ptr(d_in[0]), K,
+                                         ctypes.c_void_p(main.cuda_stream))
+            _cabi.check(rc, 'rvs_chisq_fused_multi')
+        else:
+            self._enqueue_arms(sl, obs_all, params, vmax, K, narm, d_in, d_oix, d_chi, d_flags,
+                               shared, d_ids0 if shared else None, d_w0 if shared else None)
+        sl['h_chi'][:2 * narm * K].view(2, narm, K).copy_(d_chi, non_blocking=True)
+        sl['h_flags'][:2 * narm * K].view(2, narm, K).copy_(d_flags, non_blocking=True)
+
+    def _enqueue_arms(self, sl, obs_all, params, vmax, K, narm, d_in, d_oix, d_chi, d_flags,
+                      shared, d_ids0, d_w0):
+        """The arms of a call on their own streams, one rvs_chisq_fused each (arms whose
+        banks do not share a node table, or that cannot share launches)."""
+        L = _cabi.lib()
+        torch = _dev.torch_mod()
+        main = torch.cuda.current_stream()
+        bank0 = self.arms[self.setups[0]]['bank']
+        six = sl['ix']
+        nvert = bank0.nvert
         sl['fork_event'].record(main)
         for a, name in enumerate(self.setups):
             arm = self.arms[name]
@@ -815,8 +861,6 @@ class LikelihoodEngine:
             sl['arm_events'][a].record(st)
         for a in range(narm):
             main.wait_event(sl['arm_events'][a])
-        sl['h_chi'][:2 * narm * K].view(2, narm, K).copy_(d_chi, non_blocking=True)
-        sl['h_flags'][:2 * narm * K].view(2, narm, K).copy_(d_flags, non_blocking=True)
 
     def _collect_fast(self, sl, obj, vels, outside_penalty=True):
         """Wait for a submitted evaluation: (total (K,), redo (K,) bool)."""
