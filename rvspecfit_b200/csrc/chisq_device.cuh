@@ -33,6 +33,7 @@ struct ScanArgs {
   const int32_t *resol_offs;
   int nresol;
   int resol_hw;  // max |resol_offs[]|
+  int nby;       // trial blocks per item (1-D grid of the GEMM scan kernel)
 };
 
 constexpr int SCAN_WARPS = 8;

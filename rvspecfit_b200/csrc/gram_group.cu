@@ -72,14 +72,17 @@ static int launch_scan_mma_np(const ScanArgs &a, cudaStream_t st) {
   RVS_REQUIRE(a.npp == ((NP + 1) & ~1), RVS_E_ARG, "scan: basis rows of %d doubles, expected %d",
               a.npp, (NP + 1) & ~1);
   const int by = (a.nv + NI - 1) / NI;
-  RVS_REQUIRE(by <= 65535, RVS_E_LIMIT, "scan: %d velocity trials per item", a.nv);
-  dim3 grid(a.K, by);
+  RVS_REQUIRE((int64_t)by * a.K <= 0x7fffffffLL, RVS_E_LIMIT, "scan: %d items x %d trials", a.K,
+              a.nv);
+  ScanArgs b = a;
+  b.nby = by;
+  const unsigned grid = (unsigned)((int64_t)by * a.K);
   RVS_REQUIRE(!a.resol || a.resol_hw <= RS_HW, RVS_E_LIMIT,
               "scan: resolution matrix half-bandwidth %d > %d", a.resol_hw, RS_HW);
   if (a.resol)  // resampled template staged in shared memory
-    chisq_scan_mma_kernel<NP, NT, true><<<grid, GM_THREADS, 0, st>>>(a);
+    chisq_scan_mma_kernel<NP, NT, true><<<grid, GM_THREADS, 0, st>>>(b);
   else
-    chisq_scan_mma_kernel<NP, NT, false><<<grid, GM_THREADS, 0, st>>>(a);
+    chisq_scan_mma_kernel<NP, NT, false><<<grid, GM_THREADS, 0, st>>>(b);
   RVS_LAUNCH_OK();
   return 0;
 }

@@ -58,8 +58,10 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
   __shared__ double s_rss[GM_WARPS][NI];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int r = lane >> 2, c = lane & 3;
-  const int k = blockIdx.x;
-  const int j0 = blockIdx.y * NI;
+  // 1-D grid, the trial blocks of an item adjacent: CTAs that run together read the
+  // same template (y, z) pairs -- L1 / L2 hits instead of one pass over HBM per trial block
+  const int k = blockIdx.x / a.nby;
+  const int j0 = (blockIdx.x - k * a.nby) * NI;
   const int obj = a.oix[k];
   const int64_t p0 = a.off[obj];
   const int npix = (int)(a.off[obj + 1] - p0);

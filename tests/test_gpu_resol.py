@@ -108,10 +108,13 @@ def test_get_chisq_with_resolution_matches_reference(golden):
             assert np.isclose(fb[k], gr[f'one_{i}_fb_{k}'], rtol=1e-7, atol=1e-9), k
         close(fb['probs'], gr[f'one_{i}_fb_probs'], rtol=1e-6, atol=1e-12)
         close(fb['best_param'], gr[f'one_{i}_fb_best_param'], rtol=1e-12)
-        # the continuum-only fit ignores the matrix (spec_fit.py:739-783)
+        # the continuum-only fit applies the matrix to its unit template
+        # (spec_fit.py:765-767; pinned by branches.npz in test_gpu_branches.py): the rows of
+        # a truncated Gaussian matrix sum to 1 only to rounding, so the two values agree
+        # closely but need not be identical
         a = spec_fit.get_chisq_continuum(sd_res, options=opts)['chisq_array']
         b = spec_fit.get_chisq_continuum(sd_plain, options=opts)['chisq_array']
-        assert np.array_equal(a, b)
+        close(a, b, rtol=1e-6)
 
 
 def test_three_arms_with_banded_matrices_match_reference(golden):
