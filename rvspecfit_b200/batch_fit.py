@@ -23,6 +23,8 @@ its evaluation requests (fit_steps); run_pipeline keeps one request of every
 set in flight, so the host logic of one set and the latency-bound tail of
 another (few live problems) hide under the device work of the rest.
 """
+import os
+
 import numpy as np
 
 from . import _dev, batch_bfgs, spec_fit, spec_inter, vel_fit
@@ -597,28 +599,51 @@ def _drive(gen, sel):
 
 
 # ------------------------------------------------------------ the batched fit
+def _scan_general(eng, idx, V, nv, params, vsini):
+    """Scan statistics (n, 8) through the engine's general path: chi-square matrix of every
+    arm to the host (penalties, SVD rescue, exceptions), then the statistics kernel."""
+    lock = getattr(eng, '_general_lock', None)
+    import contextlib
+    with (lock if lock is not None else contextlib.nullcontext()):
+        chi = eng.evaluate(idx, V, params, vsini)
+        st, _ = spec_fit.scan_stats(V, chi[:, None, :],
+                                    nv=None if (nv == V.shape[1]).all() else nv,
+                                    want_probs=False)
+    return st
+
+
 def _scan_round(eng, idx, grids, params, vsini):
     """find_best (one template per object) for ragged velocity grids: chi-squares
     in one launch per arm, statistics on the device per distinct grid length.
     Returns (n, 5): best_chi, best_vel, vel_err, skewness, kurtosis."""
     nv = np.array([len(g) for g in grids])
     nmax = int(nv.max())
-    if (nv == nmax).all():
+    ragged = not (nv == nmax).all()
+    if not ragged:
         V = np.stack(grids)
     else:
         V = np.empty((len(grids), nmax))
         for i, g in enumerate(grids):
             V[i, :nv[i]] = g
             V[i, nv[i]:] = g[-1]
-    chi = eng.evaluate(idx, V, params, vsini)
-    st, _ = spec_fit.scan_stats(V, chi[:, None, :], nv=None if (nv == nmax).all() else nv,
-                                want_probs=False)
+    idx = np.asarray(idx)
+    fast = eng.scan(idx, V, nv, params, vsini) \
+        if hasattr(eng, 'scan') and not os.environ.get('RVS_NO_FAST_SCAN') else None
+    if fast is not None:
+        # device-resident route; the objects it could not settle take the general one
+        st, redo = fast
+        if redo.any():
+            r = np.nonzero(redo)[0]
+            st[r] = _scan_general(eng, idx[r], V[r], nv[r], params[r],
+                                  None if vsini is None else np.asarray(vsini)[r])
+    else:
+        st = _scan_general(eng, idx, V, nv, params, vsini)
     # the reference's find_best would trip its assertion / propagate the NaN here
     # (spec_fit.py:1014, 1072-1092); vel_fit.process raises, and so does the batch
     bad = st[:, 7] != 0
     if bad.any():
         raise RuntimeError('RV scan without a usable minimum (flat or non-finite chi-square '
-                           f'around it) for object(s) {np.asarray(idx)[bad].tolist()}')
+                           f'around it) for object(s) {idx[bad].tolist()}')
     return st[:, :5]
 
 
@@ -854,8 +879,7 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
         if kind == 'f0':
             return fobj.submit0(*req[1:])
         if kind == 'scan':
-            with general_lock:
-                return _Ready(_scan_round(eng, *req[1:]))
+            return _Ready(_scan_round(eng, *req[1:]))
         if kind == 'model':
             _, idx, vel, params, vsini = req
             with general_lock:

@@ -168,6 +168,7 @@ class SpectrumBatch:
         self.d_gstart = _dev.upload(self.gstart, np.int64)
         self.d_goff = _dev.upload(self.gstart[:-1][gid], np.int64)
         self._prod, self._basis = {}, {}
+        self._mk_lock = threading.Lock()     # derived products are made once, by one thread
         # resolution matrices: band rows by output pixel on the diagonals any member
         # has (a member without a matrix gets the identity), one object pool
         self.resol_offs = self.d_resol = self.d_resol_offs = None
@@ -231,6 +232,12 @@ class SpectrumBatch:
 
     def products(self, sys_err=0.0):
         key = float(sys_err)
+        if key in self._prod:
+            return self._prod[key]
+        with self._mk_lock:
+            return self._products_locked(key)
+
+    def _products_locked(self, key):
         if key not in self._prod:
             ntot = int(self.off[-1])
             dn, einv = [_dev.empty((ntot,), np.float64) for _ in range(2)]
@@ -245,6 +252,12 @@ class SpectrumBatch:
     def basis(self, npoly, rbf):
         """(loglam, P) of the grid pools; P is pixel-major [pixel][npp]."""
         key = (int(npoly), bool(rbf))
+        if key in self._basis:
+            return self._basis[key]
+        with self._mk_lock:
+            return self._basis_locked(key, npoly, rbf)
+
+    def _basis_locked(self, key, npoly, rbf):
         if key not in self._basis:
             ntot = int(self.gstart[-1])
             npp = (npoly + 1) // 2 * 2
@@ -657,6 +670,23 @@ class LikelihoodEngine:
         self._launch(sl, K, Kp, vmax, sys_errs, params)
         return sl
 
+    def _obs_all(self, sys_errs):
+        """struct rvs_obs of every arm for the given systematic errors; the derived
+        products behind them are made once, by one thread (on its current stream: slot
+        streams wait for them through the data event, see _launch)."""
+        obs_all = self._obs_cache.get(sys_errs)
+        if obs_all is None:
+            with self._lock:
+                obs_all = self._obs_cache.get(sys_errs)
+                if obs_all is None:
+                    obs_all = [self.arms[name]['batch'].obs(self.npoly, self.rbf, sys_errs[a])
+                               for a, name in enumerate(self.setups)]
+                    _dev.torch_mod().cuda.current_stream().synchronize()
+                    self._obs_cache[sys_errs] = obs_all
+                    self._data_epoch += 1
+                    self._data_event = None
+        return obs_all
+
     def _launch(self, sl, K, Kp, vmax, sys_errs, params):
         """Start the device work of the evaluation whose inputs are in the slot's pinned
         buffers; records the slot's event behind it."""
@@ -667,14 +697,7 @@ class LikelihoodEngine:
         use_graph = sl['use_graph']
         # per-arm data products are made (once) on the caller's stream
         okey = tuple(sys_errs)
-        obs_all = self._obs_cache.get(okey)
-        if obs_all is None:
-            with self._lock:
-                obs_all = self._obs_cache[okey] = [
-                    self.arms[name]['batch'].obs(self.npoly, self.rbf, sys_errs[a])
-                    for a, name in enumerate(self.setups)]
-                self._data_epoch += 1
-                self._data_event = None
+        obs_all = self._obs_all(okey)
         # The slot's stream waits for the spectra and their derived products (uploaded /
         # computed on the caller's stream by the constructor, reload() or the first obs()
         # of a systematic error) once per such change -- not for whatever else the
@@ -886,6 +909,94 @@ class LikelihoodEngine:
         total = np.add.reduce(chi, axis=0)
         sl['busy'] = False
         return total, redo
+
+    def scan(self, obj, V, nv, params, vsini=None, quadratic=True):
+        """find_best for K objects with one template each (spec_fit.py:1018-1092), without
+        taking the chi-square matrices through the host: V (K, nvmax) velocities (row k uses
+        its first nv[k]), params (K, ndim), vsini (K,) or None.  Vertex location, template
+        build and the RV-scan GEMM per arm, the sum over arms and the statistics kernel all
+        run on the device; one (K, 8) array comes back (rvs_scan_stats: best_chi, best_vel,
+        vel_err, skewness, kurtosis, i_vel, i_par, flags).  Returns (stats, redo): redo (K,)
+        marks the objects this route could not settle (missing arms, off-grid template not
+        usable, template not covering the data, a non-finite or flagged chi-square) -- their
+        rows of `stats` are undefined and the caller takes the general path for them.
+        Returns None when the engine's banks do not allow the route at all."""
+        if not self._fast_banks:
+            return None
+        L = _cabi.lib()
+        torch = _dev.torch_mod()
+        obj = np.asarray(obj, dtype=np.int64)
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        K, nvmax = V.shape
+        nv = np.asarray(nv, dtype=np.int32)
+        params = np.array(params, dtype=np.float64, ndmin=2)
+        narm = len(self.setups)
+        banks = [self.arms[n]['bank'] for n in self.setups]
+        bank0 = banks[0]
+        sig0 = getattr(bank0, 'locate_signature', None)
+        if sig0 is None or any(getattr(b, 'locate_signature', None) != sig0 for b in banks):
+            return None
+        min_vel, max_vel = self.config['min_vel'], self.config['max_vel']
+        redo = ~self._cover0[obj] | (self._oix[:, obj] < 0).any(axis=0)
+        with np.errstate(invalid='ignore'):
+            redo |= (V.min(axis=1) < min_vel) | (V.max(axis=1) > max_vel)
+        d_V = _dev.upload(V, np.float64)
+        d_q = _dev.upload(spec_inter.map_params(params, bank0.log_ids).T, np.float64)
+        d_vs = None if vsini is None else _dev.upload(np.asarray(vsini, dtype=np.float64),
+                                                       np.float64)
+        d_ids = _dev.empty((K, bank0.nvert), np.int32)
+        d_w = _dev.empty((K, bank0.nvert), np.float64)
+        d_lflag = _dev.empty((K,), np.int32)
+        d_out_dist = _dev.empty((K,), np.float64)
+        stream = _dev.stream()
+        rc = L.rvs_locate_grid(ctypes.byref(bank0.gridmap), _dev.ptr(d_q), K, K, _dev.ptr(d_ids),
+                               _dev.ptr(d_w), _dev.ptr(d_lflag), _dev.ptr(d_out_dist), stream)
+        _cabi.check(rc, 'rvs_locate_grid')
+        d_bad = _dev.upload(self.badchi[obj], np.float64)
+        d_pen = d_out_dist * d_bad                 # off-grid penalty of one arm (spec_fit.py:895-896)
+        d_tix = torch.arange(K, dtype=torch.int32, device=d_V.device)
+        d_tot = torch.zeros((K, nvmax), dtype=torch.float64, device=d_V.device)
+        d_flag = d_lflag != 0
+        with self._lock:
+            self.n_eval += int(nv.sum()) * 1
+        obs_all = self._obs_all((0.0,) * narm)
+        for a, name in enumerate(self.setups):
+            arm = self.arms[name]
+            bank, batch = arm['bank'], arm['batch']
+            obs = obs_all[a]
+            d_oix = _dev.upload(np.maximum(self._oix[a, obj], 0), np.int32)
+            yz = _dev.empty((K, bank.npix_t, 2), np.float64)
+            d_tst = _dev.empty((K,), np.int32)
+            t0 = self.timer.start() if self.timer else None
+            rc = L.rvs_template_build(
+                _dev.ptr(bank.grid), bank.grid_f64, bank.ld, ctypes.byref(bank.knots),
+                _dev.ptr(d_ids), _dev.ptr(d_w), bank.nvert, _dev.ptr(d_vs), int(bank.log_spec),
+                K, _dev.ptr(yz), bank.npix_t, _dev.ptr(d_tst), stream)
+            _cabi.check(rc, 'rvs_template_build')
+            if t0 is not None:
+                self.timer.stop('build', t0, K)
+            d_chi = _dev.empty((K, nvmax), np.float64)
+            d_st = _dev.empty((K, nvmax), np.int32)
+            t0 = self.timer.start() if self.timer else None
+            rc = L.rvs_chisq_scan(_dev.ptr(yz), bank.npix_t, _dev.ptr(d_tix),
+                                  ctypes.byref(bank.knots), ctypes.byref(obs), _dev.ptr(d_oix),
+                                  _dev.ptr(d_V), nvmax, K, _dev.ptr(d_chi), _dev.ptr(d_st),
+                                  None, None, None, None, 0, stream)
+            _cabi.check(rc, 'rvs_chisq_scan')
+            if t0 is not None:
+                self.timer.stop('scan', t0, K * nvmax)
+            # total += penalty + chi-square of the arm, in the order the general path adds
+            d_tot += d_pen[:, None] + d_chi
+            d_flag |= (d_tst != 0) | (d_st != 0).any(dim=1)
+        d_nv = _dev.upload(nv, np.int32)
+        d_stats = _dev.empty((K, 8), np.float64)
+        rc = L.rvs_scan_stats_ragged(_dev.ptr(d_V), _dev.ptr(d_tot), K, 1, nvmax, _dev.ptr(d_nv),
+                                     int(quadratic), _dev.ptr(d_stats), None, stream)
+        _cabi.check(rc, 'rvs_scan_stats_ragged')
+        stats = _dev.download(d_stats)
+        redo |= _dev.download(d_flag.to(torch.uint8)).astype(bool)
+        redo |= ~np.isfinite(stats[:, 0])
+        return stats, redo
 
     def submit_fit(self, lay, obj32, X, logvals):
         """Optimiser-phase evaluation of the batched fit's objective for K (object,

@@ -38,7 +38,8 @@ def main():
             torch.cuda.synchronize()
             dt = time.time() - t0
             ks = timer.summary()
-            print(f'{s} rep{rep}: {B / dt:8.1f} fits/s  {dt:6.3f} s  evals/fit {(eng.n_eval - n0) / B:7.1f}  '
+            chk = (float(np.sum([r['vel'] for r in res])), float(np.sum([r['chisq'] for r in res])))
+            print(f'{s} rep{rep}: chk {chk[0]:.9f} {chk[1]:.6f} {B / dt:8.1f} fits/s  {dt:6.3f} s  evals/fit {(eng.n_eval - n0) / B:7.1f}  '
                   f'calls {ks.get("fused_eval_launches")} items/call {ks.get("fused_eval_items_per_launch", 0):.0f} '
                   f'busy {ks.get("fused_eval_ms_busy", 0):.0f} ms  sum {ks.get("fused_eval_ms_total", 0):.0f} ms  '
                   f'scan {ks.get("scan_ms_total", 0):.0f} ms build {ks.get("build_ms_total", 0):.0f} ms  '
