@@ -383,6 +383,10 @@ void *rvs_nm_create(int B, int N, const double *h_sims /* [B][N+1][N] */, double
 void rvs_nm_destroy(void *nm);
 int64_t rvs_nm_request(void *nm, int speculate_below, int32_t *h_idx, double *h_X, int64_t cap);
 int rvs_nm_feed(void *nm, const double *h_f, int64_t n);
+/* Problems still iterating (h_active [B], may be NULL, receives their flags).  The rows
+ * rvs_nm_result gives for a stopped problem are final while the others go on, so a driver
+ * may hand finished problems to the next stage of the fit without waiting for the rest. */
+int64_t rvs_nm_live(void *nm, uint8_t *h_active);
 int rvs_nm_result(void *nm, double *h_x /* [B][N] */, double *h_fun, uint8_t *h_success,
                   double *h_final_simplex, int64_t *h_nit, int64_t *h_nfev);
 
@@ -432,6 +436,72 @@ int64_t rvs_fit_collect(const rvs_fit_layout *L, int64_t K, int64_t Kp, const in
                         int shared_locate, int outside_penalty, const double *h_prior,
                         const double *h_pen, const uint8_t *h_wall, double *h_out,
                         uint8_t *h_redo);
+
+/* ---- native round loop of a lock-step Nelder-Mead stage (drive_host.cpp) -------------
+ * The optimiser loop of vel_fit.process (reference vel_fit.py:628-650) asks for one
+ * objective value after the other; the batched fit asks for one evaluation CALL after the
+ * other, and between two calls sits the host: stepper, packing, launch, wait, reduction.
+ * rvs_nm_drive runs those rounds without the interpreter on the slot the caller holds
+ * (stream, pinned staging, captured graphs of the call's launch configurations) and
+ * returns only for what the caller alone can do (the RVS_DRIVE_* codes). */
+#define RVS_DRIVE_DONE 0      /* every problem has stopped */
+#define RVS_DRIVE_PEEL 1      /* >= stop_stopped problems have stopped, others go on */
+#define RVS_DRIVE_LAUNCH 2    /* inputs packed (K, Kp, vmax set); no captured graph for this
+                                 configuration: launch it, set state = RVS_DRIVE_LAUNCHED */
+#define RVS_DRIVE_REDO 3      /* f_out collected, f_redo marks items for the general path:
+                                 patch f_out, call again */
+#define RVS_DRIVE_PYEVAL 4    /* the call does not fit the fused path: evaluate the request
+                                 (rvs_drive_request), write f_out, state = RVS_DRIVE_COLLECTED */
+#define RVS_DRIVE_IDLE 0
+#define RVS_DRIVE_PACKED 1
+#define RVS_DRIVE_LAUNCHED 2
+#define RVS_DRIVE_COLLECTED 3
+typedef struct {
+  /* the evaluation slot the caller holds for the stage */
+  void *stream;                 /* cudaStream_t */
+  double *h_in;                 /* pinned [2+nspec][Kp] */
+  int32_t *h_oix;               /* pinned [narm][Kp] */
+  const double *h_chi;          /* pinned [2][narm][Kp] */
+  const int32_t *h_flags;       /* pinned [2][narm][Kp] */
+  double *f_prior, *f_pen;      /* [cap] */
+  uint8_t *f_wall;
+  double *f_out;
+  uint8_t *f_redo;
+  int64_t cap;                  /* items the buffers above hold */
+  int32_t shared_locate;        /* one vertex location for all arms (row 0 stands for all) */
+  int32_t ngraph;               /* captured graphs of the slot: configuration -> executable */
+  const int64_t *g_kp;
+  const double *g_vmax;
+  void *const *g_exec;          /* cudaGraphExec_t */
+  const int32_t *g_nk;          /* kernels in the graph (launch accounting) */
+  /* the stage */
+  const int32_t *objmap;        /* stepper problem -> object of the engine */
+  int64_t nprob;
+  int32_t speculate_below;
+  int32_t state;                /* RVS_DRIVE_IDLE ... (in/out) */
+  int64_t stop_stopped;         /* 0: never return RVS_DRIVE_PEEL */
+  double fused_vmax;            /* largest vsini the fused path takes */
+  /* the round in progress (out) */
+  int64_t K, Kp;
+  double vmax;
+  /* counters (accumulated) */
+  int64_t rounds, items, graph_launches, graph_kernels, h2d_bytes, d2h_bytes;
+  /* optional timing: (t0, t1, K) of every graph launch, ms since epoch_event */
+  void *epoch_event;            /* cudaEvent_t recorded by the caller, NULL: no timing */
+  double *t_rec;
+  int64_t t_cap, t_n;
+  int32_t timed, pad_;
+} rvs_drive;
+/* A non-blocking stream owned by the caller (cudaStream_t; NULL on failure). */
+void *rvs_stream_create(int high_priority);
+void rvs_stream_destroy(void *stream);
+/* Item count of an evaluation call rounded up to a launch configuration. */
+int64_t rvs_fit_round_items(int64_t K);
+void *rvs_drive_create(int64_t cap /* most points of a request */, int nfit);
+void rvs_drive_destroy(void *drive);
+/* The request in progress: stepper problems, fitted vectors [K][nfit], objects. */
+int rvs_drive_request(void *drive, const int32_t **idx, const double **X, const int32_t **obj);
+int rvs_nm_drive(void *nm, void *drive, const rvs_fit_layout *lay, rvs_drive *io);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,25 @@ class FitLayout(ctypes.Structure):
                 ('h_prior_sig', c_dp), ('h_oix', c_dp), ('h_badchi', c_dp), ('h_cover', c_dp)]
 
 
+class Drive(ctypes.Structure):
+    """struct rvs_drive"""
+    _fields_ = [('stream', c_dp), ('h_in', c_dp), ('h_oix', c_dp), ('h_chi', c_dp),
+                ('h_flags', c_dp), ('f_prior', c_dp), ('f_pen', c_dp), ('f_wall', c_dp),
+                ('f_out', c_dp), ('f_redo', c_dp), ('cap', c_i64),
+                ('shared_locate', ctypes.c_int32), ('ngraph', ctypes.c_int32),
+                ('g_kp', c_dp), ('g_vmax', c_dp), ('g_exec', c_dp), ('g_nk', c_dp),
+                ('objmap', c_dp), ('nprob', c_i64), ('speculate_below', ctypes.c_int32),
+                ('state', ctypes.c_int32), ('stop_stopped', c_i64), ('fused_vmax', c_dbl),
+                ('K', c_i64), ('Kp', c_i64), ('vmax', c_dbl),
+                ('rounds', c_i64), ('items', c_i64), ('graph_launches', c_i64),
+                ('graph_kernels', c_i64), ('h2d_bytes', c_i64), ('d2h_bytes', c_i64),
+                ('epoch_event', c_dp), ('t_rec', c_dp), ('t_cap', c_i64), ('t_n', c_i64),
+                ('timed', ctypes.c_int32), ('pad_', ctypes.c_int32)]
+
+
+DRIVE_DONE, DRIVE_PEEL, DRIVE_LAUNCH, DRIVE_REDO, DRIVE_PYEVAL = range(5)
+DRIVE_IDLE, DRIVE_PACKED, DRIVE_LAUNCHED, DRIVE_COLLECTED = range(4)
+
 # name -> (restype, argtypes); every symbol include/rvs_b200.h declares
 SIGNATURES = {
     'rvs_last_error': (ctypes.c_char_p, []),
@@ -125,11 +144,20 @@ SIGNATURES = {
     'rvs_nm_destroy': (None, [ctypes.c_void_p]),
     'rvs_nm_request': (c_i64, [ctypes.c_void_p, c_int, c_dp, c_dp, c_i64]),
     'rvs_nm_feed': (c_int, [ctypes.c_void_p, c_dp, c_i64]),
+    'rvs_nm_live': (c_i64, [ctypes.c_void_p, c_dp]),
     'rvs_nm_result': (c_int, [ctypes.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'rvs_fit_pack': (c_int, [ctypes.POINTER(FitLayout), c_i64, c_i64, c_dp, c_dp, c_dp, c_dp, c_dp,
                              c_dp, c_dp, c_dp, c_dp]),
     'rvs_fit_collect': (c_i64, [ctypes.POINTER(FitLayout), c_i64, c_i64, c_dp, c_dp, c_dp, c_dp,
                                 c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    'rvs_stream_create': (ctypes.c_void_p, [c_int]),
+    'rvs_stream_destroy': (None, [ctypes.c_void_p]),
+    'rvs_fit_round_items': (c_i64, [c_i64]),
+    'rvs_drive_create': (ctypes.c_void_p, [c_i64, c_int]),
+    'rvs_drive_destroy': (None, [ctypes.c_void_p]),
+    'rvs_drive_request': (c_int, [ctypes.c_void_p, c_dp, c_dp, c_dp]),
+    'rvs_nm_drive': (c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FitLayout),
+                             ctypes.POINTER(Drive)]),
     'rvs_ccf_best': (c_int, [c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
 }
 

@@ -296,14 +296,17 @@ def _wolfe2(phi0, old_phi0, derphi0, c1, c2, amax, maxiter=10):
 
 
 # ------------------------------------------------------------- the minimiser
-def bfgs_steps(x0s, hess_inv0=None, gtol=1e-5, eps=_EPSILON, c1=1e-4, c2=0.9, maxiter=None):
+def bfgs_steps(x0s, hess_inv0=None, gtol=1e-5, eps=_EPSILON, c1=1e-4, c2=0.9, maxiter=None,
+               progress=None):
     """scipy.optimize.minimize(method='BFGS', jac=None, options=dict(hess_inv0=
     hess_inv0)) for every row of x0s (B, N), as a generator: it yields
     evaluation requests (idx (K,), X (K, N)) -- rows X of problems idx, N + 1
     consecutive rows per problem: a point and its forward-difference
     neighbours -- is sent their function values, and returns dict(x (B, N),
     fun (B,), nit (B,), status (B,) [scipy's warnflag], success (B,),
-    rounds)."""
+    rounds).  `progress`: a dict kept up to date with x (the array of current
+    points) and live (problems still searching); the rows of x of the others are
+    final, so a driver may hand them on before the slowest problem stops."""
     x = np.array(x0s, dtype=np.float64)
     B, N = x.shape
     if maxiter is None:
@@ -373,6 +376,8 @@ def bfgs_steps(x0s, hess_inv0=None, gtol=1e-5, eps=_EPSILON, c1=1e-4, c2=0.9, ma
         searching = np.concatenate([np.setdiff1d(searching, failed), to_fallback(failed)])
     while len(searching):
         s = np.sort(searching)
+        if progress is not None:
+            progress.update(x=x, live=s)
         pts = x[s] + stp[s][:, None] * pk[s]
         f1, g1 = yield from fg(s, pts)
         rounds += 1

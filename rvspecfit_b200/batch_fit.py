@@ -32,13 +32,26 @@ from . import _dev, batch_bfgs, spec_fit, spec_inter, vel_fit
 
 class KernelTimer:
     """CUDA-event timing of individual launches on the launching stream.
-    Attach with engine.timer = KernelTimer(); read summary() after the run."""
+    Attach with engine.timer = KernelTimer(); read summary() after the run.
+    Launches made by the native round loop (rvs_nm_drive) arrive as arrays of
+    (start, end, items) in ms since the timer's epoch event (add_native)."""
 
     def __init__(self):
+        torch = _dev.torch_mod()
         self.rec = []
+        self.native = {}
+        self.epoch = torch.cuda.Event(enable_timing=True)
+        self.epoch.record()
+        self.epoch.synchronize()
 
     def reset(self):
+        """Drop the records and restart the clock (event times are single-precision ms
+        since the epoch: a fresh epoch keeps them fine-grained in long runs)."""
         self.rec = []
+        self.native = {}
+        _dev.torch_mod().cuda.synchronize()
+        self.epoch.record()
+        self.epoch.synchronize()
 
     def start(self):
         torch = _dev.torch_mod()
@@ -52,23 +65,30 @@ class KernelTimer:
         e1.record()
         self.rec.append((name, e0, e1, items))
 
+    def add_native(self, name, rows):
+        self.native.setdefault(name, []).append(rows)
+
+    def intervals(self, name):
+        """(n, 3) array: start, end (ms since the epoch), items of every launch `name`."""
+        _dev.torch_mod().cuda.synchronize()
+        rows = [(self.epoch.elapsed_time(r[1]), self.epoch.elapsed_time(r[2]), r[3])
+                for r in list(self.rec) if r[0] == name]
+        parts = [np.array(rows, dtype=np.float64).reshape(-1, 3)] + list(self.native.get(name, []))
+        return np.concatenate(parts)
+
     def summary(self):
-        torch = _dev.torch_mod()
-        torch.cuda.synchronize()
         out = {}
-        for name in sorted(set(r[0] for r in self.rec)):
-            rs = [r for r in self.rec if r[0] == name]
-            ms = [r[1].elapsed_time(r[2]) for r in rs]
-            out[name + '_launches'] = len(rs)
+        for name in sorted(set(r[0] for r in list(self.rec)) | set(self.native)):
+            iv = self.intervals(name)
+            ms = iv[:, 1] - iv[:, 0]
+            out[name + '_launches'] = len(iv)
             out[name + '_ms_total'] = float(np.sum(ms))
             out[name + '_ms_per_launch'] = float(np.mean(ms))
-            out[name + '_items_per_launch'] = float(np.mean([r[3] for r in rs]))
+            out[name + '_items_per_launch'] = float(np.mean(iv[:, 2]))
             # launches of concurrent lock-step sets overlap on the device: the time
             # during which at least one of them was running
-            t0 = rs[0][1]
-            iv = sorted((t0.elapsed_time(r[1]), t0.elapsed_time(r[2])) for r in rs)
             busy, end = 0.0, -np.inf
-            for a, b in iv:
+            for a, b, _ in iv[np.argsort(iv[:, 0], kind='stable')]:
                 if b > end:
                     busy += b - max(a, end)
                     end = b
@@ -219,6 +239,11 @@ class BatchObjective:
     def submit0(self, idx, vel, vsini, params):
         """Start chisq_func0 (vel_fit.py:210-230) for K (object, point) pairs; returns
         a waiter."""
+        if len(idx) > MAX_CALL_ITEMS:
+            return _ChunkedWaiter(
+                len(idx), lambda a, b: self.submit0(idx[a:b], vel[a:b],
+                                                    None if vsini is None else vsini[a:b],
+                                                    params[a:b]))
         idx = np.asarray(idx, dtype=np.int64)
         self.nfev += len(idx)
         return _Waiter(self._start(idx, vel, params, vsini), None, self.prior_term(params), 0.0,
@@ -233,10 +258,23 @@ class BatchObjective:
             return self.eng.submit(idx, vel, params, vsini)
         return _Done(self.eng.evaluate(idx, vel, params, vsini))    # blocking engines
 
+    def redo_values(self, obj32, X):
+        """chisq_func through the engine's general path (items the fused path could not
+        settle: off-grid templates that are not usable, a normal matrix that is not
+        positive definite, ...)."""
+        idx = np.asarray(obj32, dtype=np.int64)
+        vel, vsini, params, pen = self.unpack(idx, X)
+        eng = self.eng
+        with eng._general_lock:
+            chi = eng._evaluate_general(idx, vel, params, vsini, True, None, False, False)
+        return self.prior_term(params) + chi + pen
+
     def submit(self, idx, X):
         """Start the evaluation of chisq_func for K pairs and return a waiter: a
         callable that gives the values (priors + -2 log L + penalty, 1e30 behind the
         hard walls, vel_fit.py:210-257), with ready() telling whether it would block."""
+        if len(idx) > MAX_CALL_ITEMS:
+            return _ChunkedWaiter(len(idx), lambda a, b: self.submit(idx[a:b], X[a:b]))
         lay = self.layout()
         if lay:
             obj32 = np.ascontiguousarray(idx, dtype=np.int32)
@@ -261,6 +299,34 @@ class BatchObjective:
             self.nfev += int(ok.sum())
             pend = self._start(idx[ok], vel[ok], params[ok], None if vsini is None else vsini[ok])
         return _Waiter(pend, ok, self.prior_term(params[ok]), pen[ok], len(idx))
+
+
+# Largest evaluation call: longer requests (the Hessian stencils of a large group) go out
+# in pieces, two in flight, so that the per-call device buffers stay bounded
+MAX_CALL_ITEMS = 16384
+
+
+class _ChunkedWaiter:
+    """Values of a request served by several evaluation calls, two of them in flight."""
+
+    def __init__(self, n, submit):
+        self.n, self.sub = n, submit
+        self.cuts = list(range(0, n, MAX_CALL_ITEMS)) + [n]
+        self.pend = [submit(self.cuts[i], self.cuts[i + 1])
+                     for i in range(min(2, len(self.cuts) - 1))]
+
+    def ready(self):
+        return False
+
+    def __call__(self):
+        out = np.empty(self.n)
+        nxt = len(self.pend)
+        for i in range(len(self.cuts) - 1):
+            out[self.cuts[i]:self.cuts[i + 1]] = self.pend.pop(0)()
+            if nxt < len(self.cuts) - 1:
+                self.pend.append(self.sub(self.cuts[nxt], self.cuts[nxt + 1]))
+                nxt += 1
+        return out
 
 
 class _Done:
@@ -422,44 +488,80 @@ def nelder_mead_steps(sims, xatol=1e-2, fatol=1e-3, maxiter=10000, speculate_bel
                 final_simplex=sim, nit=iterations, nfev=nfev)
 
 
-def nelder_mead_native(sims, xatol=1e-2, fatol=1e-3, maxiter=10000, speculate_below=0):
-    """nelder_mead_steps with the stepping done by the library's host-side stepper
-    (csrc/nm_host.cpp, rvs_nm_*): the same generator protocol, the same trajectories
-    (tests/test_batch_drivers.py compares both with scipy), a fraction of the host
-    time per round.  `speculate_below` may be a callable giving the threshold for the
-    coming round."""
-    import ctypes
-    from . import _cabi
-    L = _cabi.lib()
-    sim = np.array(sims, dtype=np.float64, order='C')     # own copy: receives the final simplices
-    B, N1, N = sim.shape
-    assert N1 == N + 1
-    h = L.rvs_nm_create(B, N, _dev.hptr(sim), float(xatol), float(fatol), int(maxiter))
-    if not h:
-        raise _cabi.RvsError('rvs_nm_create failed')
-    h = ctypes.c_void_p(h)
-    try:
-        cap = B * max(N1, 4)
-        idx = np.empty(cap, dtype=np.int32)
-        X = np.empty((cap, N), dtype=np.float64)
-        while True:
-            sb = speculate_below() if callable(speculate_below) else speculate_below
-            n = L.rvs_nm_request(h, int(sb), _dev.hptr(idx), _dev.hptr(X), cap)
-            if n == 0:
-                break
-            assert n <= cap
-            f = np.ascontiguousarray((yield idx[:n], X[:n]), dtype=np.float64)
-            _cabi.check(L.rvs_nm_feed(h, _dev.hptr(f), n), 'rvs_nm_feed')
+class NMStepper:
+    """The library's host-side lock-step Nelder-Mead stepper (csrc/nm_host.cpp, rvs_nm_*)
+    for B simplices: request() -> (idx, X) or None, feed(values), active(), result().
+    A stopped problem's rows of result() are final while the others go on."""
+
+    def __init__(self, sims, xatol=1e-2, fatol=1e-3, maxiter=10000):
+        import ctypes
+        from . import _cabi
+        self.L = _cabi.lib()
+        self.sim = np.array(sims, dtype=np.float64, order='C')   # receives the final simplices
+        self.B, N1, self.N = self.sim.shape
+        assert N1 == self.N + 1
+        h = self.L.rvs_nm_create(self.B, self.N, _dev.hptr(self.sim), float(xatol), float(fatol),
+                                 int(maxiter))
+        if not h:
+            raise _cabi.RvsError('rvs_nm_create failed')
+        self.h = ctypes.c_void_p(h)
+        self.cap = self.B * max(N1, 4)
+        self.idx = np.empty(self.cap, dtype=np.int32)
+        self.X = np.empty((self.cap, self.N), dtype=np.float64)
+        self.n = 0
+
+    def request(self, speculate_below=0):
+        n = self.L.rvs_nm_request(self.h, int(speculate_below), _dev.hptr(self.idx),
+                                  _dev.hptr(self.X), self.cap)
+        assert n <= self.cap
+        self.n = n
+        return (self.idx[:n], self.X[:n]) if n else None
+
+    def feed(self, f):
+        from . import _cabi
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        _cabi.check(self.L.rvs_nm_feed(self.h, _dev.hptr(f), self.n), 'rvs_nm_feed')
+
+    def active(self):
+        a = np.empty(self.B, dtype=np.uint8)
+        self.L.rvs_nm_live(self.h, _dev.hptr(a))
+        return a.astype(bool)
+
+    def result(self):
+        from . import _cabi
+        B, N = self.B, self.N
         x, fun = np.empty((B, N)), np.empty(B)
         success = np.empty(B, dtype=np.uint8)
         nit, nfev = np.empty(B, dtype=np.int64), np.empty(B, dtype=np.int64)
-        _cabi.check(L.rvs_nm_result(h, _dev.hptr(x), _dev.hptr(fun), _dev.hptr(success),
-                                    _dev.hptr(sim), _dev.hptr(nit), _dev.hptr(nfev)),
+        sim = np.empty_like(self.sim)
+        _cabi.check(self.L.rvs_nm_result(self.h, _dev.hptr(x), _dev.hptr(fun), _dev.hptr(success),
+                                         _dev.hptr(sim), _dev.hptr(nit), _dev.hptr(nfev)),
                     'rvs_nm_result')
         return dict(x=x, fun=fun, success=success.astype(bool), final_simplex=sim, nit=nit,
                     nfev=nfev)
+
+    def close(self):
+        if self.h is not None:
+            self.L.rvs_nm_destroy(self.h)
+            self.h = None
+
+
+def nelder_mead_native(sims, xatol=1e-2, fatol=1e-3, maxiter=10000, speculate_below=0):
+    """nelder_mead_steps with the stepping done by the library's host-side stepper
+    (NMStepper): the same generator protocol, the same trajectories
+    (tests/test_batch_drivers.py compares both with scipy), a fraction of the host
+    time per round.  `speculate_below` may be a callable giving the threshold for the
+    coming round."""
+    st = NMStepper(sims, xatol, fatol, maxiter)
+    try:
+        while True:
+            req = st.request(speculate_below() if callable(speculate_below) else speculate_below)
+            if req is None:
+                break
+            st.feed((yield req))
+        return st.result()
     finally:
-        L.rvs_nm_destroy(h)
+        st.close()
 
 
 def nelder_mead_lockstep(fbatch, sims, xatol=1e-2, fatol=1e-3, maxiter=10000,
@@ -527,15 +629,29 @@ def run_pipeline(gens, start):
     in flight.  `start(request)` begins serving a request and returns a waiter
     (callable giving the answer, with ready() telling whether it would block).
     Whichever coroutine's answer is ready first is advanced first, so host work
-    of one lock-step set overlaps the device work of the others.  Returns the
-    coroutines' return values in order."""
+    of one lock-step set overlaps the device work of the others.  A request
+    ('spawn', coroutine) adds a coroutine to the set.  Returns the coroutines'
+    return values, the given ones first and in order."""
+    gens = list(gens)
     out = [None] * len(gens)
     pending = []
-    for gi, gen in enumerate(gens):
+
+    def advance(gi, value, first=False):
         try:
-            pending.append((gi, start(next(gen))))
+            while True:
+                req = next(gens[gi]) if first else gens[gi].send(value)
+                first = False
+                if req[0] != 'spawn':
+                    pending.append((gi, start(req)))
+                    return
+                gens.append(req[1])
+                out.append(None)
+                advance(len(gens) - 1, None, True)
+                value = None
         except StopIteration as stop:
             out[gi] = stop.value
+    for gi in range(len(gens)):
+        advance(gi, None, True)
     while pending:
         pick = 0
         for j, (_, w) in enumerate(pending):
@@ -543,10 +659,7 @@ def run_pipeline(gens, start):
                 pick = j
                 break
         gi, wait = pending.pop(pick)
-        try:
-            pending.append((gi, start(gens[gi].send(wait()))))
-        except StopIteration as stop:
-            out[gi] = stop.value
+        advance(gi, wait())
     return out
 
 
@@ -555,21 +668,37 @@ def run_threads(gens, start, device=None, post=None):
     lock-step set is library calls that release the interpreter lock (the optimiser
     stepper rvs_nm_*, rvs_fit_pack / rvs_fit_collect, graph launches, event waits), so
     the sets' host work runs on different cores instead of queueing behind each other.
+    A request ('spawn', coroutine) starts a thread for that coroutine.
     `device`: CUDA device index the threads make current (a new thread starts on
     device 0).  `post`: applied to every coroutine's return value on its own thread (the
     result assembly of one set then runs under the device work of the others)."""
     import threading
+    gens = list(gens)
     out = [None] * len(gens)
     errors = []
+    threads = []
+    lock = threading.Lock()
 
-    def work(gi):
+    def launch(gen):
+        with lock:
+            gi = len(threads)
+            if gi >= len(out):
+                out.append(None)
+            t = threading.Thread(target=work, args=(gi, gen), daemon=True)
+            threads.append(t)
+        t.start()
+
+    def work(gi, gen):
         try:
             if device is not None:
                 _dev.torch_mod().cuda.set_device(device)
-            gen = gens[gi]
             req = next(gen)
             while not errors:
-                req = gen.send(start(req)())
+                if req[0] == 'spawn':
+                    launch(req[1])
+                    req = gen.send(None)
+                else:
+                    req = gen.send(start(req)())
         except StopIteration as stop:
             try:
                 out[gi] = stop.value if post is None else post(stop.value)
@@ -577,11 +706,16 @@ def run_threads(gens, start, device=None, post=None):
                 errors.append(exc)
         except BaseException as exc:          # noqa: BLE001  (re-raised by the caller)
             errors.append(exc)
-    threads = [threading.Thread(target=work, args=(gi,), daemon=True) for gi in range(len(gens))]
-    for t in threads:
-        t.start()
-    for t in threads:
+    for gen in gens:
+        launch(gen)
+    i = 0
+    while True:
+        with lock:
+            if i >= len(threads):
+                break
+            t = threads[i]
         t.join()
+        i += 1
     if errors:
         raise errors[0]
     return out
@@ -715,63 +849,200 @@ def simplex_starts(best_vel, fobj, specParams, fixParam, fitVsini, max_vsini):
     return sims
 
 
-def fit_steps(sel, fobj, specParams, fixParam, fitVsini, has_vsini, config, phase):
+# A lock-step stage hands the problems that have finished on to the next stage of the
+# fit as soon as that many of them wait (and at least this fraction of the stage's
+# problems), instead of keeping them until the slowest one stops
+PEEL_MIN = 128
+PEEL_FRAC = 0.2
+
+
+class _FitCtx:
+    """What the stages of one lock-step set share."""
+
+    def __init__(self, sel, fobj, specParams, fixParam, fitVsini, has_vsini, config, phase, peel,
+                 threaded=False):
+        self.sel, self.fobj, self.specParams, self.fixParam = sel, fobj, specParams, fixParam
+        self.fitVsini, self.has_vsini, self.config, self.phase = fitVsini, has_vsini, config, phase
+        self.peel, self.threaded = peel, threaded
+
+    def lap(self, name, t0):
+        import time
+        now = time.time()
+        self.phase[name] = self.phase.get(name, 0.0) + now - t0
+        return now
+
+    def enough(self, nwait, nstage):
+        return self.peel and nwait >= max(PEEL_MIN, PEEL_FRAC * nstage)
+
+
+def fit_steps(sel, fobj, specParams, fixParam, fitVsini, has_vsini, config, phase, peel=True,
+              threaded=False):
     """vel_fit.process (reference vel_fit.py:505-737) for the objects `sel` of
-    the engine as ONE coroutine: it yields requests
+    the engine as a coroutine: it yields requests
         ('scan', objects, grids, params, vsini)   find_best on ragged RV grids
         ('f', objects, X)                         chisq_func at fitted vectors X
         ('f0', objects, vel, vsini, params)       chisq_func0 (priors + -2 log L)
         ('model', objects, vel, params, vsini)    get_chisq(full_output=True)
-    is sent their answers, and returns a dict of per-object arrays.  Every object
-    follows the decision rules of the single-object path (see the module
-    docstring)."""
+        ('spawn', coroutine)                      run this coroutine beside me
+    is sent their answers, and returns a list of dicts of per-object arrays (one per
+    group of objects that finished together).  Every object follows the decision
+    rules of the single-object path (see the module docstring).  The optimisers run
+    in lock-step over the objects of a stage; with `peel` the objects that have
+    finished a stage move on in groups (a spawned coroutine each) while the slower
+    ones keep iterating, so the latency-bound tail of one stage runs beside the
+    large calls of the next instead of in front of them."""
     import time
-    t_last = [time.time()]
-
-    def lap(name):
-        now = time.time()
-        phase[name] = phase.get(name, 0.0) + now - t_last[0]
-        t_last[0] = now
+    t0 = time.time()
+    ctx = _FitCtx(sel, fobj, specParams, fixParam, fitVsini, has_vsini, config, phase, peel,
+                  threaded)
     n = len(sel)
-    loc = np.arange(n)
-    min_vel, max_vel = config['min_vel'], config['max_vel']
-    vel_step0, min_vel_step = config['vel_step0'], config['min_vel_step']
-    p0 = fobj.p0[sel]
-    vs0 = fobj.vsini0[sel] if has_vsini else None
     # 1. RV-grid scan at the starting parameters (vel_fit.py:579-602)
-    vgrid = np.arange(min_vel, max_vel, vel_step0)
-    st = yield ('scan', sel, [vgrid] * n, p0, vs0)
+    vgrid = np.arange(config['min_vel'], config['max_vel'], config['vel_step0'])
+    st = yield ('scan', sel, [vgrid] * n, fobj.p0[sel], fobj.vsini0[sel] if has_vsini else None)
     if not np.isfinite(st[:, :2]).all():
         raise RuntimeError('The log(likelihood) value is not finite in the initial RV scan of '
                            f'object(s) {sel[~np.isfinite(st[:, :2]).all(axis=1)].tolist()}')
-    lap('scan0')
-    # 2. Nelder-Mead, restarted once from its final simplex if it did not converge
-    #    (vel_fit.py:628-650)
+    ctx.lap('scan0', t0)
     sims = simplex_starts(st[:, 1], _Sub(fobj, sel), specParams, fixParam, fitVsini,
                           config['max_vsini'])
-    minimize_success = np.ones(n, dtype=bool)
-    x = np.zeros((n, sims.shape[2]))
-    todo = loc
-    for attempt in range(2):
-        res = yield from _drive(nelder_mead_native(sims[todo],
-                                                   speculate_below=lambda: SPECULATE_BELOW),
-                                sel[todo])
-        x[todo] = res['x']
-        sims[todo] = res['final_simplex']
-        failed = todo[~res['success']]
-        if attempt == 1:
-            minimize_success[failed] = False
-        todo = failed
-        if len(todo) == 0:
-            break
-    lap('nelder_mead')
-    # 3. BFGS polish (vel_fit.py:653-658)
-    if config.get('second_minimizer'):
-        names = ['vel'] + (['vsini'] if fitVsini else []) + \
-            [p for p in specParams if p not in fixParam]
-        res = yield from _drive(batch_bfgs.bfgs_steps(x, vel_fit.get_hess_inv(names)), sel)
-        x = res['x']
-    lap('bfgs')
+    return (yield from _nm_stage(ctx, np.arange(n), sims, 0))
+
+
+def _nm_stage_native(ctx, objs, sims, attempt, drive, stepper):
+    """_nm_stage with the rounds run by the library (rvs_nm_drive): no interpreter between
+    two evaluation calls.  The coroutine blocks in the library while rounds run, so it
+    wants a thread of its own (run_threads)."""
+    import time
+    from . import _cabi
+    t0 = time.time()
+    eng, fobj = ctx.fobj.eng, ctx.fobj
+    n = len(objs)
+    handed = np.zeros(n, dtype=bool)
+    try:
+        while True:
+            stop = int(handed.sum() + np.ceil(max(PEEL_MIN, PEEL_FRAC * n))) if ctx.peel else 0
+            items0 = drive['io'].items
+            rc = eng.drive_run(drive, stepper.h, SPECULATE_BELOW, stop, fobj.redo_values,
+                               lambda o, X: fobj.submit(o, X)())
+            fobj.nfev += drive['io'].items - items0
+            if rc == _cabi.DRIVE_DONE:
+                break
+            act = stepper.active()
+            j = np.nonzero(~act & ~handed)[0]
+            res = stepper.result()
+            handed[j] = True
+            t0 = ctx.lap('nelder_mead', t0)
+            yield ('spawn', _after_nm(ctx, objs[j], {k: v[j] for k, v in res.items()}, attempt))
+        res = stepper.result()
+    finally:
+        eng.drive_close(drive)
+        stepper.close()
+    ctx.lap('nelder_mead', t0)
+    j = np.nonzero(~handed)[0]
+    return (yield from _after_nm(ctx, objs[j], {k: v[j] for k, v in res.items()}, attempt))
+
+
+# rounds of a Nelder-Mead stage run by the library when the coroutine has its own thread
+NATIVE_DRIVE = True
+
+
+def _nm_stage(ctx, objs, sims, attempt):
+    """2. Nelder-Mead for the set's objects `objs` (positions in ctx.sel), restarted once
+    from its final simplex where it did not converge (vel_fit.py:628-650)."""
+    import time
+    t0 = time.time()
+    stepper = NMStepper(sims)
+    eng = ctx.fobj.eng
+    if NATIVE_DRIVE and ctx.threaded and hasattr(eng, 'drive_open') and ctx.fobj.layout():
+        drive = eng.drive_open(ctx.fobj.layout(), ctx.sel[objs], stepper.N, stepper.cap)
+        if drive is not None:
+            return (yield from _nm_stage_native(ctx, objs, sims, attempt, drive, stepper))
+    handed = np.zeros(len(objs), dtype=bool)
+    try:
+        while True:
+            req = stepper.request(SPECULATE_BELOW)
+            if req is None:
+                break
+            stepper.feed((yield ('f', ctx.sel[objs[req[0]]], req[1])))
+            if ctx.peel:
+                act = stepper.active()
+                j = np.nonzero(~act & ~handed)[0]
+                if act.any() and ctx.enough(len(j), len(objs)):
+                    res = stepper.result()
+                    handed[j] = True
+                    t0 = ctx.lap('nelder_mead', t0)
+                    yield ('spawn', _after_nm(ctx, objs[j], {k: v[j] for k, v in res.items()},
+                                              attempt))
+        res = stepper.result()
+    finally:
+        stepper.close()
+    ctx.lap('nelder_mead', t0)
+    j = np.nonzero(~handed)[0]
+    return (yield from _after_nm(ctx, objs[j], {k: v[j] for k, v in res.items()}, attempt))
+
+
+def _after_nm(ctx, objs, res, attempt):
+    out = []
+    ok = res['success']
+    msucc = np.ones(len(objs), dtype=bool)
+    if attempt == 0 and not ok.all():
+        again = np.nonzero(~ok)[0]
+        rest = _nm_stage(ctx, objs[again], res['final_simplex'][again], 1)
+        if ok.any():
+            yield ('spawn', rest)
+        else:
+            return (yield from rest)
+        go = np.nonzero(ok)[0]
+    else:
+        msucc[~ok] = False
+        go = np.arange(len(objs))
+    out += (yield from _bfgs_stage(ctx, objs[go], res['x'][go], msucc[go]))
+    return out
+
+
+def _bfgs_stage(ctx, objs, x, msucc):
+    """3. BFGS polish (vel_fit.py:653-658)."""
+    import time
+    if not ctx.config.get('second_minimizer') or len(objs) == 0:
+        return (yield from _finish_stage(ctx, objs, x, msucc))
+    t0 = time.time()
+    names = ['vel'] + (['vsini'] if ctx.fitVsini else []) + \
+        [p for p in ctx.specParams if p not in ctx.fixParam]
+    progress = {}
+    gen = batch_bfgs.bfgs_steps(x, vel_fit.get_hess_inv(names), progress=progress)
+    handed = np.zeros(len(objs), dtype=bool)
+    try:
+        idx, X = next(gen)
+        while True:
+            val = yield ('f', ctx.sel[objs[idx]], X)
+            idx, X = gen.send(val)
+            if ctx.peel:
+                fin = ~handed
+                fin[progress['live']] = False
+                j = np.nonzero(fin)[0]
+                if ctx.enough(len(j), len(objs)):
+                    handed[j] = True
+                    t0 = ctx.lap('bfgs', t0)
+                    yield ('spawn', _finish_stage(ctx, objs[j], progress['x'][j].copy(), msucc[j]))
+    except StopIteration as stop:
+        x = stop.value['x']
+    ctx.lap('bfgs', t0)
+    j = np.nonzero(~handed)[0]
+    return (yield from _finish_stage(ctx, objs[j], x[j], msucc[j]))
+
+
+def _finish_stage(ctx, objs, x, minimize_success):
+    """4.-6. of vel_fit.process for objects whose optimisers have stopped at x."""
+    import time
+    t0 = time.time()
+    n = len(objs)
+    if n == 0:
+        return []
+    sel, fobj, config = ctx.sel[objs], ctx.fobj, ctx.config
+    specParams = ctx.specParams
+    loc = np.arange(n)
+    min_vel, max_vel = config['min_vel'], config['max_vel']
+    vel_step0, min_vel_step = config['vel_step0'], config['min_vel_step']
     vel, vsini, params, _ = fobj.unpack(sel, x)
     # 4. velocity posterior on shrinking grids (vel_fit.py:315-439), all objects per round
     best_vel = np.clip(vel, min_vel, max_vel)
@@ -803,13 +1074,13 @@ def fit_steps(sel, fobj, specParams, fixParam, fitVsini, has_vsini, config, phas
         active = a2
         if len(active) == 0:
             break
-    lap('refine')
+    t0 = ctx.lap('refine', t0)
     # 5. model at the best point (vel_fit.py:688-696)
     tot, info = yield ('model', sel, best_vel, params, vsini)
     if not np.isfinite(tot).all():
         raise RuntimeError('The log(likelihood) value is not finite at the best-fit point of '
                            f'object(s) {sel[~np.isfinite(tot)].tolist()}')
-    lap('model')
+    t0 = ctx.lap('model', t0)
     # 6. Hessian over the atmospheric parameters at the optimiser's velocity and vsini
     #    (vel_fit.py:698-722: hess_func keeps best_param's own velocity)
     hsteps = [vel_fit.HESS_STEP[_] for _ in specParams]
@@ -819,10 +1090,10 @@ def fit_steps(sel, fobj, specParams, fixParam, fitVsini, has_vsini, config, phas
     vals = yield ('f0', sel[ii], vel[ii], None if vsini is None else vsini[ii],
                   P.reshape(n * npts, -1))
     hess = hessian_from_values(0.5 * vals.reshape(n, npts), hsteps)
-    lap('hessian')
-    return dict(sel=sel, x=x, vel=vel, vsini=vsini, params=params, best_vel=best_vel,
-                vstat=vstat, minimize_success=minimize_success, chisq=tot, info=info,
-                hessian=hess)
+    ctx.lap('hessian', t0)
+    return [dict(sel=sel, x=x, vel=vel, vsini=vsini, params=params, best_vel=best_vel,
+                 vstat=vstat, minimize_success=minimize_success, chisq=tot, info=info,
+                 hessian=hess)]
 
 
 class _Sub:
@@ -838,17 +1109,20 @@ class _Sub:
 FIT_GROUP = 256
 FIT_MAX_GROUPS = 2
 THREADS = True
+PEEL = False
 
 
 def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None, priors=None,
-                  engine=None, timer=None, groups=None, threads=None):
+                  engine=None, timer=None, groups=None, threads=None, peel=None):
     """vel_fit.process for a list of objects (each a list of SpecData); same
     arguments otherwise, paramDict0s one dictionary per object.  Returns the list
     of result dictionaries of vel_fit.process.  `engine`: a LikelihoodEngine
     already holding the objects on the device (then `objects` may be None).
     The objects are fitted as `groups` independent lock-step sets whose phases
     interleave on the GPU: one host thread per set (run_threads; `threads=False`:
-    all sets advanced by the calling thread, run_pipeline)."""
+    all sets advanced by the calling thread, run_pipeline).  `peel` (default: on when the
+    sets are large enough to be worth splitting): objects that have finished an optimiser
+    stage move on in groups while the slower ones keep iterating (see fit_steps)."""
     if config is None:
         raise RuntimeError('Config must be provided')
     options = options or {}
@@ -869,8 +1143,12 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
     groups = max(1, min(groups, B, eng.NSLOT))
     phase = {}
     parts = [p for p in np.array_split(np.arange(B), groups) if len(p)]
-    gens = [fit_steps(p, fobj, specParams, fixParam, fitVsini, has_vsini, config, phase)
-            for p in parts]
+    if peel is None:
+        peel = PEEL and hasattr(eng, 'submit_fit')
+    if threads is None:
+        threads = THREADS and hasattr(eng, 'submit_fit')
+    gens = [fit_steps(p, fobj, specParams, fixParam, fitVsini, has_vsini, config, phase, peel,
+                      bool(threads)) for p in parts]
 
     def start(req):
         kind = req[0]
@@ -885,8 +1163,14 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
             with general_lock:
                 return _Ready(eng.evaluate(idx, vel[:, None], params, vsini, want_model=True))
         raise ValueError(kind)
-    def assemble(r):
-        """Result dictionaries of one set: [(object index, dict)]."""
+    def assemble(parts_done):
+        """Result dictionaries of the groups a coroutine finished: [(object index, dict)]."""
+        rows_out = []
+        for r in parts_done:
+            rows_out += assemble_one(r)
+        return rows_out
+
+    def assemble_one(r):
         rows_out = []
         info = r['info']
         tot = r['chisq'][:, 0]
@@ -922,12 +1206,11 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
         return rows_out
     import contextlib
     general_lock = getattr(eng, '_general_lock', contextlib.nullcontext())
-    if threads is None:
-        threads = THREADS and len(gens) > 1 and hasattr(eng, 'submit_fit')
     try:
         if threads:
-            results = run_threads(gens, start, _dev.torch_mod().cuda.current_device(),
-                                  post=assemble)
+            device = _dev.torch_mod().cuda.current_device() if hasattr(eng, 'submit_fit') \
+                else None
+            results = run_threads(gens, start, device, post=assemble)
         else:
             results = [assemble(r) for r in run_pipeline(gens, start)]
     finally:
@@ -938,4 +1221,5 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
         for i, ret in rows:
             out[i] = ret
     process_batch.last_phase_seconds = phase
+    process_batch.last_spawned = len(results) - len(parts)
     return out

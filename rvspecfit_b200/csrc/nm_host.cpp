@@ -303,10 +303,20 @@ extern "C" int rvs_nm_feed(void *h, const double *h_f, int64_t K) {
   return 0;
 }
 
+extern "C" int64_t rvs_nm_live(void *h, uint8_t *h_active) {
+  Nm &m = *static_cast<Nm *>(h);
+  int64_t n = 0;
+  for (int b = 0; b < m.B; b++) {
+    n += m.active[b] != 0;
+    if (h_active) h_active[b] = m.active[b];
+  }
+  return n;
+}
+
 extern "C" int rvs_nm_result(void *h, double *h_x, double *h_fun, uint8_t *h_success,
                              double *h_final_simplex, int64_t *h_nit, int64_t *h_nfev) {
+  // Before every problem has stopped the rows of the stopped ones (rvs_nm_live) are final.
   Nm &m = *static_cast<Nm *>(h);
-  if (m.phase != P_DONE) return RVS_E_ARG;
   const int N = m.N, N1 = m.N1;
   for (int b = 0; b < m.B; b++) {
     if (h_x) memcpy(h_x + (size_t)b * N, m.S(b), sizeof(double) * N);

@@ -15,6 +15,7 @@ import ctypes
 import os
 import random
 import threading
+import time
 
 import numpy as np
 import scipy.linalg
@@ -297,6 +298,7 @@ class SpectrumBatch:
 # kernels launched through CUDA-graph replays by all engines of this process
 # (rvs_launch_count only sees direct launches)
 GRAPH_LAUNCHES = [0]
+LAST_DRIVE_ROUNDS = [0]     # rounds of the last native Nelder-Mead stage (tests)
 
 
 class PendingEval:
@@ -566,19 +568,28 @@ class LikelihoodEngine:
                               model=_dev.download(d_mod), moff=moff, oix=oix)
         return _dev.download(d_chi), st, outside, tstatus, extras
 
-    def _scratch(self, name, shape, dtype):
-        """Device buffer reused between calls (grown by 25 % when too small)."""
+    def _epoch(self, sl):
+        """What the validity of a slot's captured graphs hangs on: the engine's shared
+        buffers and the slot's own (a slot that grows does not invalidate the others)."""
+        return (getattr(self, '_graph_epoch', 0), sl.get('epoch', 0))
+
+    def _scratch(self, name, shape, dtype, reserve=0, sl=None):
+        """Device buffer reused between calls (grown by 25 % when too small; `reserve`:
+        elements to allocate at least, e.g. the slot's capacity)."""
         n = int(np.prod(shape))
         t = self._buf.get(name)
         if t is None or t.numel() < n:
             if t is not None:
                 _dev.torch_mod().cuda.synchronize()   # side streams may still read the old one
-            t = _dev.empty((int(n * 1.25) + 64,), dtype)
+            t = _dev.empty((max(int(n * 1.25) + 64, int(reserve)),), dtype)
             self._buf[name] = t
-            self._graph_epoch = getattr(self, '_graph_epoch', 0) + 1   # captured pointers are stale
+            if sl is not None:          # captured pointers are stale
+                sl['epoch'] = sl.get('epoch', 0) + 1
+            else:
+                self._graph_epoch = getattr(self, '_graph_epoch', 0) + 1
         return t[:n].view(*shape)
 
-    NSLOT = 8      # evaluations that may be in flight at once (submit without result)
+    NSLOT = 16     # evaluations that may be in flight at once (submit without result)
 
     def _slot(self, K, narm, nd):
         """Pinned host staging + device input buffers of one in-flight evaluation."""
@@ -587,12 +598,15 @@ class LikelihoodEngine:
             self._slots, self._slot_ix = [dict(K=0, busy=False, ix=i) for i in range(self.NSLOT)], -1
         free = [x for x in self._slots if not x['busy']]
         if not free:
-            raise RuntimeError(f'more than {self.NSLOT} evaluations in flight: call result() on '
-                               'the oldest PendingEval first')
+            return None
         sl = free[0]    # lowest free slot: its captured graphs are the warmest
+        # every slot is sized for the largest call any slot has seen, so that which
+        # slot a call lands in (it varies with the timing of concurrent drivers) never
+        # decides whether buffers grow and captured graphs are dropped
+        self._kcap = max(getattr(self, '_kcap', 0), K)
         if sl['K'] < K:
-            self._graph_epoch = getattr(self, '_graph_epoch', 0) + 1
-            cap = int(K * 1.25) + 16
+            sl['epoch'] = sl.get('epoch', 0) + 1
+            cap = max(int(K * 1.25) + 16, self._slot_cap())
             pin = dict(pin_memory=True)
             sl.update(K=cap,
                       h_in=torch.empty(((2 + nd) * cap,), dtype=torch.float64, **pin),
@@ -604,9 +618,14 @@ class LikelihoodEngine:
                       event=torch.cuda.Event())
         return sl
 
+    def _slot_cap(self):
+        return int(self._kcap * 1.25) + 16
+
     def _acquire(self, K):
         """Round the item count up to a launch configuration and take a free slot
-        (pinned staging, device inputs, streams) for it: (slot, Kp)."""
+        (pinned staging, device inputs, streams) for it: (slot, Kp).  With every slot
+        taken by other threads' evaluations the call waits for one to be collected; a
+        single-threaded driver that never collects gets the error instead."""
         L = _cabi.lib()
         narm = len(self.setups)
         bank0 = self.arms[self.setups[0]]['bank']
@@ -621,20 +640,34 @@ class LikelihoodEngine:
         # hitting the same captured launch configurations.
         Kp = K
         if use_graph:
-            Kp = 16 if K <= 16 else (1 << int(np.ceil(np.log2(K))) if K <= 128
-                                     else (K + 127) // 128 * 128)
+            Kp = int(L.rvs_fit_round_items(K))
         torch = _dev.torch_mod()
-        with self._lock:
-            sl = self._slot(Kp, narm, nd)
-            sl['busy'] = True
+        me = threading.get_ident()
+        while True:
+            with self._lock:
+                sl = self._slot(Kp, narm, nd)
+                if sl is not None:
+                    sl['busy'], sl['owner'] = True, me
+                    break
+                if all(x.get('owner') == me for x in self._slots):
+                    raise RuntimeError(f'more than {self.NSLOT} evaluations in flight: call '
+                                       'result() on the oldest PendingEval first')
+            time.sleep(2e-5)
         sl['Kp'], sl['use_graph'] = Kp, use_graph
         # Every in-flight evaluation has its own streams and scratch, so that the
         # low-occupancy tail of one (continuum solves of the last arm) runs under the
         # template kernels of the next instead of in front of them.
         if 'stream' not in sl:
-            sl['stream'] = torch.cuda.Stream()
+            # streams of the slot's own (torch.cuda.Stream() hands out the handles of a
+            # small pool round-robin: slots would share streams)
+            def own_stream():
+                h = L.rvs_stream_create(0)
+                if not h:
+                    raise _cabi.RvsError('rvs_stream_create failed')
+                return torch.cuda.ExternalStream(h)
+            sl['stream'] = own_stream()
             sl['ready'] = torch.cuda.Event()
-            sl['arm_streams'] = [torch.cuda.Stream() for _ in self.setups]
+            sl['arm_streams'] = [own_stream() for _ in self.setups]
             sl['arm_events'] = [torch.cuda.Event() for _ in self.setups]
             sl['fork_event'] = torch.cuda.Event()
         return sl, Kp
@@ -687,6 +720,16 @@ class LikelihoodEngine:
                     self._data_event = None
         return obs_all
 
+    def _wait_data(self, sl):
+        torch = _dev.torch_mod()
+        if sl.get('data_epoch') != self._data_epoch:
+            with self._lock:
+                if self._data_event is None:
+                    self._data_event = torch.cuda.Event()
+                    self._data_event.record(torch.cuda.current_stream())
+                sl['stream'].wait_event(self._data_event)
+                sl['data_epoch'] = self._data_epoch
+
     def _launch(self, sl, K, Kp, vmax, sys_errs, params):
         """Start the device work of the evaluation whose inputs are in the slot's pinned
         buffers; records the slot's event behind it."""
@@ -702,19 +745,13 @@ class LikelihoodEngine:
         # computed on the caller's stream by the constructor, reload() or the first obs()
         # of a systematic error) once per such change -- not for whatever else the
         # caller's stream carries (another lock-step set's RV scan, say)
-        if sl.get('data_epoch') != self._data_epoch:
-            with self._lock:
-                if self._data_event is None:
-                    self._data_event = torch.cuda.Event()
-                    self._data_event.record(torch.cuda.current_stream())
-                sl['stream'].wait_event(self._data_event)
-                sl['data_epoch'] = self._data_epoch
+        self._wait_data(sl)
         # The ~20 launches, copies and stream fork/joins of one evaluation are captured
         # into a CUDA graph the second time a configuration (item count, tap bound,
         # systematic error) is seen and replayed from then on: one launch per evaluation
         # instead of a host-bound launch sequence.
         key = (Kp, vmax, okey)
-        epoch = getattr(self, '_graph_epoch', 0)
+        epoch = self._epoch(sl)
         if sl.get('graph_epoch') != epoch:
             sl['graphs'], sl['seen'], sl['graph_epoch'] = {}, {}, epoch
         g = sl['graphs'].get(key) if use_graph else None
@@ -728,7 +765,7 @@ class LikelihoodEngine:
                 # may grow, which moves the graph epoch)
                 with self._lock:
                     nk, done = 0, False
-                    if use_graph and sl['seen'].get(key, 0) >= 1 and len(sl['graphs']) < 32:
+                    if use_graph and sl['seen'].get(key, 0) >= 1 and len(sl['graphs']) < 192:
                         # second sighting: every scratch buffer of this configuration exists
                         l0 = L.rvs_launch_count()
                         gr = torch.cuda.CUDAGraph()
@@ -739,10 +776,9 @@ class LikelihoodEngine:
                             gr.capture_end()
                         nk = L.rvs_launch_count() - l0
                         self._launch_skew -= nk                 # captured, not run
-                        if getattr(self, '_graph_epoch', 0) != epoch:   # a buffer moved
+                        if self._epoch(sl) != epoch:   # a buffer moved during the capture
                             sl['graphs'], sl['seen'] = {}, {}
-                            sl['graph_epoch'] = self._graph_epoch
-                            self.use_graphs = False
+                            sl['graph_epoch'] = self._epoch(sl)
                             nk = 0
                         else:
                             sl['graphs'][key] = (gr, nk)
@@ -780,8 +816,9 @@ class LikelihoodEngine:
         d_oix = sl['d_oix'][:narm * K].view(narm, K)
         d_in.copy_(sl['h_in'][:(2 + nd) * K].view(2 + nd, K), non_blocking=True)
         d_oix.copy_(sl['h_oix'][:narm * K].view(narm, K), non_blocking=True)
-        d_chi = self._scratch(f'chi_{six}', (2, narm, K), np.float64)    # chi-square | off-grid measure
-        d_flags = self._scratch(f'flags_{six}', (2, narm, K), np.int32)
+        cap = sl['K']       # scratch is sized for the slot's capacity: it grows when the slot does
+        d_chi = self._scratch(f'chi_{six}', (2, narm, K), np.float64, 2 * narm * cap, sl=sl)    # chi-square | off-grid measure
+        d_flags = self._scratch(f'flags_{six}', (2, narm, K), np.int32, 2 * narm * cap, sl=sl)
         nvert = bank0.nvert
         torch = _dev.torch_mod()
         main = torch.cuda.current_stream()
@@ -793,8 +830,8 @@ class LikelihoodEngine:
         shared = narm > 1 and sigs[0] is not None and all(s_ == sigs[0] for s_ in sigs)
         sl['shared_locate'] = shared
         if shared:      # one vertex location for all arms, before the streams fork
-            d_ids0 = self._scratch(f'ids0_{six}', (K, nvert), np.int32)
-            d_w0 = self._scratch(f'w0_{six}', (K, nvert), np.float64)
+            d_ids0 = self._scratch(f'ids0_{six}', (K, nvert), np.int32, cap * nvert, sl=sl)
+            d_w0 = self._scratch(f'w0_{six}', (K, nvert), np.float64, cap * nvert, sl=sl)
             rc = L.rvs_locate_grid(ctypes.byref(bank0.gridmap), _dev.ptr(d_in[2:]), K, K,
                                    _dev.ptr(d_ids0), _dev.ptr(d_w0), _dev.ptr(d_flags[1, 0]),
                                    _dev.ptr(d_chi[1, 0]), ctypes.c_void_p(main.cuda_stream))
@@ -808,10 +845,12 @@ class LikelihoodEngine:
                 arm = self.arms[name]
                 bank, batch = arm['bank'], arm['batch']
                 stride = batch.max_npix
-                d_tn = self._scratch(f'tn{a}_{six}', (K * stride * batch.tn_rows,), np.float64)
+                d_tn = self._scratch(f'tn{a}_{six}', (K * stride * batch.tn_rows,), np.float64,
+                                     cap * stride * batch.tn_rows, sl=sl)
                 d_work = self._scratch(
                     f'work{a}_{six}',
-                    (L.rvs_fused_workspace(K, bank.tapcap(vmax), bank.npix_t),), np.float64)
+                    (L.rvs_fused_workspace(K, bank.tapcap(vmax), bank.npix_t),), np.float64,
+                    L.rvs_fused_workspace(cap, bank.tapcap(vmax), bank.npix_t), sl=sl)
                 fa = arms[a]
                 fa.d_grid, fa.grid_f64, fa.log_spec = bank.grid.data_ptr(), bank.grid_f64, \
                     int(bank.log_spec)
@@ -857,8 +896,8 @@ class LikelihoodEngine:
             if shared:
                 d_ids, d_w = d_ids0, d_w0
             else:
-                d_ids = self._scratch(f'ids{a}_{six}', (K, nvert), np.int32)
-                d_w = self._scratch(f'w{a}_{six}', (K, nvert), np.float64)
+                d_ids = self._scratch(f'ids{a}_{six}', (K, nvert), np.int32, sl=sl)
+                d_w = self._scratch(f'w{a}_{six}', (K, nvert), np.float64, sl=sl)
                 q = d_in[2:]
                 if bank.log_ids != bank0.log_ids:
                     with torch.cuda.stream(st):
@@ -868,10 +907,10 @@ class LikelihoodEngine:
                                        _dev.ptr(d_chi[1, a]), stream)
                 _cabi.check(rc, 'rvs_locate_grid')
             stride = batch.max_npix
-            d_tn = self._scratch(f'tn{a}_{six}', (K * stride * batch.tn_rows,), np.float64)
+            d_tn = self._scratch(f'tn{a}_{six}', (K * stride * batch.tn_rows,), np.float64, sl=sl)
             d_work = self._scratch(f'work{a}_{six}',
                                    (L.rvs_fused_workspace(K, bank.tapcap(vmax), bank.npix_t),),
-                                   np.float64)
+                                   np.float64, sl=sl)
             rc = L.rvs_chisq_fused(_dev.ptr(bank.grid), bank.grid_f64, bank.ld,
                                    ctypes.byref(bank.knots), _dev.ptr(d_ids), _dev.ptr(d_w),
                                    bank.nvert, _dev.ptr(d_in[1]) if vmax > 0 else None, vmax,
@@ -997,6 +1036,142 @@ class LikelihoodEngine:
         redo |= _dev.download(d_flag.to(torch.uint8)).astype(bool)
         redo |= ~np.isfinite(stats[:, 0])
         return stats, redo
+
+    # ---- native round loop of a Nelder-Mead stage (csrc/drive_host.cpp) ----
+    def drive_open(self, lay, objmap, nfit, cap):
+        """Take an evaluation slot for a whole optimiser stage whose requests have at
+        most `cap` points of `nfit` coordinates, problems numbered like objmap (int32
+        engine objects).  Returns the stage handle for drive_run / drive_close, or None
+        when the packed fast path does not apply."""
+        if not (self.fused and self._fast_banks and self.use_graphs):
+            return None
+        L = _cabi.lib()
+        sl, Kp = self._acquire(cap)
+        if not self._same_maps or not sl['use_graph']:
+            sl['busy'] = False
+            return None
+        if sl.get('fit_cap', 0) < Kp:
+            c = sl['K']
+            sl.update(fit_cap=c, f_prior=np.empty(c), f_pen=np.empty(c),
+                      f_wall=np.empty(c, dtype=np.uint8), f_out=np.empty(c),
+                      f_redo=np.empty(c, dtype=np.uint8))
+        self._wait_data(sl)
+        h = L.rvs_drive_create(int(cap), int(nfit))
+        if not h:
+            sl['busy'] = False
+            raise _cabi.RvsError('rvs_drive_create failed')
+        io = _cabi.Drive()
+        io.stream = sl['stream'].cuda_stream
+        io.h_in, io.h_oix = sl['h_in'].data_ptr(), sl['h_oix'].data_ptr()
+        io.h_chi, io.h_flags = sl['h_chi'].data_ptr(), sl['h_flags'].data_ptr()
+        io.f_prior, io.f_pen = sl['f_prior'].ctypes.data, sl['f_pen'].ctypes.data
+        io.f_wall, io.f_out = sl['f_wall'].ctypes.data, sl['f_out'].ctypes.data
+        io.f_redo = sl['f_redo'].ctypes.data
+        io.cap = min(sl['K'], sl['fit_cap'])
+        objmap = np.ascontiguousarray(objmap, dtype=np.int32)
+        io.objmap, io.nprob = objmap.ctypes.data, len(objmap)
+        io.fused_vmax = self._fused_vmax
+        io.state = _cabi.DRIVE_IDLE
+        st = dict(sl=sl, h=ctypes.c_void_p(h), io=io, lay=lay, objmap=objmap, nfit=int(nfit),
+                  table=None, table_key=None, done=[0, 0, 0, 0, 0, 0], trec=None)
+        timer = self.timer
+        if timer is not None and getattr(timer, 'epoch', None) is not None:
+            st['trec'] = np.zeros((1 << 16, 3))
+            io.epoch_event = timer.epoch.cuda_event
+            io.t_rec, io.t_cap, io.t_n = st['trec'].ctypes.data, len(st['trec']), 0
+        return st
+
+    def _drive_table(self, st):
+        """The slot's captured graphs (systematic error 0) as the arrays rvs_nm_drive reads."""
+        sl, io = st['sl'], st['io']
+        narm = len(self.setups)
+        graphs = sl.get('graphs', {}) if sl.get('graph_epoch') == self._epoch(sl) else {}
+        key = (sl.get('graph_epoch'), len(graphs))
+        if st['table_key'] == key:
+            return
+        zero = (0.0,) * narm
+        ent = [(k[0], k[1], g) for k, g in graphs.items() if k[2] == zero]
+        kp = np.array([e[0] for e in ent], dtype=np.int64)
+        vm = np.array([e[1] for e in ent], dtype=np.float64)
+        ex = (ctypes.c_void_p * max(1, len(ent)))(*[e[2][0].raw_cuda_graph_exec() for e in ent])
+        nk = np.array([e[2][1] for e in ent], dtype=np.int32)
+        st['table'], st['table_key'] = (kp, vm, ex, nk), key
+        io.ngraph = len(ent)
+        io.g_kp, io.g_vmax, io.g_nk = kp.ctypes.data, vm.ctypes.data, nk.ctypes.data
+        io.g_exec = ctypes.cast(ex, ctypes.c_void_p).value
+
+    def _drive_flush(self, st):
+        """Counters of the rounds run so far -> the engine's."""
+        io, done = st['io'], st['done']
+        now = [io.items, io.graph_kernels, io.h2d_bytes, io.d2h_bytes, io.rounds, io.t_n]
+        with self._lock:
+            self.n_eval += now[0] - done[0]
+            self.graph_kernel_launches += now[1] - done[1]
+            GRAPH_LAUNCHES[0] += now[1] - done[1]
+            _dev.IO_BYTES[0] += now[2] - done[2]
+            _dev.IO_BYTES[1] += now[3] - done[3]
+        if st['trec'] is not None and now[5] > done[5] and self.timer is not None:
+            self.timer.add_native('fused_eval', st['trec'][done[5]:now[5]].copy())
+            if now[5] >= len(st['trec']) - 1:
+                io.t_n = 0
+                now[5] = 0
+        st['done'] = now
+        LAST_DRIVE_ROUNDS[0] = int(io.rounds)
+
+    def drive_run(self, st, nm, speculate_below, stop_stopped, redo_values, py_values):
+        """Run rounds of the Nelder-Mead stepper `nm` (rvs_nm_* handle) on the held slot
+        until every problem has stopped (returns _cabi.DRIVE_DONE) or `stop_stopped`
+        problems have (DRIVE_PEEL).  redo_values(obj32, X) -> objective values through the
+        general path for the items the fused path could not settle; py_values(obj32, X)
+        -> objective values of a whole request that does not fit the fused path."""
+        L = _cabi.lib()
+        sl, io, lay = st['sl'], st['io'], st['lay']
+        io.speculate_below, io.stop_stopped = int(speculate_below), int(stop_stopped)
+        narm = len(self.setups)
+        okey = (0.0,) * narm
+        try:
+            while True:
+                self._drive_table(st)
+                io.shared_locate = int(bool(sl.get('shared_locate')))
+                rc = L.rvs_nm_drive(nm, st['h'], ctypes.byref(lay), ctypes.byref(io))
+                if rc in (_cabi.DRIVE_DONE, _cabi.DRIVE_PEEL):
+                    return rc
+                if rc == _cabi.DRIVE_LAUNCH:
+                    sl['Kp'] = int(io.Kp)
+                    self._launch(sl, int(io.K), int(io.Kp), float(io.vmax), okey, None)
+                    nk = sl.get('graph_kernels', 0)
+                    with self._lock:
+                        self.graph_kernel_launches += nk
+                        GRAPH_LAUNCHES[0] += nk + self._launch_skew
+                        self._launch_skew = 0
+                    io.state = _cabi.DRIVE_LAUNCHED
+                elif rc in (_cabi.DRIVE_REDO, _cabi.DRIVE_PYEVAL):
+                    K, N = int(io.K), st['nfit']
+                    pX, pobj = ctypes.c_void_p(), ctypes.c_void_p()
+                    L.rvs_drive_request(st['h'], None, ctypes.byref(pX), ctypes.byref(pobj))
+                    X = np.ctypeslib.as_array(ctypes.cast(pX, ctypes.POINTER(ctypes.c_double)),
+                                              (K, N))
+                    obj = np.ctypeslib.as_array(ctypes.cast(pobj, ctypes.POINTER(ctypes.c_int32)),
+                                                (K,))
+                    if rc == _cabi.DRIVE_REDO:
+                        r = np.nonzero(sl['f_redo'][:K])[0]
+                        sl['f_out'][r] = redo_values(obj[r].copy(), X[r].copy())
+                        with self._lock:
+                            self.n_eval -= len(r)
+                    else:
+                        sl['f_out'][:K] = py_values(obj.copy(), X.copy())
+                        with self._lock:
+                            self.n_eval -= K        # counted by the route that evaluated them
+                        io.state = _cabi.DRIVE_COLLECTED
+                else:
+                    _cabi.check(rc, 'rvs_nm_drive')
+                    raise _cabi.RvsError(f'rvs_nm_drive returned {rc}')
+        finally:
+            self._drive_flush(st)
+
+    def drive_close(self, st):
+        _cabi.lib().rvs_drive_destroy(st['h'])
+        st['sl']['busy'] = False
 
     def submit_fit(self, lay, obj32, X, logvals):
         """Optimiser-phase evaluation of the batched fit's objective for K (object,

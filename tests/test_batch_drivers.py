@@ -226,6 +226,17 @@ def test_process_batch_pipeline_equals_single_object_rules(monkeypatch):
     priors = {'teff': (5600., 400.)}
     res = {g: batch_fit.process_batch(None, starts, config=cfg, options={}, engine=eng,
                                       priors=priors, groups=g) for g in (1, 3)}
+    # finished objects handed on in groups while the slower ones iterate (spawned
+    # coroutines), by the calling thread and by one thread per coroutine
+    monkeypatch.setattr(batch_fit, 'PEEL_MIN', 2)
+    monkeypatch.setattr(batch_fit, 'MAX_CALL_ITEMS', 100)
+    for key, kw in (('peel', dict(groups=1, threads=False)), ('peel-threads', dict(groups=2, threads=True))):
+        n0 = len(eng.calls)
+        res[key] = batch_fit.process_batch(None, starts, config=cfg, options={}, engine=eng,
+                                           priors=priors, peel=True, **kw)
+        assert all(r is not None for r in res[key])
+        assert max(eng.calls[n0:]) <= 600     # scans of 7 objects at most; stencils in pieces
+    assert batch_fit.process_batch.last_spawned > 0
 
     # the single-object path with the same likelihood behind the reference-shaped calls
     def get_chisq(specdata, vel, atm, rot=None, resol=None, options=None, config=None,

@@ -128,10 +128,22 @@ def test_three_arm_process_matches_reference(golden):
     objs = unpack_objects(g, 'd3_')
     cfg, opts = config(), {'npoly': 10}
     start = {'teff': 5500., 'logg': 3.0, 'feh': -1.0, 'alpha': 0.3, 'vsini': 10.}
+    # default route: Nelder-Mead rounds run by the library (rvs_nm_drive) on the set's thread
     batch = batch_fit.process_batch([_sd(o) for o in objs], [dict(start) for _ in objs],
                                     config=cfg, options=opts)
+    assert spec_fit.LAST_DRIVE_ROUNDS[0] > 100
+    # the rounds stepped from Python, and finished objects handed on in groups
+    pyroute = batch_fit.process_batch([_sd(o) for o in objs], [dict(start) for _ in objs],
+                                      config=cfg, options=opts, threads=False)
+    batch_fit.PEEL_MIN, keep = 1, batch_fit.PEEL_MIN
+    try:
+        peeled = batch_fit.process_batch([_sd(o) for o in objs], [dict(start) for _ in objs],
+                                         config=cfg, options=opts, peel=True)
+    finally:
+        batch_fit.PEEL_MIN = keep
     single = vel_fit.process(_sd(objs[0]), dict(start), config=cfg, options=opts)
-    for i, res in [(0, single)] + list(enumerate(batch)):
+    for i, res in [(0, single)] + list(enumerate(batch)) + list(enumerate(pyroute)) + \
+            list(enumerate(peeled)):
         assert abs(res['vel'] - g[f'd3_{i}_vel']) < 0.01
         close(res['vel_err'], g[f'd3_{i}_vel_err'], rtol=1e-4)
         close(res['chisq'], g[f'd3_{i}_chisq'], rtol=1e-6)

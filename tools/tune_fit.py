@@ -14,6 +14,8 @@ settings = sys.argv[2:] or ['4:128']
 
 def main():
     import torch
+    if os.environ.get('RVS_SWITCH'):
+        sys.setswitchinterval(float(os.environ['RVS_SWITCH']))
     w = bench.WORKLOADS['desi']
     cfg = bench.make_config(w)
     setups, objects, pars, vel = bench.make_inputs('desi', B, 1000)
@@ -26,7 +28,12 @@ def main():
     for s in settings:
         f = s.split(':')
         groups, spec = int(f[0]), int(f[1])
-        threads = bool(int(f[2])) if len(f) > 2 else None
+        threads = bool(int(f[2])) if len(f) > 2 and f[2] != '' else None
+        peel = bool(int(f[3])) if len(f) > 3 else None
+        if len(f) > 4:
+            batch_fit.PEEL_MIN = int(f[4])
+        if len(f) > 5:
+            batch_fit.PEEL_FRAC = float(f[5])
         batch_fit.SPECULATE_BELOW = spec
         for rep in range(3 if first else 2):
             n0 = eng.n_eval
@@ -34,11 +41,27 @@ def main():
             torch.cuda.synchronize()
             t0 = time.time()
             res = batch_fit.process_batch(None, starts, config=cfg, options={'npoly': 10},
-                                          engine=eng, groups=groups, timer=timer, threads=threads)
+                                          engine=eng, groups=groups, timer=timer, threads=threads, peel=peel)
             torch.cuda.synchronize()
             dt = time.time() - t0
             ks = timer.summary()
+            iv = timer.intervals('fused_eval')
+            ev = [(r[2], r[1] - r[0]) for r in iv]
+            hist = []
+            for lo, hi in ((0, 64), (64, 256), (256, 1024), (1024, 4096), (4096, 1 << 30)):
+                sel = [d for k, d in ev if lo <= k < hi]
+                hist.append(f'[{lo},{hi if hi < 1 << 30 else "inf"}): n={len(sel)} sum={sum(sel):.0f}ms mean={np.mean(sel) if sel else 0:.3f}')
+            print('   calls by items:', '; '.join(hist), flush=True)
+            if os.environ.get('RVS_TIMELINE') and rep >= 1:
+                names = sorted(set(r[0] for r in timer.rec) | set(timer.native))
+                ivs = [timer.intervals(n) for n in names]
+                allv = np.concatenate(ivs)
+                np.savez(os.environ['RVS_TIMELINE'], names=np.array(names),
+                         kind=np.concatenate([np.full(len(v), i) for i, v in enumerate(ivs)]),
+                         t0=allv[:, 0] - allv[:, 0].min(), t1=allv[:, 1] - allv[:, 0].min(),
+                         items=allv[:, 2].astype(np.int64), wall=dt)
             chk = (float(np.sum([r['vel'] for r in res])), float(np.sum([r['chisq'] for r in res])))
+            print(f'   spawned {batch_fit.process_batch.last_spawned}  mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB')
             print(f'{s} rep{rep}: chk {chk[0]:.9f} {chk[1]:.6f} {B / dt:8.1f} fits/s  {dt:6.3f} s  evals/fit {(eng.n_eval - n0) / B:7.1f}  '
                   f'calls {ks.get("fused_eval_launches")} items/call {ks.get("fused_eval_items_per_launch", 0):.0f} '
                   f'busy {ks.get("fused_eval_ms_busy", 0):.0f} ms  sum {ks.get("fused_eval_ms_total", 0):.0f} ms  '
