@@ -1107,7 +1107,7 @@ class _Sub:
 # objects per lock-step set and sets in flight: enough sets that the tail of one (few
 # live problems, latency-bound calls) runs under the bulk of the others
 FIT_GROUP = 256
-FIT_MAX_GROUPS = 2
+FIT_MAX_GROUPS = 3
 THREADS = True
 PEEL = False
 
@@ -1138,6 +1138,7 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
     has_vsini = 'vsini' in paramDict0s[0]
     fitVsini = has_vsini and 'vsini' not in fixParam
     fobj = BatchObjective(eng, specParams, paramDict0s, fixParam, fitVsini, config, priors)
+    fobj.layout()       # built once, before the sets' threads ask for it
     if groups is None:
         groups = int(np.clip(B // FIT_GROUP, 1, FIT_MAX_GROUPS))
     groups = max(1, min(groups, B, eng.NSLOT))

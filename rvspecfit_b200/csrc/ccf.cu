@@ -10,8 +10,13 @@
 //                      velocity grid (scipy interp1d arithmetic) -> += over arms
 //   ccf_best_kernel    + total_sse, argmin over templates and velocities,
 //                      parabola vertex
-// The inverse transforms run in place (complex rows of nfreq = n/2+1 bins become
-// real rows with a stride of 2*nfreq doubles).
+// The inverse real transform of n points is taken as ONE complex transform of n/2 points:
+// with A[k] = X[k] + conj(X[n/2-k]) and B[k] = (X[k] - conj(X[n/2-k])) e^{2 pi i k/n},
+// z = IFFT_{n/2}(A + iB) is x[2m] + i x[2m+1], i.e. the real row itself.  ccf_mult_kernel
+// writes A + iB directly, so the product spectrum crosses HBM once on the way in and the
+// correlation once on the way out; cuFFT's own Z2D spends two more passes over the data
+// on the same packing and unpacking (its preprocess / unpackC2R kernels were 40 % of the
+// accumulate stage in the launch list).
 #include <cufft.h>
 #include <math.h>
 
@@ -31,7 +36,7 @@ static int get_plan(int kind, int n, int batch, cufftHandle *out) {
   std::lock_guard<std::mutex> lk(g_plan_mu);
   int dev = 0;
   cudaGetDevice(&dev);
-  const auto key = std::make_tuple(kind + 2 * dev, n, batch);
+  const auto key = std::make_tuple(kind + 4 * dev, n, batch);
   auto it = g_plans.find(key);
   if (it == g_plans.end()) {
     cufftHandle p;
@@ -41,9 +46,12 @@ static int get_plan(int kind, int n, int batch, cufftHandle *out) {
     if (kind == 0) {  // D2Z, out of place, packed
       int in_e[1] = {n}, out_e[1] = {nfreq};
       r = cufftPlanMany(&p, 1, nn, in_e, 1, n, out_e, 1, nfreq, CUFFT_D2Z, batch);
-    } else {  // Z2D in place
+    } else if (kind == 1) {  // Z2D in place
       int in_e[1] = {nfreq}, out_e[1] = {2 * nfreq};
       r = cufftPlanMany(&p, 1, nn, in_e, 1, nfreq, out_e, 1, 2 * nfreq, CUFFT_Z2D, batch);
+    } else {  // Z2Z of n/2 points in place, rows of n/2 complex
+      int nh[1] = {n / 2};
+      r = cufftPlanMany(&p, 1, nh, nh, 1, n / 2, nh, 1, n / 2, CUFFT_Z2Z, batch);
     }
     if (r != CUFFT_SUCCESS) {
       set_error("cufftPlanMany(kind=%d, n=%d, batch=%d) failed: %d", kind, n, batch, (int)r);
@@ -108,6 +116,54 @@ __global__ void __launch_bounds__(256) ccf_mult_kernel(const double2 *T, const d
       if (edge) { p0.y = 0; p1.y = 0; }
       Z0[o] = p0;
       Z1[o] = p1;
+    }
+  }
+}
+
+// The same products packed for the half-size complex transform (see the file comment):
+// grid (ceil((n/2)/256), ntempl); thread k forms X[k] and X[n/2-k] of every object of the
+// chunk from the template bins it keeps in registers and writes Z[k] = A[k] + i B[k]
+// (rows of n/2 complex = the n real values of the correlation after the transform).
+template <bool CONT>
+__global__ void __launch_bounds__(256) ccf_mult_half_kernel(const double2 *T, const double2 *T2,
+                                                            const double2 *SF, const double2 *IF,
+                                                            int nfreq, int ntempl, int nb,
+                                                            double inv_n, double2 *Z0, double2 *Z1) {
+  const int nh = nfreq - 1;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (k >= nh) return;
+  const int kp = nh - k;                       // partner bin (k = 0: the Nyquist bin)
+  const double2 a = T[(int64_t)t * nfreq + k], c = T2[(int64_t)t * nfreq + k];
+  const double2 ap = T[(int64_t)t * nfreq + kp], cp = T2[(int64_t)t * nfreq + kp];
+  const bool edge = k == 0;                    // DC and Nyquist: imaginary parts unused
+  double tw_s, tw_c;
+  sincospi(2.0 * (double)k / (double)(2 * nh), &tw_s, &tw_c);
+  auto pack = [&](double2 x, double2 xp) {     // A + iB from X[k], X[n/2-k]
+    if (edge) { x.y = 0; xp.y = 0; }
+    const double ar = x.x + xp.x, ai = x.y - xp.y;          // X + conj(Xp)
+    const double dr = x.x - xp.x, di = x.y + xp.y;          // X - conj(Xp)
+    const double br = dr * tw_c - di * tw_s, bi = dr * tw_s + di * tw_c;
+    return make_double2(ar - bi, ai + br);
+  };
+  for (int b = 0; b < nb; b++) {
+    const double2 s = SF[(int64_t)b * nfreq + k], w = IF[(int64_t)b * nfreq + k];
+    const double2 sp = SF[(int64_t)b * nfreq + kp], wp = IF[(int64_t)b * nfreq + kp];
+    // x * conj(y) = (xr yr + xi yi) + i (xi yr - xr yi)
+    double2 p0 = make_double2(a.x * s.x + a.y * s.y, a.y * s.x - a.x * s.y);
+    double2 p1 = make_double2(c.x * w.x + c.y * w.y, c.y * w.x - c.x * w.y);
+    double2 q0 = make_double2(ap.x * sp.x + ap.y * sp.y, ap.y * sp.x - ap.x * sp.y);
+    double2 q1 = make_double2(cp.x * wp.x + cp.y * wp.y, cp.y * wp.x - cp.x * wp.y);
+    const int64_t o = ((int64_t)b * ntempl + t) * nh + k;
+    if (CONT) {
+      const double2 x = make_double2((p1.x - 2 * p0.x) * inv_n, (p1.y - 2 * p0.y) * inv_n);
+      const double2 xp = make_double2((q1.x - 2 * q0.x) * inv_n, (q1.y - 2 * q0.y) * inv_n);
+      Z0[o] = pack(x, xp);
+    } else {
+      p0.x *= inv_n; p0.y *= inv_n; p1.x *= inv_n; p1.y *= inv_n;
+      q0.x *= inv_n; q0.y *= inv_n; q1.x *= inv_n; q1.y *= inv_n;
+      Z0[o] = pack(p0, q0);
+      Z1[o] = pack(p1, q1);
     }
   }
 }
@@ -282,7 +338,7 @@ extern "C" int rvs_ccf_accumulate(const rvs_ccf_arm *arm, const double *d_pspec,
     cufftHandle fwd, inv;
     int rc = get_plan(0, n, nb, &fwd);
     if (rc) return rc;
-    rc = get_plan(1, n, nb * nt, &inv);
+    rc = get_plan(2, n, nb * nt, &inv);
     if (rc) return rc;
     RVS_REQUIRE(cufftSetStream(fwd, st) == CUFFT_SUCCESS && cufftSetStream(inv, st) == CUFFT_SUCCESS,
                 RVS_E_CUDA, "cufftSetStream failed");
@@ -291,27 +347,27 @@ extern "C" int rvs_ccf_accumulate(const rvs_ccf_arm *arm, const double *d_pspec,
     RVS_REQUIRE(cufftExecD2Z(fwd, const_cast<double *>(d_pivar) + b0 * n,
                              reinterpret_cast<cufftDoubleComplex *>(IF)) == CUFFT_SUCCESS,
                 RVS_E_CUDA, "cufftExecD2Z failed");
-    dim3 grid((unsigned)((nfreq + 255) / 256), (unsigned)nt);
+    dim3 grid((unsigned)((n / 2 + 255) / 256), (unsigned)nt);
     if (arm->continuum)
-      ccf_mult_kernel<true><<<grid, 256, 0, st>>>(T, T2, SF, IF, (int)nfreq, nt, nb, 1.0 / n, Z0, Z1);
+      ccf_mult_half_kernel<true><<<grid, 256, 0, st>>>(T, T2, SF, IF, (int)nfreq, nt, nb, 1.0 / n, Z0, Z1);
     else
-      ccf_mult_kernel<false><<<grid, 256, 0, st>>>(T, T2, SF, IF, (int)nfreq, nt, nb, 1.0 / n, Z0, Z1);
+      ccf_mult_half_kernel<false><<<grid, 256, 0, st>>>(T, T2, SF, IF, (int)nfreq, nt, nb, 1.0 / n, Z0, Z1);
     RVS_LAUNCH_OK();
-    RVS_REQUIRE(cufftExecZ2D(inv, reinterpret_cast<cufftDoubleComplex *>(Z0),
-                             reinterpret_cast<double *>(Z0)) == CUFFT_SUCCESS,
-                RVS_E_CUDA, "cufftExecZ2D failed");
+    RVS_REQUIRE(cufftExecZ2Z(inv, reinterpret_cast<cufftDoubleComplex *>(Z0),
+                             reinterpret_cast<cufftDoubleComplex *>(Z0), CUFFT_INVERSE) == CUFFT_SUCCESS,
+                RVS_E_CUDA, "cufftExecZ2Z failed");
     if (!arm->continuum)
-      RVS_REQUIRE(cufftExecZ2D(inv, reinterpret_cast<cufftDoubleComplex *>(Z1),
-                               reinterpret_cast<double *>(Z1)) == CUFFT_SUCCESS,
-                  RVS_E_CUDA, "cufftExecZ2D failed");
+      RVS_REQUIRE(cufftExecZ2Z(inv, reinterpret_cast<cufftDoubleComplex *>(Z1),
+                               reinterpret_cast<cufftDoubleComplex *>(Z1), CUFFT_INVERSE) == CUFFT_SUCCESS,
+                  RVS_E_CUDA, "cufftExecZ2Z failed");
     const unsigned rows = (unsigned)(nb * nt);
     if (arm->continuum)
       ccf_gather_kernel<true><<<rows, 128, 0, st>>>(
-          reinterpret_cast<const double *>(Z0), nullptr, 2 * nfreq, nt, nvel, arm->d_lo, arm->d_hi,
+          reinterpret_cast<const double *>(Z0), nullptr, (int64_t)n, nt, nvel, arm->d_lo, arm->d_hi,
           arm->d_dxn, arm->d_dx, d_row, (int)b0, d_chisq);
     else
       ccf_gather_kernel<false><<<rows, 128, 0, st>>>(
-          reinterpret_cast<const double *>(Z0), reinterpret_cast<const double *>(Z1), 2 * nfreq, nt,
+          reinterpret_cast<const double *>(Z0), reinterpret_cast<const double *>(Z1), (int64_t)n, nt,
           nvel, arm->d_lo, arm->d_hi, arm->d_dxn, arm->d_dx, d_row, (int)b0, d_chisq);
     RVS_LAUNCH_OK();
   }

@@ -135,6 +135,10 @@ def _stack_rows(pairs):
     return cols[0].contiguous(), cols[1].contiguous()
 
 
+# optional CUDA-event timer of the accumulate stage (batch_fit.KernelTimer; bench.py)
+timer = None
+
+
 def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=None,
               preprocess='device', want_proc_spec=True):
     """fitter_ccf.fit for many objects.  objects: list of lists of SpecData.
@@ -214,11 +218,14 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=Non
                 need = L.rvs_ccf_workspace(ctypes.byref(arm), len(rows))
                 nbytes = min(need, max(WORKSPACE_BYTES, L.rvs_ccf_workspace(ctypes.byref(arm), 1)))
                 ws = _workspace(nbytes)
+                t0 = timer.start() if timer is not None else None
                 rc = L.rvs_ccf_accumulate(ctypes.byref(arm), _dev.ptr(d_ps), _dev.ptr(d_pi),
                                           len(rows), _dev.ptr(d_row), _dev.ptr(d_chisq),
                                           _dev.ptr(d_sse), _dev.ptr(ws), ws.numel() * 8,
                                           _dev.stream())
                 _cabi.check(rc, 'rvs_ccf_accumulate')
+                if t0 is not None:
+                    timer.stop('ccf_accumulate', t0, len(rows) * ntempl)
         d_out = _dev.empty((nrow, 8), np.float64)
         d_best = _dev.empty((nrow, nvel), np.float64)
         rc = L.rvs_ccf_best(_dev.ptr(d_chisq), _dev.ptr(d_sse), _dev.ptr(d_vg), nrow, ntempl, nvel,
