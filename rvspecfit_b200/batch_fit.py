@@ -1110,6 +1110,7 @@ FIT_GROUP = 256
 FIT_MAX_GROUPS = 3
 THREADS = True
 PEEL = False
+FIT_SPLIT = {2: [3, 2], 3: [5, 4, 3], 4: [4, 3, 2, 1]}      # number of sets -> relative sizes (else equal)
 
 
 def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None, priors=None,
@@ -1143,7 +1144,11 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
         groups = int(np.clip(B // FIT_GROUP, 1, FIT_MAX_GROUPS))
     groups = max(1, min(groups, B, eng.NSLOT))
     phase = {}
-    parts = [p for p in np.array_split(np.arange(B), groups) if len(p)]
+    # sets of unequal size reach their latency-bound stretches (optimiser tails, refinement
+    # scans, model output) at different times, under the large calls of the others
+    frac = np.array(FIT_SPLIT.get(groups) or [1.0 / groups] * groups, dtype=np.float64)
+    cuts = np.round(np.cumsum(frac / frac.sum()) * B).astype(int)[:-1]
+    parts = [p for p in np.split(np.arange(B), cuts) if len(p)]
     if peel is None:
         peel = PEEL and hasattr(eng, 'submit_fit')
     if threads is None:

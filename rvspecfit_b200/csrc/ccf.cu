@@ -121,9 +121,10 @@ __global__ void __launch_bounds__(256) ccf_mult_kernel(const double2 *T, const d
 }
 
 // The same products packed for the half-size complex transform (see the file comment):
-// grid (ceil((n/2)/256), ntempl); thread k forms X[k] and X[n/2-k] of every object of the
-// chunk from the template bins it keeps in registers and writes Z[k] = A[k] + i B[k]
-// (rows of n/2 complex = the n real values of the correlation after the transform).
+// grid (ceil((n/4 + 1)/256), ntempl); thread k <= n/4 forms X[k] and X[n/2-k] of every
+// object of the chunk from the template bins it keeps in registers and writes BOTH
+// Z[k] = A + iB and Z[n/2-k] = conj(A) + i conj(B) (rows of n/2 complex = the n real values
+// of the correlation after the transform), so every product is formed once.
 template <bool CONT>
 __global__ void __launch_bounds__(256) ccf_mult_half_kernel(const double2 *T, const double2 *T2,
                                                             const double2 *SF, const double2 *IF,
@@ -132,19 +133,21 @@ __global__ void __launch_bounds__(256) ccf_mult_half_kernel(const double2 *T, co
   const int nh = nfreq - 1;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = blockIdx.y;
-  if (k >= nh) return;
+  if (2 * k > nh) return;
   const int kp = nh - k;                       // partner bin (k = 0: the Nyquist bin)
   const double2 a = T[(int64_t)t * nfreq + k], c = T2[(int64_t)t * nfreq + k];
   const double2 ap = T[(int64_t)t * nfreq + kp], cp = T2[(int64_t)t * nfreq + kp];
   const bool edge = k == 0;                    // DC and Nyquist: imaginary parts unused
+  const bool both = k > 0 && kp != k;          // Z[n/2-k] is a row element of its own
   double tw_s, tw_c;
   sincospi(2.0 * (double)k / (double)(2 * nh), &tw_s, &tw_c);
-  auto pack = [&](double2 x, double2 xp) {     // A + iB from X[k], X[n/2-k]
+  auto pack = [&](double2 x, double2 xp, double2 *Z, int64_t row) {
     if (edge) { x.y = 0; xp.y = 0; }
-    const double ar = x.x + xp.x, ai = x.y - xp.y;          // X + conj(Xp)
+    const double ar = x.x + xp.x, ai = x.y - xp.y;          // A = X + conj(Xp)
     const double dr = x.x - xp.x, di = x.y + xp.y;          // X - conj(Xp)
-    const double br = dr * tw_c - di * tw_s, bi = dr * tw_s + di * tw_c;
-    return make_double2(ar - bi, ai + br);
+    const double br = dr * tw_c - di * tw_s, bi = dr * tw_s + di * tw_c;   // B
+    Z[row + k] = make_double2(ar - bi, ai + br);             // A + iB
+    if (both) Z[row + kp] = make_double2(ar + bi, br - ai);  // conj(A) + i conj(B)
   };
   for (int b = 0; b < nb; b++) {
     const double2 s = SF[(int64_t)b * nfreq + k], w = IF[(int64_t)b * nfreq + k];
@@ -154,16 +157,16 @@ __global__ void __launch_bounds__(256) ccf_mult_half_kernel(const double2 *T, co
     double2 p1 = make_double2(c.x * w.x + c.y * w.y, c.y * w.x - c.x * w.y);
     double2 q0 = make_double2(ap.x * sp.x + ap.y * sp.y, ap.y * sp.x - ap.x * sp.y);
     double2 q1 = make_double2(cp.x * wp.x + cp.y * wp.y, cp.y * wp.x - cp.x * wp.y);
-    const int64_t o = ((int64_t)b * ntempl + t) * nh + k;
+    const int64_t row = ((int64_t)b * ntempl + t) * nh;
     if (CONT) {
       const double2 x = make_double2((p1.x - 2 * p0.x) * inv_n, (p1.y - 2 * p0.y) * inv_n);
       const double2 xp = make_double2((q1.x - 2 * q0.x) * inv_n, (q1.y - 2 * q0.y) * inv_n);
-      Z0[o] = pack(x, xp);
+      pack(x, xp, Z0, row);
     } else {
       p0.x *= inv_n; p0.y *= inv_n; p1.x *= inv_n; p1.y *= inv_n;
       q0.x *= inv_n; q0.y *= inv_n; q1.x *= inv_n; q1.y *= inv_n;
-      Z0[o] = pack(p0, q0);
-      Z1[o] = pack(p1, q1);
+      pack(p0, q0, Z0, row);
+      pack(p1, q1, Z1, row);
     }
   }
 }
@@ -347,7 +350,7 @@ extern "C" int rvs_ccf_accumulate(const rvs_ccf_arm *arm, const double *d_pspec,
     RVS_REQUIRE(cufftExecD2Z(fwd, const_cast<double *>(d_pivar) + b0 * n,
                              reinterpret_cast<cufftDoubleComplex *>(IF)) == CUFFT_SUCCESS,
                 RVS_E_CUDA, "cufftExecD2Z failed");
-    dim3 grid((unsigned)((n / 2 + 255) / 256), (unsigned)nt);
+    dim3 grid((unsigned)((n / 4 + 1 + 255) / 256), (unsigned)nt);
     if (arm->continuum)
       ccf_mult_half_kernel<true><<<grid, 256, 0, st>>>(T, T2, SF, IF, (int)nfreq, nt, nb, 1.0 / n, Z0, Z1);
     else

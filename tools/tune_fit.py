@@ -34,6 +34,10 @@ def main():
             batch_fit.PEEL_MIN = int(f[4])
         if len(f) > 5:
             batch_fit.PEEL_FRAC = float(f[5])
+        if len(f) > 6:
+            batch_fit.FIT_SPLIT = {groups: [float(x) for x in f[6].split(',')]}
+        else:
+            batch_fit.FIT_SPLIT = {groups: [1.0] * groups}
         batch_fit.SPECULATE_BELOW = spec
         for rep in range(3 if first else 2):
             n0 = eng.n_eval
