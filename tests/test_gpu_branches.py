@@ -155,6 +155,49 @@ def test_three_arm_process_matches_reference(golden):
         assert res['minimize_success'] == bool(g[f'd3_{i}_success'])
 
 
+def test_native_round_loop_exits_agree_with_the_python_route(golden):
+    """rvs_nm_drive hands a round back when the call does not fit the fused path
+    (RVS_DRIVE_PYEVAL: rotation kernel beyond 128 taps on the Gaia-RVS sampling) or when
+    items come back flagged (RVS_DRIVE_REDO).  Both routes step the same optimiser with
+    the same packing and reduction; the only arithmetic that differs is log10 of the
+    temperature (C library against numpy, <= 1 ulp), so complete fits agree to far better
+    than the reference tolerances."""
+    g = golden('branches')
+    _register('gaiarvs', 'tiny', 41)
+    objs = unpack_objects(g, 'gaia_')[:3]
+    cfg, opts = config(), {'npoly': 10}
+    start = {'teff': 5500., 'logg': 3.0, 'feh': -1.0, 'alpha': 0.3, 'vsini': 300.}
+    sds = [_sd(o) for o in objs]
+    seen, calls = [], dict(py=0, redo=0)
+    keep = spec_fit.LikelihoodEngine.drive_run
+
+    def spy(self, st, nm, spec, stop, redo_values, py_values):
+        def py2(o, X):
+            calls['py'] += 1
+            return py_values(o, X)
+
+        def redo2(o, X):
+            calls['redo'] += 1
+            return redo_values(o, X)
+        rc = keep(self, st, nm, spec, stop, redo2, py2)
+        seen.append((int(st['io'].rounds), int(st['io'].graph_launches)))
+        return rc
+    spec_fit.LikelihoodEngine.drive_run = spy
+    try:
+        native = batch_fit.process_batch(sds, [dict(start) for _ in sds], config=cfg, options=opts)
+    finally:
+        spec_fit.LikelihoodEngine.drive_run = keep
+    assert seen and seen[-1][0] > 50
+    # the start lies beyond the fused path's vsini bound: those rounds were served by the caller
+    assert calls['py'] > 0
+    pyroute = batch_fit.process_batch(sds, [dict(start) for _ in sds], config=cfg, options=opts,
+                                      threads=False)
+    for a, b in zip(native, pyroute):
+        assert abs(a['vel'] - b['vel']) < 0.01
+        close(a['chisq'], b['chisq'], rtol=1e-6)
+        assert abs(a['vsini'] - b['vsini']) <= 0.01 * max(1.0, abs(b['vsini']))
+
+
 def test_continuum_fit_applies_the_resolution_matrix(golden):
     """get_chisq_continuum with SpecData.resolution (spec_fit.py:765-767)."""
     g = golden('branches')
