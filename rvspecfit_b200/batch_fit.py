@@ -943,7 +943,7 @@ def _nm_stage_native(ctx, objs, sims, attempt, drive, stepper):
 
 
 # rounds of a Nelder-Mead stage run by the library when the coroutine has its own thread
-NATIVE_DRIVE = True
+NATIVE_DRIVE = not os.environ.get('RVS_NO_NATIVE_DRIVE')
 
 
 def _nm_stage(ctx, objs, sims, attempt):
