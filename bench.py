@@ -497,7 +497,7 @@ def run_gpu(args):
         'fallback 6650 GB/s (B200_PROFILING.md)'
     traffic = None
     try:    # DRAM bytes of one evaluation call from the committed ncu capture
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1w_traffic.json')))
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r2m_traffic.json')))
         if args.workload == 'desi':
             traffic = tj['bytes_per_call'] / tj['items_per_call']    # per evaluation
     except Exception:
@@ -518,8 +518,8 @@ def run_gpu(args):
                     frac=ach / hbm_peak,
                     traffic=None if traffic is None else traffic * (B // max(1, args.groups or 2)),
                     traffic_bytes_per_eval=traffic,
-                    traffic_source='static: ncu --set full capture of a 1024-item call, '
-                                   'profiles/r1w_traffic.json (not re-measured in this run)',
+                    traffic_source='static: ncu --set full capture of a 2048-item call, '
+                                   'profiles/r2m_traffic.json (not re-measured in this run)',
                     peak_source=peak_src,
                     algorithmic_bytes_per_eval=beval, evals_timed=evals,
                     ms_total=ksum['eval_phase_ms_total'],
@@ -538,8 +538,8 @@ def run_gpu(args):
                     frac=ach / hbm_peak,
                     traffic=None if traffic is None else traffic * ksum['fused_eval_items_per_launch'],
                     traffic_bytes_per_eval=traffic,
-                    traffic_source='static: ncu --set full capture of a 1024-item call, '
-                                   'profiles/r1w_traffic.json (not re-measured in this run)',
+                    traffic_source='static: ncu --set full capture of a 2048-item call, '
+                                   'profiles/r2m_traffic.json (not re-measured in this run)',
                     peak_source=peak_src, algorithmic_bytes_per_eval=beval,
                     evals_timed=evals, ms_busy=ksum['fused_eval_ms_busy'],
                     ms_sum_of_calls=ksum['fused_eval_ms_total'],
