@@ -227,6 +227,15 @@ int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
                    const double *d_vels, int nv, int K, double *d_chisq, int32_t *d_status,
                    double *d_coeffs, double *d_raw, double *d_model, const int64_t *d_moff,
                    int fast_interp, void *stream);
+/* The same for ragged scans: item k wants its first d_nv[k] <= nv trials only (refinement
+ * grids of different lengths padded to nv columns; the padding columns must hold valid
+ * velocities).  The GEMM form (nv >= 4, no model output) skips the trials past an item's
+ * count and writes chisq = 0, status = 0 there; d_nv == NULL: every trial. */
+int rvs_chisq_scan_ragged(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
+                          const rvs_knots *knots, const rvs_obs *obs, const int32_t *d_oix,
+                          const double *d_vels, int nv, const int32_t *d_nv, int K,
+                          double *d_chisq, int32_t *d_status, double *d_coeffs, double *d_raw,
+                          double *d_model, const int64_t *d_moff, int fast_interp, void *stream);
 
 /* Fused optimiser-phase evaluation: template build (as rvs_template_build) and
  * chi-square at ONE velocity per item without the HBM round trip of the

@@ -123,6 +123,9 @@ SIGNATURES = {
     'rvs_chisq_scan': (c_int, [c_dp, c_i64, c_dp, ctypes.POINTER(Knots), ctypes.POINTER(Obs),
                                c_dp, c_dp, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                c_int, c_dp]),
+    'rvs_chisq_scan_ragged': (c_int, [c_dp, c_i64, c_dp, ctypes.POINTER(Knots),
+                                      ctypes.POINTER(Obs), c_dp, c_dp, c_int, c_dp, c_int, c_dp,
+                                      c_dp, c_dp, c_dp, c_dp, c_dp, c_int, c_dp]),
     'rvs_gridbox_init': (c_int, [ctypes.POINTER(GridBox), c_dp, c_i64, c_int, c_dp]),
     'rvs_fused_chunks': (c_int, [c_int, c_int]),
     'rvs_fused_workspace': (c_i64, [c_int, c_int, c_int]),

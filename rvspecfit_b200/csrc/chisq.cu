@@ -344,6 +344,8 @@ int fill_scan_args(ScanArgs &a, const rvs_knots *kn, const rvs_obs *obs) {
   a.sumlog2 = obs->d_sumlog2; a.off = obs->d_off; a.goff = obs->d_goff; a.P = obs->d_P;
   a.npp = obs->npp;
   a.fast_interp = 0;
+  a.nby = 0;
+  a.nvk = nullptr;
   RVS_REQUIRE(obs->nresol >= 0 && (obs->nresol == 0) == (obs->d_resol == nullptr) &&
                   (obs->nresol == 0 || obs->d_resol_offs),
               RVS_E_ARG, "chisq: d_resol, d_resol_offs and nresol must be set together");
@@ -363,6 +365,18 @@ extern "C" int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32
                               int32_t *d_status, double *d_coeffs, double *d_raw,
                               double *d_model, const int64_t *d_moff, int fast_interp,
                               void *stream) {
+  return rvs_chisq_scan_ragged(d_yz, yz_stride, d_tix, knots, obs, d_oix, d_vels, nv, nullptr, K,
+                               d_chisq, d_status, d_coeffs, d_raw, d_model, d_moff, fast_interp,
+                               stream);
+}
+
+extern "C" int rvs_chisq_scan_ragged(const double *d_yz, int64_t yz_stride, const int32_t *d_tix,
+                                     const rvs_knots *knots, const rvs_obs *obs,
+                                     const int32_t *d_oix, const double *d_vels, int nv,
+                                     const int32_t *d_nv, int K, double *d_chisq,
+                                     int32_t *d_status, double *d_coeffs, double *d_raw,
+                                     double *d_model, const int64_t *d_moff, int fast_interp,
+                                     void *stream) {
   using namespace rvs;
   if (K == 0 || nv == 0) return 0;
   ScanArgs a;
@@ -378,6 +392,9 @@ extern "C" int rvs_chisq_scan(const double *d_yz, int64_t yz_stride, const int32
   a.coeffs = d_coeffs; a.raw = d_raw; a.model = d_model; a.moff = d_moff;
   a.fast_interp = fast_interp ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
+  // per-item trial counts are honoured by the GEMM kernel; the per-trial kernel evaluates
+  // every column (the padding columns hold valid velocities)
+  a.nvk = d_nv;
   if (nv >= 4 && !d_coeffs && !d_raw && !d_model && (!a.resol || a.resol_hw <= RS_HW)) {
     // several trials per template: the trials are the columns of an FP64 GEMM (scan_mma.cuh)
     const int np = obs->npoly;

@@ -34,6 +34,7 @@ struct ScanArgs {
   int nresol;
   int resol_hw;  // max |resol_offs[]|
   int nby;       // trial blocks per item (1-D grid of the GEMM scan kernel)
+  const int32_t *nvk;  // optional [K]: trials of item k actually wanted (<= nv), else all
 };
 
 constexpr int SCAN_WARPS = 8;

@@ -62,6 +62,16 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
   // same template (y, z) pairs -- L1 / L2 hits instead of one pass over HBM per trial block
   const int k = blockIdx.x / a.nby;
   const int j0 = (blockIdx.x - k * a.nby) * NI;
+  // ragged scans (refinement grids of different lengths padded to a.nv columns): trials
+  // past the item's own count are not evaluated; their outputs are zeroed
+  const int nvk = a.nvk ? min(a.nv, a.nvk[k]) : a.nv;
+  if (j0 >= nvk) {
+    if (tid < NI && j0 + tid < a.nv) {
+      a.chisq[(int64_t)k * a.nv + j0 + tid] = 0.0;
+      a.status[(int64_t)k * a.nv + j0 + tid] = 0;
+    }
+    return;
+  }
   const int obj = a.oix[k];
   const int64_t p0 = a.off[obj];
   const int npix = (int)(a.off[obj + 1] - p0);
@@ -80,7 +90,7 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
       const int t = idx / RS_W, q = idx - t * RS_W;
       const int pp = tile - RS_HW + q;
       double v = 0;
-      if (pp >= 0 && pp < npix && j0 + t < a.nv) {
+      if (pp >= 0 && pp < npix && j0 + t < nvk) {
         const double x = lam[pp] * s_f[t];
         v = ev(x, a.log_step ? ql[pp] + s_qf[t] : x);
       }
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
   if (tid < NI) {
     const int j = j0 + tid;
     double f = 1, qf = 0;
-    if (j < a.nv) {
+    if (j < nvk) {
       const double beta = a.vels[(int64_t)k * a.nv + j] / RVS_C_KMS;
       f = sqrt((1 - beta) / (1 + beta));
       qf = a.log_step ? log(f) : 0.0;
@@ -108,7 +118,7 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
     for (int nt = 0; nt < NT; nt++) {
       fB[nt] = s_f[nt * 8 + r];
       qfB[nt] = s_qf[nt * 8 + r];
-      onB[nt] = j0 + nt * 8 + r < a.nv;
+      onB[nt] = j0 + nt * 8 + r < nvk;
     }
     int ia[TL::MT_M], ja[TL::MT_M];
     tri_rows<NP>(r, ia, ja);
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
   }
   // ---- solve: one warp per trial
   for (int e = wid; e < NI; e += GM_WARPS) {
-    if (j0 + e >= a.nv) break;
+    if (j0 + e >= nvk) break;
     for (int o = lane; o < TL::NTRI + NP; o += 32) {
       const int row = o < TL::NTRI ? o : TL::MT_M * 8 + (o - TL::NTRI);
       const double t = s_red[row][e];
@@ -202,7 +212,7 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
 #pragma unroll
       for (int s = 0; s < KST; s++) {
         const int i = 4 * s + c;
-        bco[s][nt] = (i < NP && j0 + nt * 8 + r < a.nv) ? s_co[nt * 8 + r][i] : 0.0;
+        bco[s][nt] = (i < NP && j0 + nt * 8 + r < nvk) ? s_co[nt * 8 + r][i] : 0.0;
       }
     double fC[NT][2], qfC[NT][2], rss[NT][2];
     bool onC[NT][2];
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
         const int t = nt * 8 + 2 * c + e;
         fC[nt][e] = s_f[t];
         qfC[nt][e] = s_qf[t];
-        onC[nt][e] = j0 + t < a.nv;
+        onC[nt][e] = j0 + t < nvk;
         rss[nt][e] = 0;
       }
     const int seglen = ((npix + GM_WARPS - 1) / GM_WARPS + 7) & ~7;
@@ -286,7 +296,11 @@ __global__ void __launch_bounds__(GM_THREADS, RVS_SCAN_MINB) chisq_scan_mma_kern
       }
   }
   __syncthreads();
-  if (tid < NI && j0 + tid < a.nv) {
+  if (tid < NI && j0 + tid >= nvk && j0 + tid < a.nv) {
+    a.chisq[(int64_t)k * a.nv + j0 + tid] = 0.0;
+    a.status[(int64_t)k * a.nv + j0 + tid] = 0;
+  }
+  if (tid < NI && j0 + tid < nvk) {
     double t = 0;
 #pragma unroll
     for (int w = 0; w < GM_WARPS; w++) t += s_rss[w][tid];

@@ -999,6 +999,8 @@ class LikelihoodEngine:
         with self._lock:
             self.n_eval += int(nv.sum()) * 1
         obs_all = self._obs_all((0.0,) * narm)
+        ragged = bool((nv != nvmax).any())
+        d_nv = _dev.upload(nv, np.int32)
         for a, name in enumerate(self.setups):
             arm = self.arms[name]
             bank, batch = arm['bank'], arm['batch']
@@ -1017,17 +1019,18 @@ class LikelihoodEngine:
             d_chi = _dev.empty((K, nvmax), np.float64)
             d_st = _dev.empty((K, nvmax), np.int32)
             t0 = self.timer.start() if self.timer else None
-            rc = L.rvs_chisq_scan(_dev.ptr(yz), bank.npix_t, _dev.ptr(d_tix),
-                                  ctypes.byref(bank.knots), ctypes.byref(obs), _dev.ptr(d_oix),
-                                  _dev.ptr(d_V), nvmax, K, _dev.ptr(d_chi), _dev.ptr(d_st),
-                                  None, None, None, None, 0, stream)
-            _cabi.check(rc, 'rvs_chisq_scan')
+            # ragged refinement grids: the trials past an object's own count are skipped
+            rc = L.rvs_chisq_scan_ragged(_dev.ptr(yz), bank.npix_t, _dev.ptr(d_tix),
+                                         ctypes.byref(bank.knots), ctypes.byref(obs),
+                                         _dev.ptr(d_oix), _dev.ptr(d_V), nvmax,
+                                         _dev.ptr(d_nv) if ragged else None, K, _dev.ptr(d_chi),
+                                         _dev.ptr(d_st), None, None, None, None, 0, stream)
+            _cabi.check(rc, 'rvs_chisq_scan_ragged')
             if t0 is not None:
-                self.timer.stop('scan', t0, K * nvmax)
+                self.timer.stop('scan', t0, int(nv.sum()))
             # total += penalty + chi-square of the arm, in the order the general path adds
             d_tot += d_pen[:, None] + d_chi
             d_flag |= (d_tst != 0) | (d_st != 0).any(dim=1)
-        d_nv = _dev.upload(nv, np.int32)
         d_stats = _dev.empty((K, 8), np.float64)
         rc = L.rvs_scan_stats_ragged(_dev.ptr(d_V), _dev.ptr(d_tot), K, 1, nvmax, _dev.ptr(d_nv),
                                      int(quadratic), _dev.ptr(d_stats), None, stream)
