@@ -21,6 +21,7 @@
 // the very functions the Python route uses, so both routes visit the same points.
 #include <cuda_runtime_api.h>
 #include <math.h>
+#include <sched.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -162,7 +163,16 @@ extern "C" int rvs_nm_drive(void *nm, void *drive, const rvs_fit_layout *lay, rv
     if (io->state == RVS_DRIVE_LAUNCHED) {
       // (after RVS_DRIVE_LAUNCH the caller's launch is on the stream: the event follows it)
       if (cudaEventRecord(d->ev1, stream) != cudaSuccess) return RVS_E_CUDA;
-      if (cudaEventSynchronize(d->ev1) != cudaSuccess) return RVS_E_CUDA;
+      // poll and yield: as quick as a spinning wait when the thread has a core of its
+      // own, and out of the way of the other sets' host threads when it has not (a rank of
+      // an 8-GPU job has four cores for three such loops and the interpreter)
+      for (;;) {
+        const cudaError_t e = cudaEventQuery(d->ev1);
+        if (e == cudaSuccess) break;
+        (void)cudaGetLastError();
+        if (e != cudaErrorNotReady) return RVS_E_CUDA;
+        sched_yield();
+      }
       if (io->timed && io->t_rec && io->t_n < io->t_cap) {
         float a = 0.f, b = 0.f;
         cudaEventElapsedTime(&a, static_cast<cudaEvent_t>(io->epoch_event), d->ev0);
