@@ -398,3 +398,48 @@ def test_fit_pack_collect_equal_numpy_rules():
             assert n == r2.sum() and np.array_equal(redo.astype(bool), r2)
             fin = np.isfinite(want)
             assert np.array_equal(out[fin], want[fin])
+
+
+def test_call_size_ladder():
+    """rvs_fit_round_items: launch configurations of an evaluation call."""
+    from rvspecfit_b200 import _cabi
+    L = _cabi.lib()
+    seen = set()
+    prev = 0
+    for K in range(1, 40000):
+        Kp = L.rvs_fit_round_items(K)
+        assert Kp >= K and Kp % 16 == 0 and Kp >= prev
+        assert Kp <= max(16, int(1.25 * K) + 16), (K, Kp)       # at most a quarter of padding
+        assert L.rvs_fit_round_items(Kp) == Kp                  # a configuration maps to itself
+        prev = Kp
+        seen.add(Kp)
+    assert len(seen) <= 60          # four per octave: a few dozen captured graphs per slot
+
+
+def test_stepper_rows_of_stopped_problems_are_final():
+    """The hand-over between stages relies on it: while other problems still iterate,
+    NMStepper.result() already holds the final row of every problem that has stopped."""
+    B, N = 24, 4
+    _, fbatch = _problems(B, N, 5)
+    rs = np.random.RandomState(11)
+    x0 = rs.normal(size=(B, N))
+    sims = np.concatenate([x0[:, None, :], x0[:, None, :] + 0.7 * np.eye(N)[None]], axis=1)
+    st = batch_fit.NMStepper(sims)
+    snapshots = []
+    try:
+        while True:
+            req = st.request(0)
+            if req is None:
+                break
+            idx, X = req
+            st.feed(fbatch(idx, X))
+            act = st.active()
+            if act.any() and not act.all():
+                snapshots.append((~act, st.result()))
+        final = st.result()
+    finally:
+        st.close()
+    assert len(snapshots) > 5
+    for stopped, res in snapshots:
+        for k in ('x', 'fun', 'success', 'final_simplex', 'nit', 'nfev'):
+            assert np.array_equal(res[k][stopped], final[k][stopped]), k
