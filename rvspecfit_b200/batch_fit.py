@@ -1108,6 +1108,7 @@ class _Sub:
 # live problems, latency-bound calls) runs under the bulk of the others
 FIT_GROUP = 256
 FIT_MAX_GROUPS = 3
+FIT_MAX_SET = 4096       # objects per set at most (auto grouping)
 THREADS = True
 PEEL = False
 FIT_SPLIT = {2: [3, 2], 3: [5, 4, 3], 4: [4, 3, 2, 1]}      # number of sets -> relative sizes (else equal)
@@ -1141,8 +1142,13 @@ def process_batch(objects, paramDict0s, fixParam=None, options=None, config=None
     fobj = BatchObjective(eng, specParams, paramDict0s, fixParam, fitVsini, config, priors)
     fobj.layout()       # built once, before the sets' threads ask for it
     if groups is None:
-        groups = int(np.clip(B // FIT_GROUP, 1, FIT_MAX_GROUPS))
-    groups = max(1, min(groups, B, eng.NSLOT))
+        # a few sets whose phases interleave; more of them when the batch is so large that
+        # the first request of a set (its whole simplices) would make the per-slot device
+        # buffers huge
+        groups = int(max(np.clip(B // FIT_GROUP, 1, FIT_MAX_GROUPS), -(-B // FIT_MAX_SET)))
+    # a set holds one evaluation slot through its Nelder-Mead stage and needs up to two
+    # more for a request that goes out in pieces
+    groups = max(1, min(groups, B, eng.NSLOT // 2))
     phase = {}
     # sets of unequal size reach their latency-bound stretches (optimiser tails, refinement
     # scans, model output) at different times, under the large calls of the others
