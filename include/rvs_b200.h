@@ -511,6 +511,27 @@ void rvs_drive_destroy(void *drive);
 /* The request in progress: stepper problems, fitted vectors [K][nfit], objects. */
 int rvs_drive_request(void *drive, const int32_t **idx, const double **X, const int32_t **obj);
 int rvs_nm_drive(void *nm, void *drive, const rvs_fit_layout *lay, rvs_drive *io);
+/* The same loop around the BFGS stepper below (speculate_below is ignored). */
+int rvs_bfgs_drive(void *bfgs, void *drive, const rvs_fit_layout *lay, rvs_drive *io);
+
+/* ---- host-side lock-step BFGS stepper (bfgs_host.cpp; no device work) ----------------
+ * The polish step of vel_fit.process (reference vel_fit.py:653-658:
+ * scipy.optimize.minimize(method='BFGS', options=dict(hess_inv0=...)), forward-difference
+ * gradient) for B problems at once: scipy's `_minimize_bfgs` with the MINPACK line search
+ * DCSRCH and its fallback line_search_wolfe2, same constants and decision rules; matrix
+ * products summed in index order (scipy's go through BLAS: values agree to rounding).
+ * Protocol as rvs_nm_*: a request is N + 1 consecutive points per searching problem (a point
+ * and its forward-difference neighbours); buffers of B * (N + 1) points always suffice.
+ * status: scipy's warnflag (0 converged, 1 maxiter, 2 precision loss, 3 NaN). */
+void *rvs_bfgs_create(int B, int N, const double *h_x0 /* [B][N] */,
+                      const double *h_hess_inv0 /* [N][N] or NULL */, double gtol,
+                      int64_t maxiter /* <= 0: 200 N */);
+void rvs_bfgs_destroy(void *bfgs);
+int64_t rvs_bfgs_request(void *bfgs, int32_t *h_idx, double *h_X, int64_t cap);
+int rvs_bfgs_feed(void *bfgs, const double *h_f, int64_t n);
+int64_t rvs_bfgs_live(void *bfgs, uint8_t *h_active);
+int rvs_bfgs_result(void *bfgs, double *h_x, double *h_fun, int64_t *h_nit, int32_t *h_status,
+                    int64_t *h_rounds);
 
 #ifdef __cplusplus
 }

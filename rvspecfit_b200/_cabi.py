@@ -161,6 +161,14 @@ SIGNATURES = {
     'rvs_drive_request': (c_int, [ctypes.c_void_p, c_dp, c_dp, c_dp]),
     'rvs_nm_drive': (c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FitLayout),
                              ctypes.POINTER(Drive)]),
+    'rvs_bfgs_drive': (c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FitLayout),
+                               ctypes.POINTER(Drive)]),
+    'rvs_bfgs_create': (ctypes.c_void_p, [c_int, c_int, c_dp, c_dp, c_dbl, c_i64]),
+    'rvs_bfgs_destroy': (None, [ctypes.c_void_p]),
+    'rvs_bfgs_request': (c_i64, [ctypes.c_void_p, c_dp, c_dp, c_i64]),
+    'rvs_bfgs_feed': (c_int, [ctypes.c_void_p, c_dp, c_i64]),
+    'rvs_bfgs_live': (c_i64, [ctypes.c_void_p, c_dp]),
+    'rvs_bfgs_result': (c_int, [ctypes.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
     'rvs_ccf_best': (c_int, [c_dp, c_dp, c_dp, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
 }
 

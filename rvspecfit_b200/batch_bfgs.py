@@ -462,9 +462,85 @@ def bfgs_steps(x0s, hess_inv0=None, gtol=1e-5, eps=_EPSILON, c1=1e-4, c2=0.9, ma
     return dict(x=x, fun=fval, nit=nit, status=status, success=status == 0, rounds=rounds)
 
 
-def bfgs_lockstep(fbatch, x0s, hess_inv0=None, **kw):
-    """bfgs_steps driven with a blocking objective fbatch(idx, X) -> f."""
-    gen = bfgs_steps(x0s, hess_inv0, **kw)
+class BFGSStepper:
+    """The library's host-side lock-step BFGS stepper (csrc/bfgs_host.cpp, rvs_bfgs_*):
+    the algorithm of bfgs_steps one problem at a time in C++ -- microseconds per round
+    instead of a millisecond of numpy, and steppable without the interpreter
+    (LikelihoodEngine.drive_run).  Its matrix products are summed in index order, scipy's
+    (and bfgs_steps') go through BLAS, so the two agree to rounding, not bit for bit.
+    request() -> (idx, X) or None, feed(values), active(), result()."""
+
+    def __init__(self, x0s, hess_inv0=None, gtol=1e-5, maxiter=None):
+        import ctypes
+        from . import _cabi, _dev
+        self._dev = _dev
+        self.L = _cabi.lib()
+        x0 = np.ascontiguousarray(x0s, dtype=np.float64)
+        self.B, self.N = x0.shape
+        h0 = None if hess_inv0 is None else np.ascontiguousarray(hess_inv0, dtype=np.float64)
+        h = self.L.rvs_bfgs_create(self.B, self.N, _dev.hptr(x0),
+                                   None if h0 is None else _dev.hptr(h0), float(gtol),
+                                   int(maxiter or 0))
+        if not h:
+            raise _cabi.RvsError('rvs_bfgs_create failed')
+        self.h = ctypes.c_void_p(h)
+        self.cap = max(1, self.B * (self.N + 1))
+        self.idx = np.empty(self.cap, dtype=np.int32)
+        self.X = np.empty((self.cap, self.N), dtype=np.float64)
+        self.n = 0
+
+    def request(self):
+        n = self.L.rvs_bfgs_request(self.h, self._dev.hptr(self.idx), self._dev.hptr(self.X),
+                                    self.cap)
+        assert n <= self.cap
+        self.n = n
+        return (self.idx[:n], self.X[:n]) if n else None
+
+    def feed(self, f):
+        from . import _cabi
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        _cabi.check(self.L.rvs_bfgs_feed(self.h, self._dev.hptr(f), self.n), 'rvs_bfgs_feed')
+
+    def active(self):
+        a = np.empty(self.B, dtype=np.uint8)
+        self.L.rvs_bfgs_live(self.h, self._dev.hptr(a))
+        return a.astype(bool)
+
+    def result(self):
+        import ctypes
+        B, N = self.B, self.N
+        x, fun = np.empty((B, N)), np.empty(B)
+        nit, status = np.empty(B, dtype=np.int64), np.empty(B, dtype=np.int32)
+        rounds = ctypes.c_int64(0)
+        self.L.rvs_bfgs_result(self.h, self._dev.hptr(x), self._dev.hptr(fun), self._dev.hptr(nit),
+                               self._dev.hptr(status), ctypes.byref(rounds))
+        return dict(x=x, fun=fun, nit=nit, status=status.astype(np.int64), success=status == 0,
+                    rounds=int(rounds.value))
+
+    def close(self):
+        if self.h is not None:
+            self.L.rvs_bfgs_destroy(self.h)
+            self.h = None
+
+
+def bfgs_native(x0s, hess_inv0=None, gtol=1e-5, maxiter=None):
+    """bfgs_steps with the stepping done by BFGSStepper: the same generator protocol."""
+    st = BFGSStepper(x0s, hess_inv0, gtol, maxiter)
+    try:
+        while True:
+            req = st.request()
+            if req is None:
+                break
+            st.feed((yield req))
+        return st.result()
+    finally:
+        st.close()
+
+
+def bfgs_lockstep(fbatch, x0s, hess_inv0=None, native=False, **kw):
+    """bfgs_steps (or its native sibling) driven with a blocking objective
+    fbatch(idx, X) -> f."""
+    gen = (bfgs_native if native else bfgs_steps)(x0s, hess_inv0, **kw)
     try:
         req = next(gen)
         while True:

@@ -1000,6 +1000,43 @@ def _after_nm(ctx, objs, res, attempt):
     return out
 
 
+# BFGS rounds stepped by the library (csrc/bfgs_host.cpp) when the coroutine has its own
+# thread: microseconds per round and no interpreter lock, matrix products in index order
+# (scipy's go through BLAS, so fits agree to rounding with the numpy route, not bit for bit)
+NATIVE_BFGS = not os.environ.get('RVS_NO_NATIVE_BFGS')
+
+
+def _bfgs_stage_native(ctx, objs, x, msucc, drive, stepper):
+    import time
+    from . import _cabi
+    t0 = time.time()
+    eng, fobj = ctx.fobj.eng, ctx.fobj
+    n = len(objs)
+    handed = np.zeros(n, dtype=bool)
+    try:
+        while True:
+            stop = int(handed.sum() + np.ceil(max(PEEL_MIN, PEEL_FRAC * n))) if ctx.peel else 0
+            items0 = drive['io'].items
+            rc = eng.drive_run(drive, stepper.h, 0, stop, fobj.redo_values,
+                               lambda o, X: fobj.submit(o, X)(), kind='bfgs')
+            fobj.nfev += drive['io'].items - items0
+            if rc == _cabi.DRIVE_DONE:
+                break
+            act = stepper.active()
+            j = np.nonzero(~act & ~handed)[0]
+            res = stepper.result()
+            handed[j] = True
+            t0 = ctx.lap('bfgs', t0)
+            yield ('spawn', _finish_stage(ctx, objs[j], res['x'][j], msucc[j]))
+        res = stepper.result()
+    finally:
+        eng.drive_close(drive)
+        stepper.close()
+    ctx.lap('bfgs', t0)
+    j = np.nonzero(~handed)[0]
+    return (yield from _finish_stage(ctx, objs[j], res['x'][j], msucc[j]))
+
+
 def _bfgs_stage(ctx, objs, x, msucc):
     """3. BFGS polish (vel_fit.py:653-658)."""
     import time
@@ -1008,6 +1045,14 @@ def _bfgs_stage(ctx, objs, x, msucc):
     t0 = time.time()
     names = ['vel'] + (['vsini'] if ctx.fitVsini else []) + \
         [p for p in ctx.specParams if p not in ctx.fixParam]
+    eng = ctx.fobj.eng
+    if NATIVE_BFGS and NATIVE_DRIVE and ctx.threaded and hasattr(eng, 'drive_open') and \
+            ctx.fobj.layout() and x.shape[1] <= 22:
+        stepper = batch_bfgs.BFGSStepper(x, vel_fit.get_hess_inv(names))
+        drive = eng.drive_open(ctx.fobj.layout(), ctx.sel[objs], stepper.N, stepper.cap)
+        if drive is not None:
+            return (yield from _bfgs_stage_native(ctx, objs, x, msucc, drive, stepper))
+        stepper.close()
     progress = {}
     gen = batch_bfgs.bfgs_steps(x, vel_fit.get_hess_inv(names), progress=progress)
     handed = np.zeros(len(objs), dtype=bool)

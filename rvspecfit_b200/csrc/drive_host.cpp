@@ -98,7 +98,31 @@ extern "C" int rvs_drive_request(void *h, const int32_t **idx, const double **X,
   return 0;
 }
 
+namespace {
+// the optimiser behind the loop: Nelder-Mead (nm_host.cpp) or BFGS (bfgs_host.cpp)
+struct StepOps {
+  int64_t (*request)(void *, int, int32_t *, double *, int64_t);
+  int (*feed)(void *, const double *, int64_t);
+  int64_t (*live)(void *, uint8_t *);
+};
+int64_t bfgs_request(void *h, int, int32_t *idx, double *X, int64_t cap) {
+  return rvs_bfgs_request(h, idx, X, cap);
+}
+int drive_loop(const StepOps &ops, void *nm, void *drive, const rvs_fit_layout *lay, rvs_drive *io);
+}  // namespace
+
 extern "C" int rvs_nm_drive(void *nm, void *drive, const rvs_fit_layout *lay, rvs_drive *io) {
+  static const StepOps ops = {rvs_nm_request, rvs_nm_feed, rvs_nm_live};
+  return drive_loop(ops, nm, drive, lay, io);
+}
+
+extern "C" int rvs_bfgs_drive(void *bfgs, void *drive, const rvs_fit_layout *lay, rvs_drive *io) {
+  static const StepOps ops = {bfgs_request, rvs_bfgs_feed, rvs_bfgs_live};
+  return drive_loop(ops, bfgs, drive, lay, io);
+}
+
+namespace {
+int drive_loop(const StepOps &ops, void *nm, void *drive, const rvs_fit_layout *lay, rvs_drive *io) {
   Drive *d = static_cast<Drive *>(drive);
   if (!nm || !d || !lay || !io || !io->objmap) return RVS_E_ARG;
   const int N = lay->nfit, ns = lay->nspec, narm = lay->narm;
@@ -116,7 +140,7 @@ extern "C" int rvs_nm_drive(void *nm, void *drive, const rvs_fit_layout *lay, rv
   cudaStream_t stream = static_cast<cudaStream_t>(io->stream);
   for (;;) {
     if (io->state == RVS_DRIVE_IDLE) {
-      const int64_t n = rvs_nm_request(nm, io->speculate_below, d->idx.data(), d->X.data(), cap);
+      const int64_t n = ops.request(nm, io->speculate_below, d->idx.data(), d->X.data(), cap);
       if (n == 0) return RVS_DRIVE_DONE;
       if (n > cap || n > io->cap) return RVS_E_LIMIT;
       const int64_t Kp = rvs_fit_round_items(n);
@@ -191,15 +215,16 @@ extern "C" int rvs_nm_drive(void *nm, void *drive, const rvs_fit_layout *lay, rv
       if (nredo > 0) return RVS_DRIVE_REDO;
     }
     if (io->state == RVS_DRIVE_COLLECTED) {
-      const int rc = rvs_nm_feed(nm, io->f_out, io->K);
+      const int rc = ops.feed(nm, io->f_out, io->K);
       if (rc) return rc;
       io->rounds += 1;
       io->items += io->K;
       io->state = RVS_DRIVE_IDLE;
       if (io->stop_stopped > 0) {
-        const int64_t live = rvs_nm_live(nm, nullptr);
+        const int64_t live = ops.live(nm, nullptr);
         if (live > 0 && io->nprob - live >= io->stop_stopped) return RVS_DRIVE_PEEL;
       }
     }
   }
 }
+}  // namespace

@@ -1121,8 +1121,9 @@ class LikelihoodEngine:
         st['done'] = now
         LAST_DRIVE_ROUNDS[0] = int(io.rounds)
 
-    def drive_run(self, st, nm, speculate_below, stop_stopped, redo_values, py_values):
-        """Run rounds of the Nelder-Mead stepper `nm` (rvs_nm_* handle) on the held slot
+    def drive_run(self, st, nm, speculate_below, stop_stopped, redo_values, py_values,
+                  kind='nm'):
+        """Run rounds of the stepper `nm` (rvs_nm_* handle, or rvs_bfgs_* with kind='bfgs') on the held slot
         until every problem has stopped (returns _cabi.DRIVE_DONE) or `stop_stopped`
         problems have (DRIVE_PEEL).  redo_values(obj32, X) -> objective values through the
         general path for the items the fused path could not settle; py_values(obj32, X)
@@ -1136,7 +1137,8 @@ class LikelihoodEngine:
             while True:
                 self._drive_table(st)
                 io.shared_locate = int(bool(sl.get('shared_locate')))
-                rc = L.rvs_nm_drive(nm, st['h'], ctypes.byref(lay), ctypes.byref(io))
+                rc = (L.rvs_bfgs_drive if kind == 'bfgs' else L.rvs_nm_drive)(
+                    nm, st['h'], ctypes.byref(lay), ctypes.byref(io))
                 if rc in (_cabi.DRIVE_DONE, _cabi.DRIVE_PEEL):
                     return rc
                 if rc == _cabi.DRIVE_LAUNCH:

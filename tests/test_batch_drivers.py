@@ -115,6 +115,50 @@ def test_lockstep_bfgs_is_scipy():
     assert seen == {0, 2}      # both the converged and the precision-loss exit were met
 
 
+def test_native_bfgs_follows_the_lockstep_restatement():
+    """BFGSStepper (csrc/bfgs_host.cpp) against batch_bfgs.bfgs_steps, which is scipy bit for
+    bit: same algorithm, matrix products summed in index order instead of through BLAS.
+    The forward-difference gradient of a function of size 1e4 carries rounding noise of
+    ~1e-4 that depends on the last bits of x, so trajectories separate after a few
+    iterations whatever the implementation; the check is therefore: identical first
+    iteration, identical decisions (iteration counts, exits, rounds -- through the MINPACK
+    search, the fallback search and its zoom phase) while the paths are still close, and
+    the same exits, values and iteration counts in distribution at the end."""
+    from rvspecfit_b200 import batch_bfgs
+    for B, N, seed, noise in ((24, 4, 11, 0.0), (8, 2, 9, 0.0), (24, 6, 5, 1e-7), (16, 6, 6, 1e-9),
+                              (16, 3, 7, 1e-5), (8, 6, 8, 1e-3)):
+        f_one, fbatch = _noisy_problems(B, N, seed, noise)
+        rs = np.random.RandomState(seed + 1)
+        x0 = rs.normal(size=(B, N))
+        H0 = np.diag(np.exp(rs.normal(size=N) * 2))
+        for maxiter in (1, 2):
+            want = batch_bfgs.bfgs_lockstep(fbatch, x0, H0, maxiter=maxiter)
+            got = batch_bfgs.bfgs_lockstep(fbatch, x0, H0, native=True, maxiter=maxiter)
+            assert got['rounds'] == want['rounds'], (noise, maxiter)
+            assert np.array_equal(got['nit'], want['nit'])
+            assert np.array_equal(got['status'], want['status'])
+            if maxiter == 1:
+                assert np.allclose(got['x'], want['x'], rtol=0, atol=1e-13)
+                assert np.allclose(got['fun'], want['fun'], rtol=1e-15)
+        want = batch_bfgs.bfgs_lockstep(fbatch, x0, H0)
+        calls = []
+
+        def counted(idx, X):
+            calls.append(len(idx))
+            assert len(idx) % (N + 1) == 0
+            return fbatch(idx, X)
+        got = batch_bfgs.bfgs_lockstep(counted, x0, H0, native=True)
+        assert len(calls) == got['rounds']
+        assert np.mean(got['status'] == want['status']) >= 0.75
+        if noise == 0.0:
+            assert np.all(np.abs(got['fun'] - want['fun']) <= 1e-9 * np.abs(want['fun']))
+        # the same descent on average (a noisy gradient stalls both wherever it happens to)
+        f0 = fbatch(np.arange(B), x0)
+        dec_got, dec_want = np.mean(f0 - got['fun']), np.mean(f0 - want['fun'])
+        assert 0.8 <= dec_got / dec_want <= 1.25, (noise, dec_got, dec_want)
+        assert abs(np.mean(got['nit']) - np.mean(want['nit'])) <= 0.3 * np.mean(want['nit']) + 2
+
+
 def test_hessian_points_replay_central_hessian():
     """The vectorised Hessian stencil asks for exactly the points of
     vel_fit.central_hessian and combines their values with its arithmetic."""

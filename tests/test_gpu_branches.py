@@ -131,7 +131,7 @@ def test_three_arm_process_matches_reference(golden):
     # default route: Nelder-Mead rounds run by the library (rvs_nm_drive) on the set's thread
     batch = batch_fit.process_batch([_sd(o) for o in objs], [dict(start) for _ in objs],
                                     config=cfg, options=opts)
-    assert spec_fit.LAST_DRIVE_ROUNDS[0] > 100
+    assert spec_fit.LAST_DRIVE_ROUNDS[0] > 20      # rounds of the last native stage (BFGS)
     # the rounds stepped from Python, and finished objects handed on in groups
     pyroute = batch_fit.process_batch([_sd(o) for o in objs], [dict(start) for _ in objs],
                                       config=cfg, options=opts, threads=False)
@@ -159,9 +159,9 @@ def test_native_round_loop_exits_agree_with_the_python_route(golden):
     """rvs_nm_drive hands a round back when the call does not fit the fused path
     (RVS_DRIVE_PYEVAL: rotation kernel beyond 128 taps on the Gaia-RVS sampling) or when
     items come back flagged (RVS_DRIVE_REDO).  Both routes step the same optimiser with
-    the same packing and reduction; the only arithmetic that differs is log10 of the
-    temperature (C library against numpy, <= 1 ulp), so complete fits agree to far better
-    than the reference tolerances."""
+    the same packing and reduction; the arithmetic that differs is log10 of the temperature
+    (C library against numpy, <= 1 ulp) and the summation order of the BFGS matrix products
+    (index order against BLAS), so complete fits agree to the reference tolerances."""
     g = golden('branches')
     _register('gaiarvs', 'tiny', 41)
     objs = unpack_objects(g, 'gaia_')[:3]
@@ -171,7 +171,7 @@ def test_native_round_loop_exits_agree_with_the_python_route(golden):
     seen, calls = [], dict(py=0, redo=0)
     keep = spec_fit.LikelihoodEngine.drive_run
 
-    def spy(self, st, nm, spec, stop, redo_values, py_values):
+    def spy(self, st, nm, spec, stop, redo_values, py_values, kind='nm'):
         def py2(o, X):
             calls['py'] += 1
             return py_values(o, X)
@@ -179,7 +179,7 @@ def test_native_round_loop_exits_agree_with_the_python_route(golden):
         def redo2(o, X):
             calls['redo'] += 1
             return redo_values(o, X)
-        rc = keep(self, st, nm, spec, stop, redo2, py2)
+        rc = keep(self, st, nm, spec, stop, redo2, py2, kind=kind)
         seen.append((int(st['io'].rounds), int(st['io'].graph_launches)))
         return rc
     spec_fit.LikelihoodEngine.drive_run = spy
