@@ -852,8 +852,8 @@ def simplex_starts(best_vel, fobj, specParams, fixParam, fitVsini, max_vsini):
 # A lock-step stage hands the problems that have finished on to the next stage of the
 # fit as soon as that many of them wait (and at least this fraction of the stage's
 # problems), instead of keeping them until the slowest one stops
-PEEL_MIN = 128
-PEEL_FRAC = 0.2
+PEEL_MIN = 384
+PEEL_FRAC = 0.3
 
 
 class _FitCtx:
@@ -1152,10 +1152,10 @@ class _Sub:
 # objects per lock-step set and sets in flight: enough sets that the tail of one (few
 # live problems, latency-bound calls) runs under the bulk of the others
 FIT_GROUP = 256
-FIT_MAX_GROUPS = 3
+FIT_MAX_GROUPS = 2
 FIT_MAX_SET = 4096       # objects per set at most (auto grouping)
 THREADS = True
-PEEL = False
+PEEL = True
 FIT_SPLIT = {2: [3, 2], 3: [5, 4, 3], 4: [4, 3, 2, 1]}      # number of sets -> relative sizes (else equal)
 
 
