@@ -385,7 +385,7 @@ class _Waiter:
 
 
 # below this many active problems an iteration's candidate points go out in one call
-SPECULATE_BELOW = 256
+SPECULATE_BELOW = 128
 # smallest lock-step set worth its own evaluation calls
 NM_MIN_GROUP = 64
 
