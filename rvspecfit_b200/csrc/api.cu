@@ -5,7 +5,9 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include <cuda.h>
@@ -35,6 +37,22 @@ void set_error(const char *fmt, ...) {
 }
 
 void count_launch(int n) { g_launches += n; }
+
+cudaError_t ensure_dyn_smem_ptr(const void *kern, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> cur;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t &have = cur[std::make_pair(dev, kern)];
+  if (smem > have) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    have = smem;
+  }
+  return cudaSuccess;
+}
 
 constexpr int SPL_HALO = 32;
 constexpr int SPL_CHUNK = 33;  // rows per thread (odd)

@@ -379,12 +379,7 @@ extern "C" int rvs_ccf_preprocess(const double *d_lam, const double *d_spec, con
   const int64_t smem = rvs_ccf_prep_smem(npix, continuum ? nn : 0);
   RVS_REQUIRE(smem <= 220 * 1024, RVS_E_LIMIT,
               "rvs_ccf_preprocess: %d pixels need %lld B of shared memory", npix, (long long)smem);
-  static int64_t smem_set = 0;
-  if (smem > smem_set) {
-    RVS_CUDA_OK(cudaFuncSetAttribute(ccf_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    smem_set = smem;
-  }
+  RVS_CUDA_OK(ensure_dyn_smem(ccf_prep_kernel, (size_t)smem));
   CcfPrepArgs a;
   a.lam = d_lam; a.spec = d_spec; a.espec = d_espec; a.bad = d_bad; a.Cb = d_basis; a.bin = d_bin;
   a.left = d_left; a.wr = d_wr; a.pspec = d_pspec; a.pivar = d_pivar; a.cont = d_cont;

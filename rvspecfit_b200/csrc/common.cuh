@@ -12,6 +12,15 @@ namespace rvs {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// Raise (never lower) the dynamic shared memory limit of a kernel to at least `smem`
+// bytes.  The limit is per-function state of the device: concurrent host threads that set
+// it to the size of their own launch lower it under each other's feet ("too many
+// resources requested for launch"); here it only grows, under a lock.
+cudaError_t ensure_dyn_smem_ptr(const void *kern, size_t smem);
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kern, size_t smem) {
+  return ensure_dyn_smem_ptr(reinterpret_cast<const void *>(kern), smem);
+}
 
 // Optional per-stage timing (rvs_profile_enable): CUDA events bracket each kernel
 // of the fused evaluation on its launching stream; rvs_profile_read sums them.

@@ -28,13 +28,9 @@ int launch_gram_mma_group3(const GramMmaArgsM &, int, int, cudaStream_t);
 template <typename GT, int NV, bool TMA = false>
 static int launch_chunk(const ChunkArgsM &m, int narm, size_t smem, cudaStream_t st) {
   auto kern = chunk_kernel<GT, NV, TMA>;
-  // once per size (per instantiation): keeps the call out of CUDA-graph captures after
-  // the first, uncaptured evaluation
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    RVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  // raised once per size: keeps the call out of CUDA-graph captures after the first,
+  // uncaptured evaluation
+  RVS_CUDA_OK(ensure_dyn_smem(kern, smem));
   int64_t blocks = 0;
   for (int i = 0; i < narm; i++) {
     const int64_t warps = (int64_t)m.a[i].K * m.a[i].nch;

@@ -18,12 +18,7 @@ static int launch_gram_np(const GramArgs &a, int K, cudaStream_t st) {
   const size_t smem = sizeof(double) * GR_DEPTH * GR_THREADS * gram_slot(NP);
   RVS_REQUIRE(a.npp == ((NP + 1) & ~1), RVS_E_ARG, "gram: basis rows of %d doubles, expected %d",
               a.npp, (NP + 1) & ~1);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    RVS_CUDA_OK(cudaFuncSetAttribute(gram_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    smem_set = smem;
-  }
+  RVS_CUDA_OK(ensure_dyn_smem(gram_kernel<NP>, smem));
   gram_kernel<NP><<<K, GR_THREADS, smem, st>>>(a);
   RVS_LAUNCH_OK();
   return 0;
@@ -44,12 +39,7 @@ static int launch_gram_mma_np(GramMmaArgsM m, int narm, cudaStream_t st) {
   dim3 grid(groups, KS, narm);
   size_t tile_smem = sizeof(double) * GM_WARPS * GM_NSTG * gm_stage_doubles(a.npp, NI);
   tile_smem = std::max(tile_smem, sizeof(double) * GramTiles<NP>::ROWS * (NI + 1));  // s_red alias
-  static size_t smem_set = 0;
-  if (tile_smem > smem_set) {
-    RVS_CUDA_OK(cudaFuncSetAttribute(gram_mma_kernel<NP, NT>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-    smem_set = tile_smem;
-  }
+  RVS_CUDA_OK(ensure_dyn_smem(gram_mma_kernel<NP, NT>, tile_smem));
   prof_begin(ST_GRAM, st);
   gram_mma_kernel<NP, NT><<<grid, GM_THREADS, tile_smem, st>>>(m);
   prof_end(ST_GRAM, st);

@@ -43,8 +43,7 @@ __global__ void __launch_bounds__(TB_THREADS) template_build_kernel(TemplateArgs
 template <typename GT>
 static int launch_template(const TemplateArgs &a, int K, size_t smem, cudaStream_t st) {
   auto go = [&](auto kern) -> int {
-    RVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+    RVS_CUDA_OK(ensure_dyn_smem(kern, smem));
     kern<<<K, TB_THREADS, smem, st>>>(a);
     RVS_LAUNCH_OK();
     return 0;
