@@ -18,10 +18,15 @@ rules of the single-object path:
     forward-difference gradient per live problem and round, in one launch;
   * the Hessian is the same central-difference stencil as vel_fit's, all
     objects' points in one launch.
-The objects are split into a few lock-step sets, each a coroutine that yields
-its evaluation requests (fit_steps); run_pipeline keeps one request of every
-set in flight, so the host logic of one set and the latency-bound tail of
-another (few live problems) hide under the device work of the rest.
+The objects are split into a few lock-step sets, each a coroutine on a host thread of
+its own (fit_steps, run_threads).  The rounds of both optimiser stages are stepped by
+the library without the interpreter (rvs_nm_drive / rvs_bfgs_drive on an evaluation slot
+the stage holds: stepper, packing, captured graph launch, wait, reduction), and the
+objects that have finished a stage move on in groups while the slower ones iterate, so
+the host logic of one set and the latency-bound tail of a stage (few live problems) run
+beside the large calls of the rest.  threads=False keeps everything on the calling thread
+with the numpy steppers (nelder_mead_steps / batch_bfgs.bfgs_steps), which visit scipy's
+points bit for bit.
 """
 import os
 
