@@ -24,9 +24,9 @@ the library without the interpreter (rvs_nm_drive / rvs_bfgs_drive on an evaluat
 the stage holds: stepper, packing, captured graph launch, wait, reduction), and the
 objects that have finished a stage move on in groups while the slower ones iterate, so
 the host logic of one set and the latency-bound tail of a stage (few live problems) run
-beside the large calls of the rest.  threads=False keeps everything on the calling thread
-with the numpy steppers (nelder_mead_steps / batch_bfgs.bfgs_steps), which visit scipy's
-points bit for bit.
+beside the large calls of the rest.  threads=False keeps everything on the calling thread,
+rounds driven from Python (NMStepper / batch_bfgs.bfgs_steps, which visit scipy's points
+bit for bit).
 """
 import os
 
