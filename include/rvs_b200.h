@@ -501,7 +501,8 @@ typedef struct {
   int64_t t_cap, t_n;
   int32_t timed, pad_;
 } rvs_drive;
-/* A non-blocking stream owned by the caller (cudaStream_t; NULL on failure). */
+/* A non-blocking stream owned by the caller (cudaStream_t; NULL on failure).
+ * high_priority: 0 = least priority (the default stream's), 1 = halfway, 2 = greatest. */
 void *rvs_stream_create(int high_priority);
 void rvs_stream_destroy(void *stream);
 /* Item count of an evaluation call rounded up to a launch configuration. */

@@ -55,11 +55,13 @@ extern "C" void *rvs_stream_create(int high_priority) {
   // A stream of its own for every in-flight evaluation: framework stream pools hand the
   // same few handles out again and again, and two evaluations that share a stream cannot
   // be captured and launched by different threads.
-  int lo = 0, hi = 0;
+  // high_priority: 0 least (that of the default stream), 1 halfway, 2 greatest
+  int least = 0, greatest = 0;
   cudaStream_t st = nullptr;
-  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
-  if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, high_priority ? hi : lo) != cudaSuccess)
-    return nullptr;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return nullptr;
+  const int prio = high_priority <= 0 ? least
+                   : (high_priority == 1 ? (least + greatest) / 2 : greatest);
+  if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
   return st;
 }
 

@@ -298,6 +298,8 @@ class SpectrumBatch:
 # kernels launched through CUDA-graph replays by all engines of this process
 # (rvs_launch_count only sees direct launches)
 GRAPH_LAUNCHES = [0]
+# priority of the evaluation slots' streams (rvs_stream_create: 0 least, 1 halfway, 2 greatest)
+SLOT_STREAM_PRIORITY = int(os.environ.get('RVS_SLOT_PRIO', '0'))
 LAST_DRIVE_ROUNDS = [0]     # rounds of the last native Nelder-Mead stage (tests)
 
 
@@ -661,7 +663,7 @@ class LikelihoodEngine:
             # streams of the slot's own (torch.cuda.Stream() hands out the handles of a
             # small pool round-robin: slots would share streams)
             def own_stream():
-                h = L.rvs_stream_create(0)
+                h = L.rvs_stream_create(SLOT_STREAM_PRIORITY)
                 if not h:
                     raise _cabi.RvsError('rvs_stream_create failed')
                 return torch.cuda.ExternalStream(h)
