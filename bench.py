@@ -569,6 +569,13 @@ def run_gpu(args):
                    'fit_evals_per_spectrum': (eng.n_eval / (args.steps + args.warmup) / B
                                               if fit else args.evals),
                    'lockstep_groups': (args.groups if args.groups else 'auto'),
+                   'fit_driver': {'sets': args.groups or batch_fit.FIT_MAX_GROUPS,
+                                  'set_sizes': batch_fit.FIT_SPLIT.get(
+                                      args.groups or batch_fit.FIT_MAX_GROUPS),
+                                  'handover_min_objects': batch_fit.PEEL_MIN if batch_fit.PEEL else None,
+                                  'speculate_below': batch_fit.SPECULATE_BELOW,
+                                  'native_round_loop': bool(batch_fit.NATIVE_DRIVE),
+                                  'native_bfgs': bool(batch_fit.NATIVE_BFGS)},
                    'mode': args.mode, 'step': step_txt, 'resolution_matrix_diagonals': nd,
                    'l2': 'template grid (>=0.7 GB per arm) is larger than L2; rows gathered '
                          'at random per evaluation',
