@@ -159,6 +159,58 @@ def test_native_bfgs_follows_the_lockstep_restatement():
         assert abs(np.mean(got['nit']) - np.mean(want['nit'])) <= 0.3 * np.mean(want['nit']) + 2
 
 
+def test_native_bfgs_edge_cases_follow_the_restatement():
+    """Starts that are already stationary, objectives that turn NaN or infinite, a single
+    iteration budget: the exits (scipy's warnflag) and iteration counts of BFGSStepper equal
+    those of bfgs_steps; and while some problems still search, result() already holds the
+    final rows of those that have stopped (what the hand-over between stages relies on)."""
+    from rvspecfit_b200 import batch_bfgs
+    B, N = 12, 3
+    cen = np.linspace(-1, 1, B * N).reshape(B, N)
+
+    def fbatch(idx, X):
+        d = X - cen[idx]
+        f = 5.0 + np.sum(d**2, axis=1) + 0.1 * np.sum(d**4, axis=1)
+        f = np.where(X[:, 0] > 2.5, np.nan, f)            # a wall of NaN
+        f = np.where(X[:, 1] < -2.5, np.inf, f)           # and one of +inf
+        return f
+    x0 = cen + 0.3
+    x0[0] = cen[0]                      # stationary start: no iteration
+    x0[1] = cen[1] + [3.0, 0, 0]        # starts behind the NaN wall
+    x0[2] = cen[2] + [0, -3.2, 0]       # starts behind the inf wall
+    x0[3] = cen[3] + [2.4 - cen[3, 0], 0, 0]    # next to the NaN wall, gradient pointing away
+    for maxiter in (None, 1, 3):
+        want = batch_bfgs.bfgs_lockstep(fbatch, x0, None, maxiter=maxiter)
+        got = batch_bfgs.bfgs_lockstep(fbatch, x0, None, native=True, maxiter=maxiter)
+        assert np.array_equal(got['status'], want['status']), (maxiter, got['status'], want['status'])
+        assert np.array_equal(got['nit'], want['nit']), maxiter
+        assert got['rounds'] == want['rounds']
+        ok = np.isfinite(want['fun'])
+        assert np.array_equal(np.isfinite(got['fun']), ok)
+        assert np.allclose(got['x'][ok], want['x'][ok], rtol=0, atol=1e-7)
+        assert np.allclose(got['fun'][ok], want['fun'][ok], rtol=1e-12)
+    assert {0, 3} <= set(want['status'].tolist()) or {0, 2} <= set(want['status'].tolist())
+    # rows of stopped problems are final while the others search
+    st = batch_bfgs.BFGSStepper(x0 * np.linspace(1, 3, B)[:, None])
+    snaps = []
+    try:
+        while True:
+            req = st.request()
+            if req is None:
+                break
+            st.feed(fbatch(*req))
+            act = st.active()
+            if act.any() and not act.all():
+                snaps.append((~act, st.result()))
+        final = st.result()
+    finally:
+        st.close()
+    assert len(snaps) > 2
+    for stopped, res in snaps:
+        for k in ('x', 'fun', 'nit', 'status'):
+            assert np.array_equal(res[k][stopped], final[k][stopped], equal_nan=True), k
+
+
 def test_hessian_points_replay_central_hessian():
     """The vectorised Hessian stencil asks for exactly the points of
     vel_fit.central_hessian and combines their values with its arithmetic."""
