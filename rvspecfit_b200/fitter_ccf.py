@@ -158,15 +158,23 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=Non
     maxvel, vel_grid = _velocity_grid(config)
     nvel = len(vel_grid)
     banks = {}
+    checked = set()     # pairs of setups whose banks were compared
     for o in objects:
-        ref = get_ccf_info(o[0].name, config)
+        ref = banks.get(o[0].name)
+        if ref is None:
+            ref = banks[o[0].name] = get_ccf_info(o[0].name, config)
         for sd in o:
-            b = banks.setdefault(sd.name, get_ccf_info(sd.name, config))
+            b = banks.get(sd.name)
+            if b is None:
+                b = banks[sd.name] = get_ccf_info(sd.name, config)
+            if b is ref or (ref.name, b.name) in checked:
+                continue
             if (ref.parnames != b.parnames or not np.array_equal(ref.params, b.params)
                     or not np.array_equal(ref.vsinis, b.vsinis)):
                 raise RuntimeError('The parameters of the CCF templates do not match')
             if b.ntempl != ref.ntempl:
                 raise RuntimeError('CCF template counts are inconsistent across setups')
+            checked.add((ref.name, b.name))
     ntempl = next(iter(banks.values())).ntempl
     # host preprocessing (row f3): proc[i][a] = (proc_spec, proc_ivar); the continuum fits
     # of a batch run in a pool of host processes (make_ccf.preprocess_many)
@@ -197,7 +205,11 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=Non
     d_vg = _dev.upload(vel_grid, np.float64)
     block = max(1, int(CHISQ_BLOCK_BYTES // (ntempl * nvel * 8)))
     results = [None] * nobj
-    for i0 in range(0, nobj, block):
+    torch = _dev.torch_mod()
+
+    def enqueue(i0):
+        """Device work of the block of objects from i0: correlation of every arm, best
+        template and lag, results on their way to pinned host memory behind an event."""
         ids = range(i0, min(nobj, i0 + block))
         nrow = len(ids)
         d_chisq = _dev.zeros((nrow, ntempl, nvel), np.float64)
@@ -231,7 +243,29 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=Non
         rc = L.rvs_ccf_best(_dev.ptr(d_chisq), _dev.ptr(d_sse), _dev.ptr(d_vg), nrow, ntempl, nvel,
                             _dev.ptr(d_out), _dev.ptr(d_best), _dev.stream())
         _cabi.check(rc, 'rvs_ccf_best')
-        out, best = _dev.download(d_out), _dev.download(d_best)
+        h_out = torch.empty((nrow, 8), dtype=torch.float64, pin_memory=True)
+        h_best = torch.empty((nrow, nvel), dtype=torch.float64, pin_memory=True)
+        h_out.copy_(d_out, non_blocking=True)
+        h_best.copy_(d_best, non_blocking=True)
+        _dev.IO_BYTES[1] += (h_out.numel() + h_best.numel()) * 8
+        done = torch.cuda.Event()
+        done.record()
+        return ids, h_out, h_best, done, (d_out, d_best, d_chisq)
+
+    def rolled(model, shift):
+        """np.roll(model, shift) (fitter_ccf.py:240-244) without its bookkeeping."""
+        n = len(model)
+        s_ = shift % n
+        out = np.empty_like(model)
+        out[s_:] = model[:n - s_]
+        out[:s_] = model[n - s_:]
+        return out
+
+    def finish(ids, h_out, h_best, done, _keep):
+        """Result dictionaries of a block (host work: runs under the next block's kernels)."""
+        done.synchronize()
+        out = h_out.numpy()
+        best = h_best.numpy().copy()        # rows outlive the pinned buffer
         for r, i in enumerate(ids):
             if not out[r, 4]:
                 logging.error('Cross-correlation failed')
@@ -243,8 +277,8 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=Non
             results[i] = dict(
                 best_par=dict(zip(ref.parnames, ref.params[bid])), best_vel=bvel,
                 best_ccf=best[r], best_vsini=ref.vsinis[bid],
-                best_model={sd.name: np.roll(banks[sd.name].models[bid],
-                                             int(bvel / banks[sd.name].velstep))
+                best_model={sd.name: rolled(banks[sd.name].models[bid],
+                                            int(bvel / banks[sd.name].velstep))
                             for sd in objects[i]},
                 vel_grid=vel_grid, best_id=bid)
             if want_proc_spec:
@@ -252,6 +286,19 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=Non
                     sd.name: (proc[i][a][0] if isinstance(proc[i][a][0], np.ndarray)
                               else _dev.download(proc[i][a][0]))
                     for a, sd in enumerate(objects[i])}
+
+    # blocks in a two-deep pipeline: the host assembles the results of one block while the
+    # device correlates the next
+    if nobj >= 256:
+        block = min(block, -(-nobj // 4))
+    pending = None
+    for i0 in range(0, nobj, block):
+        ctx = enqueue(i0)
+        if pending is not None:
+            finish(*pending)
+        pending = ctx
+    if pending is not None:
+        finish(*pending)
     return results
 
 
