@@ -198,8 +198,8 @@ def fit_batch(objects, config, preprocessed=None, raise_errors=True, workers=Non
         first = objects[members[0][0]][members[0][1]]
         prep = make_ccf.device_prep(first.lam, gkey, banks[name].ccfconf)
         sds = [objects[i][a] for i, a in members]
-        d_ps, d_pi = prep(np.stack([s.spec for s in sds]), np.stack([s.espec for s in sds]),
-                          np.stack([s.badmask for s in sds]))
+        d_ps, d_pi = prep([s.spec for s in sds], [s.espec for s in sds],
+                          [s.badmask for s in sds])
         for r, (i, a) in enumerate(members):
             proc[i][a] = (d_ps[r], d_pi[r])          # device rows
     d_vg = _dev.upload(vel_grid, np.float64)

@@ -173,13 +173,21 @@ class DevicePrep:
             self.d_wr = _dev.upload(wr, np.float64)
 
     def __call__(self, spec, espec, badmask=None, maxerr=10, want_cont=False):
-        """spec, espec (n, npix) host arrays, badmask (n, npix) bool or None ->
-        device tensors (proc_spec, proc_ivar) of shape (n, npoints) [, cont, info]."""
+        """spec, espec (n, npix) host arrays -- or lists of n rows, which then go row by
+        row into pinned staging and up in one asynchronous copy each --, badmask (n, npix)
+        bool or None -> device tensors (proc_spec, proc_ivar) of shape (n, npoints)
+        [, cont, info]."""
         from . import _cabi, _dev
         torch = _dev.torch_mod()
         n = len(spec)
-        d_spec, d_espec = _dev.upload(spec, np.float64), _dev.upload(espec, np.float64)
-        d_bad = None if badmask is None else \
+        if isinstance(spec, list):
+            d_spec = _dev.upload_concat(spec, np.float64)[1]
+            d_espec = _dev.upload_concat(espec, np.float64)[1]
+            if badmask is not None:
+                badmask = _dev.upload_concat(badmask, np.bool_)[1].view(torch.uint8)
+        else:
+            d_spec, d_espec = _dev.upload(spec, np.float64), _dev.upload(espec, np.float64)
+        d_bad = None if badmask is None else badmask if torch.is_tensor(badmask) else \
             torch.from_numpy(np.ascontiguousarray(badmask, dtype=np.uint8)).to(_dev.device())
         d_ps = _dev.empty((n, self.npoints), np.float64)
         d_pi = _dev.empty((n, self.npoints), np.float64)
